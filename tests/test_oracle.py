@@ -1,0 +1,135 @@
+"""T0: the oracle (oracle/evoke_oracle.py) against the golden vectors recorded from the
+reference itself (oracle/make_golden.py), and - in the build container only - against the
+live reference through the import shim."""
+import numpy as np
+import pytest
+import torch
+
+import golden_cases as gc
+from oracle import evoke_oracle as orc
+from oracle import ref_shim
+
+G_CASES = [c for c in gc.CASES if c.kind == "G"]
+MPC_CASES = [c for c in gc.CASES if c.kind == "MPC"]
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("case", G_CASES, ids=lambda c: c.name)
+def test_g_closed_form_matches_reference_golden(case):
+    inp = gc.build_inputs(case)
+    gold = gc.load_golden(case)
+    loss, d_i, d_t, _ = orc.g_loss_closed_form(inp["image"], inp["text"], inp["ids"], case.tau)
+    rows = gold["rows"]
+    assert abs(loss - gold["loss64"]) <= 1e-11 * abs(gold["loss64"])
+    # the zero-norm row has a 1e12-scale gradient (g/eps); compare relatively
+    assert _rel(d_i[rows], gold["d_image64"]) < 1e-9
+    assert _rel(d_t[rows], gold["d_text64"]) < 1e-9
+    assert abs(np.linalg.norm(d_i) - gold["d_image_norm64"]) <= 1e-9 * gold["d_image_norm64"]
+    assert abs(np.linalg.norm(d_t) - gold["d_text_norm64"]) <= 1e-9 * gold["d_text_norm64"]
+    # the fp32 run of the reference agrees with its own fp64 run to fp32 accuracy
+    assert abs(gold["loss32"] - gold["loss64"]) <= 2e-6 * abs(gold["loss64"])
+
+
+@pytest.mark.parametrize("case", MPC_CASES, ids=lambda c: c.name)
+def test_mpc_closed_form_matches_reference_golden(case):
+    inp = gc.build_inputs(case)
+    gold = gc.load_golden(case)
+    loss, dx = orc.mpc_closed_form(inp["image"], inp["ids"], case.tau)
+    if gold["empty"]:
+        assert loss is None and tuple(gold["out_shape"]) == (1,) and gold["loss64"] == 0.0
+        assert not dx.any()
+        return
+    assert tuple(gold["out_shape"]) == ()
+    assert abs(loss - gold["loss64"]) <= 1e-11 * abs(gold["loss64"])
+    assert _rel(dx[gold["rows"]], gold["d_image64"]) < 1e-9
+    assert abs(np.linalg.norm(dx) - gold["d_image_norm64"]) <= 1e-9 * gold["d_image_norm64"]
+
+
+@pytest.mark.parametrize("case", [c for c in gc.CASES if c.n <= 1024], ids=lambda c: c.name)
+def test_packed_mask_bit_exact(case):
+    inp = gc.build_inputs(case)
+    gold = gc.load_golden(case)
+    ids = inp["ids"][: case.n] if case.kind == "G" else inp["ids"]
+    bits, counts = orc.posmask_packed(ids, clear_diag=(case.kind == "MPC"))
+    assert bits.dtype == np.uint32 and np.array_equal(bits, gold["mask_bits"])
+    assert np.array_equal(counts, gold["counts"])
+    # factorised int ids have the same equality structure as the string keys
+    bits2, counts2 = orc.posmask_packed(orc.factorize_ids(ids), clear_diag=(case.kind == "MPC"))
+    assert np.array_equal(bits2, bits) and np.array_equal(counts2, counts)
+
+
+def test_packed_mask_rectangular_and_offset():
+    rng = np.random.default_rng(0)
+    ids = rng.integers(0, 40, size=200).astype(np.int32)
+    full, _ = orc.posmask_packed(ids, clear_diag=True)
+    blk, cnt = orc.posmask_packed(ids[64:128], ids, clear_diag=True, row_offset=64)
+    assert np.array_equal(blk, full[64:128])
+    assert np.array_equal(cnt, orc.posmask_dense(ids, clear_diag=True)[64:128].sum(1))
+
+
+@pytest.mark.parametrize("case", gc.CASES, ids=lambda c: c.name)
+def test_torch_port_matches_golden(case):
+    """The timed CPU baseline (kind 'port') computes what the reference computes."""
+    inp = gc.build_inputs(case)
+    gold = gc.load_golden(case)
+    image = torch.tensor(inp["image"], dtype=torch.float64, requires_grad=True)
+    if case.kind == "G":
+        text = torch.tensor(inp["text"], dtype=torch.float64, requires_grad=True)
+        out = orc.global_alignment_loss_port(image, text, inp["ids"], case.tau)
+    else:
+        out = orc.multi_pos_contra_images_port(image, inp["ids"], case.tau)
+    assert tuple(out.shape) == tuple(gold["out_shape"])
+    assert abs(out.sum().item() - gold["loss64"]) <= 1e-11 * max(abs(gold["loss64"]), 1.0)
+    if out.grad_fn is not None:
+        out.backward()
+        assert _rel(image.grad.numpy()[gold["rows"]], gold["d_image64"]) < 1e-9
+
+
+def test_normalize_bwd_matches_autograd():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((9, 33))
+    x[4] = 0.0
+    g = rng.standard_normal((9, 33))
+    xt = torch.tensor(x, requires_grad=True)
+    torch.nn.functional.normalize(xt, dim=-1, p=2).backward(torch.tensor(g))
+    assert _rel(orc.l2_normalize_bwd(x, g), xt.grad.numpy()) < 1e-12
+
+
+# ------------------------------------------------------------------ live reference (container only)
+@pytest.mark.reference
+@pytest.mark.parametrize("n,d,tau", [(8, 16, 0.5), (50, 96, 0.07), (130, 64, 0.5)])
+def test_closed_forms_against_live_reference(n, d, tau):
+    ids = gc.synth.make_study_ids(n, seed=n)
+    x = gc.synth.make_embeddings(ids, d, seed=n + 1).astype(np.float64)
+    t = gc.synth.make_embeddings(ids, d, seed=n + 2).astype(np.float64)
+    xi = torch.tensor(x, requires_grad=True)
+    ti = torch.tensor(t, requires_grad=True)
+    ref = ref_shim.global_alignment_loss(xi, ti, ids, tau)
+    ref.backward()
+    loss, d_i, d_t, _ = orc.g_loss_closed_form(x, t, ids, tau)
+    assert abs(loss - ref.item()) < 1e-11 * abs(ref.item())
+    assert _rel(d_i, xi.grad.numpy()) < 1e-9 and _rel(d_t, ti.grad.numpy()) < 1e-9
+    xm = torch.tensor(x, requires_grad=True)
+    refm = ref_shim.multi_pos_contra_images_v0401(xm, ids, tau)
+    lossm, dxm = orc.mpc_closed_form(x, ids, tau)
+    if refm.grad_fn is None:
+        assert lossm is None
+    else:
+        refm.backward()
+        assert abs(lossm - refm.item()) < 1e-11 * abs(refm.item())
+        assert _rel(dxm, xm.grad.numpy()) < 1e-9
+
+
+@pytest.mark.reference
+def test_avgpos_variants_against_live_reference():
+    ids = gc.synth.make_study_ids(40, seed=3)
+    x = gc.synth.make_embeddings(ids, 48, seed=4).astype(np.float64)
+    t = gc.synth.make_embeddings(ids, 48, seed=5).astype(np.float64)
+    # the reference accumulates into an fp32 tensor([0.0]) (:771, :690), so 1e-7 is its own noise
+    ref = ref_shim.avgpos_global_alignment_loss(torch.tensor(x), torch.tensor(t), ids, 0.5)
+    assert abs(orc.avgpos_g_loss_closed_form(x, t, ids, 0.5) - ref.item()) < 2e-6
+    ref2 = ref_shim.avgpos_multi_pos_contra_images_v0404(torch.tensor(x), ids, 0.5)
+    assert abs(orc.avgpos_mpc_closed_form(x, ids, 0.5) - ref2.item()) < 2e-6
