@@ -1,0 +1,16 @@
+"""evoke_b200 — B200-native (sm_100a) implementation of EVOKE's multi-view, multi-positive
+image-text contrastive objective, forward and backward, behind the reference's own method
+signatures.  See DESIGN.md / INTEGRATION.md.
+
+Importing the package does not load the CUDA library; the first loss call does, and fails
+loudly if it is missing (there is no CPU or PyTorch fallback).
+"""
+from .loss import (ContrastiveObjective, global_alignment, global_alignment_loss, multi_pos_contra_images,
+                   multi_pos_contra_images_v0401, patch_pretrain)
+from .lm_loss import LanguageModelCriterion, compute_lm_loss
+
+__all__ = [
+    "ContrastiveObjective", "global_alignment", "global_alignment_loss", "multi_pos_contra_images",
+    "multi_pos_contra_images_v0401", "patch_pretrain", "LanguageModelCriterion", "compute_lm_loss",
+]
+__version__ = "0.1.0"

@@ -1,0 +1,81 @@
+"""ctypes binding of libevoke_b200.so (the C ABI declared in include/evoke_b200.h).
+
+The library is loaded lazily on first use and there is NO fallback: if it is missing or a
+call fails, a RuntimeError/ValueError carrying ``evk_last_error()`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libevoke_b200.so")
+
+EVK_OK, EVK_ERR_INVALID, EVK_ERR_CUDA, EVK_ERR_UNSUPPORTED = 0, -1, -2, -3
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+FLAG_EXCLUDE_DIAG, FLAG_NO_COLSUM, FLAG_SPLIT_BF16 = 1, 2, 4
+ABI_VERSION = 1
+
+P, I, L, F, D = c_void_p, c_int, c_int64, c_float, c_double
+
+# name -> argtypes, in header order.  tests/test_abi.py checks this table against the header.
+SIGNATURES = {
+    "evk_version": [],
+    "evk_last_error": [],
+    "evk_device_info": [I, P, P, P],
+    "evk_l2norm_fwd": [P, I, L, L, L, L, P, P, L, P, P, L, P, P],
+    "evk_l2norm_bwd": [P, I, L, L, L, L, P, P, P, L, P, F, P, I, L, I, P],
+    "evk_posmask_build": [P, P, L, P, P, L, L, I, P, L, P, P],
+    "evk_mpce_small_fwd": [P, L, P, L, L, L, L, P, L, F, I, L, P, P, P],
+    "evk_mpce_small_bwd": [P, L, P, L, L, L, L, P, L, P, P, P, F, I, L, P, L, P],
+    "evk_reduce_partials": [P, L, L, L, P, P],
+    "evk_mpce_finalize": [P, P, P, L, P, L, L, L, F, F, D, P, P, P, P],
+    "evk_mpce_fwd": [P, P, L, P, P, L, L, L, L, P, L, F, I, L, P, P, L, P, L, P],
+    "evk_mpce_bwd_w": [P, P, L, P, P, L, L, L, L, P, L, P, P, P, F, I, L, P, P, L, P],
+    "evk_mpce_bwd_gemm": [P, P, L, L, L, I, P, P, L, L, F, I, P, L, P],
+    "evk_tc_gemm_probe": [P, L, I, P, L, I, L, L, L, P, L, I, I, P],
+}
+
+_lib = None
+
+
+class EvokeLibraryError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise EvokeLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m evoke_b200.build` "
+            "(or __graft_entry__.build()).  evoke_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = ABI mismatch, fail loudly
+        fn.argtypes = argtypes
+        fn.restype = c_char_p if name == "evk_last_error" else c_int
+    ver = lib.evk_version()
+    if ver != ABI_VERSION:
+        raise EvokeLibraryError(f"libevoke_b200.so ABI version {ver} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return (load().evk_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc == EVK_OK:
+        return
+    msg = f"{what}: {last_error()} (code {rc})"
+    if rc == EVK_ERR_INVALID:
+        raise ValueError(msg)
+    raise EvokeLibraryError(msg)
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,240 @@
+// Small path: fp32 SIMT fused similarity + masked multi-positive softmax statistics (forward)
+// and the row-direction gradient contraction (backward) for reference-sized batches (the
+// reference trains with 32 studies per step, run_cxr_pt_224.sh:14).  At these sizes the work is
+// launch-latency bound; a 128x256 tcgen05 tile would be mostly padding.  Exact fp32 FMA
+// arithmetic makes this the tightest-parity path (fp32 loss ~1e-6 rel).
+//
+// One CTA owns kTM query rows and streams all key columns in tiles of 256 (one column per
+// thread).  Nothing of size n_rows x n_cols is stored; the backward recomputes the S tile.
+// Replaces, for one softmax direction, the mm + /temp + cross_entropy of
+// models/model_pretrain_finetune_v0520.py:499-502 (G) and :437-443 (MPC).
+#include "evk_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;        // = key columns per tile
+constexpr int kTM = 8;               // query rows per CTA
+constexpr int kDK = 32;              // feature chunk staged through shared memory
+constexpr int kMaxSlots = 8;         // backward: feature columns per thread per pass (8*256 = 2048)
+
+template <bool kBwd>
+__global__ void __launch_bounds__(kThreads)
+small_rows_kernel(const float* __restrict__ q, int64_t ld_q, const float* __restrict__ k, int64_t ld_k,
+                  int64_t n_rows, int64_t n_cols, int d, int d_pad, const uint32_t* __restrict__ bits,
+                  int64_t ld_words, const int32_t* __restrict__ counts, const float* __restrict__ a_row,
+                  const float* __restrict__ b_col, float inv_tau, int flags, int64_t diag_offset,
+                  float* __restrict__ row_sum, float* __restrict__ row_pos, float* __restrict__ dq,
+                  int64_t ld_dq) {
+  extern __shared__ __align__(16) float smem[];
+  float* qs = smem;                                  // [kTM][d_pad]
+  float* kt = qs + (size_t)kTM * d_pad;              // [256][kDK+1]
+  float* ws = kt + kThreads * (kDK + 1);             // [256][kTM]   (backward) / reduction scratch
+
+  const int t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * kTM;
+  const float shift = inv_tau;                       // |S| <= inv_tau for unit rows
+  const bool excl = (flags & EVK_FLAG_EXCLUDE_DIAG) != 0;
+
+  for (int i = t; i < kTM * d_pad; i += kThreads) {
+    const int r = i / d_pad, c = i - r * d_pad;
+    qs[i] = (r0 + r < n_rows && c < d) ? q[(r0 + r) * ld_q + c] : 0.f;
+  }
+
+  float a_i[kTM], neg2_over_c[kTM];
+  if (kBwd) {
+#pragma unroll
+    for (int r = 0; r < kTM; ++r) {
+      const bool ok = r0 + r < n_rows;
+      a_i[r] = ok ? a_row[r0 + r] : 0.f;
+      const int c = ok ? counts[r0 + r] : 1;
+      neg2_over_c[r] = -2.f / (float)(c > 0 ? c : 1);
+    }
+  }
+
+  float rs[kTM], rp[kTM];
+#pragma unroll
+  for (int r = 0; r < kTM; ++r) rs[r] = rp[r] = 0.f;
+
+  const int n_pass = kBwd ? (d + kMaxSlots * kThreads - 1) / (kMaxSlots * kThreads) : 1;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const int dbase = pass * kMaxSlots * kThreads;
+    float acc[kBwd ? kMaxSlots : 1][kTM];
+    if (kBwd) {
+#pragma unroll
+      for (int m = 0; m < kMaxSlots; ++m)
+#pragma unroll
+        for (int r = 0; r < kTM; ++r) acc[m][r] = 0.f;
+    }
+
+    for (int64_t j0 = 0; j0 < n_cols; j0 += kThreads) {
+      // ---- phase A: S[kTM, 256] tile, one key column per thread ----
+      float s[kTM];
+#pragma unroll
+      for (int r = 0; r < kTM; ++r) s[r] = 0.f;
+      for (int dk0 = 0; dk0 < d_pad; dk0 += kDK) {
+        __syncthreads();                             // kt (and, first time, qs) hazards
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const int row = warp * 32 + i;
+          const int64_t j = j0 + row;
+          const int c = dk0 + lane;
+          kt[row * (kDK + 1) + lane] = (j < n_cols && c < d) ? __ldg(k + j * ld_k + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d4 = 0; d4 < kDK / 4; ++d4) {
+          const float k0 = kt[t * (kDK + 1) + d4 * 4 + 0];
+          const float k1 = kt[t * (kDK + 1) + d4 * 4 + 1];
+          const float k2 = kt[t * (kDK + 1) + d4 * 4 + 2];
+          const float k3 = kt[t * (kDK + 1) + d4 * 4 + 3];
+#pragma unroll
+          for (int r = 0; r < kTM; ++r) {
+            const float4 qv = *reinterpret_cast<const float4*>(qs + r * d_pad + dk0 + d4 * 4);
+            s[r] = fmaf(qv.x, k0, s[r]);
+            s[r] = fmaf(qv.y, k1, s[r]);
+            s[r] = fmaf(qv.z, k2, s[r]);
+            s[r] = fmaf(qv.w, k3, s[r]);
+          }
+        }
+      }
+      // ---- softmax statistics / W for this tile ----
+      const int64_t j = j0 + t;
+      const bool col_ok = j < n_cols;
+      const float b_j = (kBwd && col_ok) ? b_col[j] : 0.f;
+#pragma unroll
+      for (int r = 0; r < kTM; ++r) {
+        const int64_t i = r0 + r;
+        const bool ok = col_ok && i < n_rows;
+        const float sv = s[r] * inv_tau;
+        float e = ok ? expf(sv - shift) : 0.f;
+        if (excl && j == i + diag_offset) e = 0.f;
+        const bool pos = ok && ((bits[i * ld_words + (j >> 5)] >> (j & 31)) & 1u);
+        if (!kBwd) {
+          if (pass == 0) {
+            rs[r] += e;
+            rp[r] += pos ? sv : 0.f;
+          }
+        } else {
+          float w = e * (a_i[r] + b_j) + (pos ? neg2_over_c[r] : 0.f);
+          if (excl && j == i + diag_offset) w = 0.f;
+          ws[t * kTM + r] = w;
+        }
+      }
+      if (kBwd) {
+        // ---- phase B: dq[kTM, dbase + slots] += W[kTM, tile] . k[tile, :] ----
+        __syncthreads();
+        const int jn = (int)((n_cols - j0) < kThreads ? (n_cols - j0) : kThreads);
+        for (int jj = 0; jj < jn; ++jj) {
+          const float4 w0 = *reinterpret_cast<const float4*>(ws + jj * kTM);
+          const float4 w1 = *reinterpret_cast<const float4*>(ws + jj * kTM + 4);
+          const float* kr = k + (j0 + jj) * ld_k + dbase + t;
+#pragma unroll
+          for (int m = 0; m < kMaxSlots; ++m) {
+            const int c = dbase + t + m * kThreads;
+            if (c < d) {
+              const float kv = __ldg(kr + m * kThreads);
+              acc[m][0] = fmaf(w0.x, kv, acc[m][0]);
+              acc[m][1] = fmaf(w0.y, kv, acc[m][1]);
+              acc[m][2] = fmaf(w0.z, kv, acc[m][2]);
+              acc[m][3] = fmaf(w0.w, kv, acc[m][3]);
+              acc[m][4] = fmaf(w1.x, kv, acc[m][4]);
+              acc[m][5] = fmaf(w1.y, kv, acc[m][5]);
+              acc[m][6] = fmaf(w1.z, kv, acc[m][6]);
+              acc[m][7] = fmaf(w1.w, kv, acc[m][7]);
+            }
+          }
+        }
+      }
+    }
+
+    if (kBwd) {
+#pragma unroll
+      for (int m = 0; m < kMaxSlots; ++m) {
+        const int c = dbase + t + m * kThreads;
+        if (c < d) {
+#pragma unroll
+          for (int r = 0; r < kTM; ++r)
+            if (r0 + r < n_rows) dq[(r0 + r) * ld_dq + c] = acc[m][r];
+        }
+      }
+    }
+  }
+
+  if (!kBwd) {
+    // deterministic block reduction of the per-thread (per-column-residue) partial sums
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kTM; ++r) {
+      const float a = warp_sum(rs[r]);
+      const float b = warp_sum(rp[r]);
+      if (lane == 0) {
+        ws[(warp * kTM + r) * 2 + 0] = a;
+        ws[(warp * kTM + r) * 2 + 1] = b;
+      }
+    }
+    __syncthreads();
+    if (t < kTM && r0 + t < n_rows) {
+      float a = 0.f, b = 0.f;
+      for (int wv = 0; wv < kThreads / 32; ++wv) {
+        a += ws[(wv * kTM + t) * 2 + 0];
+        b += ws[(wv * kTM + t) * 2 + 1];
+      }
+      row_sum[r0 + t] = a;
+      row_pos[r0 + t] = b;
+    }
+  }
+}
+
+size_t small_smem_bytes(int d_pad) {
+  return sizeof(float) * ((size_t)kTM * d_pad + (size_t)kThreads * (kDK + 1) + (size_t)kThreads * kTM);
+}
+
+int small_check(const float* q, const float* k, int64_t n_rows, int64_t n_cols, int64_t d, const uint32_t* bits,
+                int64_t ld_words, int64_t ld_q, int64_t ld_k) {
+  EVK_REQUIRE(q && k && bits, "evk_mpce_small: null pointer");
+  EVK_REQUIRE(n_rows > 0 && n_cols > 0 && d > 0, "evk_mpce_small: empty problem (%lld x %lld x %lld)",
+              (long long)n_rows, (long long)n_cols, (long long)d);
+  EVK_REQUIRE(d <= 4096, "evk_mpce_small: d=%lld > 4096 is not supported by the small path", (long long)d);
+  EVK_REQUIRE(ld_q >= d && ld_k >= d, "evk_mpce_small: row pitch smaller than d");
+  EVK_REQUIRE(ld_words >= (n_cols + 31) / 32, "evk_mpce_small: ld_words too small");
+  return EVK_OK;
+}
+
+}  // namespace
+
+extern "C" int evk_mpce_small_fwd(const float* q, int64_t ld_q, const float* k, int64_t ld_k, int64_t n_rows,
+                                  int64_t n_cols, int64_t d, const uint32_t* bits, int64_t ld_words, float inv_tau,
+                                  int flags, int64_t diag_offset, float* row_sum, float* row_pos,
+                                  evk_stream_t stream) {
+  int rc = small_check(q, k, n_rows, n_cols, d, bits, ld_words, ld_q, ld_k);
+  if (rc != EVK_OK) return rc;
+  EVK_REQUIRE(row_sum && row_pos, "evk_mpce_small_fwd: null output");
+  const int d_pad = (int)((d + kDK - 1) / kDK * kDK);
+  const size_t smem = small_smem_bytes(d_pad);
+  EVK_CUDA(cudaFuncSetAttribute(small_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)((n_rows + kTM - 1) / kTM);
+  small_rows_kernel<false><<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      q, ld_q, k, ld_k, n_rows, n_cols, (int)d, d_pad, bits, ld_words, nullptr, nullptr, nullptr, inv_tau, flags,
+      diag_offset, row_sum, row_pos, nullptr, 0);
+  EVK_CHECK_LAUNCH("mpce_small_fwd");
+  return EVK_OK;
+}
+
+extern "C" int evk_mpce_small_bwd(const float* q, int64_t ld_q, const float* k, int64_t ld_k, int64_t n_rows,
+                                  int64_t n_cols, int64_t d, const uint32_t* bits, int64_t ld_words,
+                                  const int32_t* counts, const float* a_row, const float* b_col, float inv_tau,
+                                  int flags, int64_t diag_offset, float* dq, int64_t ld_dq, evk_stream_t stream) {
+  int rc = small_check(q, k, n_rows, n_cols, d, bits, ld_words, ld_q, ld_k);
+  if (rc != EVK_OK) return rc;
+  EVK_REQUIRE(counts && a_row && b_col && dq && ld_dq >= d, "evk_mpce_small_bwd: null pointer or ld_dq < d");
+  const int d_pad = (int)((d + kDK - 1) / kDK * kDK);
+  const size_t smem = small_smem_bytes(d_pad);
+  EVK_CUDA(cudaFuncSetAttribute(small_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)((n_rows + kTM - 1) / kTM);
+  small_rows_kernel<true><<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      q, ld_q, k, ld_k, n_rows, n_cols, (int)d, d_pad, bits, ld_words, counts, a_row, b_col, inv_tau, flags,
+      diag_offset, nullptr, nullptr, dq, ld_dq);
+  EVK_CHECK_LAUNCH("mpce_small_bwd");
+  return EVK_OK;
+}

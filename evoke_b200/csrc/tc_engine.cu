@@ -1,0 +1,644 @@
+// Large path: one warp-specialised, persistent tcgen05 main loop (TMA -> shared memory ->
+// tcgen05.mma -> TMEM, double-buffered accumulators) with three epilogues:
+//
+//   EPI_FWD   K3  S = Qhat Khat^T tile lives only in TMEM; the epilogue turns it into
+//                 exp-sums per row / per column and the positive-logit sums (O(N) outputs).
+//                 Replaces 2x mm + 2x `/temp` + 2x cross_entropy, v0520.py:499-502 (and :437-443).
+//   EPI_BWD_W K4a recompute the S tile, form W = E (a_i + b_j) - 2 M / c_i, store it as bf16
+//                 (TMA store) into the row-strip workspace.
+//   EPI_GEMM  K4b dQhat = W X / dKhat = W^T X with MN-major operands, split-K, fp32 red.add.
+//                 K4a+K4b replace autograd's 4 mm + N^2 elementwise passes.
+//
+// Tile 128 x 256 (UMMA M=128, N=256, K=16), BK = 64 bf16 = one 128-byte swizzle row, so a
+// stage is 16 KiB (A) + 32 KiB (B).  TMEM: 2 accumulator stages x 256 fp32 columns = all 512.
+// Warps: 0 = TMA producer (one lane), 1 = MMA issuer (one lane) + TMEM allocator,
+// 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31, i.e. one tile row per thread).
+//
+// Split-bf16 (fp32-parity) mode is just a longer K loop over "segments": S = hi.hi + hi.lo + lo.hi.
+#include "evk_common.cuh"
+#include "tc_ptx.cuh"
+
+#include <string.h>
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int kABytes = BM * BK * 2;          // 16 KiB
+constexpr int kBBytes = BN * BK * 2;          // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kTmemCols = 512;
+constexpr int kMaxSegs = 3;
+
+enum { EPI_FWD = 0, EPI_BWD_W = 1, EPI_GEMM = 2 };
+
+struct alignas(64) TcParams {
+  CUtensorMap a_map[kMaxSegs];
+  CUtensorMap b_map[kMaxSegs];
+  CUtensorMap out_map[2];        // EPI_BWD_W: W hi / lo stores
+  int m_tiles, n_tiles, splits;
+  int num_segs, kb_per_seg;      // k-blocks (of BK) per segment
+  int64_t n_rows, n_cols;        // logical extent of the M x N problem (masking)
+  float inv_tau;
+  int flags;
+  int64_t diag_offset;
+  // EPI_FWD / EPI_BWD_W
+  const uint32_t* bits; int64_t ld_words;
+  float* row_sum_part; float* row_pos_part; int64_t ld_rowpart;
+  float* col_sum_part; int64_t ld_colpart;
+  const int32_t* counts; const float* a_row; const float* b_col;
+  // EPI_GEMM
+  float* out; int64_t ld_out; float alpha;
+  // descriptor bases (see tc_ptx.cuh), filled by the host so the probe can try variants
+  uint64_t desc_a, desc_b;
+  uint32_t idesc;
+};
+
+template <int EPI>
+constexpr int epi_smem_bytes() {
+  return EPI == EPI_FWD ? 4 * BN * 4 : (EPI == EPI_BWD_W ? 4 * 16384 + 2 * BN * 4 : 0);
+}
+template <int EPI, int STAGES>
+constexpr int smem_bytes_total() {
+  return 1024 /*align slack*/ + STAGES * kStageBytes + epi_smem_bytes<EPI>() + (2 * STAGES + 4) * 8 + 16;
+}
+
+// lane l ends with the sum over the warp's 32 lanes of x[l] (x is destroyed)
+__device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < s; ++k) {
+      const float send = upper ? x[k] : x[k + s];
+      const float keep = upper ? x[k + s] : x[k];
+      x[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return x[0];
+}
+
+template <int EPI, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t epi_base = smem_base + STAGES * kStageBytes;
+  uint8_t* epi_gen = smem_gen + STAGES * kStageBytes;
+  const uint32_t bar_base = epi_base + epi_smem_bytes<EPI>();
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(epi_gen + epi_smem_bytes<EPI>() + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_segs; ++s) {
+      tma_prefetch_desc(&p.a_map[s]);
+      tma_prefetch_desc(&p.b_map[s]);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), kEpiThreads / 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int total_kb = p.num_segs * p.kb_per_seg;
+  const int total_units = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int tile = u / p.splits, sp = u - tile * p.splits;
+        const int mb = tile / p.n_tiles, nb = tile - mb * p.n_tiles;
+        const int m0 = mb * BM, n0 = nb * BN;
+        const int kb0 = (int)(((int64_t)sp * total_kb) / p.splits);
+        const int kb1 = (int)(((int64_t)(sp + 1) * total_kb) / p.splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int seg = kb / p.kb_per_seg, kk = (kb - seg * p.kb_per_seg) * BK;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), kStageBytes);
+          const uint32_t a_dst = smem_base + stage * kStageBytes, b_dst = a_dst + kABytes;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &p.a_map[seg], full_bar(stage), kk, m0);
+          } else {
+#pragma unroll
+            for (int b = 0; b < BM / 64; ++b) tma_load_2d(a_dst + b * 8192, &p.a_map[seg], full_bar(stage), m0 + 64 * b, kk);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &p.b_map[seg], full_bar(stage), kk, n0);
+          } else {
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b) tma_load_2d(b_dst + b * 8192, &p.b_map[seg], full_bar(stage), n0 + 64 * b, kk);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int lu = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++lu) {
+        const int tile = u / p.splits, sp = u - tile * p.splits;
+        const int kb0 = (int)(((int64_t)sp * total_kb) / p.splits);
+        const int kb1 = (int)(((int64_t)(sp + 1) * total_kb) / p.splits);
+        const int as = lu & 1;
+        const uint32_t aphase = (lu >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * kStageBytes, b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = umma_smem_desc(p.desc_a, a_addr + (A_MN ? k * 2048 : k * 32));
+            const uint64_t bd = umma_smem_desc(p.desc_b, b_addr + (B_MN ? k * 2048 : k * 32));
+            umma_bf16(d_tmem, ad, bd, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));          // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(as));               // accumulator ready for the epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue warps
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                // tile row owned by this thread
+    const int et = (warp - 2) * 32 + lane;        // 0..127
+    const float c1 = p.inv_tau * 1.4426950408889634f;    // exp(s/tau - shift) = 2^(s*c1 - c1)
+    const bool excl = (p.flags & EVK_FLAG_EXCLUDE_DIAG) != 0;
+    int lu = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++lu) {
+      const int tile = u / p.splits;
+      const int mb = tile / p.n_tiles, nb = tile - mb * p.n_tiles;
+      const int m0 = mb * BM, n0 = nb * BN;
+      const int as = lu & 1;
+      const uint32_t aphase = (lu >> 1) & 1;
+      const int64_t i = (int64_t)m0 + row;
+      const bool row_ok = i < p.n_rows;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+
+      if (EPI == EPI_FWD) {
+        float* colpart = reinterpret_cast<float*>(epi_gen);       // [4][BN]
+        const bool want_col = (p.flags & EVK_FLAG_NO_COLSUM) == 0;
+        const uint32_t* mrow = p.bits + (row_ok ? i : 0) * p.ld_words + (n0 >> 5);
+        const int64_t dcol = i + p.diag_offset - n0;              // diagonal column inside this tile?
+        float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f, rp = 0.f;
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const uint32_t mword = row_ok ? __ldg(mrow + c) : 0u;
+          float v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait(v);
+          const int cbase = n0 + c * 32;
+          uint32_t live = (cbase + 32 <= p.n_cols) ? 0xffffffffu
+                          : (cbase >= p.n_cols ? 0u : ((1u << (int)(p.n_cols - cbase)) - 1u));
+          if (!row_ok) live = 0u;
+          if (excl && dcol >= 0 && (dcol >> 5) == c) live &= ~(1u << (int)(dcol & 31));
+          if (mword & live) {                                     // rare: a positive in this 32-col chunk
+            const uint32_t m = mword & live;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if ((m >> k) & 1u) rp = fmaf(v[k], p.inv_tau, rp);
+          }
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = ex2_approx(fmaf(v[k], c1, -c1));
+          if (live != 0xffffffffu) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = ((live >> k) & 1u) ? v[k] : 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            rs0 += v[k]; rs1 += v[k + 1]; rs2 += v[k + 2]; rs3 += v[k + 3];
+          }
+          if (want_col) {
+            const float cs = warp_transpose_sum(v, lane);
+            colpart[q * BN + c * 32 + lane] = cs;
+          }
+        }
+        // TMEM stage drained: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (row_ok) {
+          p.row_sum_part[(int64_t)nb * p.ld_rowpart + i] = (rs0 + rs1) + (rs2 + rs3);
+          p.row_pos_part[(int64_t)nb * p.ld_rowpart + i] = rp;
+        }
+        if (want_col) {
+          named_bar_sync(1, kEpiThreads);
+#pragma unroll
+          for (int h = 0; h < BN / kEpiThreads; ++h) {
+            const int cidx = h * kEpiThreads + et;
+            const float s = (colpart[cidx] + colpart[BN + cidx]) + (colpart[2 * BN + cidx] + colpart[3 * BN + cidx]);
+            if (n0 + cidx < p.n_cols) p.col_sum_part[(int64_t)mb * p.ld_colpart + n0 + cidx] = s;
+          }
+          named_bar_sync(1, kEpiThreads);                         // colpart reusable
+        }
+      } else if (EPI == EPI_BWD_W) {
+        const bool split = (p.flags & EVK_FLAG_SPLIT_BF16) != 0;
+        float* bs = reinterpret_cast<float*>(epi_gen + 4 * 16384) + as * BN;   // b_col of this tile
+        const uint32_t stg = epi_base;                            // 4 slots x 16 KiB (128 rows x 128 B)
+        const float a_i = row_ok ? __ldg(p.a_row + i) : 0.f;
+        const float n2c = row_ok ? -2.f / (float)max(__ldg(p.counts + i), 1) : 0.f;
+        const uint32_t* mrow = p.bits + (row_ok ? i : 0) * p.ld_words + (n0 >> 5);
+        const int64_t dcol = i + p.diag_offset - n0;
+#pragma unroll
+        for (int h = 0; h < BN / kEpiThreads; ++h) {
+          const int cidx = h * kEpiThreads + et;
+          bs[cidx] = (n0 + cidx < p.n_cols) ? __ldg(p.b_col + n0 + cidx) : 0.f;
+        }
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+          // the staging slots of this round must have been read by their previous TMA store
+          if (et == 0) {
+            if (split) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+          }
+          named_bar_sync(1, kEpiThreads);                         // also publishes bs[] (r == 0)
+#pragma unroll 1
+          for (int cc = 0; cc < 4; ++cc) {
+            const int c = r * 4 + cc;
+            const uint32_t mword = row_ok ? __ldg(mrow + c) : 0u;
+            float v[32];
+            tmem_ld_32x32(taddr + c * 32, v);
+            tmem_ld_wait(v);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = ex2_approx(fmaf(v[k], c1, -c1)) * (a_i + bs[c * 32 + k]);
+            if (mword) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if ((mword >> k) & 1u) v[k] += n2c;
+            }
+            if (excl && dcol >= 0 && (dcol >> 5) == c) {
+              const int dk = (int)(dcol & 31);
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (k == dk) v[k] = 0.f;
+            }
+            // rows >= n_rows / columns >= n_cols hold garbage here; the TMA store clips them.
+            const int slot_hi = split ? (cc >> 1) : (2 * r + (cc >> 1));
+            const uint32_t row_hi = stg + slot_hi * 16384 + row * 128;
+            const int u0 = (cc & 1) * 4;
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+              uint32_t h0 = pack_bf16x2(v[8 * uu + 0], v[8 * uu + 1]);
+              uint32_t h1 = pack_bf16x2(v[8 * uu + 2], v[8 * uu + 3]);
+              uint32_t h2 = pack_bf16x2(v[8 * uu + 4], v[8 * uu + 5]);
+              uint32_t h3 = pack_bf16x2(v[8 * uu + 6], v[8 * uu + 7]);
+              const uint32_t off = static_cast<uint32_t>(((u0 + uu) ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + off), "r"(h0), "r"(h1), "r"(h2),
+                           "r"(h3) : "memory");
+              if (split) {
+                float l[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const uint32_t hh = e == 0 ? h0 : (e == 1 ? h1 : (e == 2 ? h2 : h3));
+                  l[2 * e] = v[8 * uu + 2 * e] - __uint_as_float(hh << 16);
+                  l[2 * e + 1] = v[8 * uu + 2 * e + 1] - __uint_as_float(hh & 0xffff0000u);
+                }
+                const uint32_t l0 = pack_bf16x2(l[0], l[1]), l1 = pack_bf16x2(l[2], l[3]);
+                const uint32_t l2 = pack_bf16x2(l[4], l[5]), l3 = pack_bf16x2(l[6], l[7]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + 2 * 16384 + off), "r"(l0),
+                             "r"(l1), "r"(l2), "r"(l3) : "memory");
+              }
+            }
+          }
+          if (r == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+          }
+          fence_proxy_async_smem();                               // generic-proxy writes -> async proxy
+          named_bar_sync(1, kEpiThreads);
+          if (et == 0) {
+            const int cx = n0 + r * 128;
+            if (split) {
+              tma_store_2d(&p.out_map[0], stg + 0 * 16384, cx, m0);
+              tma_store_2d(&p.out_map[0], stg + 1 * 16384, cx + 64, m0);
+              tma_store_2d(&p.out_map[1], stg + 2 * 16384, cx, m0);
+              tma_store_2d(&p.out_map[1], stg + 3 * 16384, cx + 64, m0);
+            } else {
+              tma_store_2d(&p.out_map[0], stg + (2 * r) * 16384, cx, m0);
+              tma_store_2d(&p.out_map[0], stg + (2 * r + 1) * 16384, cx + 64, m0);
+            }
+            tma_store_commit();
+          }
+        }
+      } else {  // EPI_GEMM
+        float* orow = p.out + i * p.ld_out + n0;
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait(v);
+          const int cbase = n0 + c * 32;
+          if (row_ok) {
+            if (cbase + 32 <= p.n_cols) {
+#pragma unroll
+              for (int k = 0; k < 32; k += 4)
+                red_add_v4(orow + c * 32 + k, p.alpha * v[k], p.alpha * v[k + 1], p.alpha * v[k + 2], p.alpha * v[k + 3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (cbase + k < p.n_cols) atomicAdd(orow + c * 32 + k, p.alpha * v[k]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      }
+    }
+    if (EPI == EPI_BWD_W && et == 0) tma_store_wait_all<0>();     // smem must outlive the bulk stores
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2D bf16 row-major matrix [rows, cols] with pitch ld (elements); box = [box_rows, box_cols], 128B swizzle.
+int make_map_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                  int box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return evk_set_error(EVK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  EVK_REQUIRE(evk_aligned16(base) && ld % 8 == 0, "bf16 operand needs a 16-byte aligned base and ld %% 8 == 0 (ld=%lld)",
+              (long long)ld);
+  EVK_REQUIRE(rows > 0 && cols > 0 && ld >= cols, "bad operand shape rows=%lld cols=%lld ld=%lld", (long long)rows,
+              (long long)cols, (long long)ld);
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return evk_set_error(EVK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return EVK_OK;
+}
+
+// K-major operand [mn_extent rows, k_extent cols]: one box of box_mn rows x 64 k.
+// MN-major operand stored [k_extent rows, mn_extent cols]: boxes of 64 k rows x 64 mn.
+int make_operand_map(CUtensorMap* map, const void* base, bool mn_major, int64_t mn_extent, int64_t k_extent,
+                     int64_t ld, int box_mn) {
+  if (!mn_major) return make_map_bf16(map, base, mn_extent, k_extent, ld, box_mn, BK);
+  return make_map_bf16(map, base, k_extent, mn_extent, ld, BK, 64);
+}
+
+void fill_descs(TcParams& p, bool a_mn, bool b_mn, int variant) {
+  // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused.  MN-major SW128: 64-element MN
+  // atoms 8192 B apart (LBO, one TMA box each), 8-row K groups 1024 B apart (SBO).
+  const uint64_t kmaj = umma_smem_desc_base(16, 1024);
+  const uint64_t mnmaj = variant == 1 ? umma_smem_desc_base(1024, 8192) : umma_smem_desc_base(8192, 1024);
+  p.desc_a = a_mn ? mnmaj : kmaj;
+  p.desc_b = b_mn ? mnmaj : kmaj;
+  p.idesc = umma_idesc_bf16(BM, BN, a_mn, b_mn);
+}
+
+template <int EPI, bool A_MN, bool B_MN, int STAGES>
+int launch(const TcParams& p, cudaStream_t s) {
+  constexpr int smem = smem_bytes_total<EPI, STAGES>();
+  static_assert(smem <= 232448, "shared memory budget exceeded");
+  auto kern = tc_kernel<EPI, A_MN, B_MN, STAGES>;
+  EVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int units = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = units < evk_sm_count() ? units : evk_sm_count();
+  kern<<<grid, kThreads, smem, s>>>(p);
+  EVK_CHECK_LAUNCH("tc_kernel");
+  return EVK_OK;
+}
+
+int check_device() {
+  if (!evk_is_sm100())
+    return evk_set_error(EVK_ERR_UNSUPPORTED, "the tcgen05 path needs an sm_100 (B200) device; there is no fallback");
+  return EVK_OK;
+}
+
+// smallest split factor whose last wave is at least ~94% full (else the best seen)
+int choose_splits(int tiles, int total_kb) {
+  const int g = evk_sm_count();
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 16; ++s) {
+    if (total_kb / s < 8 && s > 1) break;
+    const int units = tiles * s;
+    const double eff = (double)units / (double)(((units + g - 1) / g) * g);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+    if (eff >= 0.94) { best = s; break; }
+  }
+  return best;
+}
+
+int setup_sim_operands(TcParams& p, const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi,
+                       const void* k_lo, int64_t ld_k, int64_t n_rows, int64_t n_cols, int64_t d, int flags) {
+  const bool split = (flags & EVK_FLAG_SPLIT_BF16) != 0;
+  EVK_REQUIRE(q_hi && k_hi && (!split || (q_lo && k_lo)), "null operand pointer");
+  EVK_REQUIRE(n_rows > 0 && n_cols > 0 && d > 0, "empty problem");
+  EVK_REQUIRE(n_rows < (1ll << 30) && n_cols < (1ll << 30), "problem too large");
+  p.num_segs = split ? 3 : 1;
+  p.kb_per_seg = (int)((d + BK - 1) / BK);
+  const void* qa[3] = {q_hi, q_hi, q_lo};
+  const void* ka[3] = {k_hi, k_lo, k_hi};
+  for (int s = 0; s < p.num_segs; ++s) {
+    int rc = make_operand_map(&p.a_map[s], qa[s], false, n_rows, d, ld_q, BM);
+    if (rc != EVK_OK) return rc;
+    rc = make_operand_map(&p.b_map[s], ka[s], false, n_cols, d, ld_k, BN);
+    if (rc != EVK_OK) return rc;
+  }
+  p.m_tiles = (int)((n_rows + BM - 1) / BM);
+  p.n_tiles = (int)((n_cols + BN - 1) / BN);
+  p.splits = 1;
+  p.n_rows = n_rows;
+  p.n_cols = n_cols;
+  fill_descs(p, false, false, 0);
+  return EVK_OK;
+}
+
+}  // namespace
+
+extern "C" int evk_mpce_fwd(const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi, const void* k_lo,
+                            int64_t ld_k, int64_t n_rows, int64_t n_cols, int64_t d, const uint32_t* bits,
+                            int64_t ld_words, float inv_tau, int flags, int64_t diag_offset, float* row_sum_part,
+                            float* row_pos_part, int64_t ld_rowpart, float* col_sum_part, int64_t ld_colpart,
+                            evk_stream_t stream) {
+  int rc = check_device();
+  if (rc != EVK_OK) return rc;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  rc = setup_sim_operands(p, q_hi, q_lo, ld_q, k_hi, k_lo, ld_k, n_rows, n_cols, d, flags);
+  if (rc != EVK_OK) return rc;
+  const bool want_col = (flags & EVK_FLAG_NO_COLSUM) == 0;
+  EVK_REQUIRE(bits && row_sum_part && row_pos_part && (!want_col || col_sum_part), "evk_mpce_fwd: null pointer");
+  EVK_REQUIRE(ld_words >= (int64_t)p.n_tiles * (BN / 32), "evk_mpce_fwd: ld_words=%lld must cover whole 256-column tiles (>= %lld)",
+              (long long)ld_words, (long long)p.n_tiles * (BN / 32));
+  EVK_REQUIRE(ld_rowpart >= n_rows && (!want_col || ld_colpart >= n_cols), "evk_mpce_fwd: partial pitches too small");
+  EVK_REQUIRE(inv_tau > 0.f && inv_tau <= 40.f, "evk_mpce_fwd: 1/tau=%g outside (0, 40]: the fixed-shift softmax needs exp(-2/tau) to stay normal in fp32", inv_tau);
+  p.inv_tau = inv_tau;
+  p.flags = flags;
+  p.diag_offset = diag_offset;
+  p.bits = bits;
+  p.ld_words = ld_words;
+  p.row_sum_part = row_sum_part;
+  p.row_pos_part = row_pos_part;
+  p.ld_rowpart = ld_rowpart;
+  p.col_sum_part = col_sum_part;
+  p.ld_colpart = ld_colpart;
+  return launch<EPI_FWD, false, false, 4>(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi, const void* k_lo,
+                              int64_t ld_k, int64_t n_rows, int64_t n_cols, int64_t d, const uint32_t* bits,
+                              int64_t ld_words, const int32_t* counts, const float* a_row, const float* b_col,
+                              float inv_tau, int flags, int64_t diag_offset, void* w_hi, void* w_lo, int64_t ld_w,
+                              evk_stream_t stream) {
+  int rc = check_device();
+  if (rc != EVK_OK) return rc;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  rc = setup_sim_operands(p, q_hi, q_lo, ld_q, k_hi, k_lo, ld_k, n_rows, n_cols, d, flags);
+  if (rc != EVK_OK) return rc;
+  const bool split = (flags & EVK_FLAG_SPLIT_BF16) != 0;
+  EVK_REQUIRE(bits && counts && a_row && b_col && w_hi && (!split || w_lo), "evk_mpce_bwd_w: null pointer");
+  EVK_REQUIRE(ld_words >= (int64_t)p.n_tiles * (BN / 32), "evk_mpce_bwd_w: ld_words must cover whole 256-column tiles");
+  EVK_REQUIRE(ld_w >= n_cols && ld_w % 8 == 0, "evk_mpce_bwd_w: ld_w=%lld must be >= n_cols and a multiple of 8", (long long)ld_w);
+  EVK_REQUIRE(inv_tau > 0.f && inv_tau <= 40.f, "evk_mpce_bwd_w: 1/tau=%g outside (0, 40]", inv_tau);
+  rc = make_map_bf16(&p.out_map[0], w_hi, n_rows, n_cols, ld_w, BM, 64);
+  if (rc != EVK_OK) return rc;
+  if (split) {
+    rc = make_map_bf16(&p.out_map[1], w_lo, n_rows, n_cols, ld_w, BM, 64);
+    if (rc != EVK_OK) return rc;
+  }
+  p.inv_tau = inv_tau;
+  p.flags = flags;
+  p.diag_offset = diag_offset;
+  p.bits = bits;
+  p.ld_words = ld_words;
+  p.counts = counts;
+  p.a_row = a_row;
+  p.b_col = b_col;
+  return launch<EPI_BWD_W, false, false, 3>(p, static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, const void* const* b_ptrs,
+                int64_t ldb, bool b_mn, int nsegs, int64_t m, int64_t n, int64_t k, float alpha, float* out,
+                int64_t ld_out, int variant, int force_splits, cudaStream_t s) {
+  EVK_REQUIRE(m > 0 && n > 0 && k > 0 && out, "gemm: empty problem or null output");
+  EVK_REQUIRE(m < (1ll << 30) && n < (1ll << 30) && k < (1ll << 30), "gemm: problem too large");
+  EVK_REQUIRE(ld_out >= n && ld_out % 4 == 0 && evk_aligned16(out), "gemm: out needs 16-byte alignment and ld_out %% 4 == 0");
+  p.num_segs = nsegs;
+  p.kb_per_seg = (int)((k + BK - 1) / BK);
+  for (int sg = 0; sg < nsegs; ++sg) {
+    int rc = make_operand_map(&p.a_map[sg], a_ptrs[sg], a_mn, m, k, lda, BM);
+    if (rc != EVK_OK) return rc;
+    rc = make_operand_map(&p.b_map[sg], b_ptrs[sg], b_mn, n, k, ldb, BN);
+    if (rc != EVK_OK) return rc;
+  }
+  p.m_tiles = (int)((m + BM - 1) / BM);
+  p.n_tiles = (int)((n + BN - 1) / BN);
+  p.n_rows = m;
+  p.n_cols = n;
+  const int total_kb = p.num_segs * p.kb_per_seg;
+  p.splits = force_splits > 0 ? force_splits : choose_splits(p.m_tiles * p.n_tiles, total_kb);
+  if (p.splits > total_kb) p.splits = total_kb;
+  p.out = out;
+  p.ld_out = ld_out;
+  p.alpha = alpha;
+  fill_descs(p, a_mn, b_mn, variant);
+  if (a_mn && b_mn) return launch<EPI_GEMM, true, true, 4>(p, s);
+  if (a_mn) return launch<EPI_GEMM, true, false, 4>(p, s);
+  if (b_mn) return launch<EPI_GEMM, false, true, 4>(p, s);
+  return launch<EPI_GEMM, false, false, 4>(p, s);
+}
+}  // namespace
+
+extern "C" int evk_mpce_bwd_gemm(const void* w_hi, const void* w_lo, int64_t ld_w, int64_t n_rows, int64_t n_cols,
+                                 int transpose_w, const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d,
+                                 float alpha, int flags, float* out, int64_t ld_out, evk_stream_t stream) {
+  int rc = check_device();
+  if (rc != EVK_OK) return rc;
+  const bool split = (flags & EVK_FLAG_SPLIT_BF16) != 0;
+  EVK_REQUIRE(w_hi && x_hi && (!split || (w_lo && x_lo)), "evk_mpce_bwd_gemm: null operand");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  const void* a_ptrs[3] = {w_hi, w_hi, w_lo};
+  const void* b_ptrs[3] = {x_hi, x_lo, x_hi};
+  // W is stored [n_rows, n_cols].  Not transposed: A = W is K-major (K = columns).  Transposed:
+  // A = W^T is MN-major (M = columns contiguous, K = rows).  X [K, d] is always MN-major for B.
+  const int64_t m = transpose_w ? n_cols : n_rows;
+  const int64_t k = transpose_w ? n_rows : n_cols;
+  return gemm_common(p, a_ptrs, ld_w, transpose_w != 0, b_ptrs, ld_x, true, split ? 3 : 1, m, d, k, alpha, out, ld_out,
+                     0, 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int evk_tc_gemm_probe(const void* a, int64_t lda, int a_major, const void* b, int64_t ldb, int b_major,
+                                 int64_t m, int64_t n, int64_t k, float* c, int64_t ldc, int variant, int splits,
+                                 evk_stream_t stream) {
+  int rc = check_device();
+  if (rc != EVK_OK) return rc;
+  EVK_REQUIRE(a && b, "evk_tc_gemm_probe: null operand");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  const void* a_ptrs[3] = {a, nullptr, nullptr};
+  const void* b_ptrs[3] = {b, nullptr, nullptr};
+  return gemm_common(p, a_ptrs, lda, a_major != 0, b_ptrs, ldb, b_major != 0, 1, m, n, k, 1.f, c, ldc, variant, splits,
+                     static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,301 @@
+"""Host orchestration of the contrastive hot path: torch.autograd Functions that enqueue the
+sm_100a kernels of libevoke_b200.so on the current CUDA stream.
+
+PyTorch is used for device memory (the caching allocator owns every buffer, the library
+allocates nothing), streams and autograd plumbing only; every arithmetic step of the loss
+runs in the library.  There is no CPU path and no PyTorch fallback.
+
+Math (oracle/evoke_oracle.py has the fp64 restatement; reference file:line in the docstrings
+of evoke_b200/loss.py):
+    S = Qhat Khat^T / tau,   E = exp(S - 1/tau)          (|S| <= 1/tau for unit rows)
+    R_i = sum_j E_ij,  C_j = sum_i E_ij,  pos_i = sum_j M_ij S_ij
+    G   loss = 1/(2N) [ sum_i (1/tau + ln R_i) + sum_j (1/tau + ln C_j) - 2 sum_i pos_i/c_i ]
+    MPC loss = 1/M'   [ sum_i (1/tau + ln R_i - pos_i/c_i) ]          (diagonal excluded)
+    W_ij = E_ij (1/R_i + 1/C_j) - 2 M_ij / c_i        (MPC: C := R)
+    dQhat = W Khat / (2 N tau),  dKhat = W^T Qhat / (2 N tau)         (MPC: dXhat = W Xhat / (M' tau))
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (DTYPE_BF16, DTYPE_F16, DTYPE_F32, FLAG_EXCLUDE_DIAG, FLAG_NO_COLSUM, FLAG_SPLIT_BF16)
+from .ids import DeviceIds
+
+SMALL_PATH_MAX = int(os.environ.get("EVOKE_B200_SMALL_MAX", "512"))   # rows/cols up to which the SIMT path is used
+TILE_M, TILE_N = 128, 256
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return DTYPE_BF16
+    if t.dtype == torch.float16:
+        return DTYPE_F16
+    raise TypeError(f"embeddings must be float32, bfloat16 or float16, got {t.dtype}")
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"evoke_b200: `{name}` lives on {t.device}; this library only runs on a CUDA "
+                           "(sm_100a) device and has no CPU path")
+    if t.dim() != 2:
+        raise ValueError(f"evoke_b200: `{name}` must be 2-D [N, D], got shape {tuple(t.shape)}")
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------- kernels
+@dataclass
+class Normalized:
+    """Output of K1 for one embedding matrix."""
+    n: int
+    d: int
+    norm: torch.Tensor                      # [n] fp32, unclamped
+    f32: Optional[torch.Tensor] = None      # [n, d] fp32 (small path)
+    hi: Optional[torch.Tensor] = None       # [n, ld] bf16 (tc path)
+    lo: Optional[torch.Tensor] = None       # [n, ld] bf16 (tc path, fp32-parity mode)
+    ld: int = 0
+
+
+def l2norm_fwd(x: torch.Tensor, *, want_f32: bool, want_hi: bool, want_lo: bool,
+               gather: Optional[torch.Tensor] = None) -> Normalized:
+    """K1: xhat = x / max(||x||, 1e-12) (F.normalize, v0520.py:495-496, :436), honouring the
+    strides of ``x`` and an optional row gather."""
+    n = int(gather.shape[0]) if gather is not None else int(x.shape[0])
+    d = int(x.shape[1])
+    dev = x.device
+    out = Normalized(n=n, d=d, norm=torch.empty(n, dtype=torch.float32, device=dev))
+    if want_f32:
+        out.f32 = torch.empty((n, d), dtype=torch.float32, device=dev)
+    if want_hi:
+        out.ld = _round_up(d, 8)
+        out.hi = torch.empty((n, out.ld), dtype=torch.bfloat16, device=dev)
+        if want_lo:
+            out.lo = torch.empty((n, out.ld), dtype=torch.bfloat16, device=dev)
+    _lib.call("evk_l2norm_fwd", _ptr(x), _dtype_code(x), n, d, x.stride(0), x.stride(1), _ptr(gather),
+              _ptr(out.f32), d, _ptr(out.hi), _ptr(out.lo), out.ld, _ptr(out.norm), _stream())
+    return out
+
+
+def l2norm_bwd(x: torch.Tensor, nrm: Normalized, g_hat: torch.Tensor, *, scale_dev: Optional[torch.Tensor],
+               scale_host: float, gather: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Backward of K1 fused with the loss scale; returns dx with x's shape and dtype."""
+    if gather is not None:
+        dx = torch.zeros(x.shape, dtype=x.dtype, device=x.device)       # filtered rows get zero gradient
+    else:
+        dx = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    _lib.call("evk_l2norm_bwd", _ptr(x), _dtype_code(x), nrm.n, nrm.d, x.stride(0), x.stride(1), _ptr(gather),
+              _ptr(nrm.norm), _ptr(g_hat), g_hat.stride(0), _ptr(scale_dev), float(scale_host),
+              _ptr(dx), _dtype_code(dx), dx.stride(0), 0, _stream())
+    return dx
+
+
+def posmask_build(rows: DeviceIds, cols: DeviceIds, *, clear_diag: bool, diag_offset: int = 0):
+    """K2: bit-packed positive mask [n_rows, ld_words] (uint32 stored as int32) + counts[n_rows]."""
+    n_rows, n_cols = len(rows), len(cols)
+    dev = rows.key.device
+    ld_words = _round_up(_round_up(n_cols, TILE_N) // 32, 8)             # whole 256-column tiles
+    bits = torch.empty((n_rows, ld_words), dtype=torch.int32, device=dev)
+    counts = torch.empty(n_rows, dtype=torch.int32, device=dev)
+    _lib.call("evk_posmask_build", _ptr(rows.key), _ptr(rows.key2), n_rows, _ptr(cols.key), _ptr(cols.key2),
+              n_cols, diag_offset, int(clear_diag), _ptr(bits), ld_words, _ptr(counts), _stream())
+    return bits, counts
+
+
+def reduce_partials(part: torch.Tensor, parts: int, n: int) -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.float32, device=part.device)
+    _lib.call("evk_reduce_partials", _ptr(part), parts, part.stride(0), n, _ptr(out), _stream())
+    return out
+
+
+def finalize(row_sum, row_pos, counts, col_sum, *, col_lo: int, col_hi: int, shift: float, pos_weight: float,
+             inv_count: float, want_b: bool = True):
+    n_rows = int(row_sum.shape[0])
+    dev = row_sum.device
+    a_row = torch.empty(n_rows, dtype=torch.float32, device=dev)
+    n_cols = 0 if col_sum is None else int(col_sum.shape[0])
+    b_col = torch.empty(n_cols, dtype=torch.float32, device=dev) if (col_sum is not None and want_b) else None
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    _lib.call("evk_mpce_finalize", _ptr(row_sum), _ptr(row_pos), _ptr(counts), n_rows, _ptr(col_sum), n_cols,
+              col_lo, col_hi, float(shift), float(pos_weight), float(inv_count), _ptr(a_row), _ptr(b_col),
+              _ptr(loss), _stream())
+    return a_row, b_col, loss
+
+
+# --- small path ----------------------------------------------------------------------------
+def small_fwd(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int, diag_offset: int = 0):
+    dev = q.f32.device
+    row_sum = torch.empty(q.n, dtype=torch.float32, device=dev)
+    row_pos = torch.empty(q.n, dtype=torch.float32, device=dev)
+    _lib.call("evk_mpce_small_fwd", _ptr(q.f32), q.f32.stride(0), _ptr(k.f32), k.f32.stride(0), q.n, k.n, q.d,
+              _ptr(bits), bits.stride(0), float(inv_tau), flags, diag_offset, _ptr(row_sum), _ptr(row_pos), _stream())
+    return row_sum, row_pos
+
+
+def small_bwd(q: Normalized, k: Normalized, bits, counts, a_row, b_col, inv_tau: float, flags: int,
+              diag_offset: int = 0) -> torch.Tensor:
+    dq = torch.empty((q.n, q.d), dtype=torch.float32, device=q.f32.device)
+    _lib.call("evk_mpce_small_bwd", _ptr(q.f32), q.f32.stride(0), _ptr(k.f32), k.f32.stride(0), q.n, k.n, q.d,
+              _ptr(bits), bits.stride(0), _ptr(counts), _ptr(a_row), _ptr(b_col), float(inv_tau), flags,
+              diag_offset, _ptr(dq), dq.stride(0), _stream())
+    return dq
+
+
+# --- tcgen05 path --------------------------------------------------------------------------
+def tc_fwd(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int, diag_offset: int = 0):
+    """K3.  Returns (row_sum[n_rows], row_pos[n_rows], col_sum[n_cols] | None)."""
+    dev = q.hi.device
+    n_ct = (k.n + TILE_N - 1) // TILE_N
+    n_rt = (q.n + TILE_M - 1) // TILE_M
+    want_col = not (flags & FLAG_NO_COLSUM)
+    rs_part = torch.empty((n_ct, q.n), dtype=torch.float32, device=dev)
+    rp_part = torch.empty((n_ct, q.n), dtype=torch.float32, device=dev)
+    cs_part = torch.empty((n_rt, k.n), dtype=torch.float32, device=dev) if want_col else None
+    _lib.call("evk_mpce_fwd", _ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, q.n, k.n, q.d,
+              _ptr(bits), bits.stride(0), float(inv_tau), flags, diag_offset,
+              _ptr(rs_part), _ptr(rp_part), q.n, _ptr(cs_part), k.n, _stream())
+    row_sum = reduce_partials(rs_part, n_ct, q.n)
+    row_pos = reduce_partials(rp_part, n_ct, q.n)
+    col_sum = reduce_partials(cs_part, n_rt, k.n) if want_col else None
+    return row_sum, row_pos, col_sum
+
+
+def tc_bwd_w(q: Normalized, k: Normalized, bits, counts, a_row, b_col, inv_tau: float, flags: int,
+             diag_offset: int = 0):
+    """K4a.  Returns the bf16 W strip (hi, lo|None, ld_w)."""
+    dev = q.hi.device
+    ld_w = _round_up(k.n, 64)
+    w_hi = torch.empty((q.n, ld_w), dtype=torch.bfloat16, device=dev)
+    w_lo = torch.empty((q.n, ld_w), dtype=torch.bfloat16, device=dev) if (flags & FLAG_SPLIT_BF16) else None
+    _lib.call("evk_mpce_bwd_w", _ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, q.n, k.n, q.d,
+              _ptr(bits), bits.stride(0), _ptr(counts), _ptr(a_row), _ptr(b_col), float(inv_tau), flags,
+              diag_offset, _ptr(w_hi), _ptr(w_lo), ld_w, _stream())
+    return w_hi, w_lo, ld_w
+
+
+def tc_bwd_gemm(w_hi, w_lo, ld_w: int, n_rows: int, n_cols: int, transpose_w: bool, x: Normalized, flags: int,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K4b: out (+)= W x  (or W^T x).  ``out`` fp32 [rows_out, d]; zero-initialised here if None."""
+    rows_out = n_cols if transpose_w else n_rows
+    if out is None:
+        out = torch.zeros((rows_out, _round_up(x.d, 4)), dtype=torch.float32, device=w_hi.device)
+    _lib.call("evk_mpce_bwd_gemm", _ptr(w_hi), _ptr(w_lo), ld_w, n_rows, n_cols, int(transpose_w),
+              _ptr(x.hi), _ptr(x.lo), x.ld, x.d, 1.0, flags & FLAG_SPLIT_BF16, _ptr(out), out.stride(0), _stream())
+    return out
+
+
+def tc_gemm_probe(a: torch.Tensor, b: torch.Tensor, a_major: int, b_major: int, m: int, n: int, k: int,
+                  variant: int = 0, splits: int = 0) -> torch.Tensor:
+    """Bring-up helper: C[m,n] = A B^T through the tcgen05 main loop (see the header)."""
+    c = torch.zeros((m, _round_up(n, 4)), dtype=torch.float32, device=a.device)
+    _lib.call("evk_tc_gemm_probe", _ptr(a), a.stride(0), a_major, _ptr(b), b.stride(0), b_major, m, n, k,
+              _ptr(c), c.stride(0), variant, splits, _stream())
+    return c[:, :n]
+
+
+# ------------------------------------------------------------------------------------- autograd
+@dataclass
+class LossConfig:
+    kind: str                       # "G" | "MPC"
+    inv_tau: float
+    precision: str                  # "fp32" | "bf16"
+    path: str                       # "small" | "tc"
+    row_ids: DeviceIds              # keys of the rows that take part (already truncated / filtered)
+    gather: Optional[torch.Tensor] = None   # MPC: int32 indices of the kept rows
+
+
+def choose_path(path: str, n_rows: int, n_cols: int, d: int) -> str:
+    if path in ("small", "tc"):
+        return path
+    if path != "auto":
+        raise ValueError(f"path must be 'auto', 'small' or 'tc', got {path!r}")
+    return "small" if (max(n_rows, n_cols) <= SMALL_PATH_MAX and d <= 4096) else "tc"
+
+
+class _MultiPositiveCE(torch.autograd.Function):
+    """loss = f(image[, text]); cfg carries the non-differentiable pieces."""
+
+    @staticmethod
+    def forward(ctx, cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor]):
+        small = cfg.path == "small"
+        split = (not small) and cfg.precision == "fp32"
+        flags = FLAG_SPLIT_BF16 if split else 0
+        kw = dict(want_f32=small, want_hi=not small, want_lo=split)
+        mpc = cfg.kind == "MPC"
+        qn = l2norm_fwd(image, gather=cfg.gather, **kw)
+        kn = qn if mpc else l2norm_fwd(text, **kw)
+        n = qn.n
+        bits, counts = posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc)
+        if mpc:
+            flags |= FLAG_EXCLUDE_DIAG | FLAG_NO_COLSUM
+        if small:
+            row_sum, row_pos = small_fwd(qn, kn, bits, cfg.inv_tau, flags)
+            col_sum = None if mpc else small_fwd(kn, qn, bits, cfg.inv_tau, flags)[0]
+        else:
+            row_sum, row_pos, col_sum = tc_fwd(qn, kn, bits, cfg.inv_tau, flags)
+        if mpc:
+            a_row, _, loss = finalize(row_sum, row_pos, counts, None, col_lo=0, col_hi=0, shift=cfg.inv_tau,
+                                      pos_weight=1.0, inv_count=1.0 / n)
+            b_col = a_row
+        else:
+            a_row, b_col, loss = finalize(row_sum, row_pos, counts, col_sum, col_lo=0, col_hi=n,
+                                          shift=cfg.inv_tau, pos_weight=2.0, inv_count=0.5 / n)
+        ctx.cfg, ctx.flags, ctx.qn, ctx.kn = cfg, flags, qn, kn
+        ctx.aux = (bits, counts, a_row, b_col)
+        ctx.has_text = text is not None
+        ctx.save_for_backward(image, text) if text is not None else ctx.save_for_backward(image)
+        out = loss.reshape(())
+        return out if image.dtype == torch.float32 else out.to(image.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out: torch.Tensor):
+        cfg, flags, qn, kn = ctx.cfg, ctx.flags, ctx.qn, ctx.kn
+        bits, counts, a_row, b_col = ctx.aux
+        saved = ctx.saved_tensors
+        image = saved[0]
+        text = saved[1] if ctx.has_text else None
+        mpc = cfg.kind == "MPC"
+        n = qn.n
+        g = grad_out.reshape(1).to(torch.float32).contiguous()
+        scale = cfg.inv_tau / n if mpc else 0.5 * cfg.inv_tau / n
+        need_q = ctx.needs_input_grad[1]
+        need_k = (not mpc) and ctx.needs_input_grad[2]
+        d_image = d_text = None
+        if cfg.path == "small":
+            if need_q:
+                dq = small_bwd(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
+                d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
+            if need_k:
+                dk = small_bwd(kn, qn, bits, counts, b_col, a_row, cfg.inv_tau, flags)   # M is symmetric
+                d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
+        else:
+            if need_q or need_k:
+                w_hi, w_lo, ld_w = tc_bwd_w(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
+            if need_q:
+                dq = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, False, kn, flags)
+                d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
+            if need_k:
+                dk = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, True, qn, flags)
+                d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
+        return None, d_image, d_text
+
+
+def multi_positive_ce(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor]) -> torch.Tensor:
+    return _MultiPositiveCE.apply(cfg, image, text)

@@ -1,0 +1,146 @@
+"""Drop-in replacements for the reference's contrastive loss methods.
+
+The reference implements the objective as methods of the ``Pretrain`` nn.Module
+(models/model_pretrain_finetune_v0520.py; byte-identical bodies in
+model_pretrain_finetune_v0425_ablation.py:274-294/:324-342, _v0623_large_res.py:262-282/:311-329,
+_v0520_abn.py, _v0719_twoview.py, _v0425_ori.py):
+
+    Pretrain.global_alignment_loss(self, global_image_embed, global_text_embed, patient_ids)   :486-504
+    Pretrain.multi_pos_contra_images_v0401(self, global_image_embed, patient_ids)              :421-446
+
+The two functions below keep those names, argument order and meaning, read the temperatures
+from ``self.args['instance_temp']`` / ``self.args['region_temp']`` exactly as the reference does,
+return a differentiable tensor on the input device (0-dim; shape [1] leaf of zeros when MPC
+finds no multi-view study, :427-428), and raise ordinary Python exceptions on bad input.
+``patch_pretrain`` rebinds them on a reference ``Pretrain`` class or instance.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import functional as Fn
+from . import ids as idmod
+
+DEFAULT_PRECISION = "fp32"      # the reference computes in fp32; "bf16" is the throughput mode
+
+
+def _inv_tau(temp: float) -> float:
+    temp = float(temp)
+    if not temp > 0.0:
+        raise ValueError(f"temperature must be positive, got {temp}")
+    return 1.0 / temp
+
+
+def global_alignment(image: torch.Tensor, text: torch.Tensor, patient_ids, temp: float, *,
+                     precision: str = DEFAULT_PRECISION, path: str = "auto") -> torch.Tensor:
+    """Multi-positive image<->text InfoNCE in both directions (reference :486-504).
+
+    image, text: [B, D] projected embeddings (any strides; fp32/bf16/fp16) on a CUDA device.
+    patient_ids: what the reference passes (numpy array of str/int, length >= B; only the first B
+    are used, :488), a (patient, study) pair, or an integer tensor already on the device.
+    """
+    Fn._require_cuda(image, "global_image_embed")
+    Fn._require_cuda(text, "global_text_embed")
+    if image.shape != text.shape:
+        raise ValueError(f"image/text embedding shapes differ: {tuple(image.shape)} vs {tuple(text.shape)}")
+    if image.dtype != text.dtype:
+        raise TypeError(f"image/text embedding dtypes differ: {image.dtype} vs {text.dtype}")
+    if precision not in ("fp32", "bf16"):
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+    b, d = int(image.shape[0]), int(image.shape[1])
+    if b == 0:
+        raise ValueError("empty batch")
+    dev_ids, _ = idmod.to_device_ids(patient_ids, image.device, n=b)
+    if len(dev_ids) < b:
+        raise ValueError(f"patient_ids has {len(dev_ids)} entries for a batch of {b}")
+    cfg = Fn.LossConfig(kind="G", inv_tau=_inv_tau(temp), precision=precision,
+                        path=Fn.choose_path(path, b, b, d), row_ids=dev_ids)
+    with torch.cuda.device(image.device):
+        return Fn.multi_positive_ce(cfg, image, text)
+
+
+def multi_pos_contra_images(image: torch.Tensor, patient_ids, temp: float, *,
+                            precision: str = DEFAULT_PRECISION, path: str = "auto") -> torch.Tensor:
+    """Image<->image multi-positive contrastive loss over all views (reference :421-446):
+    self-similarity excluded, views of single-view studies removed from queries and keys, one
+    direction, mean over the kept rows.  Returns tensor([0.0]) (shape [1], requires_grad leaf)
+    when no study has a second view (:427-428)."""
+    Fn._require_cuda(image, "global_image_embed")
+    if precision not in ("fp32", "bf16"):
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+    m, d = int(image.shape[0]), int(image.shape[1])
+    dev_ids, codes = idmod.to_device_ids(patient_ids, image.device, n=None)
+    if len(dev_ids) != m:
+        raise ValueError(f"patient_ids has {len(dev_ids)} entries for {m} image embeddings")
+    with torch.cuda.device(image.device):
+        if codes is not None:
+            keep_host = idmod.multi_view_rows(codes)                     # host ids: no device sync
+            keep = torch.from_numpy(keep_host).to(image.device) if len(keep_host) else None
+            n_keep = len(keep_host)
+        else:
+            # device ids: count same-key partners with K2, then one size-determining sync (the
+            # reference syncs here too: `len(idx) == 0`, :427)
+            _, cnt = Fn.posmask_build(dev_ids, dev_ids, clear_diag=True)
+            keep = torch.nonzero(cnt > 0).reshape(-1).to(torch.int32)
+            n_keep = int(keep.numel())
+        if n_keep == 0:
+            return torch.tensor([0.0], requires_grad=True, device=image.device)
+        gather = None if n_keep == m else keep.contiguous()
+        row_ids = dev_ids if gather is None else dev_ids.index(keep.long())
+        cfg = Fn.LossConfig(kind="MPC", inv_tau=_inv_tau(temp), precision=precision,
+                            path=Fn.choose_path(path, n_keep, n_keep, d), row_ids=row_ids, gather=gather)
+        return Fn.multi_positive_ce(cfg, image, None)
+
+
+# ---------------------------------------------------------------- methods with the reference's signatures
+def global_alignment_loss(self, global_image_embed, global_text_embed, patient_ids):
+    """Same signature as Pretrain.global_alignment_loss (reference :486)."""
+    return global_alignment(global_image_embed, global_text_embed, patient_ids, self.args["instance_temp"],
+                            precision=getattr(self, "_evoke_b200_precision", DEFAULT_PRECISION))
+
+
+def multi_pos_contra_images_v0401(self, global_image_embed, patient_ids):
+    """Same signature as Pretrain.multi_pos_contra_images_v0401 (reference :421)."""
+    return multi_pos_contra_images(global_image_embed, patient_ids, self.args["region_temp"],
+                                   precision=getattr(self, "_evoke_b200_precision", DEFAULT_PRECISION))
+
+
+def patch_pretrain(target, precision: str = DEFAULT_PRECISION):
+    """Rebind the two loss methods on a reference ``Pretrain`` class (affects every instance) or
+    on a single instance.  Works for all six model files because only the method names and
+    ``self.args`` are relied upon.  Returns ``target``."""
+    if precision not in ("fp32", "bf16"):
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+    if isinstance(target, type):
+        target.global_alignment_loss = global_alignment_loss
+        target.multi_pos_contra_images_v0401 = multi_pos_contra_images_v0401
+        target._evoke_b200_precision = precision
+    else:
+        import types
+        target.global_alignment_loss = types.MethodType(global_alignment_loss, target)
+        target.multi_pos_contra_images_v0401 = types.MethodType(multi_pos_contra_images_v0401, target)
+        target._evoke_b200_precision = precision
+    return target
+
+
+class ContrastiveObjective(torch.nn.Module):
+    """Stand-alone module form: holds ``args`` like the reference's Pretrain does."""
+
+    def __init__(self, instance_temp: float = 0.5, region_temp: float = 0.5, precision: str = DEFAULT_PRECISION):
+        super().__init__()
+        self.args = {"instance_temp": instance_temp, "region_temp": region_temp}
+        self._evoke_b200_precision = precision
+
+    global_alignment_loss = global_alignment_loss
+    multi_pos_contra_images_v0401 = multi_pos_contra_images_v0401
+
+    def forward(self, global_image_embed, global_text_embed, patient_ids, view_embed: Optional[torch.Tensor] = None):
+        """instance loss (+ multi-view loss over ``view_embed`` when given), as summed at :563."""
+        loss = self.global_alignment_loss(global_image_embed, global_text_embed, patient_ids)
+        if view_embed is not None:
+            loss = loss + self.multi_pos_contra_images_v0401(view_embed, np.asarray(patient_ids) if not
+                                                             isinstance(patient_ids, torch.Tensor) else patient_ids)
+        return loss

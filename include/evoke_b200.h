@@ -1,0 +1,196 @@
+/* evoke_b200.h — C ABI of libevoke_b200.so: B200 (sm_100a) kernels for EVOKE's multi-view,
+ * multi-positive image-text contrastive objective, forward and backward.
+ *
+ * What this replaces.  The reference has no FFI for this path: the objective is two Python
+ * methods of the `Pretrain` nn.Module that run as stock PyTorch eager ops
+ * (models/model_pretrain_finetune_v0520.py, same bodies in the five sibling model files):
+ *     global_alignment_loss(self, global_image_embed, global_text_embed, patient_ids)  :486-504
+ *     multi_pos_contra_images_v0401(self, global_image_embed, patient_ids)             :421-446
+ * The drop-in (python package `evoke_b200`) keeps those signatures and
+ * lowers them onto the entry points below, loaded with ctypes.  Each entry point names the
+ * reference lines it stands in for.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Every pointer is a DEVICE pointer unless it says host.
+ *  - The library never allocates, frees or retains device memory, never synchronises the
+ *    device, and enqueues on the caller's `stream` (a cudaStream_t passed as void*): calls
+ *    are CUDA-graph capturable and re-entrant.  Workspaces are sized by the *_bytes helpers
+ *    and owned by the caller.
+ *  - Return value: EVK_OK or a negative code; evk_last_error() returns a thread-local,
+ *    human-readable message for the last failing call on this thread.  Launch errors are
+ *    picked up with cudaGetLastError(), without a device sync.
+ *  - There is no CPU fallback.  On a device that is not sm_100 the tcgen05 entry points
+ *    return EVK_ERR_UNSUPPORTED.
+ *
+ * Notation:  M_ij = [id_i == id_j],  c_i = sum_j M_ij,  Qhat/Khat = L2-normalised rows,
+ * S = Qhat Khat^T * inv_tau,  shift = inv_tau (|S| <= inv_tau for unit rows),
+ * E_ij = exp(S_ij - shift).
+ */
+#ifndef EVOKE_B200_H_
+#define EVOKE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVK_OK                0
+#define EVK_ERR_INVALID      -1   /* bad argument (shape, alignment, null pointer) */
+#define EVK_ERR_CUDA         -2   /* CUDA runtime / driver error, see evk_last_error() */
+#define EVK_ERR_UNSUPPORTED  -3   /* device or configuration not supported (no fallback) */
+
+#define EVK_DTYPE_F32   0
+#define EVK_DTYPE_BF16  1
+#define EVK_DTYPE_F16   2
+
+/* flags for the mpce entry points */
+#define EVK_FLAG_EXCLUDE_DIAG  1  /* column (row + diag_offset) is removed from the softmax:
+                                     multi_pos_contra_images_v0401 :438 (fill_diagonal_(-1e9)) */
+#define EVK_FLAG_NO_COLSUM     2  /* skip column sums (symmetric problem: MPC) */
+#define EVK_FLAG_SPLIT_BF16    4  /* operands are (hi, lo) bf16 pairs: S = hi.hi + hi.lo + lo.hi,
+                                     ~2^-17 relative, the fp32-parity mode */
+
+typedef void* evk_stream_t;
+
+#if defined(__GNUC__)
+#define EVK_API __attribute__((visibility("default")))
+#else
+#define EVK_API
+#endif
+
+EVK_API int         evk_version(void);                 /* ABI version, bumped on any signature change */
+EVK_API const char* evk_last_error(void);
+/* host query; sm_count / cc may be NULL */
+EVK_API int         evk_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1: fused L2-normalise (+ bf16 hi/lo split, + row gather) --------------------------
+ * Replaces F.normalize(x, dim=-1, p=2) at :495-496 and :436: xhat = x / max(||x||_2, 1e-12).
+ * x is [*, d] with arbitrary element strides (the reference passes the strided slice
+ * `[:,0,:]` of the permuted projection-head output, :484/:399).  Output row r is computed from
+ * input row gather[r] (gather == NULL: r), which implements the row filter of :426-429.
+ * Any of out_f32 / out_hi / out_lo may be NULL.  out_hi = bf16(xhat), out_lo = bf16(xhat - hi).
+ * ld_* are row pitches in elements; ld_bf16 must be a multiple of 8 (16-byte rows for TMA).
+ * norm[r] = ||x_row||_2 (unclamped; the backward needs to know whether the clamp was active). */
+EVK_API int evk_l2norm_fwd(const void* x, int x_dtype, int64_t n_out, int64_t d,
+                   int64_t stride_row, int64_t stride_col, const int32_t* gather,
+                   float* out_f32, int64_t ld_f32,
+                   void* out_hi, void* out_lo, int64_t ld_bf16,
+                   float* norm, evk_stream_t stream);
+
+/* Backward of K1 fused with the upstream-gradient scale:
+ *   dx_row = scale * (g - xhat (xhat.g)) / ||x||      (||x|| >= 1e-12)
+ *          = scale * g / 1e-12                         (clamp active)
+ * scale = scale_host * (scale_dev ? *scale_dev : 1).  g is fp32 [n_out, ld_g] (dXhat).
+ * dx is written at row gather[r] (or r) with pitch ld_dx, dtype dx_dtype; rows that are not
+ * written are the caller's to zero.  If accumulate != 0, dx += (fp32 only). */
+EVK_API int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t d,
+                   int64_t stride_row, int64_t stride_col, const int32_t* gather,
+                   const float* norm, const float* g, int64_t ld_g,
+                   const float* scale_dev, float scale_host,
+                   void* dx, int dx_dtype, int64_t ld_dx, int accumulate, evk_stream_t stream);
+
+/* ---- K2: positive-mask builder -------------------------------------------------------------
+ * Replaces (ids.reshape(-1,1) == ids.reshape(1,-1)) + .float().to(device) + rowsum at
+ * :488-491 and :422-424/:430.  bits[r, w] bit k = [key(row r) == key(col 32w+k)], i.e. exactly
+ * np.packbits(M, axis=1, bitorder='little') as little-endian uint32; counts[r] = popcount of
+ * row r = c_r.  A key is id, or the pair (id, id2) when the id2 pointers are non-NULL
+ * (patient AND study, the reference's "p<subject>_s<study>" string, dataloaders_v0401.py:83).
+ * With clear_diag the bit at column (r + diag_offset) is cleared (:424).  All ld_words words
+ * of every row are written (bits at columns >= n_cols are zero); ld_words >= ceil(n_cols/32). */
+EVK_API int evk_posmask_build(const int32_t* ids_row, const int32_t* ids2_row, int64_t n_rows,
+                      const int32_t* ids_col, const int32_t* ids2_col, int64_t n_cols,
+                      int64_t diag_offset, int clear_diag,
+                      uint32_t* bits, int64_t ld_words, int32_t* counts, evk_stream_t stream);
+
+/* ---- small path: fp32 SIMT fused kernels (reference-sized batches, N <~ 1k) ---------------
+ * One launch handles the rows of `q` against all columns `k` (both already normalised, fp32):
+ * forward:  row_sum[i] = sum_j E_ij (diagonal excluded if flagged),
+ *           row_pos[i] = sum_j M_ij S_ij
+ * replacing the mm + `/temp` + log_softmax of :499-502 / :437-443 for one direction; the
+ * caller runs it once per direction.  Nothing of size n_rows x n_cols is ever stored. */
+EVK_API int evk_mpce_small_fwd(const float* q, int64_t ld_q, const float* k, int64_t ld_k,
+                       int64_t n_rows, int64_t n_cols, int64_t d,
+                       const uint32_t* bits, int64_t ld_words,
+                       float inv_tau, int flags, int64_t diag_offset,
+                       float* row_sum, float* row_pos, evk_stream_t stream);
+
+/* backward for the same rows:  dq[i,:] = sum_j W_ij k[j,:],
+ *   W_ij = E_ij (a_i + b_j) - 2 M_ij / c_i      (0 on an excluded diagonal)
+ * i.e. N*tau*(dS + its transpose-direction term) of the closed form in oracle/evoke_oracle.py;
+ * the 1/(2N tau) (or 1/(M' tau)) factor is applied by evk_l2norm_bwd's scale. */
+EVK_API int evk_mpce_small_bwd(const float* q, int64_t ld_q, const float* k, int64_t ld_k,
+                       int64_t n_rows, int64_t n_cols, int64_t d,
+                       const uint32_t* bits, int64_t ld_words, const int32_t* counts,
+                       const float* a_row, const float* b_col,
+                       float inv_tau, int flags, int64_t diag_offset,
+                       float* dq, int64_t ld_dq, evk_stream_t stream);
+
+/* ---- statistics -> loss ----------------------------------------------------------------------
+ * out[j] = sum_p part[p*ld + j], p < parts: deterministic reduction of per-tile partials. */
+EVK_API int evk_reduce_partials(const float* part, int64_t parts, int64_t ld, int64_t n, float* out,
+                        evk_stream_t stream);
+
+/* Turns the O(N) statistics into the loss and the backward's scale vectors.
+ *   a_row[i] = 1/row_sum[i];  b_col[j] = 1/col_sum[j]  (col_sum may be NULL: then b_col = NULL ok)
+ *   loss_out[0] = inv_count * [ sum_i (shift + ln row_sum[i] - pos_weight * row_pos[i]/c_i)
+ *                             + sum_{j in [col_lo,col_hi)} (shift + ln col_sum[j]) ]
+ * G loss (:501-503): inv_count = 1/(2N), pos_weight = 2 (the two directions share their
+ * positive term because M_ij=1 implies c_i=c_j).  MPC (:443): inv_count = 1/M', pos_weight = 1,
+ * no column part.  loss_out is a single fp32; the sum is carried in fp64. */
+EVK_API int evk_mpce_finalize(const float* row_sum, const float* row_pos, const int32_t* counts,
+                      int64_t n_rows, const float* col_sum, int64_t n_cols,
+                      int64_t col_lo, int64_t col_hi, float shift, float pos_weight,
+                      double inv_count, float* a_row, float* b_col, float* loss_out,
+                      evk_stream_t stream);
+
+/* ---- large path: tcgen05 / TMEM / TMA kernels (sm_100a only) ------------------------------
+ * All operands are bf16 row-major with 16-byte aligned base and row pitch (ld % 8 == 0).
+ * With EVK_FLAG_SPLIT_BF16 the *_lo pointers carry the low halves written by K1.
+ *
+ * K3 forward (flash-style: S tiles live only in TMEM):
+ *   row_sum_part[cb, i] / row_pos_part[cb, i] : partial over column block cb (256 columns)
+ *   col_sum_part[rb, j]                       : partial over row block rb (128 rows)
+ * pitches: ld_rowpart >= n_rows, ld_colpart >= n_cols.  Reduce with evk_reduce_partials. */
+EVK_API int evk_mpce_fwd(const void* q_hi, const void* q_lo, int64_t ld_q,
+                 const void* k_hi, const void* k_lo, int64_t ld_k,
+                 int64_t n_rows, int64_t n_cols, int64_t d,
+                 const uint32_t* bits, int64_t ld_words,
+                 float inv_tau, int flags, int64_t diag_offset,
+                 float* row_sum_part, float* row_pos_part, int64_t ld_rowpart,
+                 float* col_sum_part, int64_t ld_colpart, evk_stream_t stream);
+
+/* K4a backward, pass 1: recompute S tiles, form W (see evk_mpce_small_bwd) and store it as
+ * bf16 (w_hi, and w_lo = bf16(W - hi) with EVK_FLAG_SPLIT_BF16) in a row strip
+ * [n_rows, ld_w], ld_w % 8 == 0 and ld_w >= n_cols. */
+EVK_API int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q,
+                   const void* k_hi, const void* k_lo, int64_t ld_k,
+                   int64_t n_rows, int64_t n_cols, int64_t d,
+                   const uint32_t* bits, int64_t ld_words, const int32_t* counts,
+                   const float* a_row, const float* b_col,
+                   float inv_tau, int flags, int64_t diag_offset,
+                   void* w_hi, void* w_lo, int64_t ld_w, evk_stream_t stream);
+
+/* K4b backward, pass 2: the two gradient contractions over the W strip, fp32 accumulate in
+ * TMEM, fp32 atomic accumulation into `out` (split-K: the caller zeroes `out` first):
+ *   transpose_w == 0:  out[i, :] += alpha * sum_j W[i, j] x[j, :]    (dQhat; out is [n_rows, d])
+ *   transpose_w == 1:  out[j, :] += alpha * sum_i W[i, j] x[i, :]    (dKhat; out is [n_cols, d])
+ * x is the bf16 normalised matrix of the OTHER side (hi, lo). */
+EVK_API int evk_mpce_bwd_gemm(const void* w_hi, const void* w_lo, int64_t ld_w,
+                      int64_t n_rows, int64_t n_cols, int transpose_w,
+                      const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d,
+                      float alpha, int flags, float* out, int64_t ld_out, evk_stream_t stream);
+
+/* Debug/bring-up: plain C[m,n] = A[m,k] B[n,k]^T (or MN-major operands) through the same
+ * tcgen05 main loop, fp32 out.  a_major/b_major: 0 = K contiguous, 1 = M/N contiguous
+ * (then A is stored [k, m] / B is stored [k, n]).  c must be zeroed by the caller (the epilogue
+ * accumulates with red.add).  variant selects an alternative MN-major descriptor encoding
+ * (bring-up only; 0 is the production encoding); splits > 0 forces the split-K factor. */
+EVK_API int evk_tc_gemm_probe(const void* a, int64_t lda, int a_major, const void* b, int64_t ldb, int b_major,
+                      int64_t m, int64_t n, int64_t k, float* c, int64_t ldc, int variant, int splits,
+                      evk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVOKE_B200_H_ */
