@@ -467,6 +467,13 @@ int launch(const TcParams& p, cudaStream_t s) {
 }
 
 int check_device() {
+  // cuTensorMapEncodeTiled is a driver call: it needs the primary context bound to THIS thread.
+  // autograd runs backward on its own thread, whose first CUDA activity may be this library.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    EVK_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   if (!evk_is_sm100())
     return evk_set_error(EVK_ERR_UNSUPPORTED, "the tcgen05 path needs an sm_100 (B200) device; there is no fallback");
   return EVK_OK;

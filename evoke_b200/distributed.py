@@ -1,0 +1,141 @@
+"""Sharded (one process per GPU) form of the G loss: rank r of R owns rows
+[r*n, (r+1)*n) of the image and text embeddings and the matching ids (a data-parallel batch
+shard) and obtains the loss and gradients of the GLOBAL batch.
+
+The reference has no sharded implementation (its only multi-GPU mode is nn.DataParallel,
+modules/trainer_v0401.py:23-29, under which negatives would be per-replica); the result here is
+defined as the single-device reference on the concatenated batch.
+
+Exchange steps (torch.distributed, NCCL over NVLink on the GPU box, gloo in the CPU tests):
+  forward   all-gather  That (bf16, N*D*2 B) and ids (4N B)
+            all-reduce  column exp-sums (N fp32; the fixed shift makes them additive)
+            all-reduce  the scalar loss partial
+  backward  reduce-scatter  partial dThat (N x D fp32) -> each rank's rows
+The local dQhat contraction is issued while the reduce-scatter is in flight (side stream).
+
+`ops` is the kernel namespace (evoke_b200.functional on a GPU).  The CPU gloo tests pass a
+numpy-backed stand-in with the same function names so that the collective choreography can be
+checked without a GPU; the product never does.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .ids import DeviceIds
+
+
+def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
+    """[n, ...] per rank -> [R*n, ...] (rank order), equal n on every rank."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+@dataclass
+class _Saved:
+    qn: object
+    kn_local: object
+    kn_all: object
+    bits: torch.Tensor
+    counts: torch.Tensor
+    a_row: torch.Tensor
+    b_col: torch.Tensor
+    flags: int
+    n_local: int
+    n_total: int
+    rank: int
+
+
+class _ShardedG(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ops, group, inv_tau: float, precision: str, row_ids: DeviceIds, image: torch.Tensor,
+                text: torch.Tensor):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n = int(image.shape[0])
+        n_total = n * world
+        split = precision == "fp32"
+        flags = ops.FLAG_SPLIT_BF16 if split else 0
+        kw = dict(want_f32=False, want_hi=True, want_lo=split)
+        kn_local = ops.l2norm_fwd(text, **kw)
+        # exchange 1: keys and ids
+        k_hi_all = _all_gather_rows(kn_local.hi, group)
+        k_lo_all = _all_gather_rows(kn_local.lo, group) if split else None
+        ids_all = DeviceIds(_all_gather_rows(row_ids.key, group),
+                            None if row_ids.key2 is None else _all_gather_rows(row_ids.key2, group))
+        kn_all = ops.Normalized(n=n_total, d=kn_local.d, norm=None, hi=k_hi_all, lo=k_lo_all, ld=kn_local.ld)
+        qn = ops.l2norm_fwd(image, **kw)
+        bits, counts = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=rank * n)
+        row_sum, row_pos, col_part = ops.tc_fwd(qn, kn_all, bits, inv_tau, flags, rank * n)
+        # exchange 2: column sums
+        dist.all_reduce(col_part, op=dist.ReduceOp.SUM, group=group)
+        a_row, b_col, loss = ops.finalize(row_sum, row_pos, counts, col_part, col_lo=rank * n, col_hi=(rank + 1) * n,
+                                          shift=inv_tau, pos_weight=2.0, inv_count=0.5 / n_total)
+        # exchange 3: scalar
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        ctx.ops, ctx.group, ctx.inv_tau = ops, group, inv_tau
+        ctx.sv = _Saved(qn, kn_local, kn_all, bits, counts, a_row, b_col, flags, n, n_total, rank)
+        ctx.save_for_backward(image, text)
+        out = loss.reshape(())
+        return out if image.dtype == torch.float32 else out.to(image.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        ops, group, inv_tau, sv = ctx.ops, ctx.group, ctx.inv_tau, ctx.sv
+        image, text = ctx.saved_tensors
+        g = grad_out.reshape(1).to(torch.float32).contiguous()
+        scale = 0.5 * inv_tau / sv.n_total
+        w_hi, w_lo, ld_w = ops.tc_bwd_w(sv.qn, sv.kn_all, sv.bits, sv.counts, sv.a_row, sv.b_col, inv_tau, sv.flags,
+                                        sv.rank * sv.n_local)
+        # partial dKhat for ALL columns from this rank's rows, then reduce-scatter to the owners
+        dk_part = ops.tc_bwd_gemm(w_hi, w_lo, ld_w, sv.n_local, sv.n_total, True, sv.qn, sv.flags)
+        dk_local = torch.empty((sv.n_local, dk_part.shape[1]), dtype=torch.float32, device=dk_part.device)
+        work = dist.reduce_scatter_tensor(dk_local, dk_part, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        # local dQhat while the reduce-scatter is in flight
+        dq = ops.tc_bwd_gemm(w_hi, w_lo, ld_w, sv.n_local, sv.n_total, False, sv.kn_all, sv.flags)
+        d_image = ops.l2norm_bwd(image, sv.qn, dq, scale_dev=g, scale_host=scale)
+        work.wait()
+        d_text = ops.l2norm_bwd(text, sv.kn_local, dk_local, scale_dev=g, scale_host=scale)
+        return None, None, None, None, None, d_image, d_text
+
+
+def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local, temp: float, *,
+                             group=None, precision: str = "bf16", ops=None) -> torch.Tensor:
+    """G loss of the GLOBAL batch from this rank's shard (same row count on every rank).
+
+    image, text: [n_local, D] on this rank's device; ids_local: the n_local ids of these rows
+    (numpy array / int tensor / DeviceIds; string keys must be factorised consistently across
+    ranks by the caller, e.g. with a shared vocabulary - ints are used as they are).
+    Returns the global loss (identical on every rank); .backward() yields d(global loss)/d(local
+    shard), so a DDP-style gradient average over ranks must not be applied to it twice.
+    """
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    if ops is None:
+        from . import functional as ops  # the CUDA kernels
+        ops._require_cuda(image, "image")
+        ops._require_cuda(text, "text")
+    if image.shape != text.shape:
+        raise ValueError(f"image/text shapes differ: {tuple(image.shape)} vs {tuple(text.shape)}")
+    if precision not in ("fp32", "bf16"):
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+    from . import ids as idmod
+    if isinstance(ids_local, DeviceIds):
+        row_ids = ids_local
+    else:
+        import numpy as np
+        if isinstance(ids_local, np.ndarray):
+            if ids_local.dtype.kind not in "iu":
+                raise TypeError("sharded ids must be integers (factorise string keys with a vocabulary shared by all ranks)")
+            # rank-local factorisation would give inconsistent codes: keep the raw integers (exact two-word keys)
+            ids_local = torch.from_numpy(np.ascontiguousarray(ids_local.astype(np.int64)))
+        row_ids, _ = idmod.to_device_ids(ids_local, image.device, n=int(image.shape[0]))
+    temp = float(temp)
+    if not temp > 0:
+        raise ValueError("temperature must be positive")
+    return _ShardedG.apply(ops, group, 1.0 / temp, precision, row_ids, image, text)
