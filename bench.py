@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""Benchmark of the contrastive hot path (BASELINE.json metric): multi-positive image<->text
+contrastive loss forward+backward, pairs/s at global batch N=16384, D=768, bf16 operands.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU path
+    torchrun --nproc-per-node N bench.py --gpus N ...              # N>1: one rank per GPU (NCCL)
+
+A step is one fwd+bwd of `global_alignment_loss` over one synthetic batch.
+Prints ONE JSON line on rank 0.  `value` is device-timed with the inputs resident in HBM;
+`e2e` goes through the public API from pinned HOST buffers (H2D of the embeddings and D2H of
+the loss inside the timed region); `roofline` describes the slowest tcgen05 kernel, timed
+with CUDA events inside the same timed region; `cpu_baseline` times the oracle's PyTorch-CPU
+port of the reference on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_GLOBAL, DIM, TAU = 16384, 768, 0.5
+WORKLOAD = ("cfg3: EVOKE multi-view multi-positive image<->text contrastive loss (global_alignment_loss) fwd+bwd, "
+            "global batch 16384 pairs, D=768, study sizes {1:.25,2:.45,3:.20,4:.10} shuffled, tau=0.5")
+METRIC = "contrastive loss fwd+bwd pairs/sec at N=16384,D=768"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return dict(bf16_tflops=float(p["bf16_tflops"]), bf16_sustained=float(p.get("bf16_tflops_sustained", 0.0)),
+                    hbm_gbs=float(p["hbm_gbs"]), source="measured")
+    except Exception:
+        return dict(bf16_tflops=1590.0, bf16_sustained=1400.0, hbm_gbs=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """Polls NVML for SM clock and clock-event reasons while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        self.samples, self.reason_bits, self.ok = [], 0, False
+        self.period, self._stop = period_s, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:                                   # pragma: no cover
+            self.err = repr(e)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                try:
+                    self.reason_bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.reason_bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.ok:
+            self.thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok and self.thread.is_alive():
+            self.thread.join(timeout=1.0)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
+        s = sorted(self.samples)
+        reasons = [n for b, n in self.REASONS.items() if self.reason_bits & b]
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(s)}
+
+
+def physical_gpu_index(local_index: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_index])
+        except Exception:
+            return local_index
+    return local_index
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def cpu_port_time(n: int, d: int, reps: int, warmup: int, threads: int):
+    """Seconds per fwd+bwd of the oracle's PyTorch-CPU port of global_alignment_loss at size n."""
+    import numpy as np
+    import torch
+    from evoke_b200 import synth
+    from oracle import evoke_oracle as orc
+    torch.set_num_threads(threads)
+    ids = synth.make_study_ids(n, synth.SIZES_CFG3, seed=1234)
+    image = torch.tensor(synth.make_embeddings(ids, d, seed=1235), requires_grad=True)
+    text = torch.tensor(synth.make_embeddings(ids, d, seed=1236), requires_grad=True)
+    times = []
+    for it in range(warmup + reps):
+        image.grad = text.grad = None
+        t0 = time.perf_counter()
+        loss = orc.global_alignment_loss_port(image, text, ids, TAU)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return float(np.mean(times)), float(loss.item())
+
+
+def host_mem_gb() -> float:
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable"):
+                    return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path (its PyTorch op sequence, restated in
+    oracle/evoke_oracle.py because the Python reference cannot travel to the GPU box), all host
+    threads.  Each step is a bounded sample: the full N=16384 batch when K+W such steps fit in
+    ~3 minutes, otherwise the largest power-of-two N_s that does, converted to the metric's
+    unit with the O(N^2) work ratio (stated in `sample`)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    t_probe, _ = cpu_port_time(2048, DIM, reps=1, warmup=1, threads=threads)
+    budget = 170.0
+    total_steps = args.steps + args.warmup
+    n_s = N_GLOBAL
+    mem_ok = host_mem_gb() >= 24.0
+    while n_s > 2048 and (t_probe * (n_s / 2048.0) ** 2 * total_steps > budget or (n_s == N_GLOBAL and not mem_ok)):
+        n_s //= 2
+    t_step, loss = cpu_port_time(n_s, DIM, reps=args.steps, warmup=args.warmup, threads=threads)
+    scale = (N_GLOBAL / n_s) ** 2
+    t_full = t_step * scale
+    value = N_GLOBAL / t_full
+    sample = (f"G loss fwd+bwd, PyTorch CPU fp32 port of the reference op sequence, N_s={n_s}, D={DIM}, "
+              f"{threads} threads ({cpu_model()})")
+    if n_s != N_GLOBAL:
+        sample += f"; time scaled by (16384/{n_s})^2 = {scale:.0f}x (O(N^2) work) to the N=16384 workload"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": N_GLOBAL, "dim": DIM},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "loss": loss,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ CUDA arm
+def run_cuda(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import evoke_b200
+    from evoke_b200 import _lib, synth
+    from evoke_b200 import functional as Fn
+    from evoke_b200.ids import DeviceIds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus} (one rank per GPU)")
+        raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        from evoke_b200.distributed import global_alignment_sharded
+    if N_GLOBAL % world:
+        raise SystemExit("global batch must divide by the number of ranks")
+    n_loc = N_GLOBAL // world
+    lo, hi = rank * n_loc, (rank + 1) * n_loc
+
+    ids_np = synth.make_study_ids(N_GLOBAL, synth.SIZES_CFG3, seed=1234)
+    img_np = synth.make_embeddings(ids_np, DIM, seed=1235)[lo:hi]
+    txt_np = synth.make_embeddings(ids_np, DIM, seed=1236)[lo:hi]
+    image = torch.tensor(img_np, device=dev, requires_grad=True)
+    text = torch.tensor(txt_np, device=dev, requires_grad=True)
+    ids_dev = DeviceIds(torch.from_numpy(ids_np[lo:hi].copy()).to(dev))
+
+    def step():
+        image.grad = None
+        text.grad = None
+        if world == 1:
+            loss = evoke_b200.global_alignment(image, text, ids_dev, TAU, precision="bf16", path="tc")
+        else:
+            loss = global_alignment_sharded(image, text, ids_dev, TAU, precision="bf16")
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # per-kernel CUDA events around the tcgen05 launches (recorded on the launching stream)
+    TC = ("evk_mpce_fwd", "evk_mpce_bwd_w", "evk_mpce_bwd_gemm")
+    ev = {k: [] for k in TC}
+    pending = {}
+
+    def hook(name, phase):
+        if name not in ev:
+            return
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        if phase == "before":
+            pending[name] = e
+        else:
+            ev[name].append((pending.pop(name), e))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    if not args.no_clocks:
+        sampler.start()
+    if not args.no_kernel_events:
+        _lib.call_hook = hook
+    launches0 = _lib.launch_count
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_beg.record()
+    for _ in range(args.steps):
+        loss = step()
+    t_end.record()
+    barrier()
+    _lib.call_hook = None
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop()
+    ms_total = t_beg.elapsed_time(t_end)
+    loss_val = float(loss.item())
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = N_GLOBAL / (ms_step * 1e-3)
+
+    # roofline of the slowest tcgen05 kernel: algorithmic FLOP per launch = 2 * rows * cols * D
+    peaks = load_peaks()
+    flop_launch = 2.0 * n_loc * N_GLOBAL * DIM
+    kern = {}
+    for name, pairs in ev.items():
+        if pairs:
+            ms = [a.elapsed_time(b) for a, b in pairs]
+            kern[name] = dict(launches_per_step=len(pairs) / args.steps, avg_ms=float(np.mean(ms)),
+                              tflops=flop_launch / (float(np.mean(ms)) * 1e-3) / 1e12,
+                              share_of_step=float(np.sum(ms)) / ms_total)
+    dom = max(kern, key=lambda k: kern[k]["avg_ms"]) if kern else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    roofline = None
+    if dom:
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": kern[dom]["tflops"], "peak": peaks["bf16_tflops"],
+                    "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / peaks["bf16_tflops"], "traffic": traffic,
+                    "peak_source": peaks["source"] + " (MEASURED_PEAKS.json bf16_tflops, burst)",
+                    "flop_per_launch": flop_launch}
+    step_tflops = 6.0 * N_GLOBAL * N_GLOBAL * DIM / (ms_step * 1e-3) / 1e12
+    roofline_step = {"algorithmic_flop": 6.0 * N_GLOBAL * N_GLOBAL * DIM, "achieved": step_tflops,
+                     "peak": peaks["bf16_tflops"] * world, "unit": "TFLOP/s",
+                     "frac": step_tflops / (peaks["bf16_tflops"] * world),
+                     "frac_of_sustained": step_tflops / (peaks["bf16_sustained"] * world) if peaks["bf16_sustained"] else None}
+
+    # ---- e2e: public API, HOST (pinned) inputs, H2D + loss D2H inside the timed region; the next
+    # step's H2D is prefetched on a copy stream while the current step computes.
+    h_img = torch.from_numpy(img_np).pin_memory()
+    h_txt = torch.from_numpy(txt_np).pin_memory()
+    ids_host = ids_np[lo:hi].copy()
+    copy_stream = torch.cuda.Stream()
+    bufs = [(torch.empty_like(image), torch.empty_like(text)) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            bufs[slot][0].copy_(h_img, non_blocking=True)
+            bufs[slot][1].copy_(h_txt, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(k):
+        for s in range(2):
+            consumed[s].record(torch.cuda.current_stream())
+        prefetch(0)
+        last = None
+        for i in range(k):
+            slot = i & 1
+            if i + 1 < k:
+                prefetch(slot ^ 1)
+            torch.cuda.current_stream().wait_event(ready[slot])
+            x = bufs[slot][0].detach().requires_grad_(True)
+            y = bufs[slot][1].detach().requires_grad_(True)
+            if world == 1:
+                l = evoke_b200.global_alignment(x, y, ids_host, TAU, precision="bf16", path="tc")
+            else:
+                l = global_alignment_sharded(x, y, ids_host, TAU, precision="bf16")
+            l.backward()
+            consumed[slot].record(torch.cuda.current_stream())
+            last = l.item()                                        # D2H read of the step's result
+        return last
+
+    e2e_loop(3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": N_GLOBAL * args.steps / e2e_s, "unit": "pairs/s",
+           "h2d_bytes_per_step": int((h_img.numel() + h_txt.numel()) * 4 + ids_host.nbytes) * world,
+           "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_s / args.steps * 1e3,
+           "note": "fp32 embeddings + int32 ids from pinned host memory; next step's H2D overlaps compute"}
+
+    cpu_baseline = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_s = N_GLOBAL if host_mem_gb() >= 24.0 else 8192
+        t_probe, _ = cpu_port_time(2048, DIM, reps=1, warmup=1, threads=threads)
+        while n_s > 2048 and t_probe * (n_s / 2048.0) ** 2 * 2 > 40.0:
+            n_s //= 2
+        t_cpu, _ = cpu_port_time(n_s, DIM, reps=1, warmup=1 if n_s < N_GLOBAL else 0, threads=threads)
+        scale = (N_GLOBAL / n_s) ** 2
+        sample = f"1 fwd+bwd of the PyTorch-CPU fp32 port at N_s={n_s}, D={DIM}, {threads} threads ({cpu_model()})"
+        if n_s != N_GLOBAL:
+            sample += f"; time scaled by {scale:.0f}x (O(N^2)) to N=16384"
+        cpu_baseline = {"value": N_GLOBAL / (t_cpu * scale), "unit": "pairs/s", "cores": threads, "kind": "port",
+                        "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": N_GLOBAL, "dim": DIM, "rows_per_rank": n_loc,
+                       "precision": "bf16 operands, fp32 accumulate/statistics; fp32 inputs and gradients",
+                       "parallelism": f"dp{world} row shards" if world > 1 else "single GPU",
+                       "l2": "no explicit flush: each step streams a 0.5 GB bf16 W strip (+0.15 GB operands/grads) "
+                             "through the 126 MB L2, so no timed iteration starts with its inputs cached"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu_baseline, "loss": loss_val,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="evoke_b200", choices=["evoke_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-events", action="store_true", help="debug: skip per-kernel CUDA events")
+    ap.add_argument("--no-clocks", action="store_true", help="debug: skip the NVML clock sampler")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -77,5 +77,22 @@ def check(rc: int, what: str) -> None:
     raise EvokeLibraryError(msg)
 
 
+# kernels of this library launched by one call of each entry point (cudaMemsetAsync not counted)
+KERNELS_PER_CALL = {
+    "evk_l2norm_fwd": 1, "evk_l2norm_bwd": 1, "evk_posmask_build": 1, "evk_mpce_small_fwd": 1,
+    "evk_mpce_small_bwd": 1, "evk_reduce_partials": 1, "evk_mpce_finalize": 1, "evk_mpce_fwd": 1,
+    "evk_mpce_bwd_w": 1, "evk_mpce_bwd_gemm": 1, "evk_tc_gemm_probe": 1,
+}
+launch_count = 0          # running total, read by bench.py ("gpu_launches")
+call_hook = None          # optional callable(name, phase) with phase in {"before", "after"} (bench.py timing)
+
+
 def call(name: str, *args) -> None:
+    global launch_count
+    hook = call_hook
+    if hook is not None:
+        hook(name, "before")
     check(getattr(load(), name)(*args), name)
+    launch_count += KERNELS_PER_CALL.get(name, 0)
+    if hook is not None:
+        hook(name, "after")

@@ -18,6 +18,7 @@
 #include "evk_common.cuh"
 #include "tc_ptx.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -25,21 +26,25 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int kABytes = BM * BK * 2;          // 16 KiB
-constexpr int kBBytes = BN * BK * 2;          // 32 KiB
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kABytes = BM * BK * 2;          // 16 KiB: this CTA's 128 rows of A
+constexpr int kEpiWarps = 8;                  // two per SMSP; warp w reads TMEM lanes 32*(w%4)..+31
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;    // + TMA producer warp + MMA issuer warp
 constexpr int kTmemCols = 512;
 constexpr int kMaxSegs = 3;
+constexpr int kRowParts = kEpiWarps / 4;      // row-statistic partials written per 256-column tile
 
 enum { EPI_FWD = 0, EPI_BWD_W = 1, EPI_GEMM = 2 };
+
+// B bytes per stage held by ONE CTA: the whole 256-column tile, or half of it in CTA-pair mode
+template <bool CTA2> constexpr int b_bytes() { return (CTA2 ? BN / 2 : BN) * BK * 2; }
+template <bool CTA2> constexpr int stage_bytes() { return kABytes + b_bytes<CTA2>(); }
 
 struct alignas(64) TcParams {
   CUtensorMap a_map[kMaxSegs];
   CUtensorMap b_map[kMaxSegs];
   CUtensorMap out_map[2];        // EPI_BWD_W: W hi / lo stores
-  int m_tiles, n_tiles, splits;
+  int m_tiles, n_tiles, splits;  // m_tiles counts 128-row tiles (1-CTA) or 256-row pair tiles (CTA2)
   int num_segs, kb_per_seg;      // k-blocks (of BK) per segment
   int64_t n_rows, n_cols;        // logical extent of the M x N problem (masking)
   float inv_tau;
@@ -61,9 +66,9 @@ template <int EPI>
 constexpr int epi_smem_bytes() {
   return EPI == EPI_FWD ? 4 * BN * 4 : (EPI == EPI_BWD_W ? 4 * 16384 + 2 * BN * 4 : 0);
 }
-template <int EPI, int STAGES>
+template <int EPI, int STAGES, bool CTA2>
 constexpr int smem_bytes_total() {
-  return 1024 /*align slack*/ + STAGES * kStageBytes + epi_smem_bytes<EPI>() + (2 * STAGES + 4) * 8 + 16;
+  return 1024 /*align slack*/ + STAGES * stage_bytes<CTA2>() + epi_smem_bytes<EPI>() + (2 * STAGES + 4) * 8 + 16;
 }
 
 // lane l ends with the sum over the warp's 32 lanes of x[l] (x is destroyed)
@@ -81,13 +86,20 @@ __device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
   return x[0];
 }
 
-template <int EPI, bool A_MN, bool B_MN, int STAGES>
+// CTA2 = true: the kernel is launched as clusters of two CTAs.  A pair owns a 256 x 256 tile:
+// CTA r loads its own 128 rows of A and columns [128r, 128r+128) of B; the leader (r = 0) issues
+// tcgen05.mma.cta_group::2 (M = 256), which reads A from each CTA and B from both halves, and its
+// commits are multicast to the barriers of both CTAs.  Each CTA's TMEM holds the accumulator of
+// its own 128 rows x 256 columns, so the epilogue is the same code in both modes.
+template <int EPI, bool A_MN, bool B_MN, int STAGES, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int kStage = stage_bytes<CTA2>();
+  constexpr int kBRows = CTA2 ? BN / 2 : BN;          // B rows (tile columns) loaded by this CTA
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t epi_base = smem_base + STAGES * kStageBytes;
-  uint8_t* epi_gen = smem_gen + STAGES * kStageBytes;
+  const uint32_t epi_base = smem_base + STAGES * kStage;
+  uint8_t* epi_gen = smem_gen + STAGES * kStage;
   const uint32_t bar_base = epi_base + epi_smem_bytes<EPI>();
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -98,6 +110,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
       reinterpret_cast<volatile uint32_t*>(epi_gen + epi_smem_bytes<EPI>() + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int group_id = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;       // scheduling unit: CTA or CTA pair
+  const int num_groups = CTA2 ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_segs; ++s) {
@@ -110,16 +126,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiThreads / 32);
+      mbar_init(tempty_bar(s), kEpiWarps * (CTA2 ? 2 : 1));
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (CTA2) { tmem_alloc_cta2(tmem_slot, kTmemCols); tmem_relinquish_cta2(); }
+    else      { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -131,28 +147,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      for (int u = group_id; u < total_units; u += num_groups) {
         const int tile = u / p.splits, sp = u - tile * p.splits;
         const int mb = tile / p.n_tiles, nb = tile - mb * p.n_tiles;
-        const int m0 = mb * BM, n0 = nb * BN;
+        const int m0 = mb * (CTA2 ? 2 * BM : BM) + (int)cta_rank * BM;
+        const int n0 = nb * BN + (int)cta_rank * kBRows * (CTA2 ? 1 : 0);
         const int kb0 = (int)(((int64_t)sp * total_kb) / p.splits);
         const int kb1 = (int)(((int64_t)(sp + 1) * total_kb) / p.splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           const int seg = kb / p.kb_per_seg, kk = (kb - seg * p.kb_per_seg) * BK;
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), kStageBytes);
-          const uint32_t a_dst = smem_base + stage * kStageBytes, b_dst = a_dst + kABytes;
+          // the (leader's) full barrier expects the bytes of every CTA that feeds this stage
+          if (leader) mbar_expect_tx(full_bar(stage), kStage * (CTA2 ? 2 : 1));
+          const uint32_t a_dst = smem_base + stage * kStage, b_dst = a_dst + kABytes;
+          auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
+            if (CTA2) tma_load_2d_cta2(dst, m, full_bar(stage), c0, c1);
+            else tma_load_2d(dst, m, full_bar(stage), c0, c1);
+          };
           if (!A_MN) {
-            tma_load_2d(a_dst, &p.a_map[seg], full_bar(stage), kk, m0);
+            load(a_dst, &p.a_map[seg], kk, m0);
           } else {
 #pragma unroll
-            for (int b = 0; b < BM / 64; ++b) tma_load_2d(a_dst + b * 8192, &p.a_map[seg], full_bar(stage), m0 + 64 * b, kk);
+            for (int b = 0; b < BM / 64; ++b) load(a_dst + b * 8192, &p.a_map[seg], m0 + 64 * b, kk);
           }
           if (!B_MN) {
-            tma_load_2d(b_dst, &p.b_map[seg], full_bar(stage), kk, n0);
+            load(b_dst, &p.b_map[seg], kk, n0);
           } else {
 #pragma unroll
-            for (int b = 0; b < BN / 64; ++b) tma_load_2d(b_dst + b * 8192, &p.b_map[seg], full_bar(stage), n0 + 64 * b, kk);
+            for (int b = 0; b < kBRows / 64; ++b) load(b_dst + b * 8192, &p.b_map[seg], n0 + 64 * b, kk);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -160,12 +182,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (leader CTA)
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
       int lu = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++lu) {
+      for (int u = group_id; u < total_units; u += num_groups, ++lu) {
         const int tile = u / p.splits, sp = u - tile * p.splits;
         const int kb0 = (int)(((int64_t)sp * total_kb) / p.splits);
         const int kb1 = (int)(((int64_t)(sp + 1) * total_kb) / p.splits);
@@ -177,32 +199,47 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * kStageBytes, b_addr = a_addr + kABytes;
+          const uint32_t a_addr = smem_base + stage * kStage, b_addr = a_addr + kABytes;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ad = umma_smem_desc(p.desc_a, a_addr + (A_MN ? k * 2048 : k * 32));
             const uint64_t bd = umma_smem_desc(p.desc_b, b_addr + (B_MN ? k * 2048 : k * 32));
-            umma_bf16(d_tmem, ad, bd, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (CTA2) umma_bf16_cta2(d_tmem, ad, bd, p.idesc, acc);
+            else umma_bf16(d_tmem, ad, bd, p.idesc, acc);
           }
-          umma_commit(empty_bar(stage));          // smem slot free once these MMAs retire
+          // smem slot free (in both CTAs) once these MMAs retire
+          if (CTA2) umma_commit_cta2(empty_bar(stage)); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(as));               // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if (CTA2) umma_commit_cta2(tfull_bar(as)); else umma_commit(tfull_bar(as));
       }
     }
     __syncwarp();
   } else {
     // ===================================================================== epilogue warps
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int hh = (warp - 2) >> 2;               // which half of the tile's columns this warp owns
     const int row = q * 32 + lane;                // tile row owned by this thread
-    const int et = (warp - 2) * 32 + lane;        // 0..127
+    const int et = (warp - 2) * 32 + lane;        // 0..255
+    const int c_lo = hh * (BN / 64);              // first 32-column chunk of this warp (4 chunks)
     const float c1 = p.inv_tau * 1.4426950408889634f;    // exp(s/tau - shift) = 2^(s*c1 - c1)
     const bool excl = (p.flags & EVK_FLAG_EXCLUDE_DIAG) != 0;
+    auto release_tmem = [&](int as) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CTA2 && !leader) mbar_arrive_cluster(tempty_bar(as), 0);
+        else mbar_arrive(tempty_bar(as));
+      }
+    };
     int lu = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++lu) {
+    for (int u = group_id; u < total_units; u += num_groups, ++lu) {
       const int tile = u / p.splits;
       const int mb = tile / p.n_tiles, nb = tile - mb * p.n_tiles;
-      const int m0 = mb * BM, n0 = nb * BN;
+      const int m0 = mb * (CTA2 ? 2 * BM : BM) + (int)cta_rank * BM;
+      const int n0 = nb * BN;
       const int as = lu & 1;
       const uint32_t aphase = (lu >> 1) & 1;
       const int64_t i = (int64_t)m0 + row;
@@ -218,7 +255,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int cc = 0; cc < BN / 64; ++cc) {
+          const int c = c_lo + cc;
           const uint32_t mword = row_ok ? __ldg(mrow + c) : 0u;
           float v[32];
           tmem_ld_32x32(taddr + c * 32, v);
@@ -249,22 +287,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
             colpart[q * BN + c * 32 + lane] = cs;
           }
         }
-        // TMEM stage drained: hand it back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        release_tmem(as);                                         // TMEM stage drained
         if (row_ok) {
-          p.row_sum_part[(int64_t)nb * p.ld_rowpart + i] = (rs0 + rs1) + (rs2 + rs3);
-          p.row_pos_part[(int64_t)nb * p.ld_rowpart + i] = rp;
+          const int64_t po = ((int64_t)nb * kRowParts + hh) * p.ld_rowpart + i;
+          p.row_sum_part[po] = (rs0 + rs1) + (rs2 + rs3);
+          p.row_pos_part[po] = rp;
         }
         if (want_col) {
           named_bar_sync(1, kEpiThreads);
-#pragma unroll
-          for (int h = 0; h < BN / kEpiThreads; ++h) {
-            const int cidx = h * kEpiThreads + et;
-            const float s = (colpart[cidx] + colpart[BN + cidx]) + (colpart[2 * BN + cidx] + colpart[3 * BN + cidx]);
-            if (n0 + cidx < p.n_cols) p.col_sum_part[(int64_t)mb * p.ld_colpart + n0 + cidx] = s;
-          }
+          const float s = (colpart[et] + colpart[BN + et]) + (colpart[2 * BN + et] + colpart[3 * BN + et]);
+          // each CTA (128-row block) writes its own partial row: index = global 128-row block
+          if (n0 + et < p.n_cols && m0 < p.n_rows) p.col_sum_part[(int64_t)(m0 / BM) * p.ld_colpart + n0 + et] = s;
           named_bar_sync(1, kEpiThreads);                         // colpart reusable
         }
       } else if (EPI == EPI_BWD_W) {
@@ -275,23 +308,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
         const float n2c = row_ok ? -2.f / (float)max(__ldg(p.counts + i), 1) : 0.f;
         const uint32_t* mrow = p.bits + (row_ok ? i : 0) * p.ld_words + (n0 >> 5);
         const int64_t dcol = i + p.diag_offset - n0;
-#pragma unroll
-        for (int h = 0; h < BN / kEpiThreads; ++h) {
-          const int cidx = h * kEpiThreads + et;
-          bs[cidx] = (n0 + cidx < p.n_cols) ? __ldg(p.b_col + n0 + cidx) : 0.f;
-        }
+        bs[et] = (n0 + et < p.n_cols) ? __ldg(p.b_col + n0 + et) : 0.f;
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
+        // non-split: one round, 4 chunks per warp, hi -> slots {2h, 2h+1}
+        // split    : two rounds of 2 chunks per warp, hi -> slot h, lo -> slot 2+h
+        const int rounds = split ? 2 : 1, per_round = split ? 2 : 4;
 #pragma unroll 1
-        for (int r = 0; r < 2; ++r) {
-          // the staging slots of this round must have been read by their previous TMA store
-          if (et == 0) {
-            if (split) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
-          }
+        for (int r = 0; r < rounds; ++r) {
+          if (et == 0) tma_store_wait_read<0>();                  // staging slots free again
           named_bar_sync(1, kEpiThreads);                         // also publishes bs[] (r == 0)
 #pragma unroll 1
-          for (int cc = 0; cc < 4; ++cc) {
-            const int c = r * 4 + cc;
+          for (int cc = 0; cc < per_round; ++cc) {
+            const int c = c_lo + r * per_round + cc;
             const uint32_t mword = row_ok ? __ldg(mrow + c) : 0u;
             float v[32];
             tmem_ld_32x32(taddr + c * 32, v);
@@ -310,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
                 if (k == dk) v[k] = 0.f;
             }
             // rows >= n_rows / columns >= n_cols hold garbage here; the TMA store clips them.
-            const int slot_hi = split ? (cc >> 1) : (2 * r + (cc >> 1));
+            const int slot_hi = split ? hh : (2 * hh + (cc >> 1));
             const uint32_t row_hi = stg + slot_hi * 16384 + row * 128;
             const int u0 = (cc & 1) * 4;
 #pragma unroll
@@ -326,9 +355,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
                 float l[8];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const uint32_t hh = e == 0 ? h0 : (e == 1 ? h1 : (e == 2 ? h2 : h3));
-                  l[2 * e] = v[8 * uu + 2 * e] - __uint_as_float(hh << 16);
-                  l[2 * e + 1] = v[8 * uu + 2 * e + 1] - __uint_as_float(hh & 0xffff0000u);
+                  const uint32_t hw = e == 0 ? h0 : (e == 1 ? h1 : (e == 2 ? h2 : h3));
+                  l[2 * e] = v[8 * uu + 2 * e] - __uint_as_float(hw << 16);
+                  l[2 * e + 1] = v[8 * uu + 2 * e + 1] - __uint_as_float(hw & 0xffff0000u);
                 }
                 const uint32_t l0 = pack_bf16x2(l[0], l[1]), l1 = pack_bf16x2(l[2], l[3]);
                 const uint32_t l2 = pack_bf16x2(l[4], l[5]), l3 = pack_bf16x2(l[6], l[7]);
@@ -337,23 +366,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
               }
             }
           }
-          if (r == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
-          }
+          if (r == rounds - 1) release_tmem(as);
           fence_proxy_async_smem();                               // generic-proxy writes -> async proxy
           named_bar_sync(1, kEpiThreads);
           if (et == 0) {
-            const int cx = n0 + r * 128;
             if (split) {
+              const int cx = n0 + r * 64;
               tma_store_2d(&p.out_map[0], stg + 0 * 16384, cx, m0);
-              tma_store_2d(&p.out_map[0], stg + 1 * 16384, cx + 64, m0);
+              tma_store_2d(&p.out_map[0], stg + 1 * 16384, cx + 128, m0);
               tma_store_2d(&p.out_map[1], stg + 2 * 16384, cx, m0);
-              tma_store_2d(&p.out_map[1], stg + 3 * 16384, cx + 64, m0);
+              tma_store_2d(&p.out_map[1], stg + 3 * 16384, cx + 128, m0);
             } else {
-              tma_store_2d(&p.out_map[0], stg + (2 * r) * 16384, cx, m0);
-              tma_store_2d(&p.out_map[0], stg + (2 * r + 1) * 16384, cx + 64, m0);
+#pragma unroll
+              for (int sl = 0; sl < 4; ++sl) tma_store_2d(&p.out_map[0], stg + sl * 16384, n0 + sl * 64, m0);
             }
             tma_store_commit();
           }
@@ -363,7 +388,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int cc = 0; cc < BN / 64; ++cc) {
+          const int c = c_lo + cc;
           float v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait(v);
@@ -380,19 +406,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        release_tmem(as);
       }
     }
     if (EPI == EPI_BWD_W && et == 0) tma_store_wait_all<0>();     // smem must outlive the bulk stores
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();            // the peer may still arrive on our barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CTA2) tmem_dealloc_cta2(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -443,25 +467,57 @@ int make_operand_map(CUtensorMap* map, const void* base, bool mn_major, int64_t 
   return make_map_bf16(map, base, k_extent, mn_extent, ld, BK, 64);
 }
 
-void fill_descs(TcParams& p, bool a_mn, bool b_mn, int variant) {
+bool use_cta_pairs() {
+  // CTA-pair (cta_group::2) kernels are the default; EVK_CTA_PAIR=0 selects the single-CTA kernels.
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EVK_CTA_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+void fill_descs(TcParams& p, bool a_mn, bool b_mn, int variant, bool cta2) {
   // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused.  MN-major SW128: 64-element MN
   // atoms 8192 B apart (LBO, one TMA box each), 8-row K groups 1024 B apart (SBO).
   const uint64_t kmaj = umma_smem_desc_base(16, 1024);
-  const uint64_t mnmaj = variant == 1 ? umma_smem_desc_base(1024, 8192) : umma_smem_desc_base(8192, 1024);
+  const uint64_t mnmaj = (variant & 1) ? umma_smem_desc_base(1024, 8192) : umma_smem_desc_base(8192, 1024);
   p.desc_a = a_mn ? mnmaj : kmaj;
   p.desc_b = b_mn ? mnmaj : kmaj;
-  p.idesc = umma_idesc_bf16(BM, BN, a_mn, b_mn);
+  p.idesc = umma_idesc_bf16(cta2 ? 2 * BM : BM, BN, a_mn, b_mn);
 }
 
-template <int EPI, bool A_MN, bool B_MN, int STAGES>
+template <int EPI, bool A_MN, bool B_MN, int STAGES, bool CTA2>
 int launch(const TcParams& p, cudaStream_t s) {
-  constexpr int smem = smem_bytes_total<EPI, STAGES>();
+  constexpr int smem = smem_bytes_total<EPI, STAGES, CTA2>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
-  auto kern = tc_kernel<EPI, A_MN, B_MN, STAGES>;
-  EVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  auto kern = tc_kernel<EPI, A_MN, B_MN, STAGES, CTA2>;
+  static thread_local bool attr_set = false;          // per instantiation, per thread: cheap and race-free
+  if (!attr_set) {
+    EVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
   const int units = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = units < evk_sm_count() ? units : evk_sm_count();
-  kern<<<grid, kThreads, smem, s>>>(p);
+  const int sms = evk_sm_count();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  if (CTA2) {
+    const int groups = units < sms / 2 ? units : sms / 2;
+    cfg.gridDim = dim3(2 * groups);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(units < sms ? units : sms);
+  }
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  EVK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   EVK_CHECK_LAUNCH("tc_kernel");
   return EVK_OK;
 }
@@ -480,14 +536,13 @@ int check_device() {
 }
 
 // smallest split factor whose last wave is at least ~94% full (else the best seen)
-int choose_splits(int tiles, int total_kb) {
-  const int g = evk_sm_count();
+int choose_splits(int tiles, int total_kb, int groups) {
   int best = 1;
   double best_eff = 0.0;
   for (int s = 1; s <= 16; ++s) {
     if (total_kb / s < 8 && s > 1) break;
     const int units = tiles * s;
-    const double eff = (double)units / (double)(((units + g - 1) / g) * g);
+    const double eff = (double)units / (double)(((units + groups - 1) / groups) * groups);
     if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
     if (eff >= 0.94) { best = s; break; }
   }
@@ -495,7 +550,8 @@ int choose_splits(int tiles, int total_kb) {
 }
 
 int setup_sim_operands(TcParams& p, const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi,
-                       const void* k_lo, int64_t ld_k, int64_t n_rows, int64_t n_cols, int64_t d, int flags) {
+                       const void* k_lo, int64_t ld_k, int64_t n_rows, int64_t n_cols, int64_t d, int flags,
+                       bool cta2) {
   const bool split = (flags & EVK_FLAG_SPLIT_BF16) != 0;
   EVK_REQUIRE(q_hi && k_hi && (!split || (q_lo && k_lo)), "null operand pointer");
   EVK_REQUIRE(n_rows > 0 && n_cols > 0 && d > 0, "empty problem");
@@ -507,15 +563,16 @@ int setup_sim_operands(TcParams& p, const void* q_hi, const void* q_lo, int64_t 
   for (int s = 0; s < p.num_segs; ++s) {
     int rc = make_operand_map(&p.a_map[s], qa[s], false, n_rows, d, ld_q, BM);
     if (rc != EVK_OK) return rc;
-    rc = make_operand_map(&p.b_map[s], ka[s], false, n_cols, d, ld_k, BN);
+    rc = make_operand_map(&p.b_map[s], ka[s], false, n_cols, d, ld_k, cta2 ? BN / 2 : BN);
     if (rc != EVK_OK) return rc;
   }
-  p.m_tiles = (int)((n_rows + BM - 1) / BM);
+  const int tile_m = cta2 ? 2 * BM : BM;
+  p.m_tiles = (int)((n_rows + tile_m - 1) / tile_m);
   p.n_tiles = (int)((n_cols + BN - 1) / BN);
   p.splits = 1;
   p.n_rows = n_rows;
   p.n_cols = n_cols;
-  fill_descs(p, false, false, 0);
+  fill_descs(p, false, false, 0, cta2);
   return EVK_OK;
 }
 
@@ -528,9 +585,10 @@ extern "C" int evk_mpce_fwd(const void* q_hi, const void* q_lo, int64_t ld_q, co
                             evk_stream_t stream) {
   int rc = check_device();
   if (rc != EVK_OK) return rc;
+  const bool cta2 = use_cta_pairs();
   TcParams p;
   memset(&p, 0, sizeof(p));
-  rc = setup_sim_operands(p, q_hi, q_lo, ld_q, k_hi, k_lo, ld_k, n_rows, n_cols, d, flags);
+  rc = setup_sim_operands(p, q_hi, q_lo, ld_q, k_hi, k_lo, ld_k, n_rows, n_cols, d, flags, cta2);
   if (rc != EVK_OK) return rc;
   const bool want_col = (flags & EVK_FLAG_NO_COLSUM) == 0;
   EVK_REQUIRE(bits && row_sum_part && row_pos_part && (!want_col || col_sum_part), "evk_mpce_fwd: null pointer");
@@ -548,7 +606,8 @@ extern "C" int evk_mpce_fwd(const void* q_hi, const void* q_lo, int64_t ld_q, co
   p.ld_rowpart = ld_rowpart;
   p.col_sum_part = col_sum_part;
   p.ld_colpart = ld_colpart;
-  return launch<EPI_FWD, false, false, 4>(p, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return cta2 ? launch<EPI_FWD, false, false, 6, true>(p, s) : launch<EPI_FWD, false, false, 4, false>(p, s);
 }
 
 extern "C" int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi, const void* k_lo,
@@ -558,9 +617,10 @@ extern "C" int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q, 
                               evk_stream_t stream) {
   int rc = check_device();
   if (rc != EVK_OK) return rc;
+  const bool cta2 = use_cta_pairs();
   TcParams p;
   memset(&p, 0, sizeof(p));
-  rc = setup_sim_operands(p, q_hi, q_lo, ld_q, k_hi, k_lo, ld_k, n_rows, n_cols, d, flags);
+  rc = setup_sim_operands(p, q_hi, q_lo, ld_q, k_hi, k_lo, ld_k, n_rows, n_cols, d, flags, cta2);
   if (rc != EVK_OK) return rc;
   const bool split = (flags & EVK_FLAG_SPLIT_BF16) != 0;
   EVK_REQUIRE(bits && counts && a_row && b_col && w_hi && (!split || w_lo), "evk_mpce_bwd_w: null pointer");
@@ -581,13 +641,14 @@ extern "C" int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q, 
   p.counts = counts;
   p.a_row = a_row;
   p.b_col = b_col;
-  return launch<EPI_BWD_W, false, false, 3>(p, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return cta2 ? launch<EPI_BWD_W, false, false, 4, true>(p, s) : launch<EPI_BWD_W, false, false, 3, false>(p, s);
 }
 
 namespace {
 int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, const void* const* b_ptrs,
                 int64_t ldb, bool b_mn, int nsegs, int64_t m, int64_t n, int64_t k, float alpha, float* out,
-                int64_t ld_out, int variant, int force_splits, cudaStream_t s) {
+                int64_t ld_out, int variant, int force_splits, bool cta2, cudaStream_t s) {
   EVK_REQUIRE(m > 0 && n > 0 && k > 0 && out, "gemm: empty problem or null output");
   EVK_REQUIRE(m < (1ll << 30) && n < (1ll << 30) && k < (1ll << 30), "gemm: problem too large");
   EVK_REQUIRE(ld_out >= n && ld_out % 4 == 0 && evk_aligned16(out), "gemm: out needs 16-byte alignment and ld_out %% 4 == 0");
@@ -596,24 +657,32 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
   for (int sg = 0; sg < nsegs; ++sg) {
     int rc = make_operand_map(&p.a_map[sg], a_ptrs[sg], a_mn, m, k, lda, BM);
     if (rc != EVK_OK) return rc;
-    rc = make_operand_map(&p.b_map[sg], b_ptrs[sg], b_mn, n, k, ldb, BN);
+    rc = make_operand_map(&p.b_map[sg], b_ptrs[sg], b_mn, n, k, ldb, cta2 ? BN / 2 : BN);
     if (rc != EVK_OK) return rc;
   }
-  p.m_tiles = (int)((m + BM - 1) / BM);
+  const int tile_m = cta2 ? 2 * BM : BM;
+  p.m_tiles = (int)((m + tile_m - 1) / tile_m);
   p.n_tiles = (int)((n + BN - 1) / BN);
   p.n_rows = m;
   p.n_cols = n;
   const int total_kb = p.num_segs * p.kb_per_seg;
-  p.splits = force_splits > 0 ? force_splits : choose_splits(p.m_tiles * p.n_tiles, total_kb);
+  const int groups = cta2 ? evk_sm_count() / 2 : evk_sm_count();
+  p.splits = force_splits > 0 ? force_splits : choose_splits(p.m_tiles * p.n_tiles, total_kb, groups);
   if (p.splits > total_kb) p.splits = total_kb;
   p.out = out;
   p.ld_out = ld_out;
   p.alpha = alpha;
-  fill_descs(p, a_mn, b_mn, variant);
-  if (a_mn && b_mn) return launch<EPI_GEMM, true, true, 4>(p, s);
-  if (a_mn) return launch<EPI_GEMM, true, false, 4>(p, s);
-  if (b_mn) return launch<EPI_GEMM, false, true, 4>(p, s);
-  return launch<EPI_GEMM, false, false, 4>(p, s);
+  fill_descs(p, a_mn, b_mn, variant, cta2);
+  if (cta2) {
+    if (a_mn && b_mn) return launch<EPI_GEMM, true, true, 6, true>(p, s);
+    if (a_mn) return launch<EPI_GEMM, true, false, 6, true>(p, s);
+    if (b_mn) return launch<EPI_GEMM, false, true, 6, true>(p, s);
+    return launch<EPI_GEMM, false, false, 6, true>(p, s);
+  }
+  if (a_mn && b_mn) return launch<EPI_GEMM, true, true, 4, false>(p, s);
+  if (a_mn) return launch<EPI_GEMM, true, false, 4, false>(p, s);
+  if (b_mn) return launch<EPI_GEMM, false, true, 4, false>(p, s);
+  return launch<EPI_GEMM, false, false, 4, false>(p, s);
 }
 }  // namespace
 
@@ -633,7 +702,7 @@ extern "C" int evk_mpce_bwd_gemm(const void* w_hi, const void* w_lo, int64_t ld_
   const int64_t m = transpose_w ? n_cols : n_rows;
   const int64_t k = transpose_w ? n_rows : n_cols;
   return gemm_common(p, a_ptrs, ld_w, transpose_w != 0, b_ptrs, ld_x, true, split ? 3 : 1, m, d, k, alpha, out, ld_out,
-                     0, 0, static_cast<cudaStream_t>(stream));
+                     0, 0, use_cta_pairs(), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int evk_tc_gemm_probe(const void* a, int64_t lda, int a_major, const void* b, int64_t ldb, int b_major,
@@ -646,6 +715,8 @@ extern "C" int evk_tc_gemm_probe(const void* a, int64_t lda, int a_major, const 
   memset(&p, 0, sizeof(p));
   const void* a_ptrs[3] = {a, nullptr, nullptr};
   const void* b_ptrs[3] = {b, nullptr, nullptr};
+  // variant bit 0: alternative MN-major descriptor; bit 1: force CTA pairs; bit 2: force single CTA
+  const bool cta2 = (variant & 2) ? true : ((variant & 4) ? false : use_cta_pairs());
   return gemm_common(p, a_ptrs, lda, a_major != 0, b_ptrs, ldb, b_major != 0, 1, m, n, k, 1.f, c, ldc, variant, splits,
-                     static_cast<cudaStream_t>(stream));
+                     cta2, static_cast<cudaStream_t>(stream));
 }

@@ -28,6 +28,7 @@ from .ids import DeviceIds
 
 SMALL_PATH_MAX = int(os.environ.get("EVOKE_B200_SMALL_MAX", "512"))   # rows/cols up to which the SIMT path is used
 TILE_M, TILE_N = 128, 256
+ROW_PARTS = 2          # row-statistic partials per 256-column tile (two epilogue warps share a row)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -164,14 +165,14 @@ def tc_fwd(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int, diag_
     n_ct = (k.n + TILE_N - 1) // TILE_N
     n_rt = (q.n + TILE_M - 1) // TILE_M
     want_col = not (flags & FLAG_NO_COLSUM)
-    rs_part = torch.empty((n_ct, q.n), dtype=torch.float32, device=dev)
-    rp_part = torch.empty((n_ct, q.n), dtype=torch.float32, device=dev)
+    rs_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev)
+    rp_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev)
     cs_part = torch.empty((n_rt, k.n), dtype=torch.float32, device=dev) if want_col else None
     _lib.call("evk_mpce_fwd", _ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, q.n, k.n, q.d,
               _ptr(bits), bits.stride(0), float(inv_tau), flags, diag_offset,
               _ptr(rs_part), _ptr(rp_part), q.n, _ptr(cs_part), k.n, _stream())
-    row_sum = reduce_partials(rs_part, n_ct, q.n)
-    row_pos = reduce_partials(rp_part, n_ct, q.n)
+    row_sum = reduce_partials(rs_part, n_ct * ROW_PARTS, q.n)
+    row_pos = reduce_partials(rp_part, n_ct * ROW_PARTS, q.n)
     col_sum = reduce_partials(cs_part, n_rt, k.n) if want_col else None
     return row_sum, row_pos, col_sum
 

@@ -73,9 +73,23 @@ def stage_probe_mn0():
         _probe(am, bm, 300, 520, 200, 0)
 
 
-def stage_probe_mn1():
-    for am, bm in ((0, 1), (1, 0), (1, 1)):
-        _probe(am, bm, 128, 256, 64, 1)
+def stage_probe_cta1():
+    for am, bm in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        _probe(am, bm, 300, 520, 200, 4)
+    _probe(0, 0, 1024, 1024, 1024, 4, splits=3)
+
+
+def stage_probe_cta2_small():
+    _probe(0, 0, 256, 256, 64, 2)
+    _probe(0, 0, 256, 256, 256, 2)
+
+
+def stage_probe_cta2():
+    for am, bm in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        _probe(am, bm, 128, 256, 64, 2)
+        _probe(am, bm, 300, 520, 200, 2)
+    _probe(0, 0, 1024, 1024, 1024, 2, splits=3)
+    _probe(1, 1, 2048, 768, 4096, 2)
 
 
 def stage_tc():
@@ -97,7 +111,8 @@ def stage_smoke():
 
 
 STAGES = {"k12": stage_k12, "small": stage_small, "probe_kk": stage_probe_kk, "probe_mn0": stage_probe_mn0,
-          "probe_mn1": stage_probe_mn1, "tc": stage_tc, "smoke": stage_smoke}
+          "probe_cta1": stage_probe_cta1, "probe_cta2_small": stage_probe_cta2_small, "probe_cta2": stage_probe_cta2,
+          "tc": stage_tc, "smoke": stage_smoke}
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
@@ -106,10 +121,11 @@ if __name__ == "__main__":
         sys.exit(0)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     log = open(os.path.join(ROOT, "gpurun_out", "bringup.log"), "w")
-    for name in STAGES:
+    names = [a for a in os.environ.get("BRINGUP_STAGES", "").split(",") if a] or list(STAGES)
+    for name in names:
         t0 = time.time()
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), name], cwd=ROOT, timeout=240,
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), name], cwd=ROOT, timeout=120,
                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             out, rc = r.stdout, r.returncode
         except subprocess.TimeoutExpired as e:
