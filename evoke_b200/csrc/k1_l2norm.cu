@@ -152,6 +152,60 @@ l2norm_bwd_kernel(const void* __restrict__ x, int x_dtype, int64_t n_out, int64_
   }
 }
 
+// Fast path: fp32 x / g / dx, unit column stride, 16-byte aligned rows, d % 4 == 0, d <= kIters*128.
+// One pass: the row of x and g stays in registers between the projection and the update.
+// Algorithmic bytes per row: 4d (x) + 4d (g) read, 4d (dx) written.
+template <int kIters>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t stride_row,
+                      const int32_t* __restrict__ gather, const float* __restrict__ norm,
+                      const float* __restrict__ g, int64_t ld_g, const float* __restrict__ scale_dev,
+                      float scale_host, float* __restrict__ dx, int64_t ld_dx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  const float scale = scale_host * (scale_dev ? __ldg(scale_dev) : 1.f);
+  for (int64_t r = warp0; r < n_out; r += nwarps) {
+    const int64_t src = gather ? (int64_t)gather[r] : r;
+    const float4* xr = reinterpret_cast<const float4*>(x + src * stride_row);
+    const float4* gr = reinterpret_cast<const float4*>(g + r * ld_g);
+    float4* dr = reinterpret_cast<float4*>(dx + src * ld_dx);
+    const float nrm = norm[r];
+    const bool clamped = nrm < EVK_NORM_EPS;
+    const float den = fmaxf(nrm, EVK_NORM_EPS);
+    float4 xv[kIters], gv[kIters];
+    float proj = 0.f;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int c = it * 32 + lane;
+      if (c * 4 < d) {
+        xv[it] = __ldg(xr + c);
+        gv[it] = __ldg(gr + c);
+        xv[it].x /= den; xv[it].y /= den; xv[it].z /= den; xv[it].w /= den;     // xhat, as in the forward
+        proj = fmaf(xv[it].x, gv[it].x, proj);
+        proj = fmaf(xv[it].y, gv[it].y, proj);
+        proj = fmaf(xv[it].z, gv[it].z, proj);
+        proj = fmaf(xv[it].w, gv[it].w, proj);
+      }
+    }
+    proj = warp_sum(proj);
+    const float s_over_den = clamped ? scale / EVK_NORM_EPS : scale / den;
+    if (clamped) proj = 0.f;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int c = it * 32 + lane;
+      if (c * 4 < d) {
+        float4 o;
+        o.x = s_over_den * (gv[it].x - xv[it].x * proj);
+        o.y = s_over_den * (gv[it].y - xv[it].y * proj);
+        o.z = s_over_den * (gv[it].z - xv[it].z * proj);
+        o.w = s_over_den * (gv[it].w - xv[it].w * proj);
+        dr[c] = o;
+      }
+    }
+  }
+}
+
 inline int grid_for_rows(int64_t n) {
   const int64_t blocks = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int64_t cap = (int64_t)evk_sm_count() * 8;  // 8 resident 256-thread CTAs per SM, one wave
@@ -206,6 +260,23 @@ extern "C" int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t
                   dx_dtype <= EVK_DTYPE_F16, "evk_l2norm_bwd: bad dtype");
   EVK_REQUIRE(!accumulate || dx_dtype == EVK_DTYPE_F32, "evk_l2norm_bwd: accumulate needs fp32 dx");
   if (n_out == 0) return EVK_OK;
+  const bool vec = x_dtype == EVK_DTYPE_F32 && dx_dtype == EVK_DTYPE_F32 && !accumulate && stride_col == 1 &&
+                   d % 4 == 0 && d <= 2048 && stride_row % 4 == 0 && ld_g % 4 == 0 && ld_dx % 4 == 0 &&
+                   evk_aligned16(x) && evk_aligned16(g) && evk_aligned16(dx);
+  if (vec) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = grid_for_rows(n_out);
+    const float* xf = static_cast<const float*>(x);
+    float* df = static_cast<float*>(dx);
+    if (d <= 1024)
+      l2norm_bwd_vec_kernel<8><<<grid, kWarpsPerBlock * 32, 0, s>>>(xf, n_out, (int)d, stride_row, gather, norm, g, ld_g,
+                                                                    scale_dev, scale_host, df, ld_dx);
+    else
+      l2norm_bwd_vec_kernel<16><<<grid, kWarpsPerBlock * 32, 0, s>>>(xf, n_out, (int)d, stride_row, gather, norm, g,
+                                                                     ld_g, scale_dev, scale_host, df, ld_dx);
+    EVK_CHECK_LAUNCH("l2norm_bwd_vec");
+    return EVK_OK;
+  }
   l2norm_bwd_kernel<<<grid_for_rows(n_out), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       x, x_dtype, n_out, d, stride_row, stride_col, gather, norm, g, ld_g, scale_dev, scale_host, dx, dx_dtype,
       ld_dx, accumulate);

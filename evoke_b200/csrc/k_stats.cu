@@ -55,7 +55,112 @@ finalize_kernel(const float* __restrict__ row_sum, const float* __restrict__ row
   }
 }
 
+// Fused single-GPU form: reduce the per-tile partials, emit a_row / b_col and the loss in ONE
+// multi-CTA launch.  Each CTA owns 256 rows (and the same 256 columns), adds its terms in fp64,
+// publishes a per-CTA partial, and the last CTA to finish (atomic ticket) sums the partials in
+// index order, so the result is deterministic.
+constexpr int kStatThreads = 256;
+constexpr int kStatElems = 32;                       // rows (and columns) per CTA
+constexpr int kStatGroups = kStatThreads / kStatElems;   // partial-sum groups per element
+
+// sum of part[p*ld + i] over p = g, g+G, ... with four independent loads in flight
+__device__ __forceinline__ float strided_partial_sum(const float* __restrict__ part, int64_t parts, int64_t ld,
+                                                     int64_t i, int g) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int64_t p = g;
+  for (; p + 3 * kStatGroups < parts; p += 4 * kStatGroups) {
+    s0 += part[p * ld + i];
+    s1 += part[(p + kStatGroups) * ld + i];
+    s2 += part[(p + 2 * kStatGroups) * ld + i];
+    s3 += part[(p + 3 * kStatGroups) * ld + i];
+  }
+  for (; p < parts; p += kStatGroups) s0 += part[p * ld + i];
+  return (s0 + s1) + (s2 + s3);
+}
+
+__global__ void __launch_bounds__(kStatThreads)
+stats_fused_kernel(const float* __restrict__ rs_part, const float* __restrict__ rp_part, int64_t row_parts,
+                   int64_t ld_row, const int32_t* __restrict__ counts, int64_t n_rows,
+                   const float* __restrict__ cs_part, int64_t col_parts, int64_t ld_col, int64_t n_cols,
+                   float shift, float pos_weight, double inv_count, float* __restrict__ a_row,
+                   float* __restrict__ b_col, float* __restrict__ loss_out, double* __restrict__ cta_partial,
+                   unsigned int* __restrict__ ticket) {
+  __shared__ float s_sum[3][kStatGroups][kStatElems];
+  __shared__ double s_part[kStatElems / 32];
+  __shared__ bool s_last;
+  const int e = threadIdx.x % kStatElems, g = threadIdx.x / kStatElems;
+  const int64_t i = (int64_t)blockIdx.x * kStatElems + e;
+  s_sum[0][g][e] = i < n_rows ? strided_partial_sum(rs_part, row_parts, ld_row, i, g) : 0.f;
+  s_sum[1][g][e] = i < n_rows ? strided_partial_sum(rp_part, row_parts, ld_row, i, g) : 0.f;
+  s_sum[2][g][e] = (cs_part && i < n_cols) ? strided_partial_sum(cs_part, col_parts, ld_col, i, g) : 0.f;
+  __syncthreads();
+  if (threadIdx.x < kStatElems) {
+    double acc = 0.0;
+    float r = 0.f, pos = 0.f, c = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < kStatGroups; ++gg) {          // fixed order: deterministic
+      r += s_sum[0][gg][e];
+      pos += s_sum[1][gg][e];
+      c += s_sum[2][gg][e];
+    }
+    if (i < n_rows) {
+      const int cnt = counts[i];
+      a_row[i] = 1.f / r;
+      acc += (double)shift + (double)logf(r) - (double)pos_weight * (cnt > 0 ? (double)pos / (double)cnt : 0.0);
+    }
+    if (cs_part && i < n_cols) {
+      b_col[i] = 1.f / c;
+      acc += (double)shift + (double)logf(c);
+    }
+    acc = warp_sum_f64(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kStatElems / 32; ++w) t += s_part[w];
+    cta_partial[blockIdx.x] = t;
+    __threadfence();
+    const unsigned int done = atomicAdd(ticket, 1u);
+    s_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < 32) {
+    __threadfence();
+    // lane l sums partials l, l+32, ... ; lanes are then combined in a fixed butterfly order
+    double t = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32) t += reinterpret_cast<volatile double*>(cta_partial)[b];
+    t = warp_sum_f64(t);
+    if (threadIdx.x == 0) loss_out[0] = (float)(t * inv_count);
+  }
+}
+
 }  // namespace
+
+extern "C" int evk_mpce_stats_fused(const float* rs_part, const float* rp_part, int64_t row_parts, int64_t ld_row,
+                                    const int32_t* counts, int64_t n_rows, const float* cs_part, int64_t col_parts,
+                                    int64_t ld_col, int64_t n_cols, float shift, float pos_weight, double inv_count,
+                                    float* a_row, float* b_col, float* loss_out, void* workspace,
+                                    int64_t workspace_bytes, evk_stream_t stream) {
+  EVK_REQUIRE(rs_part && rp_part && counts && a_row && loss_out && workspace && n_rows > 0 && row_parts >= 1 &&
+                  ld_row >= n_rows, "evk_mpce_stats_fused: bad row arguments");
+  EVK_REQUIRE(!cs_part || (b_col && col_parts >= 1 && ld_col >= n_cols && n_cols > 0),
+              "evk_mpce_stats_fused: bad column arguments");
+  const int64_t n = (cs_part && n_cols > n_rows) ? n_cols : n_rows;
+  const int64_t blocks = (n + kStatElems - 1) / kStatElems;
+  EVK_REQUIRE(workspace_bytes >= 16 + 8 * blocks && evk_aligned16(workspace),
+              "evk_mpce_stats_fused: workspace needs %lld bytes, 16-byte aligned", (long long)(16 + 8 * blocks));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned int* ticket = static_cast<unsigned int*>(workspace);
+  double* partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + 16);
+  EVK_CUDA(cudaMemsetAsync(ticket, 0, 16, s));
+  stats_fused_kernel<<<(unsigned)blocks, kStatThreads, 0, s>>>(rs_part, rp_part, row_parts, ld_row, counts, n_rows,
+                                                              cs_part, col_parts, ld_col, cs_part ? n_cols : 0, shift,
+                                                              pos_weight, inv_count, a_row, b_col, loss_out, partial,
+                                                              ticket);
+  EVK_CHECK_LAUNCH("mpce_stats_fused");
+  return EVK_OK;
+}
 
 extern "C" int evk_reduce_partials(const float* part, int64_t parts, int64_t ld, int64_t n, float* out,
                                    evk_stream_t stream) {

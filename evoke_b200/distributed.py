@@ -94,7 +94,7 @@ class _ShardedG(torch.autograd.Function):
                                         sv.rank * sv.n_local)
         # partial dKhat for ALL columns from this rank's rows, then reduce-scatter to the owners
         dk_part = ops.tc_bwd_gemm(w_hi, w_lo, ld_w, sv.n_local, sv.n_total, True, sv.qn, sv.flags)
-        dk_local = torch.empty((sv.n_local, dk_part.shape[1]), dtype=torch.float32, device=dk_part.device)
+        dk_local = torch.empty((sv.n_local, dk_part.shape[1]), dtype=dk_part.dtype, device=dk_part.device)
         work = dist.reduce_scatter_tensor(dk_local, dk_part, op=dist.ReduceOp.SUM, group=group, async_op=True)
         # local dQhat while the reduce-scatter is in flight
         dq = ops.tc_bwd_gemm(w_hi, w_lo, ld_w, sv.n_local, sv.n_total, False, sv.kn_all, sv.flags)

@@ -159,8 +159,40 @@ def small_bwd(q: Normalized, k: Normalized, bits, counts, a_row, b_col, inv_tau:
 
 
 # --- tcgen05 path --------------------------------------------------------------------------
+def tc_fwd_partials(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int, diag_offset: int = 0):
+    """K3.  Returns the per-tile partials (rs_part, rp_part, cs_part | None) and their counts."""
+    dev = q.hi.device
+    n_ct = (k.n + TILE_N - 1) // TILE_N
+    n_rt = (q.n + TILE_M - 1) // TILE_M
+    want_col = not (flags & FLAG_NO_COLSUM)
+    rs_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev)
+    rp_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev)
+    cs_part = torch.empty((n_rt, k.n), dtype=torch.float32, device=dev) if want_col else None
+    _lib.call("evk_mpce_fwd", _ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, q.n, k.n, q.d,
+              _ptr(bits), bits.stride(0), float(inv_tau), flags, diag_offset,
+              _ptr(rs_part), _ptr(rp_part), q.n, _ptr(cs_part), k.n, _stream())
+    return rs_part, rp_part, cs_part
+
+
+def stats_fused(rs_part, rp_part, cs_part, counts, *, shift: float, pos_weight: float, inv_count: float):
+    """Partials -> (a_row, b_col | None, loss[1]) in one launch (single-GPU form)."""
+    dev = rs_part.device
+    n_rows = int(rs_part.shape[1])
+    n_cols = 0 if cs_part is None else int(cs_part.shape[1])
+    a_row = torch.empty(n_rows, dtype=torch.float32, device=dev)
+    b_col = torch.empty(n_cols, dtype=torch.float32, device=dev) if cs_part is not None else None
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    ws_bytes = 16 + 8 * ((max(n_rows, n_cols) + 31) // 32)
+    ws = torch.empty(_round_up(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    _lib.call("evk_mpce_stats_fused", _ptr(rs_part), _ptr(rp_part), int(rs_part.shape[0]), rs_part.stride(0),
+              _ptr(counts), n_rows, _ptr(cs_part), 0 if cs_part is None else int(cs_part.shape[0]),
+              0 if cs_part is None else cs_part.stride(0), n_cols, float(shift), float(pos_weight), float(inv_count),
+              _ptr(a_row), _ptr(b_col), _ptr(loss), _ptr(ws), ws.numel(), _stream())
+    return a_row, b_col, loss
+
+
 def tc_fwd(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int, diag_offset: int = 0):
-    """K3.  Returns (row_sum[n_rows], row_pos[n_rows], col_sum[n_cols] | None)."""
+    """K3 + partial reduction (sharded path).  Returns (row_sum, row_pos, col_sum | None)."""
     dev = q.hi.device
     n_ct = (k.n + TILE_N - 1) // TILE_N
     n_rt = (q.n + TILE_M - 1) // TILE_M
@@ -245,18 +277,18 @@ class _MultiPositiveCE(torch.autograd.Function):
         bits, counts = posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc)
         if mpc:
             flags |= FLAG_EXCLUDE_DIAG | FLAG_NO_COLSUM
+        pos_weight, inv_count = (1.0, 1.0 / n) if mpc else (2.0, 0.5 / n)
         if small:
             row_sum, row_pos = small_fwd(qn, kn, bits, cfg.inv_tau, flags)
             col_sum = None if mpc else small_fwd(kn, qn, bits, cfg.inv_tau, flags)[0]
+            a_row, b_col, loss = finalize(row_sum, row_pos, counts, col_sum, col_lo=0, col_hi=0 if mpc else n,
+                                          shift=cfg.inv_tau, pos_weight=pos_weight, inv_count=inv_count)
         else:
-            row_sum, row_pos, col_sum = tc_fwd(qn, kn, bits, cfg.inv_tau, flags)
+            rs_part, rp_part, cs_part = tc_fwd_partials(qn, kn, bits, cfg.inv_tau, flags)
+            a_row, b_col, loss = stats_fused(rs_part, rp_part, cs_part, counts, shift=cfg.inv_tau,
+                                             pos_weight=pos_weight, inv_count=inv_count)
         if mpc:
-            a_row, _, loss = finalize(row_sum, row_pos, counts, None, col_lo=0, col_hi=0, shift=cfg.inv_tau,
-                                      pos_weight=1.0, inv_count=1.0 / n)
             b_col = a_row
-        else:
-            a_row, b_col, loss = finalize(row_sum, row_pos, counts, col_sum, col_lo=0, col_hi=n,
-                                          shift=cfg.inv_tau, pos_weight=2.0, inv_count=0.5 / n)
         ctx.cfg, ctx.flags, ctx.qn, ctx.kn = cfg, flags, qn, kn
         ctx.aux = (bits, counts, a_row, b_col)
         ctx.has_text = text is not None

@@ -144,6 +144,17 @@ EVK_API int evk_mpce_finalize(const float* row_sum, const float* row_pos, const 
                       double inv_count, float* a_row, float* b_col, float* loss_out,
                       evk_stream_t stream);
 
+/* Single-GPU fused form of evk_reduce_partials (x3) + evk_mpce_finalize: takes the per-tile
+ * partials of K3 directly (rs_part/rp_part: [row_parts, ld_row], cs_part: [col_parts, ld_col] or
+ * NULL), the loss covers all rows and all columns.  workspace: >= 16 + 8*ceil(max(n_rows,n_cols)/32)
+ * bytes, 16-byte aligned, contents irrelevant.  Deterministic (fixed summation order). */
+EVK_API int evk_mpce_stats_fused(const float* rs_part, const float* rp_part, int64_t row_parts, int64_t ld_row,
+                         const int32_t* counts, int64_t n_rows,
+                         const float* cs_part, int64_t col_parts, int64_t ld_col, int64_t n_cols,
+                         float shift, float pos_weight, double inv_count,
+                         float* a_row, float* b_col, float* loss_out,
+                         void* workspace, int64_t workspace_bytes, evk_stream_t stream);
+
 /* ---- large path: tcgen05 / TMEM / TMA kernels (sm_100a only) ------------------------------
  * All operands are bf16 row-major with 16-byte aligned base and row pitch (ld % 8 == 0).
  * With EVK_FLAG_SPLIT_BF16 the *_lo pointers carry the low halves written by K1.

@@ -1,0 +1,60 @@
+"""T4 (GPU, NCCL, world_size 2): sharded G loss == single-GPU G loss on the concatenated batch,
+and both == the fp64 oracle.  Skipped on boxes with fewer than two GPUs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, n_total, d, tau, precision, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from evoke_b200 import synth
+        from evoke_b200.distributed import global_alignment_sharded
+        ids = synth.make_study_ids(n_total, seed=31)
+        xi = synth.make_embeddings(ids, d, seed=32)
+        xt = synth.make_embeddings(ids, d, seed=33)
+        n = n_total // world
+        sl = slice(rank * n, (rank + 1) * n)
+        image = torch.tensor(xi[sl], device="cuda", requires_grad=True)
+        text = torch.tensor(xt[sl], device="cuda", requires_grad=True)
+        loss = global_alignment_sharded(image, text, ids[sl].copy(), tau, precision=precision)
+        loss.backward()
+        torch.cuda.synchronize()
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=loss.item(), d_image=image.grad.cpu().numpy(),
+                 d_text=text.grad.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("precision,ltol,gtol", [("fp32", 1e-5, 1e-4), ("bf16", 2e-3, 2e-2)])
+def test_sharded_equals_oracle_on_two_gpus(tmp_path, precision, ltol, gtol):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from evoke_b200 import synth
+    from oracle import evoke_oracle as orc
+    world, n_total, d, tau = 2, 1536, 256, 0.5
+    port = 29900 + (os.getpid() % 90) + (1 if precision == "fp32" else 0)
+    mp.spawn(_worker, args=(world, port, n_total, d, tau, precision, str(tmp_path)), nprocs=world, join=True)
+    ids = synth.make_study_ids(n_total, seed=31)
+    xi = synth.make_embeddings(ids, d, seed=32)
+    xt = synth.make_embeddings(ids, d, seed=33)
+    want, d_i, d_t, _ = orc.g_loss_closed_form(xi, xt, ids, tau)
+    n = n_total // world
+    for r in range(world):
+        got = np.load(tmp_path / f"rank{r}.npz")
+        sl = slice(r * n, (r + 1) * n)
+        assert abs(float(got["loss"]) - want) <= ltol * abs(want)
+        assert np.abs(got["d_image"] - d_i[sl]).max() <= gtol * np.abs(d_i).max()
+        assert np.abs(got["d_text"] - d_t[sl]).max() <= gtol * np.abs(d_t).max()
