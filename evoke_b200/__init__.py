@@ -8,9 +8,10 @@ loudly if it is missing (there is no CPU or PyTorch fallback).
 from .loss import (ContrastiveObjective, global_alignment, global_alignment_loss, multi_pos_contra_images,
                    multi_pos_contra_images_v0401, patch_pretrain)
 from .lm_loss import LanguageModelCriterion, compute_lm_loss
+from .graphs import GraphedGlobalAlignment
 
 __all__ = [
     "ContrastiveObjective", "global_alignment", "global_alignment_loss", "multi_pos_contra_images",
-    "multi_pos_contra_images_v0401", "patch_pretrain", "LanguageModelCriterion", "compute_lm_loss",
+    "multi_pos_contra_images_v0401", "patch_pretrain", "GraphedGlobalAlignment", "LanguageModelCriterion", "compute_lm_loss",
 ]
 __version__ = "0.1.0"

@@ -156,3 +156,18 @@ def test_temperature_out_of_range_is_an_error_on_the_tc_path():
     x = torch.randn(600, 64, device=DEV)
     with pytest.raises(ValueError, match="tau"):
         evoke_b200.global_alignment(x, x, ids, 0.01, path="tc")
+
+
+def test_cuda_graph_step_matches_eager_and_tracks_new_inputs():
+    n, d = 1024, 256
+    g = evoke_b200.GraphedGlobalAlignment(n, d, 0.5, precision="fp32", path="tc").capture()
+    for seed in (1, 2):
+        ids = synth.make_study_ids(n, seed=seed)
+        xi = synth.make_embeddings(ids, d, seed=seed + 10)
+        xt = synth.make_embeddings(ids, d, seed=seed + 20)
+        g.load(torch.tensor(xi, device=DEV), torch.tensor(xt, device=DEV), torch.from_numpy(ids).to(DEV))
+        loss = g.step()
+        want, d_i, d_t, _ = orc.g_loss_closed_form(xi, xt, ids, 0.5)
+        assert abs(loss.item() - want) <= 1e-5 * abs(want)
+        assert rel_max(g.image.grad.cpu().numpy(), d_i) <= 1e-4
+        assert rel_max(g.text.grad.cpu().numpy(), d_t) <= 1e-4
