@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libevoke_b200.so")
 
 EVK_OK, EVK_ERR_INVALID, EVK_ERR_CUDA, EVK_ERR_UNSUPPORTED = 0, -1, -2, -3
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
-FLAG_EXCLUDE_DIAG, FLAG_NO_COLSUM, FLAG_SPLIT_BF16 = 1, 2, 4
+FLAG_EXCLUDE_DIAG, FLAG_NO_COLSUM, FLAG_SPLIT_BF16, FLAG_NO_POS = 1, 2, 4, 8
 ABI_VERSION = 1
 
 P, I, L, F, D = c_void_p, c_int, c_int64, c_float, c_double
@@ -31,7 +31,8 @@ SIGNATURES = {
     "evk_mpce_small_bwd": [P, L, P, L, L, L, L, P, L, P, P, P, F, I, L, P, L, P],
     "evk_reduce_partials": [P, L, L, L, P, P],
     "evk_mpce_finalize": [P, P, P, L, P, L, L, L, F, F, D, P, P, P, P],
-    "evk_mpce_stats_fused": [P, P, L, L, P, L, P, L, L, L, F, F, D, P, P, P, P, L, P],
+    "evk_mpce_stats_fused": [P, L, L, P, L, L, P, L, P, L, L, L, F, F, D, P, P, P, P, L, P],
+    "evk_mpce_pos": [P, P, L, P, P, L, L, L, L, P, L, F, P, P],
     "evk_mpce_fwd": [P, P, L, P, P, L, L, L, L, P, L, F, I, L, P, P, L, P, L, P],
     "evk_mpce_bwd_w": [P, P, L, P, P, L, L, L, L, P, L, P, P, P, F, I, L, P, P, L, P],
     "evk_mpce_bwd_gemm": [P, P, L, L, L, I, P, P, L, L, F, I, P, L, P],
@@ -81,7 +82,7 @@ def check(rc: int, what: str) -> None:
 # kernels of this library launched by one call of each entry point (cudaMemsetAsync not counted)
 KERNELS_PER_CALL = {
     "evk_l2norm_fwd": 1, "evk_l2norm_bwd": 1, "evk_posmask_build": 1, "evk_mpce_small_fwd": 1,
-    "evk_mpce_small_bwd": 1, "evk_reduce_partials": 1, "evk_mpce_finalize": 1, "evk_mpce_stats_fused": 1, "evk_mpce_fwd": 1,
+    "evk_mpce_small_bwd": 1, "evk_reduce_partials": 1, "evk_mpce_finalize": 1, "evk_mpce_stats_fused": 1, "evk_mpce_pos": 1, "evk_mpce_fwd": 1,
     "evk_mpce_bwd_w": 1, "evk_mpce_bwd_gemm": 1, "evk_tc_gemm_probe": 1,
 }
 launch_count = 0          # running total, read by bench.py ("gpu_launches")

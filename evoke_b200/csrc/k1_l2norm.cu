@@ -109,6 +109,12 @@ l2norm_fwd_generic_kernel(const void* __restrict__ x, int x_dtype, int64_t n_out
         if (out_lo) out_lo[r * ld_bf16 + c] = __float2bfloat16_rn(h - __bfloat162float(hb));
       }
     }
+    if (out_hi) {                                  // pad columns [d, ld) are defined (zero)
+      for (int64_t c = d + lane; c < ld_bf16; c += 32) {
+        out_hi[r * ld_bf16 + c] = __float2bfloat16_rn(0.f);
+        if (out_lo) out_lo[r * ld_bf16 + c] = __float2bfloat16_rn(0.f);
+      }
+    }
   }
 }
 
@@ -173,6 +179,7 @@ l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t
     const float nrm = norm[r];
     const bool clamped = nrm < EVK_NORM_EPS;
     const float den = fmaxf(nrm, EVK_NORM_EPS);
+    const float inv_den = 1.f / den;
     float4 xv[kIters], gv[kIters];
     float proj = 0.f;
 #pragma unroll
@@ -181,7 +188,7 @@ l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t
       if (c * 4 < d) {
         xv[it] = __ldg(xr + c);
         gv[it] = __ldg(gr + c);
-        xv[it].x /= den; xv[it].y /= den; xv[it].z /= den; xv[it].w /= den;     // xhat, as in the forward
+        xv[it].x *= inv_den; xv[it].y *= inv_den; xv[it].z *= inv_den; xv[it].w *= inv_den;   // xhat (1 ulp of the forward's)
         proj = fmaf(xv[it].x, gv[it].x, proj);
         proj = fmaf(xv[it].y, gv[it].y, proj);
         proj = fmaf(xv[it].z, gv[it].z, proj);

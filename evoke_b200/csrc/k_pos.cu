@@ -1,0 +1,100 @@
+// Positive-logit sums from the K2 bit mask:  row_pos[i] = sum_j M_ij * (q_i . k_j) * inv_tau.
+// This is the "sum_j Y_ij S_ij" term of the soft-target cross entropy
+// (models/model_pretrain_finetune_v0520.py:501-502, :443) before the division by c_i.  Positives
+// are sparse (about one to three per row), so the term is O(N*D) work and does not belong in the
+// N^2 tile epilogue: it runs on a side stream next to K3.
+//
+// One warp per row: the row's mask words are scanned with coalesced loads, every set bit triggers
+// a warp-cooperative bf16 dot product (128-bit loads, fp32 accumulate) over the same bf16 operands
+// the tensor cores see (hi, and hi/lo pairs in fp32-parity mode).
+// Algorithmic bytes: ld_words*4 per row (mask) + 2*D per positive.
+#include "evk_common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b) {
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 fa = __bfloat1622float2(pa[e]);
+    const float2 fb = __bfloat1622float2(pb[e]);
+    s = fmaf(fa.x, fb.x, s);
+    s = fmaf(fa.y, fb.y, s);
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+pos_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __restrict__ q_lo, int64_t ld_q,
+           const __nv_bfloat16* __restrict__ k_hi, const __nv_bfloat16* __restrict__ k_lo, int64_t ld_k,
+           int64_t n_rows, int64_t n_cols, int d_vec /* ceil(d/8) */, const uint32_t* __restrict__ bits,
+           int64_t ld_words, float inv_tau, float* __restrict__ row_pos) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  const int64_t words = (n_cols + 31) >> 5;
+  for (int64_t i = warp0; i < n_rows; i += nwarps) {
+    const uint32_t* mrow = bits + i * ld_words;
+    const uint4* qh = reinterpret_cast<const uint4*>(q_hi + i * ld_q);
+    const uint4* ql = q_lo ? reinterpret_cast<const uint4*>(q_lo + i * ld_q) : nullptr;
+    float acc = 0.f;
+    for (int64_t w0 = 0; w0 < words; w0 += 32) {
+      const int64_t w = w0 + lane;
+      uint32_t m = w < words ? __ldg(mrow + w) : 0u;
+      uint32_t any = __ballot_sync(0xffffffffu, m != 0u);
+      while (any) {
+        const int src = __ffs(any) - 1;
+        any &= any - 1;
+        uint32_t mw = __shfl_sync(0xffffffffu, m, src);
+        const int64_t jbase = (w0 + src) << 5;
+        while (mw) {
+          const int b = __ffs(mw) - 1;
+          mw &= mw - 1;
+          const int64_t j = jbase + b;
+          const uint4* kh = reinterpret_cast<const uint4*>(k_hi + j * ld_k);
+          const uint4* kl = k_lo ? reinterpret_cast<const uint4*>(k_lo + j * ld_k) : nullptr;
+          float s = 0.f;
+          for (int c = lane; c < d_vec; c += 32) {
+            const uint4 a = __ldg(qh + c), bb = __ldg(kh + c);
+            s += dot8_bf16(a, bb);
+            if (ql) {                                  // (qh+ql).(kh+kl) without the lo.lo term, as the MMA segments
+              const uint4 al = __ldg(ql + c), bl = __ldg(kl + c);
+              s += dot8_bf16(a, bl) + dot8_bf16(al, bb);
+            }
+          }
+          acc += s;
+        }
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) row_pos[i] = acc * inv_tau;
+  }
+}
+
+}  // namespace
+
+extern "C" int evk_mpce_pos(const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi, const void* k_lo,
+                            int64_t ld_k, int64_t n_rows, int64_t n_cols, int64_t d, const uint32_t* bits,
+                            int64_t ld_words, float inv_tau, float* row_pos, evk_stream_t stream) {
+  EVK_REQUIRE(q_hi && k_hi && bits && row_pos, "evk_mpce_pos: null pointer");
+  EVK_REQUIRE((q_lo == nullptr) == (k_lo == nullptr), "evk_mpce_pos: q_lo/k_lo must both be set or both null");
+  EVK_REQUIRE(n_rows > 0 && n_cols > 0 && d > 0, "evk_mpce_pos: empty problem");
+  EVK_REQUIRE(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_q >= d && ld_k >= d && evk_aligned16(q_hi) && evk_aligned16(k_hi) &&
+                  (!q_lo || (evk_aligned16(q_lo) && evk_aligned16(k_lo))),
+              "evk_mpce_pos: operands need 16-byte aligned rows (ld %% 8 == 0)");
+  EVK_REQUIRE(ld_words >= (n_cols + 31) / 32, "evk_mpce_pos: ld_words too small");
+  // rows are padded to a multiple of 8 elements by K1, which writes zeros into the pad columns
+  int64_t blocks = (n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int64_t cap = (int64_t)evk_sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  pos_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(q_hi), static_cast<const __nv_bfloat16*>(q_lo), ld_q,
+      static_cast<const __nv_bfloat16*>(k_hi), static_cast<const __nv_bfloat16*>(k_lo), ld_k, n_rows, n_cols,
+      (int)((d + 7) / 8), bits, ld_words, inv_tau, row_pos);
+  EVK_CHECK_LAUNCH("mpce_pos");
+  return EVK_OK;
+}

@@ -79,8 +79,9 @@ __device__ __forceinline__ float strided_partial_sum(const float* __restrict__ p
 }
 
 __global__ void __launch_bounds__(kStatThreads)
-stats_fused_kernel(const float* __restrict__ rs_part, const float* __restrict__ rp_part, int64_t row_parts,
-                   int64_t ld_row, const int32_t* __restrict__ counts, int64_t n_rows,
+stats_fused_kernel(const float* __restrict__ rs_part, int64_t row_parts, int64_t ld_row,
+                   const float* __restrict__ rp_part, int64_t pos_parts, int64_t ld_pos,
+                   const int32_t* __restrict__ counts, int64_t n_rows,
                    const float* __restrict__ cs_part, int64_t col_parts, int64_t ld_col, int64_t n_cols,
                    float shift, float pos_weight, double inv_count, float* __restrict__ a_row,
                    float* __restrict__ b_col, float* __restrict__ loss_out, double* __restrict__ cta_partial,
@@ -91,7 +92,7 @@ stats_fused_kernel(const float* __restrict__ rs_part, const float* __restrict__ 
   const int e = threadIdx.x % kStatElems, g = threadIdx.x / kStatElems;
   const int64_t i = (int64_t)blockIdx.x * kStatElems + e;
   s_sum[0][g][e] = i < n_rows ? strided_partial_sum(rs_part, row_parts, ld_row, i, g) : 0.f;
-  s_sum[1][g][e] = i < n_rows ? strided_partial_sum(rp_part, row_parts, ld_row, i, g) : 0.f;
+  s_sum[1][g][e] = i < n_rows ? strided_partial_sum(rp_part, pos_parts, ld_pos, i, g) : 0.f;
   s_sum[2][g][e] = (cs_part && i < n_cols) ? strided_partial_sum(cs_part, col_parts, ld_col, i, g) : 0.f;
   __syncthreads();
   if (threadIdx.x < kStatElems) {
@@ -137,13 +138,14 @@ stats_fused_kernel(const float* __restrict__ rs_part, const float* __restrict__ 
 
 }  // namespace
 
-extern "C" int evk_mpce_stats_fused(const float* rs_part, const float* rp_part, int64_t row_parts, int64_t ld_row,
-                                    const int32_t* counts, int64_t n_rows, const float* cs_part, int64_t col_parts,
+extern "C" int evk_mpce_stats_fused(const float* rs_part, int64_t row_parts, int64_t ld_row, const float* rp_part,
+                                    int64_t pos_parts, int64_t ld_pos, const int32_t* counts, int64_t n_rows,
+                                    const float* cs_part, int64_t col_parts,
                                     int64_t ld_col, int64_t n_cols, float shift, float pos_weight, double inv_count,
                                     float* a_row, float* b_col, float* loss_out, void* workspace,
                                     int64_t workspace_bytes, evk_stream_t stream) {
   EVK_REQUIRE(rs_part && rp_part && counts && a_row && loss_out && workspace && n_rows > 0 && row_parts >= 1 &&
-                  ld_row >= n_rows, "evk_mpce_stats_fused: bad row arguments");
+                  ld_row >= n_rows && pos_parts >= 1 && ld_pos >= n_rows, "evk_mpce_stats_fused: bad row arguments");
   EVK_REQUIRE(!cs_part || (b_col && col_parts >= 1 && ld_col >= n_cols && n_cols > 0),
               "evk_mpce_stats_fused: bad column arguments");
   const int64_t n = (cs_part && n_cols > n_rows) ? n_cols : n_rows;
@@ -154,7 +156,8 @@ extern "C" int evk_mpce_stats_fused(const float* rs_part, const float* rp_part, 
   unsigned int* ticket = static_cast<unsigned int*>(workspace);
   double* partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + 16);
   EVK_CUDA(cudaMemsetAsync(ticket, 0, 16, s));
-  stats_fused_kernel<<<(unsigned)blocks, kStatThreads, 0, s>>>(rs_part, rp_part, row_parts, ld_row, counts, n_rows,
+  stats_fused_kernel<<<(unsigned)blocks, kStatThreads, 0, s>>>(rs_part, row_parts, ld_row, rp_part, pos_parts, ld_pos,
+                                                              counts, n_rows,
                                                               cs_part, col_parts, ld_col, cs_part ? n_cols : 0, shift,
                                                               pos_weight, inv_count, a_row, b_col, loss_out, partial,
                                                               ticket);

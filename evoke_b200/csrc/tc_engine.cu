@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
       if (EPI == EPI_FWD) {
         float* colpart = reinterpret_cast<float*>(epi_gen);       // [4][BN]
         const bool want_col = (p.flags & EVK_FLAG_NO_COLSUM) == 0;
-        const uint32_t* mrow = p.bits + (row_ok ? i : 0) * p.ld_words + (n0 >> 5);
+        const bool want_pos = (p.flags & EVK_FLAG_NO_POS) == 0;   // else evk_mpce_pos supplies the positive sums
+        const uint32_t* mrow = want_pos ? p.bits + (row_ok ? i : 0) * p.ld_words + (n0 >> 5) : nullptr;
         const int64_t dcol = i + p.diag_offset - n0;              // diagonal column inside this tile?
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f, rp = 0.f;
         mbar_wait(tfull_bar(as), aphase);
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
 #pragma unroll 1
         for (int cc = 0; cc < BN / 64; ++cc) {
           const int c = c_lo + cc;
-          const uint32_t mword = row_ok ? __ldg(mrow + c) : 0u;
+          const uint32_t mword = (want_pos && row_ok) ? __ldg(mrow + c) : 0u;
           float v[32];
           if (p.flags & 0x800) {                                  // bring-up knockout: no TMEM read
 #pragma unroll
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
         if (row_ok) {
           const int64_t po = ((int64_t)nb * kRowParts + hh) * p.ld_rowpart + i;
           p.row_sum_part[po] = (rs0 + rs1) + (rs2 + rs3);
-          p.row_pos_part[po] = rp;
+          if (want_pos) p.row_pos_part[po] = rp;
         }
         if (want_col) {
           named_bar_sync(1, kEpiThreads);
@@ -606,8 +607,9 @@ extern "C" int evk_mpce_fwd(const void* q_hi, const void* q_lo, int64_t ld_q, co
   rc = setup_sim_operands(p, q_hi, q_lo, ld_q, k_hi, k_lo, ld_k, n_rows, n_cols, d, flags, cta2);
   if (rc != EVK_OK) return rc;
   const bool want_col = (flags & EVK_FLAG_NO_COLSUM) == 0;
-  EVK_REQUIRE(bits && row_sum_part && row_pos_part && (!want_col || col_sum_part), "evk_mpce_fwd: null pointer");
-  EVK_REQUIRE(ld_words >= (int64_t)p.n_tiles * (BN / 32), "evk_mpce_fwd: ld_words=%lld must cover whole 256-column tiles (>= %lld)",
+  const bool want_pos = (flags & EVK_FLAG_NO_POS) == 0;
+  EVK_REQUIRE(row_sum_part && (!want_pos || (bits && row_pos_part)) && (!want_col || col_sum_part), "evk_mpce_fwd: null pointer");
+  EVK_REQUIRE(!want_pos || ld_words >= (int64_t)p.n_tiles * (BN / 32), "evk_mpce_fwd: ld_words=%lld must cover whole 256-column tiles (>= %lld)",
               (long long)ld_words, (long long)p.n_tiles * (BN / 32));
   EVK_REQUIRE(ld_rowpart >= n_rows && (!want_col || ld_colpart >= n_cols), "evk_mpce_fwd: partial pitches too small");
   EVK_REQUIRE(inv_tau > 0.f && inv_tau <= 40.f, "evk_mpce_fwd: 1/tau=%g outside (0, 40]: the fixed-shift softmax needs exp(-2/tau) to stay normal in fp32", inv_tau);

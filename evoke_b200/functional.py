@@ -23,12 +23,14 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (DTYPE_BF16, DTYPE_F16, DTYPE_F32, FLAG_EXCLUDE_DIAG, FLAG_NO_COLSUM, FLAG_SPLIT_BF16)
+from ._lib import (DTYPE_BF16, DTYPE_F16, DTYPE_F32, FLAG_EXCLUDE_DIAG, FLAG_NO_COLSUM, FLAG_NO_POS,
+                   FLAG_SPLIT_BF16)
 from .ids import DeviceIds
 
 SMALL_PATH_MAX = int(os.environ.get("EVOKE_B200_SMALL_MAX", "512"))   # rows/cols up to which the SIMT path is used
 TILE_M, TILE_N = 128, 256
 ROW_PARTS = 2          # row-statistic partials per 256-column tile (two epilogue warps share a row)
+OVERLAP_STREAMS = os.environ.get("EVOKE_B200_OVERLAP", "0") == "1"   # side-stream overlap outside graph capture too
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -59,6 +61,28 @@ def _require_cuda(t: torch.Tensor, name: str):
 
 def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device: torch.device) -> torch.cuda.Stream:
+    """One auxiliary stream per device for work that runs next to the tensor-bound kernels
+    (mask builder, positive sums, zero fills, the second gradient contraction).  It is always
+    forked from and joined back into the caller's stream, so the sequence stays capturable."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(idx)
+    if st is None:
+        st = torch.cuda.Stream(device=idx)
+        _SIDE_STREAMS[idx] = st
+    return st
+
+
+def _shared_with(stream: torch.cuda.Stream, *tensors):
+    """Tell the caching allocator that `tensors` are also used on `stream`."""
+    for t in tensors:
+        if t is not None:
+            t.record_stream(stream)
 
 
 # ------------------------------------------------------------------------------------- kernels
@@ -165,18 +189,30 @@ def tc_fwd_partials(q: Normalized, k: Normalized, bits, inv_tau: float, flags: i
     n_ct = (k.n + TILE_N - 1) // TILE_N
     n_rt = (q.n + TILE_M - 1) // TILE_M
     want_col = not (flags & FLAG_NO_COLSUM)
+    want_pos = not (flags & FLAG_NO_POS)
     rs_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev)
-    rp_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev)
+    rp_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev) if want_pos else None
     cs_part = torch.empty((n_rt, k.n), dtype=torch.float32, device=dev) if want_col else None
     _lib.call("evk_mpce_fwd", _ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, q.n, k.n, q.d,
-              _ptr(bits), bits.stride(0), float(inv_tau), flags, diag_offset,
+              _ptr(bits) if want_pos else None, bits.stride(0) if want_pos else 0, float(inv_tau), flags, diag_offset,
               _ptr(rs_part), _ptr(rp_part), q.n, _ptr(cs_part), k.n, _stream())
     return rs_part, rp_part, cs_part
 
 
+def tc_pos(q: Normalized, k: Normalized, bits, inv_tau: float) -> torch.Tensor:
+    """row_pos[i] = sum_j M_ij S_ij from the bit mask (for K3 launched with FLAG_NO_POS)."""
+    row_pos = torch.empty(q.n, dtype=torch.float32, device=q.hi.device)
+    _lib.call("evk_mpce_pos", _ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, q.n, k.n, q.d,
+              _ptr(bits), bits.stride(0), float(inv_tau), _ptr(row_pos), _stream())
+    return row_pos
+
+
 def stats_fused(rs_part, rp_part, cs_part, counts, *, shift: float, pos_weight: float, inv_count: float):
-    """Partials -> (a_row, b_col | None, loss[1]) in one launch (single-GPU form)."""
+    """Partials -> (a_row, b_col | None, loss[1]) in one launch (single-GPU form).  rp_part is
+    either K3's [parts, n] partials or the [n] vector written by tc_pos."""
     dev = rs_part.device
+    if rp_part.dim() == 1:
+        rp_part = rp_part.unsqueeze(0)
     n_rows = int(rs_part.shape[1])
     n_cols = 0 if cs_part is None else int(cs_part.shape[1])
     a_row = torch.empty(n_rows, dtype=torch.float32, device=dev)
@@ -184,7 +220,8 @@ def stats_fused(rs_part, rp_part, cs_part, counts, *, shift: float, pos_weight: 
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     ws_bytes = 16 + 8 * ((max(n_rows, n_cols) + 31) // 32)
     ws = torch.empty(_round_up(ws_bytes, 16), dtype=torch.uint8, device=dev)
-    _lib.call("evk_mpce_stats_fused", _ptr(rs_part), _ptr(rp_part), int(rs_part.shape[0]), rs_part.stride(0),
+    _lib.call("evk_mpce_stats_fused", _ptr(rs_part), int(rs_part.shape[0]), rs_part.stride(0),
+              _ptr(rp_part), int(rp_part.shape[0]), max(int(rp_part.stride(0)), n_rows),
               _ptr(counts), n_rows, _ptr(cs_part), 0 if cs_part is None else int(cs_part.shape[0]),
               0 if cs_part is None else cs_part.stride(0), n_cols, float(shift), float(pos_weight), float(inv_count),
               _ptr(a_row), _ptr(b_col), _ptr(loss), _ptr(ws), ws.numel(), _stream())
@@ -271,19 +308,39 @@ class _MultiPositiveCE(torch.autograd.Function):
         flags = FLAG_SPLIT_BF16 if split else 0
         kw = dict(want_f32=small, want_hi=not small, want_lo=split)
         mpc = cfg.kind == "MPC"
-        qn = l2norm_fwd(image, gather=cfg.gather, **kw)
-        kn = qn if mpc else l2norm_fwd(text, **kw)
-        n = qn.n
-        bits, counts = posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc)
         if mpc:
             flags |= FLAG_EXCLUDE_DIAG | FLAG_NO_COLSUM
-        pos_weight, inv_count = (1.0, 1.0 / n) if mpc else (2.0, 0.5 / n)
         if small:
+            qn = l2norm_fwd(image, gather=cfg.gather, **kw)
+            kn = qn if mpc else l2norm_fwd(text, **kw)
+            n = qn.n
+            pos_weight, inv_count = (1.0, 1.0 / n) if mpc else (2.0, 0.5 / n)
+            bits, counts = posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc)
             row_sum, row_pos = small_fwd(qn, kn, bits, cfg.inv_tau, flags)
             col_sum = None if mpc else small_fwd(kn, qn, bits, cfg.inv_tau, flags)[0]
             a_row, b_col, loss = finalize(row_sum, row_pos, counts, col_sum, col_lo=0, col_hi=0 if mpc else n,
                                           shift=cfg.inv_tau, pos_weight=pos_weight, inv_count=inv_count)
         else:
+            # K2 (integer-ALU bound) runs on a side stream next to the two HBM-bound K1 launches
+            # when the sequence is being captured into a CUDA graph.  The positive-logit sums stay
+            # in the K3 epilogue: ln R_i and pos_i must come from the same tensor-core accumulators
+            # for their rounding to cancel in the loss (cold temperatures).
+            overlap = OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
+            if overlap:
+                main = torch.cuda.current_stream()
+                side = _side_stream(image.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    bits, counts = posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc)
+            else:
+                bits, counts = posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc)
+            qn = l2norm_fwd(image, gather=cfg.gather, **kw)
+            kn = qn if mpc else l2norm_fwd(text, **kw)
+            n = qn.n
+            pos_weight, inv_count = (1.0, 1.0 / n) if mpc else (2.0, 0.5 / n)
+            if overlap:
+                main.wait_stream(side)
+                _shared_with(main, bits, counts)
             rs_part, rp_part, cs_part = tc_fwd_partials(qn, kn, bits, cfg.inv_tau, flags)
             a_row, b_col, loss = stats_fused(rs_part, rp_part, cs_part, counts, shift=cfg.inv_tau,
                                              pos_weight=pos_weight, inv_count=inv_count)
@@ -318,15 +375,46 @@ class _MultiPositiveCE(torch.autograd.Function):
             if need_k:
                 dk = small_bwd(kn, qn, bits, counts, b_col, a_row, cfg.inv_tau, flags)   # M is symmetric
                 d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
-        else:
-            if need_q or need_k:
+        elif need_q or need_k:
+            dev = image.device
+            width = _round_up(qn.d, 4)
+            overlap = OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
+            if not overlap:
                 w_hi, w_lo, ld_w = tc_bwd_w(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
-            if need_q:
-                dq = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, False, kn, flags)
-                d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
-            if need_k:
-                dk = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, True, qn, flags)
-                d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
+                if need_q:
+                    dq = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, False, kn, flags)
+                    d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
+                if need_k:
+                    dk = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, True, qn, flags)
+                    d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
+            else:
+                main = torch.cuda.current_stream()
+                side = _side_stream(dev)
+                # zero-filled split-K accumulators: filled on the side stream while K4a runs
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    dq = torch.zeros((qn.n, width), dtype=torch.float32, device=dev) if need_q else None
+                    dk = torch.zeros((kn.n, width), dtype=torch.float32, device=dev) if need_k else None
+                    filled = side.record_event()
+                w_hi, w_lo, ld_w = tc_bwd_w(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
+                main.wait_event(filled)
+                _shared_with(main, dq, dk)
+                if need_q:
+                    tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, False, kn, flags, out=dq)
+                if need_k:
+                    # second contraction + its normalise-backward on the side stream: its CTAs take
+                    # over the SMs as the first contraction drains, and the image-side K1b overlaps it
+                    w_ready = main.record_event()
+                    with torch.cuda.stream(side):
+                        side.wait_event(w_ready)
+                        tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, True, qn, flags, out=dk)
+                        d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
+                    _shared_with(side, w_hi, w_lo, qn.hi, qn.lo, g, text, kn.norm)
+                if need_q:
+                    d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
+                if need_k:
+                    main.wait_stream(side)
+                    _shared_with(main, d_text)
         return None, d_image, d_text
 
 

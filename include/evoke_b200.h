@@ -48,6 +48,7 @@ extern "C" {
 #define EVK_FLAG_EXCLUDE_DIAG  1  /* column (row + diag_offset) is removed from the softmax:
                                      multi_pos_contra_images_v0401 :438 (fill_diagonal_(-1e9)) */
 #define EVK_FLAG_NO_COLSUM     2  /* skip column sums (symmetric problem: MPC) */
+#define EVK_FLAG_NO_POS        8  /* K3 leaves the positive-logit sums to evk_mpce_pos (bits may be NULL) */
 #define EVK_FLAG_SPLIT_BF16    4  /* operands are (hi, lo) bf16 pairs: S = hi.hi + hi.lo + lo.hi,
                                      ~2^-17 relative, the fp32-parity mode */
 
@@ -145,10 +146,11 @@ EVK_API int evk_mpce_finalize(const float* row_sum, const float* row_pos, const 
                       evk_stream_t stream);
 
 /* Single-GPU fused form of evk_reduce_partials (x3) + evk_mpce_finalize: takes the per-tile
- * partials of K3 directly (rs_part/rp_part: [row_parts, ld_row], cs_part: [col_parts, ld_col] or
- * NULL), the loss covers all rows and all columns.  workspace: >= 16 + 8*ceil(max(n_rows,n_cols)/32)
+ * partials of K3 directly (rs_part: [row_parts, ld_row]; rp_part: [pos_parts, ld_pos] - K3's
+ * partials, or the single row written by evk_mpce_pos; cs_part: [col_parts, ld_col] or NULL), the loss covers all rows and all columns.  workspace: >= 16 + 8*ceil(max(n_rows,n_cols)/32)
  * bytes, 16-byte aligned, contents irrelevant.  Deterministic (fixed summation order). */
-EVK_API int evk_mpce_stats_fused(const float* rs_part, const float* rp_part, int64_t row_parts, int64_t ld_row,
+EVK_API int evk_mpce_stats_fused(const float* rs_part, int64_t row_parts, int64_t ld_row,
+                         const float* rp_part, int64_t pos_parts, int64_t ld_pos,
                          const int32_t* counts, int64_t n_rows,
                          const float* cs_part, int64_t col_parts, int64_t ld_col, int64_t n_cols,
                          float shift, float pos_weight, double inv_count,
@@ -170,6 +172,16 @@ EVK_API int evk_mpce_fwd(const void* q_hi, const void* q_lo, int64_t ld_q,
                  float inv_tau, int flags, int64_t diag_offset,
                  float* row_sum_part, float* row_pos_part, int64_t ld_rowpart,
                  float* col_sum_part, int64_t ld_colpart, evk_stream_t stream);
+
+/* Positive-logit sums from the bit mask, for use with EVK_FLAG_NO_POS:
+ *   row_pos[i] = sum_j M_ij S_ij = inv_tau * sum_{j: bit (i,j) set} q_i . k_j
+ * (the sum_j Y_ij S_ij term of the soft-target CE, :501-502 / :443, before the 1/c_i).  O(N*D) work;
+ * meant to run on a side stream concurrently with evk_mpce_fwd.  q_lo/k_lo: both NULL or both set. */
+EVK_API int evk_mpce_pos(const void* q_hi, const void* q_lo, int64_t ld_q,
+                 const void* k_hi, const void* k_lo, int64_t ld_k,
+                 int64_t n_rows, int64_t n_cols, int64_t d,
+                 const uint32_t* bits, int64_t ld_words, float inv_tau,
+                 float* row_pos, evk_stream_t stream);
 
 /* K4a backward, pass 1: recompute S tiles, form W (see evk_mpce_small_bwd) and store it as
  * bf16 (w_hi, and w_lo = bf16(W - hi) with EVK_FLAG_SPLIT_BF16) in a row strip

@@ -115,3 +115,22 @@ def test_reduce_partials_and_finalize():
     want = (0.5 / n) * ((2.0 + rs.double().log() - 2.0 * rp.double() / cnt.double()).sum() + (2.0 + cs.double().log()).sum())
     assert abs(loss.item() - want.item()) < 1e-5 * abs(want.item())
     assert torch.allclose(a, 1.0 / rs) and torch.allclose(b, 1.0 / cs)
+
+
+def test_pos_kernel_matches_mask_times_similarity():
+    """evk_mpce_pos (optional O(N*D) form of the positive-logit sums) against a dense evaluation."""
+    n, d = 700, 264
+    ids = synth.make_study_ids(n, seed=3)
+    x = torch.tensor(synth.make_embeddings(ids, d, seed=4), device=DEV)
+    y = torch.tensor(synth.make_embeddings(ids, d, seed=5), device=DEV)
+    dev = idmod.DeviceIds(torch.from_numpy(ids).to(DEV))
+    bits, _ = Fn.posmask_build(dev, dev, clear_diag=True)
+    for split in (False, True):
+        q = Fn.l2norm_fwd(x, want_f32=False, want_hi=True, want_lo=split)
+        k = Fn.l2norm_fwd(y, want_f32=False, want_hi=True, want_lo=split)
+        got = Fn.tc_pos(q, k, bits, 2.0).cpu().numpy()
+        qf = q.hi[:, :d].double() + (q.lo[:, :d].double() if split else 0)
+        kf = k.hi[:, :d].double() + (k.lo[:, :d].double() if split else 0)
+        m = torch.from_numpy(orc.posmask_dense(ids, clear_diag=True)).to(DEV)
+        want = ((qf @ kf.t()) * 2.0 * m).sum(1).cpu().numpy()
+        assert rel_max(got, want) < (2e-6 if not split else 2e-5)
