@@ -63,11 +63,13 @@ struct alignas(64) TcParams {
   // descriptor bases (see tc_ptx.cuh), filled by the host so the probe can try variants
   uint64_t desc_a, desc_b;
   uint32_t idesc;
+  // L2 policies: operands reused by every CTA are kept, the N^2 W stream is not
+  uint64_t policy_a, policy_b, policy_out;
 };
 
 template <int EPI>
 constexpr int epi_smem_bytes() {
-  return EPI == EPI_FWD ? 4 * BN * 4 : (EPI == EPI_BWD_W ? 4 * 16384 + 2 * BN * 4 : 0);
+  return EPI == EPI_FWD ? 4 * BN * 4 : (EPI == EPI_BWD_W ? kEpiWarps * 8192 : 0);
 }
 template <int EPI, int STAGES, bool CTA2>
 constexpr int smem_bytes_total() {
@@ -163,21 +165,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
           // the (leader's) full barrier expects the bytes of every CTA that feeds this stage
           if (leader) mbar_expect_tx(full_bar(stage), kStage * (CTA2 ? 2 : 1));
           const uint32_t a_dst = smem_base + stage * kStage, b_dst = a_dst + kABytes;
-          auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
-            if (CTA2) tma_load_2d_cta2(dst, m, full_bar(stage), c0, c1);
-            else tma_load_2d(dst, m, full_bar(stage), c0, c1);
+          auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1, uint64_t pol) {
+            if (CTA2) tma_load_2d_cta2(dst, m, full_bar(stage), c0, c1, pol);
+            else tma_load_2d(dst, m, full_bar(stage), c0, c1, pol);
           };
           if (!A_MN) {
-            load(a_dst, &p.a_map[seg], kk, m0);
+            load(a_dst, &p.a_map[seg], kk, m0, p.policy_a);
           } else {
 #pragma unroll
-            for (int b = 0; b < BM / 64; ++b) load(a_dst + b * 8192, &p.a_map[seg], m0 + 64 * b, kk);
+            for (int b = 0; b < BM / 64; ++b) load(a_dst + b * 8192, &p.a_map[seg], m0 + 64 * b, kk, p.policy_a);
           }
           if (!B_MN) {
-            load(b_dst, &p.b_map[seg], kk, n0);
+            load(b_dst, &p.b_map[seg], kk, n0, p.policy_b);
           } else {
 #pragma unroll
-            for (int b = 0; b < kBRows / 64; ++b) load(b_dst + b * 8192, &p.b_map[seg], n0 + 64 * b, kk);
+            for (int b = 0; b < kBRows / 64; ++b) load(b_dst + b * 8192, &p.b_map[seg], n0 + 64 * b, kk, p.policy_b);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -317,23 +319,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
           named_bar_sync(1, kEpiThreads);                         // colpart reusable
         }
       } else if (EPI == EPI_BWD_W) {
+        // Every warp stages and stores its own 32 rows x 128 columns: private 8 KiB staging region,
+        // own 32-row TMA stores, own bulk-group accounting -> no CTA-level barrier in this epilogue.
         const bool split = (p.flags & EVK_FLAG_SPLIT_BF16) != 0;
-        float* bs = reinterpret_cast<float*>(epi_gen + 4 * 16384) + as * BN;   // b_col of this tile
-        const uint32_t stg = epi_base;                            // 4 slots x 16 KiB (128 rows x 128 B)
+        const uint32_t wstg = epi_base + warp * 8192;             // [2 boxes][32 rows][128 B], 128B-swizzled
         const float a_i = row_ok ? __ldg(p.a_row + i) : 0.f;
         const float n2c = row_ok ? -2.f / (float)max(__ldg(p.counts + i), 1) : 0.f;
         const uint32_t* mrow = p.bits + (row_ok ? i : 0) * p.ld_words + (n0 >> 5);
         const int64_t dcol = i + p.diag_offset - n0;
-        bs[et] = (n0 + et < p.n_cols) ? __ldg(p.b_col + n0 + et) : 0.f;
+        const int m_warp = m0 + q * 32;                           // first row of this warp's boxes
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
-        // non-split: one round, 4 chunks per warp, hi -> slots {2h, 2h+1}
-        // split    : two rounds of 2 chunks per warp, hi -> slot h, lo -> slot 2+h
+        // non-split: one round of 4 chunks: box 0 = chunks 0,1, box 1 = chunks 2,3 (hi)
+        // split    : two rounds of 2 chunks: box 0 = hi, box 1 = lo
         const int rounds = split ? 2 : 1, per_round = split ? 2 : 4;
 #pragma unroll 1
         for (int r = 0; r < rounds; ++r) {
-          if (et == 0) tma_store_wait_read<0>();                  // staging slots free again
-          named_bar_sync(1, kEpiThreads);                         // also publishes bs[] (r == 0)
+          if (lane == 0) tma_store_wait_read<0>();                // this warp's previous stores have left smem
+          __syncwarp();
 #pragma unroll 1
           for (int cc = 0; cc < per_round; ++cc) {
             const int c = c_lo + r * per_round + cc;
@@ -341,8 +344,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
             float v[32];
             tmem_ld_32x32(taddr + c * 32, v);
             tmem_ld_wait(v);
+            if (!(p.flags & 0x400)) {                             // (0x400: bring-up knockout of the math)
+              const int cbase = n0 + c * 32;
+              if (cbase + 32 <= p.n_cols) {
+                const float4* bp = reinterpret_cast<const float4*>(p.b_col + cbase);   // warp-uniform: broadcast loads
 #pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = ex2_approx(fmaf(v[k], c1, -c1)) * (a_i + bs[c * 32 + k]);
+                for (int k4 = 0; k4 < 8; ++k4) {
+                  const float4 b4 = __ldg(bp + k4);
+                  v[4 * k4 + 0] = ex2_approx(fmaf(v[4 * k4 + 0], c1, -c1)) * (a_i + b4.x);
+                  v[4 * k4 + 1] = ex2_approx(fmaf(v[4 * k4 + 1], c1, -c1)) * (a_i + b4.y);
+                  v[4 * k4 + 2] = ex2_approx(fmaf(v[4 * k4 + 2], c1, -c1)) * (a_i + b4.z);
+                  v[4 * k4 + 3] = ex2_approx(fmaf(v[4 * k4 + 3], c1, -c1)) * (a_i + b4.w);
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                  const float bj = (cbase + k < p.n_cols) ? __ldg(p.b_col + cbase + k) : 0.f;
+                  v[k] = ex2_approx(fmaf(v[k], c1, -c1)) * (a_i + bj);
+                }
+              }
+            }
             if (mword) {
 #pragma unroll
               for (int k = 0; k < 32; ++k)
@@ -355,8 +376,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
                 if (k == dk) v[k] = 0.f;
             }
             // rows >= n_rows / columns >= n_cols hold garbage here; the TMA store clips them.
-            const int slot_hi = split ? hh : (2 * hh + (cc >> 1));
-            const uint32_t row_hi = stg + slot_hi * 16384 + row * 128;
+            const int box_hi = split ? 0 : (cc >> 1);
+            const uint32_t row_hi = wstg + box_hi * 4096 + lane * 128;
             const int u0 = (cc & 1) * 4;
 #pragma unroll
             for (int uu = 0; uu < 4; ++uu) {
@@ -364,7 +385,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
               uint32_t h1 = pack_bf16x2(v[8 * uu + 2], v[8 * uu + 3]);
               uint32_t h2 = pack_bf16x2(v[8 * uu + 4], v[8 * uu + 5]);
               uint32_t h3 = pack_bf16x2(v[8 * uu + 6], v[8 * uu + 7]);
-              const uint32_t off = static_cast<uint32_t>(((u0 + uu) ^ (row & 7)) << 4);
+              const uint32_t off = static_cast<uint32_t>(((u0 + uu) ^ (lane & 7)) << 4);
+              if (!(p.flags & 0x1000))
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + off), "r"(h0), "r"(h1), "r"(h2),
                            "r"(h3) : "memory");
               if (split) {
@@ -377,24 +399,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
                 }
                 const uint32_t l0 = pack_bf16x2(l[0], l[1]), l1 = pack_bf16x2(l[2], l[3]);
                 const uint32_t l2 = pack_bf16x2(l[4], l[5]), l3 = pack_bf16x2(l[6], l[7]);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + 2 * 16384 + off), "r"(l0),
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + 4096 + off), "r"(l0),
                              "r"(l1), "r"(l2), "r"(l3) : "memory");
               }
             }
           }
           if (r == rounds - 1) release_tmem(as);
           fence_proxy_async_smem();                               // generic-proxy writes -> async proxy
-          named_bar_sync(1, kEpiThreads);
-          if (et == 0) {
+          __syncwarp();
+          if (lane == 0 && !(p.flags & 0x3000)) {
+            const int cx = n0 + (c_lo + r * per_round) * 32;      // first column of this round
             if (split) {
-              const int cx = n0 + r * 64;
-              tma_store_2d(&p.out_map[0], stg + 0 * 16384, cx, m0);
-              tma_store_2d(&p.out_map[0], stg + 1 * 16384, cx + 128, m0);
-              tma_store_2d(&p.out_map[1], stg + 2 * 16384, cx, m0);
-              tma_store_2d(&p.out_map[1], stg + 3 * 16384, cx + 128, m0);
+              tma_store_2d(&p.out_map[0], wstg, cx, m_warp, p.policy_out);
+              tma_store_2d(&p.out_map[1], wstg + 4096, cx, m_warp, p.policy_out);
             } else {
-#pragma unroll
-              for (int sl = 0; sl < 4; ++sl) tma_store_2d(&p.out_map[0], stg + sl * 16384, n0 + sl * 64, m0);
+              tma_store_2d(&p.out_map[0], wstg, cx, m_warp, p.policy_out);
+              tma_store_2d(&p.out_map[0], wstg + 4096, cx + 64, m_warp, p.policy_out);
             }
             tma_store_commit();
           }
@@ -425,7 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
         release_tmem(as);
       }
     }
-    if (EPI == EPI_BWD_W && et == 0) tma_store_wait_all<0>();     // smem must outlive the bulk stores
+    if (EPI == EPI_BWD_W && lane == 0) tma_store_wait_all<0>();   // smem must outlive each warp's bulk stores
   }
 
   tc_fence_before();
@@ -588,6 +608,11 @@ int setup_sim_operands(TcParams& p, const void* q_hi, const void* q_lo, int64_t 
   p.splits = 1;
   p.n_rows = n_rows;
   p.n_cols = n_cols;
+  p.policy_a = p.policy_b = kEvictLast;       // Qhat / Khat are re-read by every tile of the sweep
+  p.policy_out = kEvictFirst;                 // the W strip is written once and streamed back later
+  if (const char* e = getenv("EVK_L2_HINTS")) {
+    if (e[0] == '0') p.policy_a = p.policy_b = p.policy_out = kEvictNormal;
+  }
   fill_descs(p, false, false, 0, cta2);
   return EVK_OK;
 }
@@ -641,13 +666,14 @@ extern "C" int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q, 
   if (rc != EVK_OK) return rc;
   const bool split = (flags & EVK_FLAG_SPLIT_BF16) != 0;
   EVK_REQUIRE(bits && counts && a_row && b_col && w_hi && (!split || w_lo), "evk_mpce_bwd_w: null pointer");
+  EVK_REQUIRE(evk_aligned16(b_col), "evk_mpce_bwd_w: b_col must be 16-byte aligned");
   EVK_REQUIRE(ld_words >= (int64_t)p.n_tiles * (BN / 32), "evk_mpce_bwd_w: ld_words must cover whole 256-column tiles");
   EVK_REQUIRE(ld_w >= n_cols && ld_w % 8 == 0, "evk_mpce_bwd_w: ld_w=%lld must be >= n_cols and a multiple of 8", (long long)ld_w);
   EVK_REQUIRE(inv_tau > 0.f && inv_tau <= 40.f, "evk_mpce_bwd_w: 1/tau=%g outside (0, 40]", inv_tau);
-  rc = make_map_bf16(&p.out_map[0], w_hi, n_rows, n_cols, ld_w, BM, 64);
+  rc = make_map_bf16(&p.out_map[0], w_hi, n_rows, n_cols, ld_w, 32, 64);
   if (rc != EVK_OK) return rc;
   if (split) {
-    rc = make_map_bf16(&p.out_map[1], w_lo, n_rows, n_cols, ld_w, BM, 64);
+    rc = make_map_bf16(&p.out_map[1], w_lo, n_rows, n_cols, ld_w, 32, 64);
     if (rc != EVK_OK) return rc;
   }
   p.inv_tau = inv_tau;
@@ -659,7 +685,7 @@ extern "C" int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q, 
   p.a_row = a_row;
   p.b_col = b_col;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return cta2 ? launch<EPI_BWD_W, false, false, 4, true>(p, s) : launch<EPI_BWD_W, false, false, 3, false>(p, s);
+  return cta2 ? launch<EPI_BWD_W, false, false, 5, true>(p, s) : launch<EPI_BWD_W, false, false, 3, false>(p, s);
 }
 
 namespace {
@@ -689,6 +715,12 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
   p.out = out;
   p.ld_out = ld_out;
   p.alpha = alpha;
+  p.policy_a = kEvictFirst;                   // W: N^2 stream, each element used by n_tiles (3) column tiles only
+  p.policy_b = kEvictLast;                    // X: re-read by every row tile
+  p.policy_out = kEvictNormal;
+  if (const char* e = getenv("EVK_L2_HINTS")) {
+    if (e[0] == '0') p.policy_a = p.policy_b = kEvictNormal;
+  }
   fill_descs(p, a_mn, b_mn, variant, cta2);
   if (variant & 8) p.flags |= 0x100;      // bring-up: run the main loop, drop the output
   if (cta2) {
