@@ -219,16 +219,20 @@ def run_cuda(args):
     text = torch.tensor(txt_np, device=dev, requires_grad=True)
     ids_dev = DeviceIds(torch.from_numpy(ids_np[lo:hi].copy()).to(dev))
 
+    def make_graphed():
+        g = evoke_b200.GraphedGlobalAlignment(n_loc, DIM, TAU, device=dev, precision="bf16", path="tc",
+                                              sharded=world > 1)
+        g.load(image.detach(), text.detach(), ids_dev.key)
+        g._warmup = max(args.warmup, 3)
+        return g.capture()
+
     graphed = None
-    if world == 1 and not args.no_graph:
-        # whole fwd+bwd step captured once in a CUDA graph (evoke_b200.GraphedGlobalAlignment)
-        graphed = evoke_b200.GraphedGlobalAlignment(n_loc, DIM, TAU, device=dev, precision="bf16", path="tc")
-        graphed.load(image.detach(), text.detach(), ids_dev.key)
-        graphed._warmup = max(args.warmup, 3)
+    if not args.no_graph:
+        # whole fwd+bwd step (NCCL collectives included when sharded) captured once in a CUDA graph
         before = _lib.launch_count
-        graphed.capture()
+        graphed = make_graphed()
         # kernels of this library inside ONE replay = launches seen while capturing (warm-up excluded)
-        launches_per_replay = (_lib.launch_count - before) // (graphed._warmup + 1)
+        launches_per_replay = (_lib.launch_count - before) // (max(args.warmup, 3) + 1)
 
     def step():
         if graphed is not None:
@@ -271,7 +275,10 @@ def run_cuda(args):
     def eager_step():
         image.grad = None
         text.grad = None
-        l = evoke_b200.global_alignment(image, text, ids_dev, TAU, precision="bf16", path="tc")
+        if world == 1:
+            l = evoke_b200.global_alignment(image, text, ids_dev, TAU, precision="bf16", path="tc")
+        else:
+            l = global_alignment_sharded(image, text, ids_dev, TAU, precision="bf16")
         l.backward()
         return l
 
@@ -358,10 +365,7 @@ def run_cuda(args):
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     if graphed is not None:
         # ping-pong two captured steps; H2D lands directly in each graph's static input buffers
-        second = evoke_b200.GraphedGlobalAlignment(n_loc, DIM, TAU, device=dev, precision="bf16", path="tc")
-        second.load(image.detach(), text.detach(), ids_dev.key)
-        second.capture()
-        slots = [graphed, second]
+        slots = [graphed, make_graphed()]
     else:
         bufs = [(torch.empty_like(image), torch.empty_like(text), torch.empty_like(ids_dev.key)) for _ in range(2)]
 
@@ -448,7 +452,15 @@ def run_cuda(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL work: drop them and drain the device before tearing the group
+        # down, and do not let a slow communicator teardown keep the process alive
+        sys.stdout.flush()
+        try:
+            slots = graphed = None                                # noqa: F841
+            torch.cuda.synchronize()
+            dist.barrier()
+        finally:
+            os._exit(0)
 
 
 def main():

@@ -83,9 +83,9 @@ stats_fused_kernel(const float* __restrict__ rs_part, int64_t row_parts, int64_t
                    const float* __restrict__ rp_part, int64_t pos_parts, int64_t ld_pos,
                    const int32_t* __restrict__ counts, int64_t n_rows,
                    const float* __restrict__ cs_part, int64_t col_parts, int64_t ld_col, int64_t n_cols,
-                   float shift, float pos_weight, double inv_count, float* __restrict__ a_row,
-                   float* __restrict__ b_col, float* __restrict__ loss_out, double* __restrict__ cta_partial,
-                   unsigned int* __restrict__ ticket) {
+                   int64_t col_lo, int64_t col_hi, float shift, float pos_weight, double inv_count,
+                   float* __restrict__ a_row, float* __restrict__ b_col, float* __restrict__ loss_out,
+                   double* __restrict__ cta_partial, unsigned int* __restrict__ ticket) {
   __shared__ float s_sum[3][kStatGroups][kStatElems];
   __shared__ double s_part[kStatElems / 32];
   __shared__ bool s_last;
@@ -111,7 +111,7 @@ stats_fused_kernel(const float* __restrict__ rs_part, int64_t row_parts, int64_t
     }
     if (cs_part && i < n_cols) {
       b_col[i] = 1.f / c;
-      acc += (double)shift + (double)logf(c);
+      if (i >= col_lo && i < col_hi) acc += (double)shift + (double)logf(c);
     }
     acc = warp_sum_f64(acc);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
@@ -141,9 +141,9 @@ stats_fused_kernel(const float* __restrict__ rs_part, int64_t row_parts, int64_t
 extern "C" int evk_mpce_stats_fused(const float* rs_part, int64_t row_parts, int64_t ld_row, const float* rp_part,
                                     int64_t pos_parts, int64_t ld_pos, const int32_t* counts, int64_t n_rows,
                                     const float* cs_part, int64_t col_parts,
-                                    int64_t ld_col, int64_t n_cols, float shift, float pos_weight, double inv_count,
-                                    float* a_row, float* b_col, float* loss_out, void* workspace,
-                                    int64_t workspace_bytes, evk_stream_t stream) {
+                                    int64_t ld_col, int64_t n_cols, int64_t col_lo, int64_t col_hi, float shift,
+                                    float pos_weight, double inv_count, float* a_row, float* b_col, float* loss_out,
+                                    void* workspace, int64_t workspace_bytes, evk_stream_t stream) {
   EVK_REQUIRE(rs_part && rp_part && counts && a_row && loss_out && workspace && n_rows > 0 && row_parts >= 1 &&
                   ld_row >= n_rows && pos_parts >= 1 && ld_pos >= n_rows, "evk_mpce_stats_fused: bad row arguments");
   EVK_REQUIRE(!cs_part || (b_col && col_parts >= 1 && ld_col >= n_cols && n_cols > 0),
@@ -158,9 +158,9 @@ extern "C" int evk_mpce_stats_fused(const float* rs_part, int64_t row_parts, int
   EVK_CUDA(cudaMemsetAsync(ticket, 0, 16, s));
   stats_fused_kernel<<<(unsigned)blocks, kStatThreads, 0, s>>>(rs_part, row_parts, ld_row, rp_part, pos_parts, ld_pos,
                                                               counts, n_rows,
-                                                              cs_part, col_parts, ld_col, cs_part ? n_cols : 0, shift,
-                                                              pos_weight, inv_count, a_row, b_col, loss_out, partial,
-                                                              ticket);
+                                                              cs_part, col_parts, ld_col, cs_part ? n_cols : 0, col_lo,
+                                                              col_hi, shift, pos_weight, inv_count, a_row, b_col,
+                                                              loss_out, partial, ticket);
   EVK_CHECK_LAUNCH("mpce_stats_fused");
   return EVK_OK;
 }

@@ -28,12 +28,12 @@ import torch.distributed as dist
 from .ids import DeviceIds
 
 
-def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
-    """[n, ...] per rank -> [R*n, ...] (rank order), equal n on every rank."""
+def _all_gather_rows(t: torch.Tensor, group, async_op: bool = False):
+    """[n, ...] per rank -> [R*n, ...] (rank order), equal n on every rank.  Returns (out, work)."""
     world = dist.get_world_size(group)
     out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
-    return out
+    work = dist.all_gather_into_tensor(out, t.contiguous(), group=group, async_op=async_op)
+    return out, work
 
 
 @dataclass
@@ -61,20 +61,29 @@ class _ShardedG(torch.autograd.Function):
         split = precision == "fp32"
         flags = ops.FLAG_SPLIT_BF16 if split else 0
         kw = dict(want_f32=False, want_hi=True, want_lo=split)
+        # exchange 1 (asynchronous): ids first (tiny, K2 needs them), then the normalised keys; both
+        # overlap the image-side K1 and K2
+        key_all, w_ids = _all_gather_rows(row_ids.key, group, async_op=True)
+        key2_all, w_ids2 = (None, None) if row_ids.key2 is None else _all_gather_rows(row_ids.key2, group, async_op=True)
         kn_local = ops.l2norm_fwd(text, **kw)
-        # exchange 1: keys and ids
-        k_hi_all = _all_gather_rows(kn_local.hi, group)
-        k_lo_all = _all_gather_rows(kn_local.lo, group) if split else None
-        ids_all = DeviceIds(_all_gather_rows(row_ids.key, group),
-                            None if row_ids.key2 is None else _all_gather_rows(row_ids.key2, group))
-        kn_all = ops.Normalized(n=n_total, d=kn_local.d, norm=None, hi=k_hi_all, lo=k_lo_all, ld=kn_local.ld)
+        k_hi_all, w_hi = _all_gather_rows(kn_local.hi, group, async_op=True)
+        k_lo_all, w_lo = _all_gather_rows(kn_local.lo, group, async_op=True) if split else (None, None)
         qn = ops.l2norm_fwd(image, **kw)
+        w_ids.wait()
+        if w_ids2 is not None:
+            w_ids2.wait()
+        ids_all = DeviceIds(key_all, key2_all)
         bits, counts = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=rank * n)
-        row_sum, row_pos, col_part = ops.tc_fwd(qn, kn_all, bits, inv_tau, flags, rank * n)
-        # exchange 2: column sums
-        dist.all_reduce(col_part, op=dist.ReduceOp.SUM, group=group)
-        a_row, b_col, loss = ops.finalize(row_sum, row_pos, counts, col_part, col_lo=rank * n, col_hi=(rank + 1) * n,
-                                          shift=inv_tau, pos_weight=2.0, inv_count=0.5 / n_total)
+        w_hi.wait()
+        if w_lo is not None:
+            w_lo.wait()
+        kn_all = ops.Normalized(n=n_total, d=kn_local.d, norm=None, hi=k_hi_all, lo=k_lo_all, ld=kn_local.ld)
+        rs_part, rp_part, cs_part = ops.tc_fwd_partials(qn, kn_all, bits, inv_tau, flags, rank * n)
+        col_sum = ops.reduce_partials(cs_part, int(cs_part.shape[0]), n_total)
+        # exchange 2: column sums (the fixed shift makes them additive across ranks)
+        dist.all_reduce(col_sum, op=dist.ReduceOp.SUM, group=group)
+        a_row, b_col, loss = ops.stats_fused(rs_part, rp_part, col_sum, counts, shift=inv_tau, pos_weight=2.0,
+                                             inv_count=0.5 / n_total, col_lo=rank * n, col_hi=(rank + 1) * n)
         # exchange 3: scalar
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
         ctx.ops, ctx.group, ctx.inv_tau = ops, group, inv_tau

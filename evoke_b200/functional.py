@@ -207,12 +207,15 @@ def tc_pos(q: Normalized, k: Normalized, bits, inv_tau: float) -> torch.Tensor:
     return row_pos
 
 
-def stats_fused(rs_part, rp_part, cs_part, counts, *, shift: float, pos_weight: float, inv_count: float):
+def stats_fused(rs_part, rp_part, cs_part, counts, *, shift: float, pos_weight: float, inv_count: float,
+                col_lo: int = 0, col_hi: Optional[int] = None):
     """Partials -> (a_row, b_col | None, loss[1]) in one launch (single-GPU form).  rp_part is
     either K3's [parts, n] partials or the [n] vector written by tc_pos."""
     dev = rs_part.device
     if rp_part.dim() == 1:
         rp_part = rp_part.unsqueeze(0)
+    if cs_part is not None and cs_part.dim() == 1:
+        cs_part = cs_part.unsqueeze(0)
     n_rows = int(rs_part.shape[1])
     n_cols = 0 if cs_part is None else int(cs_part.shape[1])
     a_row = torch.empty(n_rows, dtype=torch.float32, device=dev)
@@ -223,7 +226,8 @@ def stats_fused(rs_part, rp_part, cs_part, counts, *, shift: float, pos_weight: 
     _lib.call("evk_mpce_stats_fused", _ptr(rs_part), int(rs_part.shape[0]), rs_part.stride(0),
               _ptr(rp_part), int(rp_part.shape[0]), max(int(rp_part.stride(0)), n_rows),
               _ptr(counts), n_rows, _ptr(cs_part), 0 if cs_part is None else int(cs_part.shape[0]),
-              0 if cs_part is None else cs_part.stride(0), n_cols, float(shift), float(pos_weight), float(inv_count),
+              0 if cs_part is None else max(int(cs_part.stride(0)), n_cols), n_cols,
+              int(col_lo), int(n_cols if col_hi is None else col_hi), float(shift), float(pos_weight), float(inv_count),
               _ptr(a_row), _ptr(b_col), _ptr(loss), _ptr(ws), ws.numel(), _stream())
     return a_row, b_col, loss
 

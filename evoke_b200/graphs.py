@@ -20,7 +20,12 @@ from .ids import DeviceIds
 
 class GraphedGlobalAlignment:
     def __init__(self, n: int, d: int, temp: float, *, device=None, dtype=torch.float32,
-                 precision: str = "bf16", path: str = "auto", two_keys: bool = False, warmup: int = 3):
+                 precision: str = "bf16", path: str = "auto", two_keys: bool = False, warmup: int = 3,
+                 sharded: bool = False, group=None):
+        """n = rows held by THIS process (the whole batch, or this rank's shard when sharded=True:
+        the step then is evoke_b200.distributed.global_alignment_sharded, NCCL collectives captured
+        with it; every rank must capture and replay in lockstep)."""
+        self.sharded, self.group = sharded, group
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.n, self.d, self.temp, self.precision, self.path = n, d, float(temp), precision, path
         self.image = torch.zeros((n, d), device=device, dtype=dtype, requires_grad=True)
@@ -36,8 +41,13 @@ class GraphedGlobalAlignment:
             self.text.normal_()
 
     def _eager(self):
-        out = _loss.global_alignment(self.image, self.text, self._ids, self.temp, precision=self.precision,
-                                     path=self.path)
+        if self.sharded:
+            from .distributed import global_alignment_sharded
+            out = global_alignment_sharded(self.image, self.text, self._ids, self.temp, group=self.group,
+                                           precision=self.precision)
+        else:
+            out = _loss.global_alignment(self.image, self.text, self._ids, self.temp, precision=self.precision,
+                                         path=self.path)
         out.backward()
         return out
 

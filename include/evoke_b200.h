@@ -153,6 +153,7 @@ EVK_API int evk_mpce_stats_fused(const float* rs_part, int64_t row_parts, int64_
                          const float* rp_part, int64_t pos_parts, int64_t ld_pos,
                          const int32_t* counts, int64_t n_rows,
                          const float* cs_part, int64_t col_parts, int64_t ld_col, int64_t n_cols,
+                         int64_t col_lo, int64_t col_hi,
                          float shift, float pos_weight, double inv_count,
                          float* a_row, float* b_col, float* loss_out,
                          void* workspace, int64_t workspace_bytes, evk_stream_t stream);

@@ -56,7 +56,23 @@ def _oracle_ops():
         s, e = _e(q, k, inv_tau)
         return e.sum(1), (s * bits).sum(1), e.sum(0)
 
-    def finalize(row_sum, row_pos, counts, col_sum, *, col_lo, col_hi, shift, pos_weight, inv_count, want_b=True):
+    def tc_fwd_partials(q, k, bits, inv_tau, flags, diag_offset=0):
+        s, e = _e(q, k, inv_tau)
+        # two row partials and three column partials, as the tiled kernel would produce
+        half = e.shape[1] // 2
+        rs = torch.stack([e[:, :half].sum(1), e[:, half:].sum(1)])
+        rp = torch.stack([(s * bits)[:, :half].sum(1), (s * bits)[:, half:].sum(1)])
+        third = max(e.shape[0] // 3, 1)
+        cs = torch.stack([e[:third].sum(0), e[third:2 * third].sum(0), e[2 * third:].sum(0)])
+        return rs, rp, cs
+
+    def reduce_partials(part, parts, n):
+        return part[:parts, :n].sum(0)
+
+    def stats_fused(rs_part, rp_part, cs_part, counts, *, shift, pos_weight, inv_count, col_lo=0, col_hi=None):
+        row_sum, row_pos = rs_part.sum(0), rp_part.sum(0)
+        col_sum = cs_part if cs_part.dim() == 1 else cs_part.sum(0)
+        col_hi = col_sum.shape[0] if col_hi is None else col_hi
         acc = (shift + row_sum.log() - pos_weight * row_pos / counts).sum()
         acc = acc + (shift + col_sum[col_lo:col_hi].log()).sum()
         return 1.0 / row_sum, 1.0 / col_sum, (acc * inv_count).reshape(1)
@@ -74,7 +90,8 @@ def _oracle_ops():
         g = orc.l2_normalize_bwd(x.detach().double().numpy(), g_hat.numpy())
         return (torch.from_numpy(g) * (scale_host * scale_dev.double().item())).to(x.dtype)
 
-    for f in (l2norm_fwd, posmask_build, tc_fwd, finalize, tc_bwd_w, tc_bwd_gemm, l2norm_bwd):
+    for f in (l2norm_fwd, posmask_build, tc_fwd, tc_fwd_partials, reduce_partials, stats_fused, tc_bwd_w, tc_bwd_gemm,
+              l2norm_bwd):
         setattr(ops, f.__name__, f)
     return ops
 
