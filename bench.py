@@ -221,7 +221,7 @@ def run_cuda(args):
 
     def make_graphed():
         g = evoke_b200.GraphedGlobalAlignment(n_loc, DIM, TAU, device=dev, precision="bf16", path="tc",
-                                              sharded=world > 1)
+                                              sharded=world > 1, shard_mode=args.shard_mode)
         g.load(image.detach(), text.detach(), ids_dev.key)
         g._warmup = max(args.warmup, 3)
         return g.capture()
@@ -242,7 +242,7 @@ def run_cuda(args):
         if world == 1:
             loss = evoke_b200.global_alignment(image, text, ids_dev, TAU, precision="bf16", path="tc")
         else:
-            loss = global_alignment_sharded(image, text, ids_dev, TAU, precision="bf16")
+            loss = global_alignment_sharded(image, text, ids_dev, TAU, precision="bf16", mode=args.shard_mode)
         loss.backward()
         return loss
 
@@ -278,7 +278,7 @@ def run_cuda(args):
         if world == 1:
             l = evoke_b200.global_alignment(image, text, ids_dev, TAU, precision="bf16", path="tc")
         else:
-            l = global_alignment_sharded(image, text, ids_dev, TAU, precision="bf16")
+            l = global_alignment_sharded(image, text, ids_dev, TAU, precision="bf16", mode=args.shard_mode)
         l.backward()
         return l
 
@@ -398,7 +398,7 @@ def run_cuda(args):
                 if world == 1:
                     l = evoke_b200.global_alignment(x, y, DeviceIds(bufs[slot][2]), TAU, precision="bf16", path="tc")
                 else:
-                    l = global_alignment_sharded(x, y, DeviceIds(bufs[slot][2]), TAU, precision="bf16")
+                    l = global_alignment_sharded(x, y, DeviceIds(bufs[slot][2]), TAU, precision="bf16", mode=args.shard_mode)
                 l.backward()
             consumed[slot].record(torch.cuda.current_stream())
             last = l.item()                                        # D2H read of the step's result
@@ -442,7 +442,7 @@ def run_cuda(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": N_GLOBAL, "dim": DIM, "rows_per_rank": n_loc,
                        "precision": "bf16 operands, fp32 accumulate/statistics; fp32 inputs and gradients",
-                       "parallelism": f"dp{world} row shards" if world > 1 else "single GPU",
+                       "parallelism": (f"dp{world} row shards, shard_mode={args.shard_mode}" if world > 1 else "single GPU"),
                        "l2": "no explicit flush: each step streams a 0.5 GB bf16 W strip (+0.15 GB operands/grads) "
                              "through the 126 MB L2, so no timed iteration starts with its inputs cached"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
@@ -473,6 +473,8 @@ def main():
     ap.add_argument("--no-kernel-events", action="store_true", help="debug: skip per-kernel CUDA events")
     ap.add_argument("--no-clocks", action="store_true", help="debug: skip the NVML clock sampler")
     ap.add_argument("--no-graph", action="store_true", help="run the eager launch sequence instead of the CUDA graph")
+    ap.add_argument("--shard-mode", default="auto", choices=["auto", "rs", "sym"],
+                    help="N>1: reduce-scatter of partial dK (rs) or recomputed key-side block (sym); auto = sym from 4 ranks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -29,7 +29,7 @@ SIGNATURES = {
     "evk_posmask_build": [P, P, L, P, P, L, L, I, P, L, P, P],
     "evk_mpce_small_fwd": [P, L, P, L, L, L, L, P, L, F, I, L, P, P, P],
     "evk_mpce_small_bwd": [P, L, P, L, L, L, L, P, L, P, P, P, F, I, L, P, L, P],
-    "evk_reduce_partials": [P, L, L, L, P, P],
+    "evk_reduce_partials": [P, L, L, L, P, P, P],
     "evk_mpce_finalize": [P, P, P, L, P, L, L, L, F, F, D, P, P, P, P],
     "evk_mpce_stats_fused": [P, L, L, P, L, L, P, L, P, L, L, L, L, L, F, F, D, P, P, P, P, L, P],
     "evk_mpce_pos": [P, P, L, P, P, L, L, L, L, P, L, F, P, P],

@@ -7,10 +7,14 @@
 namespace {
 
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int64_t parts, int64_t ld, int64_t n,
-                                       float* __restrict__ out) {
+                                       const int32_t* __restrict__ divisor, float* __restrict__ out) {
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
     float acc = 0.f;
     for (int64_t p = 0; p < parts; ++p) acc += part[p * ld + j];   // fixed order: deterministic
+    if (divisor) {
+      const int c = divisor[j];
+      acc = c > 0 ? acc / (float)c : 0.f;
+    }
     out[j] = acc;
   }
 }
@@ -105,7 +109,7 @@ stats_fused_kernel(const float* __restrict__ rs_part, int64_t row_parts, int64_t
       c += s_sum[2][gg][e];
     }
     if (i < n_rows) {
-      const int cnt = counts[i];
+      const int cnt = counts ? counts[i] : 1;
       a_row[i] = 1.f / r;
       acc += (double)shift + (double)logf(r) - (double)pos_weight * (cnt > 0 ? (double)pos / (double)cnt : 0.0);
     }
@@ -144,7 +148,7 @@ extern "C" int evk_mpce_stats_fused(const float* rs_part, int64_t row_parts, int
                                     int64_t ld_col, int64_t n_cols, int64_t col_lo, int64_t col_hi, float shift,
                                     float pos_weight, double inv_count, float* a_row, float* b_col, float* loss_out,
                                     void* workspace, int64_t workspace_bytes, evk_stream_t stream) {
-  EVK_REQUIRE(rs_part && rp_part && counts && a_row && loss_out && workspace && n_rows > 0 && row_parts >= 1 &&
+  EVK_REQUIRE(rs_part && rp_part && a_row && loss_out && workspace && n_rows > 0 && row_parts >= 1 &&
                   ld_row >= n_rows && pos_parts >= 1 && ld_pos >= n_rows, "evk_mpce_stats_fused: bad row arguments");
   EVK_REQUIRE(!cs_part || (b_col && col_parts >= 1 && ld_col >= n_cols && n_cols > 0),
               "evk_mpce_stats_fused: bad column arguments");
@@ -165,14 +169,14 @@ extern "C" int evk_mpce_stats_fused(const float* rs_part, int64_t row_parts, int
   return EVK_OK;
 }
 
-extern "C" int evk_reduce_partials(const float* part, int64_t parts, int64_t ld, int64_t n, float* out,
-                                   evk_stream_t stream) {
+extern "C" int evk_reduce_partials(const float* part, int64_t parts, int64_t ld, int64_t n, const int32_t* divisor,
+                                   float* out, evk_stream_t stream) {
   EVK_REQUIRE(part && out && parts >= 1 && ld >= n && n >= 0, "evk_reduce_partials: bad arguments");
   if (n == 0) return EVK_OK;
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = (int64_t)evk_sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  reduce_partials_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(part, parts, ld, n, out);
+  reduce_partials_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(part, parts, ld, n, divisor, out);
   EVK_CHECK_LAUNCH("reduce_partials");
   return EVK_OK;
 }

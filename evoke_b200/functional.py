@@ -143,9 +143,12 @@ def posmask_build(rows: DeviceIds, cols: DeviceIds, *, clear_diag: bool, diag_of
     return bits, counts
 
 
-def reduce_partials(part: torch.Tensor, parts: int, n: int) -> torch.Tensor:
-    out = torch.empty(n, dtype=torch.float32, device=part.device)
-    _lib.call("evk_reduce_partials", _ptr(part), parts, part.stride(0), n, _ptr(out), _stream())
+def reduce_partials(part: torch.Tensor, parts: int, n: int, out: Optional[torch.Tensor] = None,
+                    divisor: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[j] = sum_p part[p, j] (/ divisor[j] if given); `out` may be a slice of a larger buffer."""
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=part.device)
+    _lib.call("evk_reduce_partials", _ptr(part), parts, part.stride(0), n, _ptr(divisor), _ptr(out), _stream())
     return out
 
 
@@ -209,9 +212,12 @@ def tc_pos(q: Normalized, k: Normalized, bits, inv_tau: float) -> torch.Tensor:
 
 def stats_fused(rs_part, rp_part, cs_part, counts, *, shift: float, pos_weight: float, inv_count: float,
                 col_lo: int = 0, col_hi: Optional[int] = None):
+    # counts=None: rp_part already holds pos_i / c_i
     """Partials -> (a_row, b_col | None, loss[1]) in one launch (single-GPU form).  rp_part is
     either K3's [parts, n] partials or the [n] vector written by tc_pos."""
     dev = rs_part.device
+    if rs_part.dim() == 1:
+        rs_part = rs_part.unsqueeze(0)
     if rp_part.dim() == 1:
         rp_part = rp_part.unsqueeze(0)
     if cs_part is not None and cs_part.dim() == 1:
@@ -223,7 +229,7 @@ def stats_fused(rs_part, rp_part, cs_part, counts, *, shift: float, pos_weight: 
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     ws_bytes = 16 + 8 * ((max(n_rows, n_cols) + 31) // 32)
     ws = torch.empty(_round_up(ws_bytes, 16), dtype=torch.uint8, device=dev)
-    _lib.call("evk_mpce_stats_fused", _ptr(rs_part), int(rs_part.shape[0]), rs_part.stride(0),
+    _lib.call("evk_mpce_stats_fused", _ptr(rs_part), int(rs_part.shape[0]), max(int(rs_part.stride(0)), n_rows),
               _ptr(rp_part), int(rp_part.shape[0]), max(int(rp_part.stride(0)), n_rows),
               _ptr(counts), n_rows, _ptr(cs_part), 0 if cs_part is None else int(cs_part.shape[0]),
               0 if cs_part is None else max(int(cs_part.stride(0)), n_cols), n_cols,

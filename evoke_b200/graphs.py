@@ -21,11 +21,11 @@ from .ids import DeviceIds
 class GraphedGlobalAlignment:
     def __init__(self, n: int, d: int, temp: float, *, device=None, dtype=torch.float32,
                  precision: str = "bf16", path: str = "auto", two_keys: bool = False, warmup: int = 3,
-                 sharded: bool = False, group=None):
+                 sharded: bool = False, group=None, shard_mode: str = "auto"):
         """n = rows held by THIS process (the whole batch, or this rank's shard when sharded=True:
         the step then is evoke_b200.distributed.global_alignment_sharded, NCCL collectives captured
         with it; every rank must capture and replay in lockstep)."""
-        self.sharded, self.group = sharded, group
+        self.sharded, self.group, self.shard_mode = sharded, group, shard_mode
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.n, self.d, self.temp, self.precision, self.path = n, d, float(temp), precision, path
         self.image = torch.zeros((n, d), device=device, dtype=dtype, requires_grad=True)
@@ -44,7 +44,7 @@ class GraphedGlobalAlignment:
         if self.sharded:
             from .distributed import global_alignment_sharded
             out = global_alignment_sharded(self.image, self.text, self._ids, self.temp, group=self.group,
-                                           precision=self.precision)
+                                           precision=self.precision, mode=self.shard_mode)
         else:
             out = _loss.global_alignment(self.image, self.text, self._ids, self.temp, precision=self.precision,
                                          path=self.path)

@@ -128,9 +128,10 @@ EVK_API int evk_mpce_small_bwd(const float* q, int64_t ld_q, const float* k, int
                        float* dq, int64_t ld_dq, evk_stream_t stream);
 
 /* ---- statistics -> loss ----------------------------------------------------------------------
- * out[j] = sum_p part[p*ld + j], p < parts: deterministic reduction of per-tile partials. */
-EVK_API int evk_reduce_partials(const float* part, int64_t parts, int64_t ld, int64_t n, float* out,
-                        evk_stream_t stream);
+ * out[j] = sum_p part[p*ld + j], p < parts: deterministic reduction of per-tile partials;
+ * if divisor != NULL the sum is divided by divisor[j] (0 where divisor[j] <= 0): pos_j / c_j. */
+EVK_API int evk_reduce_partials(const float* part, int64_t parts, int64_t ld, int64_t n,
+                        const int32_t* divisor, float* out, evk_stream_t stream);
 
 /* Turns the O(N) statistics into the loss and the backward's scale vectors.
  *   a_row[i] = 1/row_sum[i];  b_col[j] = 1/col_sum[j]  (col_sum may be NULL: then b_col = NULL ok)

@@ -66,14 +66,23 @@ def _oracle_ops():
         cs = torch.stack([e[:third].sum(0), e[third:2 * third].sum(0), e[2 * third:].sum(0)])
         return rs, rp, cs
 
-    def reduce_partials(part, parts, n):
-        return part[:parts, :n].sum(0)
+    def reduce_partials(part, parts, n, out=None, divisor=None):
+        r = part[:parts, :n].sum(0)
+        if divisor is not None:
+            r = r / divisor
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r
 
     def stats_fused(rs_part, rp_part, cs_part, counts, *, shift, pos_weight, inv_count, col_lo=0, col_hi=None):
-        row_sum, row_pos = rs_part.sum(0), rp_part.sum(0)
+        row_sum = rs_part if rs_part.dim() == 1 else rs_part.sum(0)
+        row_pos = rp_part if rp_part.dim() == 1 else rp_part.sum(0)
         col_sum = cs_part if cs_part.dim() == 1 else cs_part.sum(0)
         col_hi = col_sum.shape[0] if col_hi is None else col_hi
-        acc = (shift + row_sum.log() - pos_weight * row_pos / counts).sum()
+        if counts is not None:
+            row_pos = row_pos / counts
+        acc = (shift + row_sum.log() - pos_weight * row_pos).sum()
         acc = acc + (shift + col_sum[col_lo:col_hi].log()).sum()
         return 1.0 / row_sum, 1.0 / col_sum, (acc * inv_count).reshape(1)
 
@@ -96,7 +105,7 @@ def _oracle_ops():
     return ops
 
 
-def _worker(rank, world, port, n_total, d, tau, precision, out_dir):
+def _worker(rank, world, port, n_total, d, tau, precision, mode, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -114,7 +123,7 @@ def _worker(rank, world, port, n_total, d, tau, precision, out_dir):
         image = torch.tensor(xi[sl], requires_grad=True)
         text = torch.tensor(xt[sl], requires_grad=True)
         row_ids = DeviceIds(torch.from_numpy(ids[sl].copy()))
-        loss = global_alignment_sharded(image, text, row_ids, tau, precision=precision, ops=_oracle_ops())
+        loss = global_alignment_sharded(image, text, row_ids, tau, precision=precision, mode=mode, ops=_oracle_ops())
         (2.5 * loss).backward()
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=loss.item(), d_image=image.grad.numpy(),
                  d_text=text.grad.numpy())
@@ -122,13 +131,13 @@ def _worker(rank, world, port, n_total, d, tau, precision, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32"])
-def test_sharded_choreography_equals_global_batch(tmp_path, precision):
+@pytest.mark.parametrize("precision,mode", [("bf16", "rs"), ("fp32", "rs"), ("bf16", "sym"), ("fp32", "sym")])
+def test_sharded_choreography_equals_global_batch(tmp_path, precision, mode):
     from evoke_b200 import synth
     from oracle import evoke_oracle as orc
     world, n_total, d, tau = 2, 48, 24, 0.5
-    port = 29700 + (os.getpid() % 200) + (1 if precision == "fp32" else 0)
-    mp.spawn(_worker, args=(world, port, n_total, d, tau, precision, str(tmp_path)), nprocs=world, join=True)
+    port = 29700 + (os.getpid() % 200) + (1 if precision == "fp32" else 0) + (2 if mode == "sym" else 0)
+    mp.spawn(_worker, args=(world, port, n_total, d, tau, precision, mode, str(tmp_path)), nprocs=world, join=True)
     ids = synth.make_study_ids(n_total, seed=21)
     xi = synth.make_embeddings(ids, d, seed=22).astype(np.float64)
     xt = synth.make_embeddings(ids, d, seed=23).astype(np.float64)

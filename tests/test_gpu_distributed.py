@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, n_total, d, tau, precision, out_dir):
+def _worker(rank, world, port, n_total, d, tau, precision, mode, out_dir):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -29,7 +29,7 @@ def _worker(rank, world, port, n_total, d, tau, precision, out_dir):
         sl = slice(rank * n, (rank + 1) * n)
         image = torch.tensor(xi[sl], device="cuda", requires_grad=True)
         text = torch.tensor(xt[sl], device="cuda", requires_grad=True)
-        loss = global_alignment_sharded(image, text, ids[sl].copy(), tau, precision=precision)
+        loss = global_alignment_sharded(image, text, ids[sl].copy(), tau, precision=precision, mode=mode)
         loss.backward()
         torch.cuda.synchronize()
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=loss.item(), d_image=image.grad.cpu().numpy(),
@@ -38,15 +38,16 @@ def _worker(rank, world, port, n_total, d, tau, precision, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("mode", ["rs", "sym"])
 @pytest.mark.parametrize("precision,ltol,gtol", [("fp32", 1e-5, 1e-4), ("bf16", 2e-3, 2e-2)])
-def test_sharded_equals_oracle_on_two_gpus(tmp_path, precision, ltol, gtol):
+def test_sharded_equals_oracle_on_two_gpus(tmp_path, precision, ltol, gtol, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     from evoke_b200 import synth
     from oracle import evoke_oracle as orc
     world, n_total, d, tau = 2, 1536, 256, 0.5
-    port = 29900 + (os.getpid() % 90) + (1 if precision == "fp32" else 0)
-    mp.spawn(_worker, args=(world, port, n_total, d, tau, precision, str(tmp_path)), nprocs=world, join=True)
+    port = 29900 + (os.getpid() % 90) + (1 if precision == "fp32" else 0) + (2 if mode == "sym" else 0)
+    mp.spawn(_worker, args=(world, port, n_total, d, tau, precision, mode, str(tmp_path)), nprocs=world, join=True)
     ids = synth.make_study_ids(n_total, seed=31)
     xi = synth.make_embeddings(ids, d, seed=32)
     xt = synth.make_embeddings(ids, d, seed=33)
