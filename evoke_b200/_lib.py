@@ -36,6 +36,8 @@ SIGNATURES = {
     "evk_mpce_fwd": [P, P, L, P, P, L, L, L, L, P, L, F, I, L, P, P, L, P, L, P],
     "evk_mpce_bwd_w": [P, P, L, P, P, L, L, L, L, P, L, P, P, P, F, I, L, P, P, L, P],
     "evk_mpce_bwd_gemm": [P, P, L, L, L, I, P, P, L, L, F, I, P, L, P],
+    "evk_l2norm_fwd_bcast": [P, I, L, L, L, L, I, P, P, L, L, P, P],
+    "evk_peer_bcast": [P, L, I, P, L, P],
     "evk_tc_gemm_probe": [P, L, I, P, L, I, L, L, L, P, L, I, I, P],
 }
 
@@ -83,7 +85,8 @@ def check(rc: int, what: str) -> None:
 KERNELS_PER_CALL = {
     "evk_l2norm_fwd": 1, "evk_l2norm_bwd": 1, "evk_posmask_build": 1, "evk_mpce_small_fwd": 1,
     "evk_mpce_small_bwd": 1, "evk_reduce_partials": 1, "evk_mpce_finalize": 1, "evk_mpce_stats_fused": 1, "evk_mpce_pos": 1, "evk_mpce_fwd": 1,
-    "evk_mpce_bwd_w": 1, "evk_mpce_bwd_gemm": 1, "evk_tc_gemm_probe": 1,
+    "evk_mpce_bwd_w": 1, "evk_mpce_bwd_gemm": 1, "evk_tc_gemm_probe": 1, "evk_l2norm_fwd_bcast": 1,
+    "evk_peer_bcast": 1,
 }
 launch_count = 0          # running total, read by bench.py ("gpu_launches")
 call_hook = None          # optional callable(name, phase) with phase in {"before", "after"} (bench.py timing)

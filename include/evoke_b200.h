@@ -206,6 +206,24 @@ EVK_API int evk_mpce_bwd_gemm(const void* w_hi, const void* w_lo, int64_t ld_w,
                       const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d,
                       float alpha, int flags, float* out, int64_t ld_out, evk_stream_t stream);
 
+/* ---- peer-memory transport for the sharded path (NVLink / NVSwitch) --------------------------
+ * dst_* are HOST arrays of n_dst device base addresses: the per-rank buffers of one symmetric
+ * allocation (peer-mapped pointers, the local rank included).  Ordering across ranks is the caller's
+ * (symmetric-memory barrier between producer and consumer kernels).
+ *
+ * K1 fused with the all-gather: row r of this rank is normalised and written as bf16 at row
+ * (row_offset + r) of EVERY destination (hi, and lo when dst_lo != NULL).  Contiguous fp32 input,
+ * d % 8 == 0, d <= 2048. */
+EVK_API int evk_l2norm_fwd_bcast(const void* x, int x_dtype, int64_t n_rows, int64_t d,
+                         int64_t stride_row, int64_t stride_col,
+                         int n_dst, const uint64_t* dst_hi, const uint64_t* dst_lo,
+                         int64_t ld_bf16, int64_t row_offset, float* norm, evk_stream_t stream);
+
+/* Copy `bytes` (multiple of 16) from src to byte offset dst_offset_bytes of every destination:
+ * ids shard, per-rank statistics slot. */
+EVK_API int evk_peer_bcast(const void* src, int64_t bytes, int n_dst, const uint64_t* dst,
+                   int64_t dst_offset_bytes, evk_stream_t stream);
+
 /* Debug/bring-up: plain C[m,n] = A[m,k] B[n,k]^T (or MN-major operands) through the same
  * tcgen05 main loop, fp32 out.  a_major/b_major: 0 = K contiguous, 1 = M/N contiguous
  * (then A is stored [k, m] / B is stored [k, n]).  c must be zeroed by the caller (the epilogue
