@@ -252,8 +252,9 @@ def run_cuda(args):
         torch.cuda.synchronize()
 
     # per-kernel CUDA events around the tcgen05 launches (recorded on the launching stream)
-    TC = ("evk_mpce_fwd", "evk_mpce_bwd_w", "evk_mpce_bwd_gemm")
-    ev = {k: [] for k in TC}
+    TC = ("evk_mpce_fwd", "evk_mpce_fwd_store", "evk_mpce_bwd_w", "evk_mpce_bwd_gemm")
+    HBM_K = ("evk_mpce_w_from_e",)        # K4t: 4 B per (i, j) read+written, + 1 mask bit
+    ev = {k: [] for k in TC + HBM_K}
     pending = {}
 
     def hook(name, phase):
@@ -332,9 +333,14 @@ def run_cuda(args):
         if pairs:
             ms = [a.elapsed_time(b) for a, b in pairs]
             kern[name] = dict(launches_per_step=len(pairs) / args.steps, avg_ms=float(np.mean(ms)),
-                              tflops=flop_launch / (float(np.mean(ms)) * 1e-3) / 1e12,
                               share_of_step=float(np.sum(ms)) / (ms_eager_total or ms_total))
-    dom = max(kern, key=lambda k: kern[k]["avg_ms"]) if kern else None
+            if name in HBM_K:
+                kern[name]["gbs"] = (4.125 * n_loc * N_GLOBAL) / (float(np.mean(ms)) * 1e-3) / 1e9
+                kern[name]["frac_of_hbm_peak"] = kern[name]["gbs"] / peaks["hbm_gbs"]
+            else:
+                kern[name]["tflops"] = flop_launch / (float(np.mean(ms)) * 1e-3) / 1e12
+    tck = [k for k in kern if k in TC]
+    dom = max(tck, key=lambda k: kern[k]["avg_ms"]) if tck else None
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
@@ -473,8 +479,9 @@ def main():
     ap.add_argument("--no-kernel-events", action="store_true", help="debug: skip per-kernel CUDA events")
     ap.add_argument("--no-clocks", action="store_true", help="debug: skip the NVML clock sampler")
     ap.add_argument("--no-graph", action="store_true", help="run the eager launch sequence instead of the CUDA graph")
-    ap.add_argument("--shard-mode", default="auto", choices=["auto", "rs", "sym"],
-                    help="N>1: reduce-scatter of partial dK (rs) or recomputed key-side block (sym); auto = sym from 4 ranks")
+    ap.add_argument("--shard-mode", default="auto", choices=["auto", "rs", "sym", "peer"],
+                    help="N>1: peer = exchanges by this library's kernels over peer-mapped memory (default when possible); "
+                         "rs / sym = NCCL transports (reduce-scatter of partial dK / recomputed key-side block)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

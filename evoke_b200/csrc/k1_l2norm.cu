@@ -122,7 +122,8 @@ l2norm_fwd_generic_kernel(const void* __restrict__ x, int x_dtype, int64_t n_out
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_bwd_kernel(const void* __restrict__ x, int x_dtype, int64_t n_out, int64_t d, int64_t stride_row,
                   int64_t stride_col, const int32_t* __restrict__ gather, const float* __restrict__ norm,
-                  const float* __restrict__ g, int64_t ld_g, const float* __restrict__ scale_dev,
+                  const float* __restrict__ g, int64_t ld_g, int n_parts, int64_t part_stride,
+                  const float* __restrict__ scale_dev,
                   float scale_host, void* __restrict__ dx, int dx_dtype, int64_t ld_dx, int accumulate) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -135,21 +136,27 @@ l2norm_bwd_kernel(const void* __restrict__ x, int x_dtype, int64_t n_out, int64_
     const bool clamped = nrm < EVK_NORM_EPS;
     const float den = fmaxf(nrm, EVK_NORM_EPS);
     const float* gr = g + r * ld_g;
+    auto gval = [&](int64_t c) {                   // upstream gradient = sum of the partial buffers (rank order)
+      float v = gr[c];
+      for (int p = 1; p < n_parts; ++p) v += gr[p * part_stride + c];
+      return v;
+    };
     float proj = 0.f;
     if (!clamped) {
       for (int64_t c = lane; c < d; c += 32) {
         const float h = load_as_float(x, x_dtype, base + c * stride_col) / den;
-        proj = fmaf(h, gr[c], proj);
+        proj = fmaf(h, gval(c), proj);
       }
       proj = warp_sum(proj);
     }
     for (int64_t c = lane; c < d; c += 32) {
       float o;
+      const float gc = gval(c);
       if (clamped) {
-        o = scale * (gr[c] / EVK_NORM_EPS);
+        o = scale * (gc / EVK_NORM_EPS);
       } else {
         const float h = load_as_float(x, x_dtype, base + c * stride_col) / den;
-        o = scale * ((gr[c] - h * proj) / den);
+        o = scale * ((gc - h * proj) / den);
       }
       const int64_t oi = src * ld_dx + c;
       if (accumulate && dx_dtype == EVK_DTYPE_F32) reinterpret_cast<float*>(dx)[oi] += o;
@@ -165,7 +172,8 @@ template <int kIters>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t stride_row,
                       const int32_t* __restrict__ gather, const float* __restrict__ norm,
-                      const float* __restrict__ g, int64_t ld_g, const float* __restrict__ scale_dev,
+                      const float* __restrict__ g, int64_t ld_g, int n_parts, int64_t part_stride,
+                      const float* __restrict__ scale_dev,
                       float scale_host, float* __restrict__ dx, int64_t ld_dx) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -188,6 +196,10 @@ l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t
       if (c * 4 < d) {
         xv[it] = __ldg(xr + c);
         gv[it] = __ldg(gr + c);
+        for (int p = 1; p < n_parts; ++p) {        // partial dXhat buffers written by the ranks' K4b epilogues
+          const float4 t = __ldg(gr + p * (part_stride >> 2) + c);
+          gv[it].x += t.x; gv[it].y += t.y; gv[it].z += t.z; gv[it].w += t.w;
+        }
         xv[it].x *= inv_den; xv[it].y *= inv_den; xv[it].z *= inv_den; xv[it].w *= inv_den;   // xhat (1 ulp of the forward's)
         proj = fmaf(xv[it].x, gv[it].x, proj);
         proj = fmaf(xv[it].y, gv[it].y, proj);
@@ -257,18 +269,20 @@ extern "C" int evk_l2norm_fwd(const void* x, int x_dtype, int64_t n_out, int64_t
   return EVK_OK;
 }
 
-extern "C" int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t d, int64_t stride_row,
-                              int64_t stride_col, const int32_t* gather, const float* norm, const float* g,
-                              int64_t ld_g, const float* scale_dev, float scale_host, void* dx, int dx_dtype,
-                              int64_t ld_dx, int accumulate, evk_stream_t stream) {
+extern "C" int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, int64_t d, int64_t stride_row,
+                                    int64_t stride_col, const int32_t* gather, const float* norm, const float* g,
+                                    int64_t ld_g, int n_parts, int64_t part_stride, const float* scale_dev,
+                                    float scale_host, void* dx, int dx_dtype, int64_t ld_dx, int accumulate,
+                                    evk_stream_t stream) {
   EVK_REQUIRE(x && norm && g && dx, "evk_l2norm_bwd: null pointer");
+  EVK_REQUIRE(n_parts >= 1 && (n_parts == 1 || part_stride >= n_out * ld_g), "evk_l2norm_bwd_parts: bad partial-buffer layout");
   EVK_REQUIRE(n_out >= 0 && d > 0 && ld_g >= d && ld_dx >= d, "evk_l2norm_bwd: bad shape");
   EVK_REQUIRE(x_dtype >= EVK_DTYPE_F32 && x_dtype <= EVK_DTYPE_F16 && dx_dtype >= EVK_DTYPE_F32 &&
                   dx_dtype <= EVK_DTYPE_F16, "evk_l2norm_bwd: bad dtype");
   EVK_REQUIRE(!accumulate || dx_dtype == EVK_DTYPE_F32, "evk_l2norm_bwd: accumulate needs fp32 dx");
   if (n_out == 0) return EVK_OK;
   const bool vec = x_dtype == EVK_DTYPE_F32 && dx_dtype == EVK_DTYPE_F32 && !accumulate && stride_col == 1 &&
-                   d % 4 == 0 && d <= 2048 && stride_row % 4 == 0 && ld_g % 4 == 0 && ld_dx % 4 == 0 &&
+                   d % 4 == 0 && d <= 2048 && stride_row % 4 == 0 && ld_g % 4 == 0 && ld_dx % 4 == 0 && part_stride % 4 == 0 &&
                    evk_aligned16(x) && evk_aligned16(g) && evk_aligned16(dx);
   if (vec) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -277,16 +291,24 @@ extern "C" int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t
     float* df = static_cast<float*>(dx);
     if (d <= 1024)
       l2norm_bwd_vec_kernel<8><<<grid, kWarpsPerBlock * 32, 0, s>>>(xf, n_out, (int)d, stride_row, gather, norm, g, ld_g,
-                                                                    scale_dev, scale_host, df, ld_dx);
+                                                                    n_parts, part_stride, scale_dev, scale_host, df, ld_dx);
     else
       l2norm_bwd_vec_kernel<16><<<grid, kWarpsPerBlock * 32, 0, s>>>(xf, n_out, (int)d, stride_row, gather, norm, g,
-                                                                     ld_g, scale_dev, scale_host, df, ld_dx);
+                                                                     ld_g, n_parts, part_stride, scale_dev, scale_host, df, ld_dx);
     EVK_CHECK_LAUNCH("l2norm_bwd_vec");
     return EVK_OK;
   }
   l2norm_bwd_kernel<<<grid_for_rows(n_out), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, x_dtype, n_out, d, stride_row, stride_col, gather, norm, g, ld_g, scale_dev, scale_host, dx, dx_dtype,
+      x, x_dtype, n_out, d, stride_row, stride_col, gather, norm, g, ld_g, n_parts, part_stride, scale_dev, scale_host, dx, dx_dtype,
       ld_dx, accumulate);
   EVK_CHECK_LAUNCH("l2norm_bwd");
   return EVK_OK;
+}
+
+extern "C" int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t d, int64_t stride_row,
+                              int64_t stride_col, const int32_t* gather, const float* norm, const float* g,
+                              int64_t ld_g, const float* scale_dev, float scale_host, void* dx, int dx_dtype,
+                              int64_t ld_dx, int accumulate, evk_stream_t stream) {
+  return evk_l2norm_bwd_parts(x, x_dtype, n_out, d, stride_row, stride_col, gather, norm, g, ld_g, 1, 0, scale_dev,
+                              scale_host, dx, dx_dtype, ld_dx, accumulate, stream);
 }

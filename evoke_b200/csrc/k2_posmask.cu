@@ -3,89 +3,109 @@
 // models/model_pretrain_finetune_v0520.py:488-491 and :422-424/:430.
 //
 // Layout: bits[r, w] (uint32, row pitch ld_words), bit k of word w <=> column 32*w + k, which is
-// np.packbits(M, axis=1, bitorder='little') read as little-endian uint32.  Each thread owns one
-// word column: it keeps the 32 column keys of that word in registers and walks kRows rows, so
-// a warp writes 128 contiguous bytes per row and the column keys are read once per kRows rows.
-// Algorithmic bytes: ld_words*4 per row written + 4*(n_rows + n_cols) read; the kernel is bound
-// by the n_rows*n_cols integer compares (1 ISETP + 1 predicated LOP per pair), not by HBM.
+// np.packbits(M, axis=1, bitorder='little') read as little-endian uint32.
+//
+// The mask is sparse (a study has a handful of views), so the N^2 compares of the reference are not
+// executed.  A CTA owns a block of 1024 columns x kRowsPerCta rows: it hashes the block's column keys
+// into an open-addressing multiset in shared memory (duplicates take consecutive slots), then every
+// lane looks its own row key up - each match is one bit set in a per-warp [32 rows x 32 words] tile in
+// shared memory - and the warp streams the tile out with 128-bit stores.  Work per row and column block
+// is a probe sequence (about two slots) instead of 1024 compares, which leaves the kernel bound by
+// writing the mask: algorithmic bytes ld_words*4 per row written + 4*(n_rows + n_cols) read.
+// Degenerate inputs (every key equal) degrade gracefully to one compare per pair.  Exact: keys are
+// compared in full, the hash only picks the starting slot.
+//
+// Optional second output: pos_idx[r, s] = column of the s-th positive of row r (s < pos_slots; the order
+// within a row is unspecified, rows with more positives keep only the first pos_slots - counts[r] tells).
+// The O(N) consumers of the positives (exact W entries, K4t) then need no scan of the N^2/8-byte mask.
 #include "evk_common.cuh"
 
 namespace {
 
-constexpr int kThreads = 128;   // words per CTA along a row
-constexpr int kRows = 32;       // rows per CTA
+constexpr int kThreads = 128;                 // 4 warps
+constexpr int kWarps = kThreads / 32;
+constexpr int kColsPerCta = 1024;             // 32 words
+constexpr int kSlots = 2048;                  // load factor <= 0.5
+constexpr int kRowsPerCta = 256;              // 2 x 32 rows per warp
+constexpr int kTilePitch = 36;                // words per tile row (16-byte aligned rows, banks staggered)
+
+__device__ __forceinline__ uint32_t slot_hash(int32_t k, int32_t k2) {
+  uint32_t h = (uint32_t)k * 0x9E3779B1u;
+  h ^= (uint32_t)k2 * 0x85EBCA6Bu;
+  h ^= h >> 15;
+  return h & (kSlots - 1);
+}
 
 template <bool kTwoKeys>
 __global__ void __launch_bounds__(kThreads)
 posmask_kernel(const int32_t* __restrict__ ids_row, const int32_t* __restrict__ ids2_row, int64_t n_rows,
                const int32_t* __restrict__ ids_col, const int32_t* __restrict__ ids2_col, int64_t n_cols,
                int64_t diag_offset, int clear_diag, uint32_t* __restrict__ bits, int64_t ld_words,
-               int32_t* __restrict__ counts) {
-  __shared__ int32_t s_row[kRows];
-  __shared__ int32_t s_row2[kRows];
-  const int64_t w = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const int64_t r0 = (int64_t)blockIdx.y * kRows;
-  if (threadIdx.x < kRows) {
-    const int64_t r = r0 + threadIdx.x;
-    s_row[threadIdx.x] = r < n_rows ? ids_row[r] : 0;
-    if (kTwoKeys) s_row2[threadIdx.x] = r < n_rows ? ids2_row[r] : 0;
+               int32_t* __restrict__ counts, int vec_ok, int32_t* __restrict__ pos_idx, int pos_slots) {
+  __shared__ int32_t t_col[kSlots];                      // column (0..1023) held by the slot, -1 = empty
+  __shared__ int32_t t_key[kSlots];
+  __shared__ int32_t t_key2[kTwoKeys ? kSlots : 1];
+  __shared__ __align__(16) uint32_t tile[kWarps][32 * kTilePitch];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t c0 = (int64_t)blockIdx.x * kColsPerCta;
+  const int64_t w0 = c0 >> 5;
+  const int64_t r_cta = (int64_t)blockIdx.y * kRowsPerCta;
+
+  for (int s = threadIdx.x; s < kSlots; s += kThreads) t_col[s] = -1;
+  for (int k = lane; k < 32 * kTilePitch; k += 32) tile[warp][k] = 0u;
+  __syncthreads();
+  for (int c = threadIdx.x; c < kColsPerCta; c += kThreads) {
+    if (c0 + c < n_cols) {
+      const int32_t key = __ldg(ids_col + c0 + c);
+      const int32_t key2 = kTwoKeys ? __ldg(ids2_col + c0 + c) : 0;
+      uint32_t s = slot_hash(key, key2);
+      while (atomicCAS(&t_col[s], -1, c) != -1) s = (s + 1) & (kSlots - 1);
+      t_key[s] = key;
+      if (kTwoKeys) t_key2[s] = key2;
+    }
   }
   __syncthreads();
 
-  const int64_t c0 = w * 32;
-  const bool in_row = w < ld_words;
-  // column keys of this word, and which of its 32 bits are real columns
-  int32_t ck[32];
-  int32_t ck2[kTwoKeys ? 32 : 1];
-  uint32_t valid = 0u;
-  if (in_row && c0 + 32 <= n_cols) {
-    valid = 0xffffffffu;
-    const int4* p = reinterpret_cast<const int4*>(ids_col + c0);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int4 v = __ldg(p + q);
-      ck[4 * q] = v.x; ck[4 * q + 1] = v.y; ck[4 * q + 2] = v.z; ck[4 * q + 3] = v.w;
-    }
-    if (kTwoKeys) {
-      const int4* p2 = reinterpret_cast<const int4*>(ids2_col + c0);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int4 v = __ldg(p2 + q);
-        ck2[4 * q] = v.x; ck2[4 * q + 1] = v.y; ck2[4 * q + 2] = v.z; ck2[4 * q + 3] = v.w;
+  uint32_t* my = tile[warp];
+  for (int64_t rb = r_cta + warp * 32; rb < r_cta + kRowsPerCta && rb < n_rows; rb += kWarps * 32) {
+    const int64_t r = rb + lane;
+    if (r < n_rows) {
+      const int32_t key = __ldg(ids_row + r);
+      const int32_t key2 = kTwoKeys ? __ldg(ids2_row + r) : 0;
+      const int64_t diag = clear_diag ? r + diag_offset - c0 : -1;    // column of this block to leave clear
+      uint32_t s = slot_hash(key, key2);
+      for (int probes = 0; probes < kSlots; ++probes) {
+        const int32_t c = t_col[s];
+        if (c < 0) break;
+        if (t_key[s] == key && (!kTwoKeys || t_key2[s] == key2) && (int64_t)c != diag) {
+          my[lane * kTilePitch + (c >> 5)] |= 1u << (c & 31);
+          // positives are rare: one atomic each; its return value is the entry's slot in the row's list
+          const int slot = atomicAdd(counts + r, 1);
+          if (pos_idx && slot < pos_slots) pos_idx[r * pos_slots + slot] = (int32_t)(c0 + c);
+        }
+        s = (s + 1) & (kSlots - 1);
       }
     }
-  } else {
+    __syncwarp();
+    // stream the 32 x 32-word tile out (and clear it for the next row group)
+    if (vec_ok) {
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const bool ok = in_row && (c0 + k < n_cols);
-      ck[k] = ok ? __ldg(ids_col + c0 + k) : 0;
-      if (kTwoKeys) ck2[k] = ok ? __ldg(ids2_col + c0 + k) : 0;
-      valid |= ok ? (1u << k) : 0u;
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3), wq = (lane & 7) * 4;
+        uint4* src = reinterpret_cast<uint4*>(my + row * kTilePitch + wq);
+        const uint4 v = *src;
+        *src = make_uint4(0u, 0u, 0u, 0u);
+        if (rb + row < n_rows && w0 + wq < ld_words)
+          *reinterpret_cast<uint4*>(bits + (rb + row) * ld_words + w0 + wq) = v;
+      }
+    } else {
+      for (int row = 0; row < 32; ++row) {
+        const uint32_t v = my[row * kTilePitch + lane];
+        my[row * kTilePitch + lane] = 0u;
+        if (rb + row < n_rows && w0 + lane < ld_words) bits[(rb + row) * ld_words + w0 + lane] = v;
+      }
     }
-  }
-
-  const int lane = threadIdx.x & 31;
-  for (int rr = 0; rr < kRows; ++rr) {
-    const int64_t r = r0 + rr;
-    if (r >= n_rows) break;                      // uniform across the CTA
-    const int32_t key = s_row[rr];
-    uint32_t word = 0u;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      bool eq = (ck[k] == key);
-      if (kTwoKeys) eq = eq && (ck2[k] == s_row2[rr]);
-      word |= eq ? (1u << k) : 0u;
-    }
-    word &= valid;
-    if (clear_diag) {
-      const int64_t dc = r + diag_offset - c0;   // bit position of the diagonal in this word
-      if (dc >= 0 && dc < 32) word &= ~(1u << (int)dc);
-    }
-    if (in_row) bits[r * ld_words + w] = word;
-    int pc = __popc(word);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
-    if (lane == 0 && pc != 0) atomicAdd(counts + r, pc);
+    __syncwarp();
   }
 }
 
@@ -94,24 +114,25 @@ posmask_kernel(const int32_t* __restrict__ ids_row, const int32_t* __restrict__ 
 extern "C" int evk_posmask_build(const int32_t* ids_row, const int32_t* ids2_row, int64_t n_rows,
                                  const int32_t* ids_col, const int32_t* ids2_col, int64_t n_cols,
                                  int64_t diag_offset, int clear_diag, uint32_t* bits, int64_t ld_words,
-                                 int32_t* counts, evk_stream_t stream) {
+                                 int32_t* counts, int32_t* pos_idx, int pos_slots, evk_stream_t stream) {
   EVK_REQUIRE(ids_row && ids_col && bits && counts, "evk_posmask_build: null pointer");
   EVK_REQUIRE((ids2_row == nullptr) == (ids2_col == nullptr), "evk_posmask_build: ids2_row/ids2_col must both be set or both null");
   EVK_REQUIRE(n_rows >= 0 && n_cols >= 0, "evk_posmask_build: negative size");
   EVK_REQUIRE(ld_words >= (n_cols + 31) / 32, "evk_posmask_build: ld_words=%lld < ceil(n_cols/32)", (long long)ld_words);
-  EVK_REQUIRE(evk_aligned16(ids_col) && (!ids2_col || evk_aligned16(ids2_col)), "evk_posmask_build: column ids must be 16-byte aligned");
+  EVK_REQUIRE(!pos_idx || (pos_slots >= 1 && pos_slots <= 64), "evk_posmask_build: pos_slots must be in 1..64");
   if (n_rows == 0) return EVK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   EVK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_rows, s));
   if (ld_words == 0) return EVK_OK;
-  const dim3 grid((unsigned)((ld_words + kThreads - 1) / kThreads), (unsigned)((n_rows + kRows - 1) / kRows));
+  const dim3 grid((unsigned)((ld_words * 32 + kColsPerCta - 1) / kColsPerCta), (unsigned)((n_rows + kRowsPerCta - 1) / kRowsPerCta));
   EVK_REQUIRE(grid.y <= 65535u, "evk_posmask_build: n_rows=%lld too large for one launch", (long long)n_rows);
+  const int vec_ok = (ld_words % 4 == 0 && evk_aligned16(bits)) ? 1 : 0;
   if (ids2_row)
     posmask_kernel<true><<<grid, kThreads, 0, s>>>(ids_row, ids2_row, n_rows, ids_col, ids2_col, n_cols, diag_offset,
-                                                   clear_diag, bits, ld_words, counts);
+                                                   clear_diag, bits, ld_words, counts, vec_ok, pos_idx, pos_slots);
   else
     posmask_kernel<false><<<grid, kThreads, 0, s>>>(ids_row, ids2_row, n_rows, ids_col, ids2_col, n_cols, diag_offset,
-                                                    clear_diag, bits, ld_words, counts);
+                                                    clear_diag, bits, ld_words, counts, vec_ok, pos_idx, pos_slots);
   EVK_CHECK_LAUNCH("posmask");
   return EVK_OK;
 }

@@ -92,6 +92,76 @@ peer_bcast_kernel(const uint4* __restrict__ src, int64_t n_vec, PeerDst dst, int
   }
 }
 
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Cross-GPU barrier over a symmetric flag area: flags[r] on every rank is written by rank r only.
+// Thread t signals peer t (release at system scope, after a system fence that publishes this GPU's
+// earlier peer writes) and then waits for peer t's signal in its own flag area.  The epoch lives in
+// device memory and is advanced by the kernel itself, so the launch can sit in a replayed CUDA graph.
+// A peer that never arrives does not hang the GPU: after timeout_ns the kernel raises *error and returns.
+struct PeerFlags {
+  uint32_t* flags[kMaxPeers];      // flags[t] = base of rank t's flag area (kMaxPeers uint32 slots)
+  int n, rank;
+};
+
+__global__ void __launch_bounds__(32)
+peer_barrier_kernel(PeerFlags pf, uint32_t* __restrict__ epoch, int* __restrict__ error, uint64_t timeout_ns) {
+  const int t = threadIdx.x;
+  const uint32_t e = *epoch + 1u;
+  __syncwarp();
+  if (t < pf.n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.flags[t] + pf.rank), "r"(e) : "memory");
+    const uint32_t* mine = pf.flags[pf.rank] + t;
+    const uint64_t t0 = global_timer_ns();
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int32_t)(v - e) >= 0) break;
+      if (global_timer_ns() - t0 > timeout_ns) {
+        atomicExch(error, 1);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncwarp();
+  if (t == 0) *epoch = e;
+}
+
+// Closes the sharded forward once every rank's statistics slot has landed (slot r = rank r's partial
+// column exp-sums over its rows [n_cols floats] followed by its row-side loss term [1 float]):
+//   b_col[j] = 1 / sum_r slot_r[j]        loss = sum_r slot_r[n_cols] + inv_count * sum_j (shift + ln C_j)
+// Fixed summation order (slots in rank order, fp64 accumulation of the loss): every rank gets the same bits.
+constexpr int kFinishThreads = 1024;
+__global__ void __launch_bounds__(kFinishThreads)
+shard_finish_kernel(const float* __restrict__ slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
+                    double inv_count, float* __restrict__ b_col, float* __restrict__ loss_out) {
+  __shared__ double s_part[kFinishThreads / 32];
+  double acc = 0.0;
+  for (int64_t j = threadIdx.x; j < n_cols; j += kFinishThreads) {
+    float c = 0.f;
+    for (int r = 0; r < n_slots; ++r) c += slots[r * ld_slot + j];
+    b_col[j] = 1.f / c;
+    acc += (double)shift + (double)logf(c);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kFinishThreads / 32; ++w) t += s_part[w];
+    t *= inv_count;
+    for (int r = 0; r < n_slots; ++r) t += (double)slots[r * ld_slot + n_cols];
+    loss_out[0] = (float)t;
+  }
+}
+
 int fill_dst(PeerDst& dst, int n_dst, const uint64_t* hi, const uint64_t* lo) {
   EVK_REQUIRE(n_dst >= 1 && n_dst <= kMaxPeers && hi, "peer destinations: need 1..%d base pointers", kMaxPeers);
   memset(&dst, 0, sizeof(dst));
@@ -147,5 +217,72 @@ extern "C" int evk_peer_bcast(const void* src, int64_t bytes, int n_dst, const u
   peer_bcast_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(src), n_vec, d, dst_offset_bytes / 16);
   EVK_CHECK_LAUNCH("peer_bcast");
+  return EVK_OK;
+}
+
+// ---- symmetric buffers: allocation and CUDA-IPC exchange ------------------------------------------
+extern "C" int evk_peer_alloc(int64_t bytes, void** ptr_out) {
+  EVK_REQUIRE(bytes > 0 && ptr_out, "evk_peer_alloc: bad arguments");
+  void* p = nullptr;
+  EVK_CUDA(cudaMalloc(&p, (size_t)bytes));
+  EVK_CUDA(cudaMemset(p, 0, (size_t)bytes));
+  *ptr_out = p;
+  return EVK_OK;
+}
+
+extern "C" int evk_peer_free(void* ptr) {
+  if (ptr) EVK_CUDA(cudaFree(ptr));
+  return EVK_OK;
+}
+
+extern "C" int evk_peer_export(const void* ptr, void* handle_out) {
+  EVK_REQUIRE(ptr && handle_out, "evk_peer_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  cudaIpcMemHandle_t h;
+  EVK_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+  memcpy(handle_out, &h, sizeof(h));
+  return EVK_OK;
+}
+
+extern "C" int evk_peer_open(const void* handle, void** ptr_out) {
+  EVK_REQUIRE(handle && ptr_out, "evk_peer_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  EVK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr_out = p;
+  return EVK_OK;
+}
+
+extern "C" int evk_peer_close(void* ptr) {
+  if (ptr) EVK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return EVK_OK;
+}
+
+extern "C" int evk_peer_barrier(const uint64_t* flag_ptrs, int n_ranks, int rank, uint32_t* epoch, int* error,
+                                int64_t timeout_ms, evk_stream_t stream) {
+  EVK_REQUIRE(flag_ptrs && epoch && error && n_ranks >= 1 && n_ranks <= kMaxPeers && rank >= 0 && rank < n_ranks,
+              "evk_peer_barrier: bad arguments (1..%d ranks)", kMaxPeers);
+  PeerFlags pf;
+  memset(&pf, 0, sizeof(pf));
+  pf.n = n_ranks;
+  pf.rank = rank;
+  for (int t = 0; t < n_ranks; ++t) {
+    pf.flags[t] = reinterpret_cast<uint32_t*>(flag_ptrs[t]);
+    EVK_REQUIRE(pf.flags[t], "evk_peer_barrier: null flag area");
+  }
+  const uint64_t timeout_ns = (uint64_t)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
+  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, epoch, error, timeout_ns);
+  EVK_CHECK_LAUNCH("peer_barrier");
+  return EVK_OK;
+}
+
+extern "C" int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
+                                     double inv_count, float* b_col, float* loss_out, evk_stream_t stream) {
+  EVK_REQUIRE(slots && b_col && loss_out && n_slots >= 1 && n_cols > 0 && ld_slot > n_cols,
+              "evk_mpce_shard_finish: bad arguments (ld_slot must exceed n_cols: the loss term follows the column sums)");
+  shard_finish_kernel<<<1, kFinishThreads, 0, static_cast<cudaStream_t>(stream)>>>(slots, n_slots, ld_slot, n_cols, shift,
+                                                                                 inv_count, b_col, loss_out);
+  EVK_CHECK_LAUNCH("shard_finish");
   return EVK_OK;
 }

@@ -75,7 +75,59 @@ pos_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __restri
   }
 }
 
+// raw dot products of the listed positives: pos_dot[i, s] = q_i . k_{pos_idx[i, s]} over the bf16 operands the
+// tensor cores see, fp32 accumulate.  One warp per row, the query row stays in registers (kQVec 128-bit words
+// per lane).  Runs on a side stream next to K3; the backward turns the values into exact W entries.
+template <int kQVec>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+pos_logits_kernel(const __nv_bfloat16* __restrict__ q_hi, int64_t ld_q, const __nv_bfloat16* __restrict__ k_hi,
+                  int64_t ld_k, int64_t n_rows, int d_vec, const int32_t* __restrict__ pos_idx,
+                  const int32_t* __restrict__ counts, int pos_slots, float* __restrict__ pos_dot) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (i >= n_rows) return;
+  const int c = min(__ldg(counts + i), pos_slots);
+  if (c <= 0) return;
+  const int32_t myj = lane < c ? __ldg(pos_idx + i * pos_slots + lane) : 0;
+  const uint4* qa = reinterpret_cast<const uint4*>(q_hi + i * ld_q);
+  uint4 qv[kQVec];
+#pragma unroll
+  for (int t = 0; t < kQVec; ++t) qv[t] = (lane + 32 * t < d_vec) ? __ldg(qa + lane + 32 * t) : make_uint4(0u, 0u, 0u, 0u);
+  for (int s = 0; s < c; ++s) {
+    const int64_t j = __shfl_sync(0xffffffffu, myj, s);
+    const uint4* kb = reinterpret_cast<const uint4*>(k_hi + j * ld_k);
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < kQVec; ++t)
+      if (lane + 32 * t < d_vec) acc += dot8_bf16(qv[t], __ldg(kb + lane + 32 * t));
+    acc = warp_sum(acc);
+    if (lane == 0) pos_dot[i * pos_slots + s] = acc;
+  }
+}
+
 }  // namespace
+
+extern "C" int evk_mpce_pos_logits(const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k, int64_t n_rows,
+                                   int64_t d, const int32_t* pos_idx, const int32_t* counts, int pos_slots,
+                                   float* pos_dot, evk_stream_t stream) {
+  EVK_REQUIRE(q_hi && k_hi && pos_idx && counts && pos_dot, "evk_mpce_pos_logits: null pointer");
+  EVK_REQUIRE(n_rows > 0 && d > 0 && d <= 4096 && pos_slots >= 1 && pos_slots <= 32, "evk_mpce_pos_logits: bad shape (d <= 4096, 1..32 slots)");
+  EVK_REQUIRE(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_q >= d && ld_k >= d && evk_aligned16(q_hi) && evk_aligned16(k_hi),
+              "evk_mpce_pos_logits: operands need 16-byte aligned rows (ld %% 8 == 0)");
+  const int64_t blocks = (n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int d_vec = (int)((d + 7) / 8);
+  auto* qp = static_cast<const __nv_bfloat16*>(q_hi);
+  auto* kp = static_cast<const __nv_bfloat16*>(k_hi);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d_vec <= 128)
+    pos_logits_kernel<4><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, s>>>(qp, ld_q, kp, ld_k, n_rows, d_vec, pos_idx, counts,
+                                                                        pos_slots, pos_dot);
+  else
+    pos_logits_kernel<16><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, s>>>(qp, ld_q, kp, ld_k, n_rows, d_vec, pos_idx, counts,
+                                                                         pos_slots, pos_dot);
+  EVK_CHECK_LAUNCH("mpce_pos_logits");
+  return EVK_OK;
+}
 
 extern "C" int evk_mpce_pos(const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi, const void* k_lo,
                             int64_t ld_k, int64_t n_rows, int64_t n_cols, int64_t d, const uint32_t* bits,

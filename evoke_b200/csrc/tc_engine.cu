@@ -37,7 +37,7 @@ constexpr int kTmemCols = 512;
 constexpr int kMaxSegs = 3;
 constexpr int kRowParts = kEpiWarps / 4;      // row-statistic partials written per 256-column tile
 
-enum { EPI_FWD = 0, EPI_BWD_W = 1, EPI_GEMM = 2 };
+enum { EPI_FWD = 0, EPI_BWD_W = 1, EPI_GEMM = 2, EPI_FWD_E = 3 };   // EPI_FWD_E: K3 that also stores E as bf16
 
 // B bytes per stage held by ONE CTA: the whole 256-column tile, or half of it in CTA-pair mode
 template <bool CTA2> constexpr int b_bytes() { return (CTA2 ? BN / 2 : BN) * BK * 2; }
@@ -60,6 +60,9 @@ struct alignas(64) TcParams {
   const int32_t* counts; const float* a_row; const float* b_col;
   // EPI_GEMM
   float* out; int64_t ld_out; float alpha;
+  // EPI_GEMM, reduce-scatter fused into the epilogue: output row i belongs to rank i / rows_per_owner and
+  // is accumulated (red.add over NVLink) into that rank's buffer at row i % rows_per_owner
+  float* out_peer[16]; int64_t rows_per_owner;
   // descriptor bases (see tc_ptx.cuh), filled by the host so the probe can try variants
   uint64_t desc_a, desc_b;
   uint32_t idesc;
@@ -69,12 +72,55 @@ struct alignas(64) TcParams {
 
 template <int EPI>
 constexpr int epi_smem_bytes() {
-  return EPI == EPI_FWD ? 4 * BN * 4 : (EPI == EPI_BWD_W ? kEpiWarps * 8192 : 0);
+  return EPI == EPI_FWD ? 4 * BN * 4
+         : (EPI == EPI_BWD_W ? kEpiWarps * 8192 : (EPI == EPI_FWD_E ? 4 * BN * 4 + kEpiWarps * 8192 : 0));
 }
 template <int EPI, int STAGES, bool CTA2>
 constexpr int smem_bytes_total() {
   return 1024 /*align slack*/ + STAGES * stage_bytes<CTA2>() + epi_smem_bytes<EPI>() + (2 * STAGES + 4) * 8 + 16;
 }
+
+// Work decomposition, identical in the three warp roles.
+//  splits >= 1: units = (tile, split) pairs dealt round-robin to the groups (CTAs or CTA pairs); tiles are
+//               numbered row-block-major (nb fastest).  Used by K3 / K4a (splits = 1) and as a fallback.
+//  splits == 0: stream-K for the gradient contractions.  The tiles' k-blocks form one sequence of
+//               tiles * total_kb items, cut into one contiguous, equally long range per group: every group
+//               does the same number of MMAs (no wave quantisation) and the fp32 red.add epilogue runs once
+//               per tile plus once per range boundary, instead of `splits` times per tile.  Tiles are
+//               numbered column-block-major (mb fastest) so that the groups working on the same rows of W
+//               at the same time are the ones with different nb: the strip is read from HBM once.
+struct Sched {
+  int splits, total_kb, m_tiles, n_tiles, num_groups, u, total_units;
+  int64_t pos, end;
+  __device__ __forceinline__ void init(int splits_, int total_kb_, int m_tiles_, int n_tiles_, int group_id,
+                                       int num_groups_) {
+    splits = splits_; total_kb = total_kb_; m_tiles = m_tiles_; n_tiles = n_tiles_; num_groups = num_groups_;
+    u = group_id;
+    total_units = m_tiles * n_tiles * (splits > 0 ? splits : 1);
+    const int64_t items = (int64_t)m_tiles * n_tiles * total_kb;
+    pos = (items * group_id) / num_groups;
+    end = (items * (group_id + 1)) / num_groups;
+  }
+  __device__ __forceinline__ bool next(int& mb, int& nb, int& kb0, int& kb1) {
+    if (splits > 0) {
+      if (u >= total_units) return false;
+      const int tile = u / splits, sp = u - tile * splits;
+      mb = tile / n_tiles; nb = tile - mb * n_tiles;
+      kb0 = (int)(((int64_t)sp * total_kb) / splits);
+      kb1 = (int)(((int64_t)(sp + 1) * total_kb) / splits);
+      u += num_groups;
+      return true;
+    }
+    if (pos >= end) return false;
+    const int tile = (int)(pos / total_kb);
+    nb = tile / m_tiles; mb = tile - nb * m_tiles;
+    kb0 = (int)(pos - (int64_t)tile * total_kb);
+    const int64_t left = end - pos;
+    kb1 = (left < (int64_t)(total_kb - kb0)) ? kb0 + (int)left : total_kb;
+    pos += kb1 - kb0;
+    return true;
+  }
+};
 
 // lane l ends with the sum over the warp's 32 lanes of x[l] (x is destroyed)
 __device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
@@ -97,7 +143,8 @@ __device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
 // commits are multicast to the barriers of both CTAs.  Each CTA's TMEM holds the accumulator of
 // its own 128 rows x 256 columns, so the epilogue is the same code in both modes.
 template <int EPI, bool A_MN, bool B_MN, int STAGES, bool CTA2>
-__global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
+// (the contraction kernels are capped at 128 registers - bound 512 threads - so that K4t CTAs fit beside them)
+__global__ void __launch_bounds__(EPI == EPI_GEMM ? 512 : kThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int kStage = stage_bytes<CTA2>();
   constexpr int kBRows = CTA2 ? BN / 2 : BN;          // B rows (tile columns) loaded by this CTA
   extern __shared__ uint8_t smem_raw[];
@@ -145,20 +192,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot_gen;
 
   const int total_kb = p.num_segs * p.kb_per_seg;
-  const int total_units = p.m_tiles * p.n_tiles * p.splits;
+  Sched sched;
+  sched.init(p.splits, total_kb, p.m_tiles, p.n_tiles, group_id, num_groups);
+  int mb, nb, kb0, kb1;
 
   if (warp == kProducerWarp) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = group_id; u < total_units; u += num_groups) {
-        const int tile = u / p.splits, sp = u - tile * p.splits;
-        const int mb = tile / p.n_tiles, nb = tile - mb * p.n_tiles;
+      while (sched.next(mb, nb, kb0, kb1)) {
         const int m0 = mb * (CTA2 ? 2 * BM : BM) + (int)cta_rank * BM;
         const int n0 = nb * BN + (int)cta_rank * kBRows * (CTA2 ? 1 : 0);
-        const int kb0 = (int)(((int64_t)sp * total_kb) / p.splits);
-        const int kb1 = (int)(((int64_t)(sp + 1) * total_kb) / p.splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           const int seg = kb / p.kb_per_seg, kk = (kb - seg * p.kb_per_seg) * BK;
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -195,10 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
       const uint64_t a_desc0 = umma_smem_desc(p.desc_a, smem_base);
       const uint64_t b_desc0 = umma_smem_desc(p.desc_b, smem_base + kABytes);
       const uint32_t idesc = p.idesc;
-      for (int u = group_id; u < total_units; u += num_groups, ++lu) {
-        const int tile = u / p.splits, sp = u - tile * p.splits;
-        const int kb0 = (int)(((int64_t)sp * total_kb) / p.splits);
-        const int kb1 = (int)(((int64_t)(sp + 1) * total_kb) / p.splits);
+      for (; sched.next(mb, nb, kb0, kb1); ++lu) {
         const int as = lu & 1;
         const uint32_t aphase = (lu >> 1) & 1;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -245,9 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
       }
     };
     int lu = 0;
-    for (int u = group_id; u < total_units; u += num_groups, ++lu) {
-      const int tile = u / p.splits;
-      const int mb = tile / p.n_tiles, nb = tile - mb * p.n_tiles;
+    for (; sched.next(mb, nb, kb0, kb1); ++lu) {
       const int m0 = mb * (CTA2 ? 2 * BM : BM) + (int)cta_rank * BM;
       const int n0 = nb * BN;
       const int as = lu & 1;
@@ -256,13 +296,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
       const bool row_ok = i < p.n_rows;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 
-      if (EPI == EPI_FWD) {
+      if (EPI == EPI_FWD || EPI == EPI_FWD_E) {
+        constexpr bool kStoreE = EPI == EPI_FWD_E;
         float* colpart = reinterpret_cast<float*>(epi_gen);       // [4][BN]
+        // EPI_FWD_E: this warp's private staging for its 32 rows x 128 columns of E (bf16), two
+        // 128B-swizzled [32 x 64] boxes, stored with its own TMA stores (as in EPI_BWD_W)
+        const uint32_t wstg = epi_base + 4 * BN * 4 + warp * 8192;
         const bool want_col = (p.flags & EVK_FLAG_NO_COLSUM) == 0;
         const bool want_pos = (p.flags & EVK_FLAG_NO_POS) == 0;   // else evk_mpce_pos supplies the positive sums
         const uint32_t* mrow = want_pos ? p.bits + (row_ok ? i : 0) * p.ld_words + (n0 >> 5) : nullptr;
         const int64_t dcol = i + p.diag_offset - n0;              // diagonal column inside this tile?
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f, rp = 0.f;
+        if (kStoreE) {
+          if (lane == 0) tma_store_wait_read<0>();                // this warp's previous stores have left smem
+          __syncwarp();
+        }
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
 #pragma unroll 1
@@ -300,12 +348,36 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
           for (int k = 0; k < 32; k += 4) {
             rs0 += v[k]; rs1 += v[k + 1]; rs2 += v[k + 2]; rs3 += v[k + 3];
           }
+          if (kStoreE) {                                          // E -> bf16 -> swizzled staging (dead entries are 0)
+            const uint32_t row_st = wstg + (cc >> 1) * 4096 + lane * 128;
+            const int u0 = (cc & 1) * 4;
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+              const uint32_t h0 = pack_bf16x2(v[8 * uu + 0], v[8 * uu + 1]);
+              const uint32_t h1 = pack_bf16x2(v[8 * uu + 2], v[8 * uu + 3]);
+              const uint32_t h2 = pack_bf16x2(v[8 * uu + 4], v[8 * uu + 5]);
+              const uint32_t h3 = pack_bf16x2(v[8 * uu + 6], v[8 * uu + 7]);
+              const uint32_t off = static_cast<uint32_t>(((u0 + uu) ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_st + off), "r"(h0), "r"(h1), "r"(h2),
+                           "r"(h3) : "memory");
+            }
+          }
           if (want_col) {
             const float cs = warp_transpose_sum(v, lane);
             colpart[q * BN + c * 32 + lane] = cs;
           }
         }
         release_tmem(as);                                         // TMEM stage drained
+        if (kStoreE) {
+          fence_proxy_async_smem();                               // generic-proxy writes -> async proxy
+          __syncwarp();
+          if (lane == 0) {
+            const int cx = n0 + c_lo * 32, m_warp = m0 + q * 32;  // OOB rows / columns are clipped by the map
+            tma_store_2d(&p.out_map[0], wstg, cx, m_warp, p.policy_out);
+            tma_store_2d(&p.out_map[0], wstg + 4096, cx + 64, m_warp, p.policy_out);
+            tma_store_commit();
+          }
+        }
         if (row_ok) {
           const int64_t po = ((int64_t)nb * kRowParts + hh) * p.ld_rowpart + i;
           p.row_sum_part[po] = (rs0 + rs1) + (rs2 + rs3);
@@ -420,7 +492,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
           }
         }
       } else {  // EPI_GEMM
-        float* orow = p.out + i * p.ld_out + n0;
+        float* orow;
+        if (p.rows_per_owner > 0) {
+          const int64_t owner = i / p.rows_per_owner;
+          orow = p.out_peer[row_ok ? owner : 0] + (i - owner * p.rows_per_owner) * p.ld_out + n0;
+        } else {
+          orow = p.out + i * p.ld_out + n0;
+        }
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
 #pragma unroll 1
@@ -431,7 +509,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
           tmem_ld_wait(v);
           const int cbase = n0 + c * 32;
           if (row_ok && !(p.flags & 0x100)) {
-            if (cbase + 32 <= p.n_cols) {
+            if (p.flags & 0x200) {                               // whole-K units: plain (posted) stores, no accumulation
+              if (cbase + 32 <= p.n_cols) {
+#pragma unroll
+                for (int k = 0; k < 32; k += 4)
+                  *reinterpret_cast<float4*>(orow + c * 32 + k) =
+                      make_float4(p.alpha * v[k], p.alpha * v[k + 1], p.alpha * v[k + 2], p.alpha * v[k + 3]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                  if (cbase + k < p.n_cols) orow[c * 32 + k] = p.alpha * v[k];
+              }
+            } else if (cbase + 32 <= p.n_cols) {
 #pragma unroll
               for (int k = 0; k < 32; k += 4)
                 red_add_v4(orow + c * 32 + k, p.alpha * v[k], p.alpha * v[k + 1], p.alpha * v[k + 2], p.alpha * v[k + 3]);
@@ -445,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
         release_tmem(as);
       }
     }
-    if (EPI == EPI_BWD_W && lane == 0) tma_store_wait_all<0>();   // smem must outlive each warp's bulk stores
+    if ((EPI == EPI_BWD_W || EPI == EPI_FWD_E) && lane == 0) tma_store_wait_all<0>();   // smem must outlive each warp's bulk stores
   }
 
   tc_fence_before();
@@ -513,6 +602,18 @@ bool use_cta_pairs() {
   return v != 0;
 }
 
+bool use_stream_k() {
+  // EVK_STREAMK=1 selects the stream-K work decomposition of the gradient contractions.  Measured on B200 at
+  // the bench shape it is 5% SLOWER than tile x split-K units (322 vs 305 us per contraction: the split-K
+  // units of one row block run concurrently on different SMs and share the W rows through L2), so it is off.
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EVK_STREAMK");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
 void fill_descs(TcParams& p, bool a_mn, bool b_mn, int variant, bool cta2) {
   // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused.  MN-major SW128: 64-element MN
   // atoms 8192 B apart (LBO, one TMA box each), 8-row K groups 1024 B apart (SBO).
@@ -533,8 +634,10 @@ int launch(const TcParams& p, cudaStream_t s) {
     EVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int units = p.m_tiles * p.n_tiles * p.splits;
   const int sms = evk_sm_count();
+  // stream-K (splits == 0): every group gets a range; a range should hold at least a few k-blocks
+  const int64_t items = (int64_t)p.m_tiles * p.n_tiles * p.num_segs * p.kb_per_seg;
+  const int units = p.splits > 0 ? p.m_tiles * p.n_tiles * p.splits : (int)(items / 4 < sms ? (items / 4 > 0 ? items / 4 : 1) : sms);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
@@ -619,11 +722,12 @@ int setup_sim_operands(TcParams& p, const void* q_hi, const void* q_lo, int64_t 
 
 }  // namespace
 
-extern "C" int evk_mpce_fwd(const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi, const void* k_lo,
-                            int64_t ld_k, int64_t n_rows, int64_t n_cols, int64_t d, const uint32_t* bits,
-                            int64_t ld_words, float inv_tau, int flags, int64_t diag_offset, float* row_sum_part,
-                            float* row_pos_part, int64_t ld_rowpart, float* col_sum_part, int64_t ld_colpart,
-                            evk_stream_t stream) {
+namespace {
+int mpce_fwd_impl(const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi, const void* k_lo,
+                  int64_t ld_k, int64_t n_rows, int64_t n_cols, int64_t d, const uint32_t* bits,
+                  int64_t ld_words, float inv_tau, int flags, int64_t diag_offset, float* row_sum_part,
+                  float* row_pos_part, int64_t ld_rowpart, float* col_sum_part, int64_t ld_colpart,
+                  void* e_out, int64_t ld_e, evk_stream_t stream) {
   int rc = check_device();
   if (rc != EVK_OK) return rc;
   const bool cta2 = use_cta_pairs();
@@ -649,7 +753,34 @@ extern "C" int evk_mpce_fwd(const void* q_hi, const void* q_lo, int64_t ld_q, co
   p.col_sum_part = col_sum_part;
   p.ld_colpart = ld_colpart;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (e_out) {
+    EVK_REQUIRE((flags & EVK_FLAG_SPLIT_BF16) == 0, "evk_mpce_fwd_store: the E strip is a bf16-mode feature (no split operands)");
+    EVK_REQUIRE(ld_e >= n_cols && ld_e % 8 == 0, "evk_mpce_fwd_store: ld_e=%lld must be >= n_cols and a multiple of 8", (long long)ld_e);
+    rc = make_map_bf16(&p.out_map[0], e_out, n_rows, n_cols, ld_e, 32, 64);
+    if (rc != EVK_OK) return rc;
+    return cta2 ? launch<EPI_FWD_E, false, false, 4, true>(p, s) : launch<EPI_FWD_E, false, false, 3, false>(p, s);
+  }
   return cta2 ? launch<EPI_FWD, false, false, 6, true>(p, s) : launch<EPI_FWD, false, false, 4, false>(p, s);
+}
+}  // namespace
+
+extern "C" int evk_mpce_fwd(const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi, const void* k_lo,
+                            int64_t ld_k, int64_t n_rows, int64_t n_cols, int64_t d, const uint32_t* bits,
+                            int64_t ld_words, float inv_tau, int flags, int64_t diag_offset, float* row_sum_part,
+                            float* row_pos_part, int64_t ld_rowpart, float* col_sum_part, int64_t ld_colpart,
+                            evk_stream_t stream) {
+  return mpce_fwd_impl(q_hi, q_lo, ld_q, k_hi, k_lo, ld_k, n_rows, n_cols, d, bits, ld_words, inv_tau, flags, diag_offset,
+                       row_sum_part, row_pos_part, ld_rowpart, col_sum_part, ld_colpart, nullptr, 0, stream);
+}
+
+extern "C" int evk_mpce_fwd_store(const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k, int64_t n_rows,
+                                  int64_t n_cols, int64_t d, const uint32_t* bits, int64_t ld_words, float inv_tau,
+                                  int flags, int64_t diag_offset, float* row_sum_part, float* row_pos_part,
+                                  int64_t ld_rowpart, float* col_sum_part, int64_t ld_colpart, void* e_out, int64_t ld_e,
+                                  evk_stream_t stream) {
+  EVK_REQUIRE(e_out && evk_aligned16(e_out), "evk_mpce_fwd_store: e_out must be a 16-byte aligned device pointer");
+  return mpce_fwd_impl(q_hi, nullptr, ld_q, k_hi, nullptr, ld_k, n_rows, n_cols, d, bits, ld_words, inv_tau, flags,
+                       diag_offset, row_sum_part, row_pos_part, ld_rowpart, col_sum_part, ld_colpart, e_out, ld_e, stream);
 }
 
 extern "C" int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi, const void* k_lo,
@@ -692,6 +823,7 @@ namespace {
 int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, const void* const* b_ptrs,
                 int64_t ldb, bool b_mn, int nsegs, int64_t m, int64_t n, int64_t k, float alpha, float* out,
                 int64_t ld_out, int variant, int force_splits, bool cta2, cudaStream_t s) {
+  if (p.rows_per_owner > 0) out = p.out_peer[0];
   EVK_REQUIRE(m > 0 && n > 0 && k > 0 && out, "gemm: empty problem or null output");
   EVK_REQUIRE(m < (1ll << 30) && n < (1ll << 30) && k < (1ll << 30), "gemm: problem too large");
   EVK_REQUIRE(ld_out >= n && ld_out % 4 == 0 && evk_aligned16(out), "gemm: out needs 16-byte alignment and ld_out %% 4 == 0");
@@ -710,7 +842,8 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
   p.n_cols = n;
   const int total_kb = p.num_segs * p.kb_per_seg;
   const int groups = cta2 ? evk_sm_count() / 2 : evk_sm_count();
-  p.splits = force_splits > 0 ? force_splits : choose_splits(p.m_tiles * p.n_tiles, total_kb, groups);
+  p.splits = force_splits > 0 ? force_splits : (use_stream_k() ? 0 : choose_splits(p.m_tiles * p.n_tiles, total_kb, groups));
+  if (p.flags & 0x200) p.splits = 1;      // store epilogue: every output element is written by exactly one unit
   if (p.splits > total_kb) p.splits = total_kb;
   p.out = out;
   p.ld_out = ld_out;
@@ -752,6 +885,33 @@ extern "C" int evk_mpce_bwd_gemm(const void* w_hi, const void* w_lo, int64_t ld_
   const int64_t m = transpose_w ? n_cols : n_rows;
   const int64_t k = transpose_w ? n_rows : n_cols;
   return gemm_common(p, a_ptrs, ld_w, transpose_w != 0, b_ptrs, ld_x, true, split ? 3 : 1, m, d, k, alpha, out, ld_out,
+                     0, 0, use_cta_pairs(), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int64_t ld_w, int64_t n_rows, int64_t n_cols,
+                                         const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d, float alpha,
+                                         int flags, const uint64_t* out_ptrs, int n_owners, int64_t rows_per_owner,
+                                         int64_t ld_out, int store, evk_stream_t stream) {
+  int rc = check_device();
+  if (rc != EVK_OK) return rc;
+  const bool split = (flags & EVK_FLAG_SPLIT_BF16) != 0;
+  EVK_REQUIRE(w_hi && x_hi && (!split || (w_lo && x_lo)) && out_ptrs, "evk_mpce_bwd_gemm_scatter: null operand");
+  EVK_REQUIRE(n_owners >= 1 && n_owners <= 16 && rows_per_owner > 0 && rows_per_owner % 128 == 0 &&
+                  (int64_t)n_owners * rows_per_owner >= n_cols,
+              "evk_mpce_bwd_gemm_scatter: need 1..16 owners of rows_per_owner %% 128 == 0 rows covering all %lld columns",
+              (long long)n_cols);
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  for (int r = 0; r < n_owners; ++r) {
+    p.out_peer[r] = reinterpret_cast<float*>(out_ptrs[r]);
+    EVK_REQUIRE(p.out_peer[r] && evk_aligned16(p.out_peer[r]), "evk_mpce_bwd_gemm_scatter: owner buffers must be 16-byte aligned");
+  }
+  p.rows_per_owner = rows_per_owner;
+  if (store) p.flags |= 0x200;
+  const void* a_ptrs[3] = {w_hi, w_hi, w_lo};
+  const void* b_ptrs[3] = {x_hi, x_lo, x_hi};
+  // dKhat partial of this rank's rows: A = W^T (MN-major), K = n_rows; out rows = the n_cols keys
+  return gemm_common(p, a_ptrs, ld_w, true, b_ptrs, ld_x, true, split ? 3 : 1, n_cols, d, n_rows, alpha, nullptr, ld_out,
                      0, 0, use_cta_pairs(), static_cast<cudaStream_t>(stream));
 }
 

@@ -146,6 +146,100 @@ class _ShardedG(torch.autograd.Function):
         return None, None, None, None, None, None, d_image, d_text
 
 
+class _ShardedGPeer(torch.autograd.Function):
+    """Peer-memory form (bf16 mode): the three exchange steps are done by this library's own kernels over
+    NVLink - K1 stores the normalised key rows into every rank's buffer (all-gather), the statistics slots
+    are pushed the same way, and the key-side gradient contraction stores its tiles straight into the
+    owning rank's per-source buffer, which K1b sums (reduce-scatter fused into the GEMM epilogue).  Three flag barriers per step
+    order them; NCCL is not on the data path.  The forward keeps E as a bf16 strip (K3 store variant), so the
+    backward needs no second similarity sweep: 6 nND FLOP per rank."""
+
+    @staticmethod
+    def forward(ctx, ops, pc, inv_tau: float, row_ids: DeviceIds, image: torch.Tensor, text: torch.Tensor):
+        from . import _lib
+        world, rank = pc.world, pc.rank
+        n, n_total = pc.n_local, pc.n_total
+        lo_ = rank * n
+        stream = torch.cuda.current_stream().cuda_stream
+        dev = image.device
+        need_grad = any(ctx.needs_input_grad[4:])
+        # exchange 1: normalised keys and ids land in every rank's buffers
+        k_norm = torch.empty(n, dtype=torch.float32, device=dev)
+        _lib.call("evk_l2norm_fwd_bcast", text.data_ptr(), ops._dtype_code(text), n, pc.d, text.stride(0), text.stride(1),
+                  world, pc.table("khat"), None, pc.ld, lo_, k_norm.data_ptr(), stream)
+        _lib.call("evk_peer_bcast", row_ids.key.data_ptr(), n * 4, world, pc.table("ids"), lo_ * 4, stream)
+        if row_ids.key2 is not None:
+            _lib.call("evk_peer_bcast", row_ids.key2.data_ptr(), n * 4, world, pc.table("ids2"), lo_ * 4, stream)
+        qn = ops.l2norm_fwd(image, want_f32=False, want_hi=True, want_lo=False)
+        pc.barrier()
+        kn_all = ops.Normalized(n=n_total, d=pc.d, norm=None, hi=pc.khat, lo=None, ld=pc.ld)
+        kn_local = ops.Normalized(n=n, d=pc.d, norm=k_norm, hi=pc.khat[lo_:lo_ + n], lo=None, ld=pc.ld)
+        ids_all = DeviceIds(pc.ids, pc.ids2 if row_ids.key2 is not None else None)
+        pos = None
+        if need_grad:
+            bits, counts, pos_idx = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_, want_list=True)
+            pos = (pos_idx, ops.pos_logits(qn, kn_all, pos_idx, counts))
+            rs_part, rp_part, cs_part, e, ld_e = ops.tc_fwd_store(qn, kn_all, bits, inv_tau, 0, lo_)
+        else:
+            bits, counts = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_)
+            rs_part, rp_part, cs_part = ops.tc_fwd_partials(qn, kn_all, bits, inv_tau, 0, lo_)
+            e, ld_e = None, 0
+        # exchange 2: this rank's slot = partial column sums of its rows + its row-side loss term
+        stage = torch.empty(pc.ld_slot, dtype=torch.float32, device=dev)
+        ops.reduce_partials(cs_part, int(cs_part.shape[0]), n_total, out=stage[:n_total])
+        row_sum = ops.reduce_partials(rs_part, int(rs_part.shape[0]), n)
+        row_pos = ops.reduce_partials(rp_part, int(rp_part.shape[0]), n)
+        a_row = torch.empty(n, dtype=torch.float32, device=dev)
+        _lib.call("evk_mpce_finalize", row_sum.data_ptr(), row_pos.data_ptr(), counts.data_ptr(), n, None, 0, 0, 0,
+                  float(inv_tau), 2.0, 0.5 / n_total, a_row.data_ptr(), None, stage[n_total:].data_ptr(), stream)
+        _lib.call("evk_peer_bcast", stage.data_ptr(), pc.ld_slot * 4, world, pc.table("slots"), rank * pc.ld_slot * 4, stream)
+        pc.barrier()
+        b_col = torch.empty(n_total, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.call("evk_mpce_shard_finish", pc.slots.data_ptr(), world, pc.ld_slot, n_total, float(inv_tau), 0.5 / n_total,
+                  b_col.data_ptr(), loss.data_ptr(), stream)
+        ctx.ops, ctx.pc, ctx.inv_tau = ops, pc, inv_tau
+        ctx.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, e, ld_e)
+        ctx.pos = pos
+        ctx.save_for_backward(image, text)
+        out = loss.reshape(())
+        return out if image.dtype == torch.float32 else out.to(image.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        from . import _lib
+        ops, pc, inv_tau = ctx.ops, ctx.pc, ctx.inv_tau
+        qn, kn_local, kn_all, bits, counts, a_row, b_col, e, ld_e = ctx.sv
+        if e is None:
+            raise RuntimeError("evoke_b200: backward called twice on the sharded loss (the E strip was consumed)")
+        image, text = ctx.saved_tensors
+        n, n_total = pc.n_local, pc.n_total
+        g = grad_out.reshape(1).to(torch.float32).contiguous()
+        scale = 0.5 * inv_tau / n_total
+        stream = torch.cuda.current_stream().cuda_stream
+        ops.tc_w_from_e(e, ld_e, n_total, bits, counts, a_row, b_col, qn, kn_all, inv_tau, pos=ctx.pos)
+        # exchange 3, fused: the tiles of this rank's partial dKhat are stored straight into their owners'
+        # per-source buffers (posted NVLink stores from the GEMM epilogue; no split-K, no zero fill)
+        _lib.call("evk_mpce_bwd_gemm_scatter", e.data_ptr(), None, ld_e, n, n_total, qn.hi.data_ptr(), None, qn.ld, qn.d,
+                  1.0, 0, pc.table("dk_mine"), pc.world, n, pc.width, 1, stream)
+        dq = ops.tc_bwd_gemm(e, None, ld_e, n, n_total, False, kn_all, 0)
+        d_image = ops.l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale)
+        pc.barrier()                           # every rank's partial for these rows has landed
+        d_text = ops.l2norm_bwd(text, kn_local, pc.dk_parts[0], scale_dev=g, scale_host=scale,
+                                parts=(pc.world, n * pc.width))
+        ctx.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, None, 0)
+        return None, None, None, None, d_image, d_text
+
+
+def peer_eligible(image: torch.Tensor, text: torch.Tensor, precision: str, world: int) -> bool:
+    """Static conditions of the peer-memory path (identical on every rank for equal shapes/dtypes)."""
+    n, d = int(image.shape[0]), int(image.shape[1])
+    return (precision == "bf16" and image.is_cuda and world <= 16 and n % 128 == 0 and d % 8 == 0 and d <= 2048
+            and text.dtype == torch.float32 and text.stride(1) == 1 and text.stride(0) % 4 == 0
+            and text.data_ptr() % 16 == 0)
+
+
 def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local, temp: float, *,
                              group=None, precision: str = "bf16", mode: str = "auto", ops=None) -> torch.Tensor:
     """G loss of the GLOBAL batch from this rank's shard (same row count on every rank).
@@ -156,10 +250,12 @@ def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local,
     Returns the global loss (identical on every rank); .backward() yields d(global loss)/d(local
     shard), so a DDP-style gradient average over ranks must not be applied to it twice.
 
-    mode: "rs"  - partial dKhat for all N keys + reduce-scatter (8 nND FLOP per rank, N*D fp32 exchanged);
+    mode: "peer" - exchanges done by this library's kernels over peer-mapped memory (NVLink): K1 stores into every
+                  rank's key buffer, K4b's epilogue red.adds into the owner's dKhat (6 nND FLOP per rank); bf16 mode;
+          "rs"  - partial dKhat for all N keys + reduce-scatter (8 nND FLOP per rank, N*D fp32 exchanged);
           "sym" - queries are all-gathered as well and the key-side row block is recomputed locally
                   (10 nND FLOP per rank, no reduce-scatter, no N*D buffer);
-          "auto" - "sym" from 8 ranks up, where the N*D exchange dominates (measured: rs wins at 2-4, sym at 8).
+          "auto" - "peer" when its conditions hold and CUDA-IPC mapping works, else "sym" from 8 ranks up, where the N*D exchange dominates (measured: rs wins at 2-4, sym at 8).
     """
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
@@ -185,7 +281,19 @@ def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local,
     temp = float(temp)
     if not temp > 0:
         raise ValueError("temperature must be positive")
-    if mode not in ("auto", "rs", "sym"):
-        raise ValueError(f"mode must be 'auto', 'rs' or 'sym', got {mode!r}")
-    sym = mode == "sym" or (mode == "auto" and dist.get_world_size(group) >= 8)
+    if mode not in ("auto", "rs", "sym", "peer"):
+        raise ValueError(f"mode must be 'auto', 'rs', 'sym' or 'peer', got {mode!r}")
+    world = dist.get_world_size(group)
+    if mode in ("auto", "peer") and hasattr(ops, "tc_fwd_store"):
+        pc = None
+        if peer_eligible(image, text, precision, world):
+            from . import peer
+            pc = peer.get_context(group, int(image.shape[0]), int(image.shape[1]), image.device,
+                                  two_keys=row_ids.key2 is not None)
+        if pc is not None:
+            return _ShardedGPeer.apply(ops, pc, 1.0 / temp, row_ids, image, text)
+        if mode == "peer":
+            raise RuntimeError("evoke_b200: mode='peer' needs bf16 precision, contiguous fp32 text rows, n_local % 128 == 0, "
+                               "d % 8 == 0 and CUDA-IPC peer mapping between the ranks' GPUs")
+    sym = mode == "sym" or (mode in ("auto", "peer") and world >= 8)
     return _ShardedG.apply(ops, group, 1.0 / temp, precision, sym, row_ids, image, text)

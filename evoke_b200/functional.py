@@ -31,6 +31,9 @@ SMALL_PATH_MAX = int(os.environ.get("EVOKE_B200_SMALL_MAX", "512"))   # rows/col
 TILE_M, TILE_N = 128, 256
 ROW_PARTS = 2          # row-statistic partials per 256-column tile (two epilogue warps share a row)
 OVERLAP_STREAMS = os.environ.get("EVOKE_B200_OVERLAP", "0") == "1"   # side-stream overlap outside graph capture too
+# bf16 mode: K3 stores E = exp(S - 1/tau) as a bf16 row strip and the backward turns it into W in place
+# (HBM-bound K4t) instead of recomputing the similarity tiles (K4a): 6 N^2 D executed FLOP instead of 8.
+E_STRIP = os.environ.get("EVOKE_B200_ESTRIP", "1") == "1"
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -66,15 +69,15 @@ def _round_up(x: int, m: int) -> int:
 _SIDE_STREAMS: dict = {}
 
 
-def _side_stream(device: torch.device) -> torch.cuda.Stream:
+def _side_stream(device: torch.device, which: int = 0) -> torch.cuda.Stream:
     """One auxiliary stream per device for work that runs next to the tensor-bound kernels
     (mask builder, positive sums, zero fills, the second gradient contraction).  It is always
     forked from and joined back into the caller's stream, so the sequence stays capturable."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    st = _SIDE_STREAMS.get(idx)
+    st = _SIDE_STREAMS.get((idx, which))
     if st is None:
         st = torch.cuda.Stream(device=idx)
-        _SIDE_STREAMS[idx] = st
+        _SIDE_STREAMS[(idx, which)] = st
     return st
 
 
@@ -119,28 +122,44 @@ def l2norm_fwd(x: torch.Tensor, *, want_f32: bool, want_hi: bool, want_lo: bool,
 
 
 def l2norm_bwd(x: torch.Tensor, nrm: Normalized, g_hat: torch.Tensor, *, scale_dev: Optional[torch.Tensor],
-               scale_host: float, gather: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Backward of K1 fused with the loss scale; returns dx with x's shape and dtype."""
+               scale_host: float, gather: Optional[torch.Tensor] = None, parts=None) -> torch.Tensor:
+    """Backward of K1 fused with the loss scale; returns dx with x's shape and dtype.
+    parts = (n_parts, stride_in_elements): g_hat is the first of n_parts partial buffers to be summed."""
     if gather is not None:
         dx = torch.zeros(x.shape, dtype=x.dtype, device=x.device)       # filtered rows get zero gradient
     else:
         dx = torch.empty(x.shape, dtype=x.dtype, device=x.device)
-    _lib.call("evk_l2norm_bwd", _ptr(x), _dtype_code(x), nrm.n, nrm.d, x.stride(0), x.stride(1), _ptr(gather),
-              _ptr(nrm.norm), _ptr(g_hat), g_hat.stride(0), _ptr(scale_dev), float(scale_host),
-              _ptr(dx), _dtype_code(dx), dx.stride(0), 0, _stream())
+    n_parts, part_stride = parts if parts is not None else (1, 0)
+    _lib.call("evk_l2norm_bwd_parts", _ptr(x), _dtype_code(x), nrm.n, nrm.d, x.stride(0), x.stride(1), _ptr(gather),
+              _ptr(nrm.norm), _ptr(g_hat), g_hat.stride(0), int(n_parts), int(part_stride), _ptr(scale_dev),
+              float(scale_host), _ptr(dx), _dtype_code(dx), dx.stride(0), 0, _stream())
     return dx
 
 
-def posmask_build(rows: DeviceIds, cols: DeviceIds, *, clear_diag: bool, diag_offset: int = 0):
-    """K2: bit-packed positive mask [n_rows, ld_words] (uint32 stored as int32) + counts[n_rows]."""
+POS_SLOTS = 8          # listed positives per row (rows with more fall back to scanning the mask)
+
+
+def posmask_build(rows: DeviceIds, cols: DeviceIds, *, clear_diag: bool, diag_offset: int = 0, want_list: bool = False):
+    """K2: bit-packed positive mask [n_rows, ld_words] (uint32 stored as int32) + counts[n_rows]
+    (+ pos_idx [n_rows, POS_SLOTS], the first positives of every row, with want_list)."""
     n_rows, n_cols = len(rows), len(cols)
     dev = rows.key.device
     ld_words = _round_up(_round_up(n_cols, TILE_N) // 32, 8)             # whole 256-column tiles
     bits = torch.empty((n_rows, ld_words), dtype=torch.int32, device=dev)
     counts = torch.empty(n_rows, dtype=torch.int32, device=dev)
+    pos_idx = torch.empty((n_rows, POS_SLOTS), dtype=torch.int32, device=dev) if want_list else None
     _lib.call("evk_posmask_build", _ptr(rows.key), _ptr(rows.key2), n_rows, _ptr(cols.key), _ptr(cols.key2),
-              n_cols, diag_offset, int(clear_diag), _ptr(bits), ld_words, _ptr(counts), _stream())
-    return bits, counts
+              n_cols, diag_offset, int(clear_diag), _ptr(bits), ld_words, _ptr(counts), _ptr(pos_idx), POS_SLOTS,
+              _stream())
+    return (bits, counts, pos_idx) if want_list else (bits, counts)
+
+
+def pos_logits(q: Normalized, k: Normalized, pos_idx: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """pos_dot[i, s] = qhat_i . khat_{pos_idx[i, s]} for the listed positives (side-stream work next to K3)."""
+    pos_dot = torch.empty((q.n, POS_SLOTS), dtype=torch.float32, device=q.hi.device)
+    _lib.call("evk_mpce_pos_logits", _ptr(q.hi), q.ld, _ptr(k.hi), k.ld, q.n, q.d, _ptr(pos_idx), _ptr(counts),
+              POS_SLOTS, _ptr(pos_dot), _stream())
+    return pos_dot
 
 
 def reduce_partials(part: torch.Tensor, parts: int, n: int, out: Optional[torch.Tensor] = None,
@@ -200,6 +219,47 @@ def tc_fwd_partials(q: Normalized, k: Normalized, bits, inv_tau: float, flags: i
               _ptr(bits) if want_pos else None, bits.stride(0) if want_pos else 0, float(inv_tau), flags, diag_offset,
               _ptr(rs_part), _ptr(rp_part), q.n, _ptr(cs_part), k.n, _stream())
     return rs_part, rp_part, cs_part
+
+
+def tc_fwd_store(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int, diag_offset: int = 0):
+    """K3 that also writes the bf16 E strip [q.n, ld_e].  Returns (rs_part, rp_part, cs_part | None, e, ld_e)."""
+    dev = q.hi.device
+    n_ct = (k.n + TILE_N - 1) // TILE_N
+    n_rt = (q.n + TILE_M - 1) // TILE_M
+    want_col = not (flags & FLAG_NO_COLSUM)
+    want_pos = not (flags & FLAG_NO_POS)
+    rs_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev)
+    rp_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev) if want_pos else None
+    cs_part = torch.empty((n_rt, k.n), dtype=torch.float32, device=dev) if want_col else None
+    ld_e = _round_up(k.n, 64)
+    e = torch.empty((q.n, ld_e), dtype=torch.bfloat16, device=dev)
+    _lib.call("evk_mpce_fwd_store", _ptr(q.hi), q.ld, _ptr(k.hi), k.ld, q.n, k.n, q.d,
+              _ptr(bits) if want_pos else None, bits.stride(0) if want_pos else 0, float(inv_tau), flags, diag_offset,
+              _ptr(rs_part), _ptr(rp_part), q.n, _ptr(cs_part), k.n, _ptr(e), ld_e, _stream())
+    return rs_part, rp_part, cs_part, e, ld_e
+
+
+def tc_w_from_e(e: torch.Tensor, ld_e: int, n_cols: int, bits, counts, a_row, b_col, q: Optional[Normalized],
+                k: Optional[Normalized], inv_tau: float, row0: int = 0, rows: Optional[int] = None,
+                pos=None) -> None:
+    """K4t: rows [row0, row0+rows) of the E strip become W, in place.  q / k: the forward's operands, from
+    which the positive entries are recomputed in fp32 (None: every entry from the strip).
+    pos = (pos_idx, pos_dot): the forward's positive lists - then no mask scan / dot products are needed."""
+    rows = int(e.shape[0]) - row0 if rows is None else rows
+    exact = q is not None and k is not None
+    _lib.call("evk_mpce_w_from_e", _ptr(e[row0:]), ld_e, rows, n_cols, _ptr(bits[row0:]), bits.stride(0),
+              _ptr(counts[row0:]), _ptr(a_row[row0:]), _ptr(b_col),
+              _ptr(q.hi[row0:]) if exact else None, q.ld if exact else 0, _ptr(k.hi) if exact else None,
+              k.ld if exact else 0, q.d if exact else 0, float(inv_tau),
+              _ptr(pos[0][row0:]) if pos is not None else None, _ptr(pos[1][row0:]) if pos is not None else None,
+              POS_SLOTS, _stream())
+
+
+def rows_of(x: Normalized, r0: int, r1: int) -> Normalized:
+    """Row range of a normalised matrix (views, no copy)."""
+    return Normalized(n=r1 - r0, d=x.d, norm=None if x.norm is None else x.norm[r0:r1],
+                      f32=None if x.f32 is None else x.f32[r0:r1], hi=None if x.hi is None else x.hi[r0:r1],
+                      lo=None if x.lo is None else x.lo[r0:r1], ld=x.ld)
 
 
 def tc_pos(q: Normalized, k: Normalized, bits, inv_tau: float) -> torch.Tensor:
@@ -313,6 +373,8 @@ class _MultiPositiveCE(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor]):
+        ctx.e_strip = None
+        ctx.pos = None
         small = cfg.path == "small"
         split = (not small) and cfg.precision == "fp32"
         flags = FLAG_SPLIT_BF16 if split else 0
@@ -336,24 +398,49 @@ class _MultiPositiveCE(torch.autograd.Function):
             # in the K3 epilogue: ln R_i and pos_i must come from the same tensor-core accumulators
             # for their rounding to cancel in the loss (cold temperatures).
             overlap = OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
+            use_strip = E_STRIP and not split and any(ctx.needs_input_grad[1:])
+            pos_idx = pos_dot = None
+
+            def build_mask():
+                if use_strip:
+                    return posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc, want_list=True)
+                return posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc) + (None,)
+
             if overlap:
                 main = torch.cuda.current_stream()
                 side = _side_stream(image.device)
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    bits, counts = posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc)
+                    bits, counts, pos_idx = build_mask()
             else:
-                bits, counts = posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc)
+                bits, counts, pos_idx = build_mask()
             qn = l2norm_fwd(image, gather=cfg.gather, **kw)
             kn = qn if mpc else l2norm_fwd(text, **kw)
             n = qn.n
             pos_weight, inv_count = (1.0, 1.0 / n) if mpc else (2.0, 0.5 / n)
             if overlap:
                 main.wait_stream(side)
-                _shared_with(main, bits, counts)
-            rs_part, rp_part, cs_part = tc_fwd_partials(qn, kn, bits, cfg.inv_tau, flags)
+                _shared_with(main, bits, counts, pos_idx)
+            if use_strip:
+                # exact logits of the listed positives (O(N*D)), next to K3 on the side stream; the backward's
+                # K4t needs them for the entries where softmax and target cancel
+                if overlap:
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        pos_dot = pos_logits(qn, kn, pos_idx, counts)
+                    _shared_with(side, qn.hi, kn.hi, pos_idx, counts)
+                else:
+                    pos_dot = pos_logits(qn, kn, pos_idx, counts)
+                rs_part, rp_part, cs_part, e_strip, ld_e = tc_fwd_store(qn, kn, bits, cfg.inv_tau, flags)
+                ctx.e_strip = (e_strip, ld_e)
+                ctx.pos = (pos_idx, pos_dot)
+            else:
+                rs_part, rp_part, cs_part = tc_fwd_partials(qn, kn, bits, cfg.inv_tau, flags)
             a_row, b_col, loss = stats_fused(rs_part, rp_part, cs_part, counts, shift=cfg.inv_tau,
                                              pos_weight=pos_weight, inv_count=inv_count)
+            if use_strip and overlap:
+                main.wait_stream(side)
+                _shared_with(main, pos_dot)
         if mpc:
             b_col = a_row
         ctx.cfg, ctx.flags, ctx.qn, ctx.kn = cfg, flags, qn, kn
@@ -389,8 +476,22 @@ class _MultiPositiveCE(torch.autograd.Function):
             dev = image.device
             width = _round_up(qn.d, 4)
             overlap = OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
+            strip = ctx.e_strip
+            if strip is not None:
+                if strip[0] is None:
+                    raise RuntimeError("evoke_b200: backward called twice: the E strip saved by the forward is turned "
+                                       "into W in place (set EVOKE_B200_ESTRIP=0 if the graph must be retained)")
+
+            def weights():
+                """W strip for the whole row block: K4t over the saved E strip, or K4a (recompute)."""
+                if strip is None:
+                    return tc_bwd_w(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
+                e, ld_e = strip
+                tc_w_from_e(e, ld_e, kn.n, bits, counts, a_row, b_col, qn, kn, cfg.inv_tau, pos=ctx.pos)
+                return e, None, ld_e
+
             if not overlap:
-                w_hi, w_lo, ld_w = tc_bwd_w(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
+                w_hi, w_lo, ld_w = weights()
                 if need_q:
                     dq = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, False, kn, flags)
                     d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
@@ -400,13 +501,13 @@ class _MultiPositiveCE(torch.autograd.Function):
             else:
                 main = torch.cuda.current_stream()
                 side = _side_stream(dev)
-                # zero-filled split-K accumulators: filled on the side stream while K4a runs
+                # zero-filled split-K accumulators: filled on the side stream while K4a / K4t runs
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     dq = torch.zeros((qn.n, width), dtype=torch.float32, device=dev) if need_q else None
                     dk = torch.zeros((kn.n, width), dtype=torch.float32, device=dev) if need_k else None
                     filled = side.record_event()
-                w_hi, w_lo, ld_w = tc_bwd_w(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
+                w_hi, w_lo, ld_w = weights()
                 main.wait_event(filled)
                 _shared_with(main, dq, dk)
                 if need_q:
@@ -425,6 +526,8 @@ class _MultiPositiveCE(torch.autograd.Function):
                 if need_k:
                     main.wait_stream(side)
                     _shared_with(main, d_text)
+            if strip is not None:
+                ctx.e_strip = (None, 0)                  # drop the N^2 buffer as soon as it has been consumed
         return None, d_image, d_text
 
 

@@ -91,6 +91,15 @@ EVK_API int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t d,
                    const float* scale_dev, float scale_host,
                    void* dx, int dx_dtype, int64_t ld_dx, int accumulate, evk_stream_t stream);
 
+/* Same, with the upstream gradient given as n_parts partial buffers that are summed on the fly (in index
+ * order): g_total[r, c] = sum_p g[p * part_stride + r * ld_g + c].  Closes the fused reduce-scatter of
+ * evk_mpce_bwd_gemm_scatter(store = 1): part p is what rank p's contraction stored for this rank's rows. */
+EVK_API int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, int64_t d,
+                         int64_t stride_row, int64_t stride_col, const int32_t* gather,
+                         const float* norm, const float* g, int64_t ld_g, int n_parts, int64_t part_stride,
+                         const float* scale_dev, float scale_host,
+                         void* dx, int dx_dtype, int64_t ld_dx, int accumulate, evk_stream_t stream);
+
 /* ---- K2: positive-mask builder -------------------------------------------------------------
  * Replaces (ids.reshape(-1,1) == ids.reshape(1,-1)) + .float().to(device) + rowsum at
  * :488-491 and :422-424/:430.  bits[r, w] bit k = [key(row r) == key(col 32w+k)], i.e. exactly
@@ -98,11 +107,15 @@ EVK_API int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t d,
  * row r = c_r.  A key is id, or the pair (id, id2) when the id2 pointers are non-NULL
  * (patient AND study, the reference's "p<subject>_s<study>" string, dataloaders_v0401.py:83).
  * With clear_diag the bit at column (r + diag_offset) is cleared (:424).  All ld_words words
- * of every row are written (bits at columns >= n_cols are zero); ld_words >= ceil(n_cols/32). */
+ * of every row are written (bits at columns >= n_cols are zero); ld_words >= ceil(n_cols/32).
+ * pos_idx (may be NULL): [n_rows, pos_slots] int32, pos_idx[r, s] = column of the s-th positive of row r for
+ * s < min(counts[r], pos_slots), unspecified order, other entries untouched: the sparse form of the same mask
+ * for the O(N) consumers (evk_mpce_pos_logits, evk_mpce_w_from_e). */
 EVK_API int evk_posmask_build(const int32_t* ids_row, const int32_t* ids2_row, int64_t n_rows,
                       const int32_t* ids_col, const int32_t* ids2_col, int64_t n_cols,
                       int64_t diag_offset, int clear_diag,
-                      uint32_t* bits, int64_t ld_words, int32_t* counts, evk_stream_t stream);
+                      uint32_t* bits, int64_t ld_words, int32_t* counts,
+                      int32_t* pos_idx, int pos_slots, evk_stream_t stream);
 
 /* ---- small path: fp32 SIMT fused kernels (reference-sized batches, N <~ 1k) ---------------
  * One launch handles the rows of `q` against all columns `k` (both already normalised, fp32):
@@ -175,6 +188,41 @@ EVK_API int evk_mpce_fwd(const void* q_hi, const void* q_lo, int64_t ld_q,
                  float* row_sum_part, float* row_pos_part, int64_t ld_rowpart,
                  float* col_sum_part, int64_t ld_colpart, evk_stream_t stream);
 
+/* K3 that ALSO stores E_ij = exp(S_ij - inv_tau) as bf16 in the row strip e_out [n_rows, ld_e]
+ * (ld_e % 8 == 0, ld_e >= n_cols; entries outside the softmax - the excluded diagonal - are 0).
+ * bf16 mode only (no split operands).  With the strip the backward needs no second sweep over the
+ * similarity tiles: evk_mpce_w_from_e turns E into W in place and the step executes 6 N^2 D FLOP
+ * instead of 8 N^2 D.  Same statistics outputs as evk_mpce_fwd. */
+EVK_API int evk_mpce_fwd_store(const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k,
+                       int64_t n_rows, int64_t n_cols, int64_t d,
+                       const uint32_t* bits, int64_t ld_words,
+                       float inv_tau, int flags, int64_t diag_offset,
+                       float* row_sum_part, float* row_pos_part, int64_t ld_rowpart,
+                       float* col_sum_part, int64_t ld_colpart,
+                       void* e_out, int64_t ld_e, evk_stream_t stream);
+
+/* Raw logits of the listed positives: pos_dot[i, s] = q_i . k_{pos_idx[i, s]} (bf16 operands, fp32 accumulate)
+ * for s < min(counts[i], pos_slots).  O(N*D); meant for a side stream next to K3.  evk_mpce_w_from_e turns
+ * them into exact W entries without touching the mask or the operands again. */
+EVK_API int evk_mpce_pos_logits(const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k,
+                        int64_t n_rows, int64_t d, const int32_t* pos_idx, const int32_t* counts, int pos_slots,
+                        float* pos_dot, evk_stream_t stream);
+
+/* K4t, in place over the strip written by evk_mpce_fwd_store (or any row range of it: offset the
+ * strip / bits / counts / a_row pointers):  strip[i, j] <- bf16( E_ij (a_row[i] + b_col[j]) - 2 M_ij / c_i ),
+ * the W of evk_mpce_small_bwd; HBM-bound (4 bytes per (i, j) + 1 mask bit).  MPC: pass b_col = a_row.
+ * q_hi / k_hi (the bf16 operands of the forward, K1's padded rows; d, inv_tau as in the forward) let the
+ * kernel recompute the POSITIVE entries from S_ij in fp32 instead of from the bf16-rounded E: that is
+ * where softmax and target cancel, and it keeps cold temperatures inside the bf16-mode tolerance.
+ * q_hi == NULL skips this (all entries from the strip).  With pos_idx / pos_dot (K2's lists and
+ * evk_mpce_pos_logits' values, [n_rows, pos_slots]) rows with at most pos_slots positives take their exact
+ * entries from the lists - no mask scan, no dot products in the backward; the other rows scan the mask. */
+EVK_API int evk_mpce_w_from_e(void* strip, int64_t ld_e, int64_t n_rows, int64_t n_cols,
+                      const uint32_t* bits, int64_t ld_words, const int32_t* counts,
+                      const float* a_row, const float* b_col,
+                      const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k, int64_t d, float inv_tau,
+                      const int32_t* pos_idx, const float* pos_dot, int pos_slots, evk_stream_t stream);
+
 /* Positive-logit sums from the bit mask, for use with EVK_FLAG_NO_POS:
  *   row_pos[i] = sum_j M_ij S_ij = inv_tau * sum_{j: bit (i,j) set} q_i . k_j
  * (the sum_j Y_ij S_ij term of the soft-target CE, :501-502 / :443, before the 1/c_i).  O(N*D) work;
@@ -223,6 +271,50 @@ EVK_API int evk_l2norm_fwd_bcast(const void* x, int x_dtype, int64_t n_rows, int
  * ids shard, per-rank statistics slot. */
 EVK_API int evk_peer_bcast(const void* src, int64_t bytes, int n_dst, const uint64_t* dst,
                    int64_t dst_offset_bytes, evk_stream_t stream);
+
+/* Symmetric buffers for that transport.  evk_peer_alloc is the one place the library allocates device
+ * memory (cudaMalloc, zero-filled): CUDA-IPC handles name whole allocations, so the exchanged buffers
+ * cannot come out of a caching allocator.  The caller frees them with evk_peer_free.  evk_peer_export
+ * writes the 64-byte IPC handle of such a buffer to HOST memory; evk_peer_open maps a peer's handle
+ * (received through any host channel, e.g. torch.distributed) into this process; evk_peer_close unmaps. */
+EVK_API int evk_peer_alloc(int64_t bytes, void** ptr_out);
+EVK_API int evk_peer_free(void* ptr);
+EVK_API int evk_peer_export(const void* ptr, void* handle_out_64_bytes);
+EVK_API int evk_peer_open(const void* handle_64_bytes, void** ptr_out);
+EVK_API int evk_peer_close(void* ptr);
+
+/* Barrier across the ranks' GPUs, enqueued on `stream` (one tiny kernel, CUDA-graph capturable).
+ * flag_ptrs: HOST array of n_ranks device addresses, entry t = rank t's flag area (>= 16 uint32, zeroed at
+ * start, peer-mapped).  epoch: this rank's device-resident uint32 counter (zeroed at start; advanced by the
+ * kernel).  Everything this rank wrote to peer memory in earlier kernels of the stream is visible to the peers
+ * once they pass.  If a peer does not arrive within timeout_ms (<= 0: 2000) *error (device int) is set to 1
+ * and the kernel returns: a dead peer must not hang the GPU. */
+EVK_API int evk_peer_barrier(const uint64_t* flag_ptrs, int n_ranks, int rank, uint32_t* epoch, int* error,
+                     int64_t timeout_ms, evk_stream_t stream);
+
+/* Closes the sharded forward after the statistics exchange.  slots: [n_slots, ld_slot] fp32, slot r = rank r's
+ * partial column exp-sums over its own rows (n_cols floats) followed by its row-side loss term
+ * inv_count * sum_{i in rows of r} (shift + ln R_i - 2 pos_i / c_i) at index n_cols.
+ *   b_col[j] = 1 / sum_r slots[r][j];   loss_out[0] = sum_r slots[r][n_cols] + inv_count * sum_j (shift + ln C_j)
+ * (:501-503 on the concatenated batch).  Fixed summation order: every rank computes identical bits. */
+EVK_API int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
+                          double inv_count, float* b_col, float* loss_out, evk_stream_t stream);
+
+/* K4b with the reduce-scatter fused into its epilogue: the partial dKhat of this rank's row block,
+ *   out_owner(j)[j % rows_per_owner, :] += alpha * sum_i W[i, j] x[i, :],   owner(j) = j / rows_per_owner,
+ * accumulated with fp32 red.add straight into the owning rank's buffer (out_ptrs: HOST array of n_owners
+ * peer-mapped device addresses, each [rows_per_owner, ld_out] fp32, zeroed by its owner before any rank
+ * starts).  Replaces evk_mpce_bwd_gemm(transpose_w = 1) + ncclReduceScatter.
+ * store != 0: no split-K and plain 128-bit stores instead of red.add - every element of the owners' buffers
+ * is written exactly once, so out_ptrs[o] must be a buffer private to THIS source rank (the owner then adds the
+ * per-source buffers up: evk_l2norm_bwd_parts) and needs no zero fill.  Posted stores use NVLink far better
+ * than 16-byte atomics. */
+EVK_API int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int64_t ld_w,
+                              int64_t n_rows, int64_t n_cols,
+                              const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d,
+                              float alpha, int flags,
+                              const uint64_t* out_ptrs, int n_owners, int64_t rows_per_owner, int64_t ld_out,
+                              int store, evk_stream_t stream);
 
 /* Debug/bring-up: plain C[m,n] = A[m,k] B[n,k]^T (or MN-major operands) through the same
  * tcgen05 main loop, fp32 out.  a_major/b_major: 0 = K contiguous, 1 = M/N contiguous

@@ -47,4 +47,4 @@ def test_argument_validation_needs_no_gpu():
     rc = lib.evk_l2norm_fwd(None, 0, 4, 8, 8, 1, None, None, 8, None, None, 8, None, None)
     assert rc == _lib.EVK_ERR_INVALID and "non-null" in _lib.last_error()
     with pytest.raises(ValueError):
-        _lib.call("evk_posmask_build", None, None, 4, None, None, 4, 0, 0, None, 1, None, None)
+        _lib.call("evk_posmask_build", None, None, 4, None, None, 4, 0, 0, None, 1, None, None, 0, None)

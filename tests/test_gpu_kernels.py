@@ -91,6 +91,30 @@ def test_posmask_rectangular_block_with_offset_and_two_keys():
     assert np.array_equal(counts.cpu().numpy(), want_counts)
 
 
+@pytest.mark.parametrize("clear_diag", [False, True])
+def test_posmask_positive_lists_are_the_sparse_form_of_the_mask(clear_diag):
+    """pos_idx[r, :min(c_r, slots)] = the set bits of row r (any order); degenerate ids (one big group) and
+    a long row of equal keys exercise duplicate-heavy hash chains."""
+    rng = np.random.default_rng(5)
+    ids = np.concatenate([synth.make_study_ids(3000, seed=9), np.full(40, 777777, dtype=np.int32)])
+    ids = ids[rng.permutation(len(ids))]
+    dev = idmod.DeviceIds(torch.from_numpy(ids).to(DEV))
+    bits, counts, pos_idx = Fn.posmask_build(dev, dev, clear_diag=clear_diag, want_list=True)
+    want_bits, want_counts = orc.posmask_packed(ids, clear_diag=clear_diag)
+    got = bits.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got[:, : want_bits.shape[1]], want_bits)
+    cnt = counts.cpu().numpy()
+    assert np.array_equal(cnt, want_counts)
+    dense = np.unpackbits(want_bits.view(np.uint8), axis=1, bitorder="little")[:, : len(ids)]
+    lists = pos_idx.cpu().numpy()
+    for r in range(len(ids)):
+        k = min(int(cnt[r]), Fn.POS_SLOTS)
+        cols = lists[r, :k]
+        assert len(set(cols.tolist())) == k and dense[r, cols].all()
+        if cnt[r] <= Fn.POS_SLOTS:
+            assert set(cols.tolist()) == set(np.nonzero(dense[r])[0].tolist())
+
+
 def test_posmask_string_ids_equal_int_ids():
     ids = synth.make_study_ids(130, seed=8)
     d1, _ = idmod.to_device_ids(synth.ids_as_strings(ids), torch.device(DEV))
