@@ -252,14 +252,13 @@ def run_cuda(args):
         torch.cuda.synchronize()
 
     # per-kernel CUDA events around the tcgen05 launches (recorded on the launching stream)
-    TC = ("evk_mpce_fwd", "evk_mpce_fwd_store", "evk_mpce_bwd_w", "evk_mpce_bwd_gemm")
-    HBM_K = ("evk_mpce_w_from_e",)        # K4t: 4 B per (i, j) read+written, + 1 mask bit
-    ev = {k: [] for k in TC + HBM_K}
+    TC = ("evk_mpce_fwd", "evk_mpce_fwd_store", "evk_mpce_bwd_w", "evk_mpce_bwd_gemm", "evk_mpce_bwd_gemm_scatter")
+    HBM_K = ("evk_mpce_w_from_e",)        # K4t: 4 B per (i, j) read+written
+    ev = {}                               # every entry point of the library gets its own event pairs
     pending = {}
 
     def hook(name, phase):
-        if name not in ev:
-            return
+        ev.setdefault(name, [])
         e = torch.cuda.Event(enable_timing=True)
         e.record(torch.cuda.current_stream())
         if phase == "before":
@@ -335,9 +334,9 @@ def run_cuda(args):
             kern[name] = dict(launches_per_step=len(pairs) / args.steps, avg_ms=float(np.mean(ms)),
                               share_of_step=float(np.sum(ms)) / (ms_eager_total or ms_total))
             if name in HBM_K:
-                kern[name]["gbs"] = (4.125 * n_loc * N_GLOBAL) / (float(np.mean(ms)) * 1e-3) / 1e9
+                kern[name]["gbs"] = (4.0 * n_loc * N_GLOBAL) / (float(np.mean(ms)) * 1e-3) / 1e9
                 kern[name]["frac_of_hbm_peak"] = kern[name]["gbs"] / peaks["hbm_gbs"]
-            else:
+            elif name in TC:
                 kern[name]["tflops"] = flop_launch / (float(np.mean(ms)) * 1e-3) / 1e12
     tck = [k for k in kern if k in TC]
     dom = max(tck, key=lambda k: kern[k]["avg_ms"]) if tck else None

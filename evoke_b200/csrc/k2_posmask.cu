@@ -6,11 +6,11 @@
 // np.packbits(M, axis=1, bitorder='little') read as little-endian uint32.
 //
 // The mask is sparse (a study has a handful of views), so the N^2 compares of the reference are not
-// executed.  A CTA owns a block of 1024 columns x kRowsPerCta rows: it hashes the block's column keys
+// executed.  A CTA owns a block of 256 columns x kRowsPerCta rows: it hashes the block's column keys
 // into an open-addressing multiset in shared memory (duplicates take consecutive slots), then every
-// lane looks its own row key up - each match is one bit set in a per-warp [32 rows x 32 words] tile in
+// lane looks its own row key up - each match is one bit set in a per-warp [32 rows x 8 words] tile in
 // shared memory - and the warp streams the tile out with 128-bit stores.  Work per row and column block
-// is a probe sequence (about two slots) instead of 1024 compares, which leaves the kernel bound by
+// is a probe sequence (about two slots) instead of 256 compares, which leaves the kernel bound by
 // writing the mask: algorithmic bytes ld_words*4 per row written + 4*(n_rows + n_cols) read.
 // Degenerate inputs (every key equal) degrade gracefully to one compare per pair.  Exact: keys are
 // compared in full, the hash only picks the starting slot.
@@ -22,12 +22,13 @@
 
 namespace {
 
-constexpr int kThreads = 128;                 // 4 warps
+constexpr int kThreads = 256;                 // 8 warps; one column key inserted per thread
 constexpr int kWarps = kThreads / 32;
-constexpr int kColsPerCta = 1024;             // 32 words
-constexpr int kSlots = 2048;                  // load factor <= 0.5
-constexpr int kRowsPerCta = 256;              // 2 x 32 rows per warp
-constexpr int kTilePitch = 36;                // words per tile row (16-byte aligned rows, banks staggered)
+constexpr int kColsPerCta = 256;              // 8 words
+constexpr int kWordsPerCta = kColsPerCta / 32;
+constexpr int kSlots = 512;                   // load factor <= 0.5
+constexpr int kRowsPerCta = 512;              // 2 x 32 rows per warp: the table build is 1/3 of a CTA's work
+constexpr int kTilePitch = 12;                // words per tile row (16-byte aligned rows, banks staggered)
 
 __device__ __forceinline__ uint32_t slot_hash(int32_t k, int32_t k2) {
   uint32_t h = (uint32_t)k * 0x9E3779B1u;
@@ -87,11 +88,11 @@ posmask_kernel(const int32_t* __restrict__ ids_row, const int32_t* __restrict__ 
       }
     }
     __syncwarp();
-    // stream the 32 x 32-word tile out (and clear it for the next row group)
+    // stream the 32 x 8-word tile out (and clear it for the next row group): 32 bytes per row
     if (vec_ok) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int row = it * 4 + (lane >> 3), wq = (lane & 7) * 4;
+      for (int it = 0; it < 2; ++it) {
+        const int row = it * 16 + (lane >> 1), wq = (lane & 1) * 4;
         uint4* src = reinterpret_cast<uint4*>(my + row * kTilePitch + wq);
         const uint4 v = *src;
         *src = make_uint4(0u, 0u, 0u, 0u);
@@ -99,10 +100,11 @@ posmask_kernel(const int32_t* __restrict__ ids_row, const int32_t* __restrict__ 
           *reinterpret_cast<uint4*>(bits + (rb + row) * ld_words + w0 + wq) = v;
       }
     } else {
-      for (int row = 0; row < 32; ++row) {
-        const uint32_t v = my[row * kTilePitch + lane];
-        my[row * kTilePitch + lane] = 0u;
-        if (rb + row < n_rows && w0 + lane < ld_words) bits[(rb + row) * ld_words + w0 + lane] = v;
+      for (int k = lane; k < 32 * kWordsPerCta; k += 32) {
+        const int row = k / kWordsPerCta, wq = k % kWordsPerCta;
+        const uint32_t v = my[row * kTilePitch + wq];
+        my[row * kTilePitch + wq] = 0u;
+        if (rb + row < n_rows && w0 + wq < ld_words) bits[(rb + row) * ld_words + w0 + wq] = v;
       }
     }
     __syncwarp();

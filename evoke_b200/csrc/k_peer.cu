@@ -84,6 +84,82 @@ l2norm_fwd_bcast_kernel(const float* __restrict__ x, int64_t n_rows, int d, int6
   }
 }
 
+// Prologue of a sharded step in ONE launch: K1 of the key rows (text) stored into every rank's buffer
+// (all-gather), K1 of the query rows (image) kept local, the id shard pushed to every rank, and the zero fill
+// of the split-K accumulator of the local gradient contraction (same [n, D] shape as the query rows).
+struct Prologue {
+  const float* text; int64_t text_stride;
+  const float* image; int64_t image_stride;
+  PeerDst khat;                         // destinations of the normalised key rows
+  __nv_bfloat16* q_hi;                  // local normalised query rows
+  float* k_norm; float* q_norm;
+  const int32_t* ids; const int32_t* ids2;
+  int32_t* ids_dst[kMaxPeers]; int32_t* ids2_dst[kMaxPeers];
+  float* zero; int64_t ld_zero; int zero_width;
+  int64_t n, ld, row_offset;
+  int d;
+};
+
+template <int kIters>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+shard_prologue_kernel(const Prologue p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  // ids: one element per thread, pushed to every rank
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < p.n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t v = __ldg(p.ids + t);
+    const int32_t v2 = p.ids2 ? __ldg(p.ids2 + t) : 0;
+    for (int q = 0; q < p.khat.n; ++q) {
+      p.ids_dst[q][p.row_offset + t] = v;
+      if (p.ids2) p.ids2_dst[q][p.row_offset + t] = v2;
+    }
+  }
+  for (int64_t rr = warp0; rr < 2 * p.n; rr += nwarps) {
+    const bool is_text = rr < p.n;
+    const int64_t r = is_text ? rr : rr - p.n;
+    const float* xr = is_text ? p.text + r * p.text_stride : p.image + r * p.image_stride;
+    float v[kIters][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int c = (it * 32 + lane) * 8;
+      if (c < p.d) {
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(xr + c));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(xr + c + 4));
+        v[it][0] = p0.x; v[it][1] = p0.y; v[it][2] = p0.z; v[it][3] = p0.w;
+        v[it][4] = p1.x; v[it][5] = p1.y; v[it][6] = p1.z; v[it][7] = p1.w;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss = fmaf(v[it][e], v[it][e], ss);
+      }
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    const float den = fmaxf(nrm, EVK_NORM_EPS);
+    if (lane == 0) (is_text ? p.k_norm : p.q_norm)[r] = nrm;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int c = (it * 32 + lane) * 8;
+      if (c < p.d) {
+        uint4 hi;
+        hi.x = pack2(v[it][0] / den, v[it][1] / den); hi.y = pack2(v[it][2] / den, v[it][3] / den);
+        hi.z = pack2(v[it][4] / den, v[it][5] / den); hi.w = pack2(v[it][6] / den, v[it][7] / den);
+        if (is_text) {
+          const int64_t off = (p.row_offset + r) * p.ld + c;
+          for (int q = 0; q < p.khat.n; ++q)       // one 128-bit store per destination rank (NVLink for peers)
+            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.khat.hi[q]) + off) = hi;
+        } else {
+          *reinterpret_cast<uint4*>(p.q_hi + r * p.ld + c) = hi;
+        }
+      }
+    }
+    if (!is_text && p.zero) {
+      float4* z = reinterpret_cast<float4*>(p.zero + r * p.ld_zero);
+      for (int c = lane; c * 4 < p.zero_width; c += 32) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 peer_bcast_kernel(const uint4* __restrict__ src, int64_t n_vec, PeerDst dst, int64_t dst_offset_vec) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -136,18 +212,22 @@ peer_barrier_kernel(PeerFlags pf, uint32_t* __restrict__ epoch, int* __restrict_
 // Closes the sharded forward once every rank's statistics slot has landed (slot r = rank r's partial
 // column exp-sums over its rows [n_cols floats] followed by its row-side loss term [1 float]):
 //   b_col[j] = 1 / sum_r slot_r[j]        loss = sum_r slot_r[n_cols] + inv_count * sum_j (shift + ln C_j)
-// Fixed summation order (slots in rank order, fp64 accumulation of the loss): every rank gets the same bits.
-constexpr int kFinishThreads = 1024;
+// Multi-CTA, fixed summation order (slots in rank order; per-CTA fp64 partials added up in index order by the
+// last CTA to finish): every rank gets the same bits.
+constexpr int kFinishThreads = 256;
 __global__ void __launch_bounds__(kFinishThreads)
 shard_finish_kernel(const float* __restrict__ slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
-                    double inv_count, float* __restrict__ b_col, float* __restrict__ loss_out) {
+                    double inv_count, float* __restrict__ b_col, float* __restrict__ loss_out,
+                    double* __restrict__ cta_partial, unsigned int* __restrict__ ticket) {
   __shared__ double s_part[kFinishThreads / 32];
+  __shared__ bool s_last;
+  const int64_t j = (int64_t)blockIdx.x * kFinishThreads + threadIdx.x;
   double acc = 0.0;
-  for (int64_t j = threadIdx.x; j < n_cols; j += kFinishThreads) {
+  if (j < n_cols) {
     float c = 0.f;
     for (int r = 0; r < n_slots; ++r) c += slots[r * ld_slot + j];
     b_col[j] = 1.f / c;
-    acc += (double)shift + (double)logf(c);
+    acc = (double)shift + (double)logf(c);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -156,9 +236,22 @@ shard_finish_kernel(const float* __restrict__ slots, int n_slots, int64_t ld_slo
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < kFinishThreads / 32; ++w) t += s_part[w];
-    t *= inv_count;
-    for (int r = 0; r < n_slots; ++r) t += (double)slots[r * ld_slot + n_cols];
-    loss_out[0] = (float)t;
+    cta_partial[blockIdx.x] = t;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < 32) {                  // the last CTA adds the partials up in index order
+    __threadfence();
+    double t = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32) t += reinterpret_cast<volatile double*>(cta_partial)[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) {
+      t *= inv_count;
+      for (int r = 0; r < n_slots; ++r) t += (double)slots[r * ld_slot + n_cols];
+      loss_out[0] = (float)t;
+    }
   }
 }
 
@@ -278,11 +371,55 @@ extern "C" int evk_peer_barrier(const uint64_t* flag_ptrs, int n_ranks, int rank
 }
 
 extern "C" int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
-                                     double inv_count, float* b_col, float* loss_out, evk_stream_t stream) {
+                                     double inv_count, float* b_col, float* loss_out, void* workspace,
+                                     int64_t workspace_bytes, evk_stream_t stream) {
   EVK_REQUIRE(slots && b_col && loss_out && n_slots >= 1 && n_cols > 0 && ld_slot > n_cols,
               "evk_mpce_shard_finish: bad arguments (ld_slot must exceed n_cols: the loss term follows the column sums)");
-  shard_finish_kernel<<<1, kFinishThreads, 0, static_cast<cudaStream_t>(stream)>>>(slots, n_slots, ld_slot, n_cols, shift,
-                                                                                 inv_count, b_col, loss_out);
+  const int64_t blocks = (n_cols + kFinishThreads - 1) / kFinishThreads;
+  EVK_REQUIRE(workspace && evk_aligned16(workspace) && workspace_bytes >= 16 + 8 * blocks,
+              "evk_mpce_shard_finish: workspace needs %lld bytes, 16-byte aligned", (long long)(16 + 8 * blocks));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned int* ticket = static_cast<unsigned int*>(workspace);
+  double* partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + 16);
+  EVK_CUDA(cudaMemsetAsync(ticket, 0, 16, s));
+  shard_finish_kernel<<<(unsigned)blocks, kFinishThreads, 0, s>>>(slots, n_slots, ld_slot, n_cols, shift, inv_count, b_col,
+                                                                 loss_out, partial, ticket);
   EVK_CHECK_LAUNCH("shard_finish");
+  return EVK_OK;
+}
+
+extern "C" int evk_shard_prologue(const float* text, int64_t text_stride, const float* image, int64_t image_stride,
+                                  int64_t n_rows, int64_t d, int n_dst, const uint64_t* khat_ptrs, int64_t ld_bf16,
+                                  int64_t row_offset, float* k_norm, void* q_hi, float* q_norm, const int32_t* ids,
+                                  const int32_t* ids2, const uint64_t* ids_ptrs, const uint64_t* ids2_ptrs,
+                                  float* zero_buf, int64_t ld_zero, evk_stream_t stream) {
+  EVK_REQUIRE(text && image && k_norm && q_hi && q_norm && ids && ids_ptrs && khat_ptrs && n_rows > 0 && d > 0,
+              "evk_shard_prologue: null pointer or empty shape");
+  EVK_REQUIRE(d % 8 == 0 && d <= 2048 && text_stride % 4 == 0 && image_stride % 4 == 0 && evk_aligned16(text) &&
+                  evk_aligned16(image) && evk_aligned16(q_hi) && ld_bf16 >= d && ld_bf16 % 8 == 0 && row_offset >= 0,
+              "evk_shard_prologue: needs contiguous fp32 rows, d %% 8 == 0, d <= 2048, 16-byte aligned buffers");
+  EVK_REQUIRE((ids2 == nullptr) == (ids2_ptrs == nullptr), "evk_shard_prologue: ids2 / ids2_ptrs must both be set or both null");
+  EVK_REQUIRE(!zero_buf || (ld_zero % 4 == 0 && ld_zero >= d && evk_aligned16(zero_buf)), "evk_shard_prologue: bad zero buffer");
+  Prologue p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_dst(p.khat, n_dst, khat_ptrs, nullptr);
+  if (rc != EVK_OK) return rc;
+  for (int q = 0; q < n_dst; ++q) {
+    p.ids_dst[q] = reinterpret_cast<int32_t*>(ids_ptrs[q]);
+    p.ids2_dst[q] = ids2_ptrs ? reinterpret_cast<int32_t*>(ids2_ptrs[q]) : nullptr;
+    EVK_REQUIRE(p.ids_dst[q] && (!ids2_ptrs || p.ids2_dst[q]), "evk_shard_prologue: null id destination");
+  }
+  p.text = text; p.text_stride = text_stride; p.image = image; p.image_stride = image_stride;
+  p.q_hi = static_cast<__nv_bfloat16*>(q_hi); p.k_norm = k_norm; p.q_norm = q_norm;
+  p.ids = ids; p.ids2 = ids2;
+  p.zero = zero_buf; p.ld_zero = ld_zero; p.zero_width = (int)(((d + 3) / 4) * 4);
+  p.n = n_rows; p.ld = ld_bf16; p.row_offset = row_offset; p.d = (int)d;
+  int64_t blocks = (2 * n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int64_t cap = (int64_t)evk_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d <= 1024) shard_prologue_kernel<4><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, s>>>(p);
+  else shard_prologue_kernel<8><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, s>>>(p);
+  EVK_CHECK_LAUNCH("shard_prologue");
   return EVK_OK;
 }

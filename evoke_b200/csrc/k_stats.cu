@@ -4,6 +4,8 @@
 // (l1 + l2)/2 of models/model_pretrain_finetune_v0520.py:501-503 (and :443 for MPC).
 #include "evk_common.cuh"
 
+#include <string.h>
+
 namespace {
 
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int64_t parts, int64_t ld, int64_t n,
@@ -63,6 +65,15 @@ finalize_kernel(const float* __restrict__ row_sum, const float* __restrict__ row
 // multi-CTA launch.  Each CTA owns 256 rows (and the same 256 columns), adds its terms in fp64,
 // publishes a per-CTA partial, and the last CTA to finish (atomic ticket) sums the partials in
 // index order, so the result is deterministic.
+// Sharded form: instead of b_col = 1/C_j the RAW partial column sums of this rank's rows, and instead of the
+// final loss this rank's row-side loss term, are stored into the statistics slot of EVERY rank (peer-mapped
+// pointers), i.e. the reduce + finalize + all-gather of the sharded forward in one launch.
+struct StatPush {
+  float* dst[16];
+  int n;
+  int64_t offset;        // element offset of this rank's slot inside each destination
+};
+
 constexpr int kStatThreads = 256;
 constexpr int kStatElems = 32;                       // rows (and columns) per CTA
 constexpr int kStatGroups = kStatThreads / kStatElems;   // partial-sum groups per element
@@ -89,7 +100,7 @@ stats_fused_kernel(const float* __restrict__ rs_part, int64_t row_parts, int64_t
                    const float* __restrict__ cs_part, int64_t col_parts, int64_t ld_col, int64_t n_cols,
                    int64_t col_lo, int64_t col_hi, float shift, float pos_weight, double inv_count,
                    float* __restrict__ a_row, float* __restrict__ b_col, float* __restrict__ loss_out,
-                   double* __restrict__ cta_partial, unsigned int* __restrict__ ticket) {
+                   double* __restrict__ cta_partial, unsigned int* __restrict__ ticket, const StatPush push) {
   __shared__ float s_sum[3][kStatGroups][kStatElems];
   __shared__ double s_part[kStatElems / 32];
   __shared__ bool s_last;
@@ -114,8 +125,12 @@ stats_fused_kernel(const float* __restrict__ rs_part, int64_t row_parts, int64_t
       acc += (double)shift + (double)logf(r) - (double)pos_weight * (cnt > 0 ? (double)pos / (double)cnt : 0.0);
     }
     if (cs_part && i < n_cols) {
-      b_col[i] = 1.f / c;
-      if (i >= col_lo && i < col_hi) acc += (double)shift + (double)logf(c);
+      if (push.n > 0) {
+        for (int p = 0; p < push.n; ++p) push.dst[p][push.offset + i] = c;
+      } else {
+        b_col[i] = 1.f / c;
+        if (i >= col_lo && i < col_hi) acc += (double)shift + (double)logf(c);
+      }
     }
     acc = warp_sum_f64(acc);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
@@ -136,21 +151,29 @@ stats_fused_kernel(const float* __restrict__ rs_part, int64_t row_parts, int64_t
     double t = 0.0;
     for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32) t += reinterpret_cast<volatile double*>(cta_partial)[b];
     t = warp_sum_f64(t);
-    if (threadIdx.x == 0) loss_out[0] = (float)(t * inv_count);
+    if (threadIdx.x == 0) {
+      const float l = (float)(t * inv_count);
+      if (push.n > 0) {
+        for (int p = 0; p < push.n; ++p) push.dst[p][push.offset + n_cols] = l;
+      } else {
+        loss_out[0] = l;
+      }
+    }
   }
 }
 
 }  // namespace
 
-extern "C" int evk_mpce_stats_fused(const float* rs_part, int64_t row_parts, int64_t ld_row, const float* rp_part,
-                                    int64_t pos_parts, int64_t ld_pos, const int32_t* counts, int64_t n_rows,
-                                    const float* cs_part, int64_t col_parts,
-                                    int64_t ld_col, int64_t n_cols, int64_t col_lo, int64_t col_hi, float shift,
-                                    float pos_weight, double inv_count, float* a_row, float* b_col, float* loss_out,
-                                    void* workspace, int64_t workspace_bytes, evk_stream_t stream) {
-  EVK_REQUIRE(rs_part && rp_part && a_row && loss_out && workspace && n_rows > 0 && row_parts >= 1 &&
+namespace {
+int stats_fused_impl(const float* rs_part, int64_t row_parts, int64_t ld_row, const float* rp_part,
+                     int64_t pos_parts, int64_t ld_pos, const int32_t* counts, int64_t n_rows,
+                     const float* cs_part, int64_t col_parts,
+                     int64_t ld_col, int64_t n_cols, int64_t col_lo, int64_t col_hi, float shift,
+                     float pos_weight, double inv_count, float* a_row, float* b_col, float* loss_out,
+                     void* workspace, int64_t workspace_bytes, const StatPush& push, evk_stream_t stream) {
+  EVK_REQUIRE(rs_part && rp_part && a_row && (loss_out || push.n > 0) && workspace && n_rows > 0 && row_parts >= 1 &&
                   ld_row >= n_rows && pos_parts >= 1 && ld_pos >= n_rows, "evk_mpce_stats_fused: bad row arguments");
-  EVK_REQUIRE(!cs_part || (b_col && col_parts >= 1 && ld_col >= n_cols && n_cols > 0),
+  EVK_REQUIRE(!cs_part || ((b_col || push.n > 0) && col_parts >= 1 && ld_col >= n_cols && n_cols > 0),
               "evk_mpce_stats_fused: bad column arguments");
   const int64_t n = (cs_part && n_cols > n_rows) ? n_cols : n_rows;
   const int64_t blocks = (n + kStatElems - 1) / kStatElems;
@@ -164,9 +187,43 @@ extern "C" int evk_mpce_stats_fused(const float* rs_part, int64_t row_parts, int
                                                               counts, n_rows,
                                                               cs_part, col_parts, ld_col, cs_part ? n_cols : 0, col_lo,
                                                               col_hi, shift, pos_weight, inv_count, a_row, b_col,
-                                                              loss_out, partial, ticket);
+                                                              loss_out, partial, ticket, push);
   EVK_CHECK_LAUNCH("mpce_stats_fused");
   return EVK_OK;
+}
+}  // namespace
+
+extern "C" int evk_mpce_stats_fused(const float* rs_part, int64_t row_parts, int64_t ld_row, const float* rp_part,
+                                    int64_t pos_parts, int64_t ld_pos, const int32_t* counts, int64_t n_rows,
+                                    const float* cs_part, int64_t col_parts,
+                                    int64_t ld_col, int64_t n_cols, int64_t col_lo, int64_t col_hi, float shift,
+                                    float pos_weight, double inv_count, float* a_row, float* b_col, float* loss_out,
+                                    void* workspace, int64_t workspace_bytes, evk_stream_t stream) {
+  StatPush push;
+  memset(&push, 0, sizeof(push));
+  return stats_fused_impl(rs_part, row_parts, ld_row, rp_part, pos_parts, ld_pos, counts, n_rows, cs_part, col_parts, ld_col,
+                          n_cols, col_lo, col_hi, shift, pos_weight, inv_count, a_row, b_col, loss_out, workspace,
+                          workspace_bytes, push, stream);
+}
+
+extern "C" int evk_mpce_shard_stats_push(const float* rs_part, int64_t row_parts, int64_t ld_row, const float* rp_part,
+                                         int64_t pos_parts, int64_t ld_pos, const int32_t* counts, int64_t n_rows,
+                                         const float* cs_part, int64_t col_parts, int64_t ld_col, int64_t n_cols,
+                                         float shift, float pos_weight, double inv_count, float* a_row,
+                                         const uint64_t* slot_ptrs, int n_dst, int64_t slot_offset, void* workspace,
+                                         int64_t workspace_bytes, evk_stream_t stream) {
+  EVK_REQUIRE(slot_ptrs && n_dst >= 1 && n_dst <= 16 && slot_offset >= 0 && cs_part, "evk_mpce_shard_stats_push: bad destinations");
+  StatPush push;
+  memset(&push, 0, sizeof(push));
+  push.n = n_dst;
+  push.offset = slot_offset;
+  for (int p = 0; p < n_dst; ++p) {
+    push.dst[p] = reinterpret_cast<float*>(slot_ptrs[p]);
+    EVK_REQUIRE(push.dst[p], "evk_mpce_shard_stats_push: null destination");
+  }
+  return stats_fused_impl(rs_part, row_parts, ld_row, rp_part, pos_parts, ld_pos, counts, n_rows, cs_part, col_parts, ld_col,
+                          n_cols, 0, 0, shift, pos_weight, inv_count, a_row, nullptr, nullptr, workspace, workspace_bytes,
+                          push, stream);
 }
 
 extern "C" int evk_reduce_partials(const float* part, int64_t parts, int64_t ld, int64_t n, const int32_t* divisor,

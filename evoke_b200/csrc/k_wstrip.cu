@@ -119,9 +119,17 @@ w_pos_kernel(__nv_bfloat16* __restrict__ strip, int64_t ld_e, int64_t n_rows, in
   const int64_t nwarps = (int64_t)gridDim.x * kPatchWarps;
   const int64_t words = (n_cols + 31) >> 5;
   const float c1 = inv_tau * 1.4426950408889634f;
-  for (int64_t i = warp0; i < n_rows; i += nwarps) {
-    const int cnt = __ldg(counts + i);
-    if (cnt <= skip_upto) continue;                    // handled by the list kernel (or no positives at all)
+  // a warp takes 32 consecutive rows at a time and keeps those that still need the mask scan (with the
+  // positive lists at hand that is none, or the few rows with more positives than list slots)
+  const int span = skip_upto > 0 ? 32 : 1;               // without lists every row is a candidate: one per warp
+  for (int64_t rb = warp0 * span; rb < n_rows; rb += nwarps * span) {
+   const int cnt_l = (lane < span && rb + lane < n_rows) ? __ldg(counts + rb + lane) : 0;
+   uint32_t need = __ballot_sync(0xffffffffu, cnt_l > skip_upto);
+   while (need) {
+    const int rl = __ffs(need) - 1;
+    need &= need - 1;
+    const int64_t i = rb + rl;
+    const int cnt = __shfl_sync(0xffffffffu, cnt_l, rl);
     const uint32_t* mrow = bits + i * ld_words;
     const float ai = __ldg(a_row + i);
     const float pc = -2.f / (float)max(cnt, 1);
@@ -184,6 +192,7 @@ w_pos_kernel(__nv_bfloat16* __restrict__ strip, int64_t ld_e, int64_t n_rows, in
         }
       }
     }
+   }
   }
 }
 
@@ -215,7 +224,7 @@ extern "C" int evk_mpce_w_from_e(void* strip, int64_t ld_e, int64_t n_rows, int6
   w_scale_kernel<<<dim3((unsigned)gx, (unsigned)gy), kThreads, 0, s>>>(static_cast<uint4*>(strip), ld_e / 8, n_rows, n_cols,
                                                                       a_row, b_col);
   EVK_CHECK_LAUNCH("w_scale");
-  const int64_t blocks = (n_rows + kPatchWarps - 1) / kPatchWarps;     // one row per warp: the pass is latency-bound
+
   int skip_upto = 0;                                  // rows with counts <= skip_upto need no mask scan
   if (pos_idx && pos_dot) {
     EVK_REQUIRE(pos_slots >= 1 && pos_slots <= 64, "evk_mpce_w_from_e: pos_slots must be in 1..64");
@@ -225,6 +234,9 @@ extern "C" int evk_mpce_w_from_e(void* strip, int64_t ld_e, int64_t n_rows, int6
     EVK_CHECK_LAUNCH("w_pos_list");
     skip_upto = pos_slots;
   }
+  // with lists: 32 rows per warp-iteration and nearly every warp finds nothing to do
+  const int64_t blocks = skip_upto > 0 ? (n_rows + 32 * kPatchWarps - 1) / (32 * kPatchWarps)
+                                       : (n_rows + kPatchWarps - 1) / kPatchWarps;
   const int d_vec = (int)((d + 7) / 8);
   const int mask_vec_ok = (ld_words % 4 == 0 && evk_aligned16(bits)) ? 1 : 0;
   auto* sp = static_cast<__nv_bfloat16*>(strip);

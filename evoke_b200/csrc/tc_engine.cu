@@ -37,7 +37,10 @@ constexpr int kTmemCols = 512;
 constexpr int kMaxSegs = 3;
 constexpr int kRowParts = kEpiWarps / 4;      // row-statistic partials written per 256-column tile
 
-enum { EPI_FWD = 0, EPI_BWD_W = 1, EPI_GEMM = 2, EPI_FWD_E = 3 };   // EPI_FWD_E: K3 that also stores E as bf16
+enum { EPI_FWD = 0, EPI_BWD_W = 1, EPI_GEMM = 2, EPI_FWD_E = 3, EPI_GEMM_TMA = 4 };
+// EPI_FWD_E: K3 that also stores E as bf16.  EPI_GEMM_TMA: K4b whose fp32 tiles leave through shared memory and
+// TMA (store, or reduce-add in L2): whole 128-byte lines per request instead of 16-byte red.add / st per lane,
+// which is what peer memory over NVLink needs and also takes the accumulation off the epilogue warps.
 
 // B bytes per stage held by ONE CTA: the whole 256-column tile, or half of it in CTA-pair mode
 template <bool CTA2> constexpr int b_bytes() { return (CTA2 ? BN / 2 : BN) * BK * 2; }
@@ -63,6 +66,8 @@ struct alignas(64) TcParams {
   // EPI_GEMM, reduce-scatter fused into the epilogue: output row i belongs to rank i / rows_per_owner and
   // is accumulated (red.add over NVLink) into that rank's buffer at row i % rows_per_owner
   float* out_peer[16]; int64_t rows_per_owner;
+  // EPI_GEMM_TMA: fp32 output maps (box 32 rows x 32 columns), one per owner (entry 0 for a local output)
+  CUtensorMap peer_map[16];
   // descriptor bases (see tc_ptx.cuh), filled by the host so the probe can try variants
   uint64_t desc_a, desc_b;
   uint32_t idesc;
@@ -73,7 +78,8 @@ struct alignas(64) TcParams {
 template <int EPI>
 constexpr int epi_smem_bytes() {
   return EPI == EPI_FWD ? 4 * BN * 4
-         : (EPI == EPI_BWD_W ? kEpiWarps * 8192 : (EPI == EPI_FWD_E ? 4 * BN * 4 + kEpiWarps * 8192 : 0));
+         : (EPI == EPI_BWD_W ? kEpiWarps * 8192
+            : (EPI == EPI_FWD_E ? 4 * BN * 4 + kEpiWarps * 8192 : (EPI == EPI_GEMM_TMA ? kEpiWarps * 8192 : 0)));
 }
 template <int EPI, int STAGES, bool CTA2>
 constexpr int smem_bytes_total() {
@@ -144,7 +150,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
 // its own 128 rows x 256 columns, so the epilogue is the same code in both modes.
 template <int EPI, bool A_MN, bool B_MN, int STAGES, bool CTA2>
 // (the contraction kernels are capped at 128 registers - bound 512 threads - so that K4t CTAs fit beside them)
-__global__ void __launch_bounds__(EPI == EPI_GEMM ? 512 : kThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512 : kThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int kStage = stage_bytes<CTA2>();
   constexpr int kBRows = CTA2 ? BN / 2 : BN;          // B rows (tile columns) loaded by this CTA
   extern __shared__ uint8_t smem_raw[];
@@ -491,6 +497,45 @@ __global__ void __launch_bounds__(EPI == EPI_GEMM ? 512 : kThreads, 1) tc_kernel
             tma_store_commit();
           }
         }
+      } else if (EPI == EPI_GEMM_TMA) {
+        // Each warp moves its 32 rows x 128 columns in four [32 x 32] fp32 boxes through a private,
+        // double-buffered, 128B-swizzled staging area; one elected lane issues the TMA store / reduce-add.
+        const uint32_t wstg = epi_base + warp * 8192;
+        const int m_warp = m0 + q * 32;
+        int owner = 0, row_in_owner = m_warp;
+        if (p.rows_per_owner > 0) {
+          owner = (int)(m_warp / p.rows_per_owner);
+          row_in_owner = (int)(m_warp - (int64_t)owner * p.rows_per_owner);
+        }
+        const CUtensorMap* omap = &p.peer_map[m_warp < p.n_rows ? owner : 0];
+        const bool reduce = (p.flags & 0x200) == 0;
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 64; ++cc) {
+          const int c = c_lo + cc;
+          float v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait(v);
+          if (cc == BN / 64 - 1) release_tmem(as);
+          if (lane == 0) tma_store_wait_read<1>();              // the buffer used two boxes ago has left smem
+          __syncwarp();
+          const uint32_t row_st = wstg + (cc & 1) * 4096 + lane * 128;
+#pragma unroll
+          for (int uu = 0; uu < 8; ++uu) {
+            const uint32_t off = static_cast<uint32_t>((uu ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row_st + off), "f"(p.alpha * v[4 * uu]),
+                         "f"(p.alpha * v[4 * uu + 1]), "f"(p.alpha * v[4 * uu + 2]), "f"(p.alpha * v[4 * uu + 3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && m_warp < p.n_rows && !(p.flags & 0x100)) {
+            // rows / columns beyond the output are clipped by the tensor map
+            if (reduce) tma_reduce_add_2d(omap, wstg + (cc & 1) * 4096, n0 + c * 32, row_in_owner);
+            else tma_store_2d(omap, wstg + (cc & 1) * 4096, n0 + c * 32, row_in_owner, p.policy_out);
+          }
+          if (lane == 0) tma_store_commit();
+        }
       } else {  // EPI_GEMM
         float* orow;
         if (p.rows_per_owner > 0) {
@@ -534,7 +579,7 @@ __global__ void __launch_bounds__(EPI == EPI_GEMM ? 512 : kThreads, 1) tc_kernel
         release_tmem(as);
       }
     }
-    if ((EPI == EPI_BWD_W || EPI == EPI_FWD_E) && lane == 0) tma_store_wait_all<0>();   // smem must outlive each warp's bulk stores
+    if ((EPI == EPI_BWD_W || EPI == EPI_FWD_E || EPI == EPI_GEMM_TMA) && lane == 0) tma_store_wait_all<0>();   // smem must outlive each warp's bulk stores
   }
 
   tc_fence_before();
@@ -582,6 +627,32 @@ int make_map_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return evk_set_error(EVK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return EVK_OK;
+}
+
+// fp32 row-major output [rows, cols] with pitch ld (elements); box = [32 rows, 32 columns] (128-byte rows), 128B swizzle
+int make_map_f32_out(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return evk_set_error(EVK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  EVK_REQUIRE(evk_aligned16(base) && ld % 4 == 0 && rows > 0 && cols > 0 && ld >= cols, "fp32 output needs a 16-byte aligned base and ld %% 4 == 0");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return evk_set_error(EVK_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 output) failed with CUresult %d", (int)r);
+  return EVK_OK;
+}
+
+bool use_tma_epilogue() {
+  // EVK_GEMM_EPI=red selects the per-lane red.add / st epilogue of the gradient contractions
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EVK_GEMM_EPI");
+    v = (e && e[0] == 'r') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 // K-major operand [mn_extent rows, k_extent cols]: one box of box_mn rows x 64 k.
@@ -856,6 +927,23 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
   }
   fill_descs(p, a_mn, b_mn, variant, cta2);
   if (variant & 8) p.flags |= 0x100;      // bring-up: run the main loop, drop the output
+  if (cta2 && use_tma_epilogue() && !(variant & 16) && (b_mn) ) {
+    // output tiles leave through TMA (store, or reduce-add when units are split along K)
+    int rc;
+    if (p.rows_per_owner > 0) {
+      const int owners = (int)((m + p.rows_per_owner - 1) / p.rows_per_owner);
+      for (int o = 0; o < owners; ++o) {
+        const int64_t rows_o = (o + 1) * p.rows_per_owner <= m ? p.rows_per_owner : m - o * p.rows_per_owner;
+        rc = make_map_f32_out(&p.peer_map[o], p.out_peer[o], rows_o, n, ld_out);
+        if (rc != EVK_OK) return rc;
+      }
+    } else {
+      rc = make_map_f32_out(&p.peer_map[0], out, m, n, ld_out);
+      if (rc != EVK_OK) return rc;
+    }
+    if (a_mn) return launch<EPI_GEMM_TMA, true, true, 5, true>(p, s);
+    return launch<EPI_GEMM_TMA, false, true, 5, true>(p, s);
+  }
   if (cta2) {
     if (a_mn && b_mn) return launch<EPI_GEMM, true, true, 6, true>(p, s);
     if (a_mn) return launch<EPI_GEMM, true, false, 6, true>(p, s);

@@ -148,58 +148,76 @@ class _ShardedG(torch.autograd.Function):
 
 class _ShardedGPeer(torch.autograd.Function):
     """Peer-memory form (bf16 mode): the three exchange steps are done by this library's own kernels over
-    NVLink - K1 stores the normalised key rows into every rank's buffer (all-gather), the statistics slots
-    are pushed the same way, and the key-side gradient contraction stores its tiles straight into the
-    owning rank's per-source buffer, which K1b sums (reduce-scatter fused into the GEMM epilogue).  Three flag barriers per step
-    order them; NCCL is not on the data path.  The forward keeps E as a bf16 strip (K3 store variant), so the
-    backward needs no second similarity sweep: 6 nND FLOP per rank."""
+    NVLink - the prologue kernel stores the normalised key rows and the ids into every rank's buffers
+    (all-gather), the statistics slots are pushed the same way, and the key-side gradient contraction stores
+    its tiles straight into the owning rank's per-source buffer, which K1b sums (reduce-scatter fused into the
+    GEMM epilogue).  Three flag barriers per step order them; NCCL is not on the data path.  The forward keeps
+    E as a bf16 strip (K3 store variant), so the backward needs no second similarity sweep: 6 nND FLOP per rank.
+    15 launches per step: prologue, barrier, K2, positives, K3, statistics+push, barrier, finish | K4t x3,
+    contraction+scatter, contraction, K1b, barrier, K1b."""
 
     @staticmethod
     def forward(ctx, ops, pc, inv_tau: float, row_ids: DeviceIds, image: torch.Tensor, text: torch.Tensor):
         from . import _lib
         world, rank = pc.world, pc.rank
-        n, n_total = pc.n_local, pc.n_total
+        n, n_total, d = pc.n_local, pc.n_total, pc.d
         lo_ = rank * n
-        stream = torch.cuda.current_stream().cuda_stream
         dev = image.device
         need_grad = any(ctx.needs_input_grad[4:])
-        # exchange 1: normalised keys and ids land in every rank's buffers
+        overlap = ops.OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
+        main = torch.cuda.current_stream()
+        side = ops._side_stream(dev)
+        stream = main.cuda_stream
+        two = row_ids.key2 is not None
+        # exchange 1 (one launch): normalised keys + ids into every rank's buffers, local queries, zeroed dQhat
         k_norm = torch.empty(n, dtype=torch.float32, device=dev)
-        _lib.call("evk_l2norm_fwd_bcast", text.data_ptr(), ops._dtype_code(text), n, pc.d, text.stride(0), text.stride(1),
-                  world, pc.table("khat"), None, pc.ld, lo_, k_norm.data_ptr(), stream)
-        _lib.call("evk_peer_bcast", row_ids.key.data_ptr(), n * 4, world, pc.table("ids"), lo_ * 4, stream)
-        if row_ids.key2 is not None:
-            _lib.call("evk_peer_bcast", row_ids.key2.data_ptr(), n * 4, world, pc.table("ids2"), lo_ * 4, stream)
-        qn = ops.l2norm_fwd(image, want_f32=False, want_hi=True, want_lo=False)
+        q_norm = torch.empty(n, dtype=torch.float32, device=dev)
+        q_hi = torch.empty((n, pc.ld), dtype=torch.bfloat16, device=dev)
+        dq = torch.empty((n, pc.width), dtype=torch.float32, device=dev) if need_grad else None
+        _lib.call("evk_shard_prologue", text.data_ptr(), text.stride(0), image.data_ptr(), image.stride(0), n, d, world,
+                  pc.table("khat"), pc.ld, lo_, k_norm.data_ptr(), q_hi.data_ptr(), q_norm.data_ptr(),
+                  row_ids.key.data_ptr(), row_ids.key2.data_ptr() if two else None, pc.table("ids"),
+                  pc.table("ids2") if two else None, None if dq is None else dq.data_ptr(), pc.width, stream)
         pc.barrier()
-        kn_all = ops.Normalized(n=n_total, d=pc.d, norm=None, hi=pc.khat, lo=None, ld=pc.ld)
-        kn_local = ops.Normalized(n=n, d=pc.d, norm=k_norm, hi=pc.khat[lo_:lo_ + n], lo=None, ld=pc.ld)
-        ids_all = DeviceIds(pc.ids, pc.ids2 if row_ids.key2 is not None else None)
+        qn = ops.Normalized(n=n, d=d, norm=q_norm, hi=q_hi, lo=None, ld=pc.ld)
+        kn_all = ops.Normalized(n=n_total, d=d, norm=None, hi=pc.khat, lo=None, ld=pc.ld)
+        kn_local = ops.Normalized(n=n, d=d, norm=k_norm, hi=pc.khat[lo_:lo_ + n], lo=None, ld=pc.ld)
+        ids_all = DeviceIds(pc.ids, pc.ids2 if two else None)
         pos = None
         if need_grad:
             bits, counts, pos_idx = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_, want_list=True)
-            pos = (pos_idx, ops.pos_logits(qn, kn_all, pos_idx, counts))
+            if overlap:                        # exact positive logits (O(n D)) next to K3
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    pos_dot = ops.pos_logits(qn, kn_all, pos_idx, counts)
+                ops._shared_with(side, q_hi, pos_idx, counts)
+            else:
+                pos_dot = ops.pos_logits(qn, kn_all, pos_idx, counts)
+            pos = (pos_idx, pos_dot)
             rs_part, rp_part, cs_part, e, ld_e = ops.tc_fwd_store(qn, kn_all, bits, inv_tau, 0, lo_)
         else:
             bits, counts = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_)
             rs_part, rp_part, cs_part = ops.tc_fwd_partials(qn, kn_all, bits, inv_tau, 0, lo_)
             e, ld_e = None, 0
-        # exchange 2: this rank's slot = partial column sums of its rows + its row-side loss term
-        stage = torch.empty(pc.ld_slot, dtype=torch.float32, device=dev)
-        ops.reduce_partials(cs_part, int(cs_part.shape[0]), n_total, out=stage[:n_total])
-        row_sum = ops.reduce_partials(rs_part, int(rs_part.shape[0]), n)
-        row_pos = ops.reduce_partials(rp_part, int(rp_part.shape[0]), n)
+        # exchange 2 (one launch): partials -> a_row, and this rank's slot (partial column sums of its rows +
+        # its row-side loss term) into every rank's slot buffer
         a_row = torch.empty(n, dtype=torch.float32, device=dev)
-        _lib.call("evk_mpce_finalize", row_sum.data_ptr(), row_pos.data_ptr(), counts.data_ptr(), n, None, 0, 0, 0,
-                  float(inv_tau), 2.0, 0.5 / n_total, a_row.data_ptr(), None, stage[n_total:].data_ptr(), stream)
-        _lib.call("evk_peer_bcast", stage.data_ptr(), pc.ld_slot * 4, world, pc.table("slots"), rank * pc.ld_slot * 4, stream)
+        ws = torch.empty(_round_up(16 + 8 * ((n_total + 31) // 32), 16), dtype=torch.uint8, device=dev)
+        _lib.call("evk_mpce_shard_stats_push", rs_part.data_ptr(), int(rs_part.shape[0]), n, rp_part.data_ptr(),
+                  int(rp_part.shape[0]), n, counts.data_ptr(), n, cs_part.data_ptr(), int(cs_part.shape[0]), n_total,
+                  n_total, float(inv_tau), 2.0, 0.5 / n_total, a_row.data_ptr(), pc.table("slots"), world,
+                  rank * pc.ld_slot, ws.data_ptr(), ws.numel(), stream)
         pc.barrier()
         b_col = torch.empty(n_total, dtype=torch.float32, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
+        ws2 = torch.empty(_round_up(16 + 8 * ((n_total + 255) // 256), 16), dtype=torch.uint8, device=dev)
         _lib.call("evk_mpce_shard_finish", pc.slots.data_ptr(), world, pc.ld_slot, n_total, float(inv_tau), 0.5 / n_total,
-                  b_col.data_ptr(), loss.data_ptr(), stream)
+                  b_col.data_ptr(), loss.data_ptr(), ws2.data_ptr(), ws2.numel(), stream)
+        if need_grad and overlap:
+            main.wait_stream(side)
+            ops._shared_with(main, pos_dot)
         ctx.ops, ctx.pc, ctx.inv_tau = ops, pc, inv_tau
-        ctx.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, e, ld_e)
+        ctx.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, e, ld_e, dq)
         ctx.pos = pos
         ctx.save_for_backward(image, text)
         out = loss.reshape(())
@@ -210,26 +228,47 @@ class _ShardedGPeer(torch.autograd.Function):
     def backward(ctx, grad_out):
         from . import _lib
         ops, pc, inv_tau = ctx.ops, ctx.pc, ctx.inv_tau
-        qn, kn_local, kn_all, bits, counts, a_row, b_col, e, ld_e = ctx.sv
+        qn, kn_local, kn_all, bits, counts, a_row, b_col, e, ld_e, dq = ctx.sv
         if e is None:
             raise RuntimeError("evoke_b200: backward called twice on the sharded loss (the E strip was consumed)")
         image, text = ctx.saved_tensors
         n, n_total = pc.n_local, pc.n_total
         g = grad_out.reshape(1).to(torch.float32).contiguous()
         scale = 0.5 * inv_tau / n_total
-        stream = torch.cuda.current_stream().cuda_stream
+        overlap = ops.OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
+        main = torch.cuda.current_stream()
         ops.tc_w_from_e(e, ld_e, n_total, bits, counts, a_row, b_col, qn, kn_all, inv_tau, pos=ctx.pos)
         # exchange 3, fused: the tiles of this rank's partial dKhat are stored straight into their owners'
         # per-source buffers (posted NVLink stores from the GEMM epilogue; no split-K, no zero fill)
         _lib.call("evk_mpce_bwd_gemm_scatter", e.data_ptr(), None, ld_e, n, n_total, qn.hi.data_ptr(), None, qn.ld, qn.d,
-                  1.0, 0, pc.table("dk_mine"), pc.world, n, pc.width, 1, stream)
-        dq = ops.tc_bwd_gemm(e, None, ld_e, n, n_total, False, kn_all, 0)
-        d_image = ops.l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale)
+                  1.0, 0, pc.table("dk_mine"), pc.world, n, pc.width, 1, main.cuda_stream)
+
+        def image_side():
+            ops.tc_bwd_gemm(e, None, ld_e, n, n_total, False, kn_all, 0, out=dq)      # dq was zeroed by the prologue
+            return ops.l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale)
+
+        if overlap:
+            # the local contraction fills the SMs as the scattering one drains (it may be NVLink-bound)
+            side = ops._side_stream(image.device)
+            w_ready = main.record_event()
+            with torch.cuda.stream(side):
+                side.wait_event(w_ready)
+                d_image = image_side()
+            ops._shared_with(side, e, dq, g, image, qn.norm)
+        else:
+            d_image = image_side()
         pc.barrier()                           # every rank's partial for these rows has landed
         d_text = ops.l2norm_bwd(text, kn_local, pc.dk_parts[0], scale_dev=g, scale_host=scale,
                                 parts=(pc.world, n * pc.width))
-        ctx.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, None, 0)
+        if overlap:
+            main.wait_stream(side)
+            ops._shared_with(main, d_image)
+        ctx.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, None, 0, None)
         return None, None, None, None, d_image, d_text
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
 
 
 def peer_eligible(image: torch.Tensor, text: torch.Tensor, precision: str, world: int) -> bool:

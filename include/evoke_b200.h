@@ -272,6 +272,31 @@ EVK_API int evk_l2norm_fwd_bcast(const void* x, int x_dtype, int64_t n_rows, int
 EVK_API int evk_peer_bcast(const void* src, int64_t bytes, int n_dst, const uint64_t* dst,
                    int64_t dst_offset_bytes, evk_stream_t stream);
 
+/* Prologue of a sharded step in one launch: K1 of this rank's key rows (text) stored as bf16 at rows
+ * row_offset.. of EVERY rank's key buffer (khat_ptrs: host table, n_dst entries), K1 of its query rows (image)
+ * into the local q_hi, the id shard(s) pushed to offset row_offset of every rank's id buffer(s), and - if
+ * zero_buf != NULL - the zero fill of an fp32 [n_rows, ld_zero] accumulator (the split-K output of the local
+ * gradient contraction).  Contiguous fp32 inputs, d % 8 == 0, d <= 2048.  F.normalize of :495-496 for both
+ * sides plus what a sharded run must exchange before the similarity sweep. */
+EVK_API int evk_shard_prologue(const float* text, int64_t text_stride, const float* image, int64_t image_stride,
+                       int64_t n_rows, int64_t d, int n_dst, const uint64_t* khat_ptrs, int64_t ld_bf16,
+                       int64_t row_offset, float* k_norm, void* q_hi, float* q_norm,
+                       const int32_t* ids, const int32_t* ids2, const uint64_t* ids_ptrs, const uint64_t* ids2_ptrs,
+                       float* zero_buf, int64_t ld_zero, evk_stream_t stream);
+
+/* Sharded form of evk_mpce_stats_fused: reduces K3's partials of this rank's row block, writes a_row, and
+ * stores this rank's statistics slot - the raw partial column sums (n_cols floats) followed by its row-side
+ * loss term inv_count * sum_i (shift + ln R_i - pos_weight pos_i / c_i) - at element offset slot_offset of
+ * EVERY rank's slot buffer (slot_ptrs: host table of n_dst peer-mapped addresses).  evk_mpce_shard_finish
+ * closes the forward after a barrier.  workspace as for evk_mpce_stats_fused. */
+EVK_API int evk_mpce_shard_stats_push(const float* rs_part, int64_t row_parts, int64_t ld_row,
+                              const float* rp_part, int64_t pos_parts, int64_t ld_pos,
+                              const int32_t* counts, int64_t n_rows,
+                              const float* cs_part, int64_t col_parts, int64_t ld_col, int64_t n_cols,
+                              float shift, float pos_weight, double inv_count, float* a_row,
+                              const uint64_t* slot_ptrs, int n_dst, int64_t slot_offset,
+                              void* workspace, int64_t workspace_bytes, evk_stream_t stream);
+
 /* Symmetric buffers for that transport.  evk_peer_alloc is the one place the library allocates device
  * memory (cudaMalloc, zero-filled): CUDA-IPC handles name whole allocations, so the exchanged buffers
  * cannot come out of a caching allocator.  The caller frees them with evk_peer_free.  evk_peer_export
@@ -296,9 +321,11 @@ EVK_API int evk_peer_barrier(const uint64_t* flag_ptrs, int n_ranks, int rank, u
  * partial column exp-sums over its own rows (n_cols floats) followed by its row-side loss term
  * inv_count * sum_{i in rows of r} (shift + ln R_i - 2 pos_i / c_i) at index n_cols.
  *   b_col[j] = 1 / sum_r slots[r][j];   loss_out[0] = sum_r slots[r][n_cols] + inv_count * sum_j (shift + ln C_j)
- * (:501-503 on the concatenated batch).  Fixed summation order: every rank computes identical bits. */
+ * (:501-503 on the concatenated batch).  Fixed summation order: every rank computes identical bits.
+ * workspace: >= 16 + 8*ceil(n_cols/256) bytes, 16-byte aligned, contents irrelevant. */
 EVK_API int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
-                          double inv_count, float* b_col, float* loss_out, evk_stream_t stream);
+                          double inv_count, float* b_col, float* loss_out,
+                          void* workspace, int64_t workspace_bytes, evk_stream_t stream);
 
 /* K4b with the reduce-scatter fused into its epilogue: the partial dKhat of this rank's row block,
  *   out_owner(j)[j % rows_per_owner, :] += alpha * sum_i W[i, j] x[i, :],   owner(j) = j / rows_per_owner,

@@ -1,0 +1,19 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_estrip.py tests/test_gpu_parity.py -q -m gpu -x > gpurun_out/t_all.log 2>&1; echo "single rc=$?"
+tail -6 gpurun_out/t_all.log
+timeout 600 python -m pytest tests/test_gpu_distributed.py -q -m gpu -x > gpurun_out/t_dist.log 2>&1; echo "dist rc=$?"
+tail -6 gpurun_out/t_dist.log
+for mode in peer rs; do
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 30 --warmup 5 --no-cpu-baseline --shard-mode $mode > gpurun_out/b2_$mode.json 2> gpurun_out/b2_$mode.err; echo "bench2 $mode rc=$?"
+done
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/b1.json 2> gpurun_out/b1.err
+for f in b2_peer b2_rs b1; do python - <<PY
+import json
+try:
+    d=json.loads([l for l in open("gpurun_out/$f.json").read().strip().splitlines() if l.startswith("{")][-1])
+    print("$f", round(d["ms_per_step"],4), "ms", round(d["value"]/1e6,3), "Mpairs/s", "eager", round(d.get("ms_per_step_eager") or 0,4), {k:round(v["avg_ms"],4) for k,v in d["kernels"].items()}, d["clocks"]["reasons"], "e2e", round(d["e2e"]["ms_per_step"],3))
+except Exception as e:
+    print("$f failed", e); print(open("gpurun_out/$f.err").read()[-2500:])
+PY
+done
