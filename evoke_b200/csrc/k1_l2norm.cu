@@ -122,7 +122,7 @@ l2norm_fwd_generic_kernel(const void* __restrict__ x, int x_dtype, int64_t n_out
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_bwd_kernel(const void* __restrict__ x, int x_dtype, int64_t n_out, int64_t d, int64_t stride_row,
                   int64_t stride_col, const int32_t* __restrict__ gather, const float* __restrict__ norm,
-                  const float* __restrict__ g, int64_t ld_g, int n_parts, int64_t part_stride,
+                  const void* __restrict__ g, int g_dtype, int64_t ld_g, int n_parts, int64_t part_stride,
                   const float* __restrict__ scale_dev,
                   float scale_host, void* __restrict__ dx, int dx_dtype, int64_t ld_dx, int accumulate) {
   const int lane = threadIdx.x & 31;
@@ -135,10 +135,9 @@ l2norm_bwd_kernel(const void* __restrict__ x, int x_dtype, int64_t n_out, int64_
     const float nrm = norm[r];
     const bool clamped = nrm < EVK_NORM_EPS;
     const float den = fmaxf(nrm, EVK_NORM_EPS);
-    const float* gr = g + r * ld_g;
     auto gval = [&](int64_t c) {                   // upstream gradient = sum of the partial buffers (rank order)
-      float v = gr[c];
-      for (int p = 1; p < n_parts; ++p) v += gr[p * part_stride + c];
+      float v = load_as_float(g, g_dtype, r * ld_g + c);
+      for (int p = 1; p < n_parts; ++p) v += load_as_float(g, g_dtype, p * part_stride + r * ld_g + c);
       return v;
     };
     float proj = 0.f;
@@ -168,11 +167,12 @@ l2norm_bwd_kernel(const void* __restrict__ x, int x_dtype, int64_t n_out, int64_
 // Fast path: fp32 x / g / dx, unit column stride, 16-byte aligned rows, d % 4 == 0, d <= kIters*128.
 // One pass: the row of x and g stays in registers between the projection and the update.
 // Algorithmic bytes per row: 4d (x) + 4d (g) read, 4d (dx) written.
-template <int kIters>
+// kBf16G: the partial buffers hold bf16 (the compressed exchange of the sharded path): 4 values = one 64-bit load
+template <int kIters, bool kBf16G>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t stride_row,
                       const int32_t* __restrict__ gather, const float* __restrict__ norm,
-                      const float* __restrict__ g, int64_t ld_g, int n_parts, int64_t part_stride,
+                      const void* __restrict__ g, int64_t ld_g, int n_parts, int64_t part_stride,
                       const float* __restrict__ scale_dev,
                       float scale_host, float* __restrict__ dx, int64_t ld_dx) {
   const int lane = threadIdx.x & 31;
@@ -182,7 +182,14 @@ l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t
   for (int64_t r = warp0; r < n_out; r += nwarps) {
     const int64_t src = gather ? (int64_t)gather[r] : r;
     const float4* xr = reinterpret_cast<const float4*>(x + src * stride_row);
-    const float4* gr = reinterpret_cast<const float4*>(g + r * ld_g);
+    auto gload = [&](int p, int c) -> float4 {       // 4 consecutive values of part p, row r
+      if (kBf16G) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(g) + p * part_stride + r * ld_g) + c);
+        return make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u), __uint_as_float(t.y << 16),
+                           __uint_as_float(t.y & 0xffff0000u));
+      }
+      return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(g) + p * part_stride + r * ld_g) + c);
+    };
     float4* dr = reinterpret_cast<float4*>(dx + src * ld_dx);
     const float nrm = norm[r];
     const bool clamped = nrm < EVK_NORM_EPS;
@@ -195,9 +202,9 @@ l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t
       const int c = it * 32 + lane;
       if (c * 4 < d) {
         xv[it] = __ldg(xr + c);
-        gv[it] = __ldg(gr + c);
+        gv[it] = gload(0, c);
         for (int p = 1; p < n_parts; ++p) {        // partial dXhat buffers written by the ranks' K4b epilogues
-          const float4 t = __ldg(gr + p * (part_stride >> 2) + c);
+          const float4 t = gload(p, c);
           gv[it].x += t.x; gv[it].y += t.y; gv[it].z += t.z; gv[it].w += t.w;
         }
         xv[it].x *= inv_den; xv[it].y *= inv_den; xv[it].z *= inv_den; xv[it].w *= inv_den;   // xhat (1 ulp of the forward's)
@@ -270,12 +277,13 @@ extern "C" int evk_l2norm_fwd(const void* x, int x_dtype, int64_t n_out, int64_t
 }
 
 extern "C" int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, int64_t d, int64_t stride_row,
-                                    int64_t stride_col, const int32_t* gather, const float* norm, const float* g,
-                                    int64_t ld_g, int n_parts, int64_t part_stride, const float* scale_dev,
+                                    int64_t stride_col, const int32_t* gather, const float* norm, const void* g,
+                                    int g_dtype, int64_t ld_g, int n_parts, int64_t part_stride, const float* scale_dev,
                                     float scale_host, void* dx, int dx_dtype, int64_t ld_dx, int accumulate,
                                     evk_stream_t stream) {
   EVK_REQUIRE(x && norm && g && dx, "evk_l2norm_bwd: null pointer");
   EVK_REQUIRE(n_parts >= 1 && (n_parts == 1 || part_stride >= n_out * ld_g), "evk_l2norm_bwd_parts: bad partial-buffer layout");
+  EVK_REQUIRE(g_dtype == EVK_DTYPE_F32 || g_dtype == EVK_DTYPE_BF16, "evk_l2norm_bwd_parts: partial buffers must be fp32 or bf16");
   EVK_REQUIRE(n_out >= 0 && d > 0 && ld_g >= d && ld_dx >= d, "evk_l2norm_bwd: bad shape");
   EVK_REQUIRE(x_dtype >= EVK_DTYPE_F32 && x_dtype <= EVK_DTYPE_F16 && dx_dtype >= EVK_DTYPE_F32 &&
                   dx_dtype <= EVK_DTYPE_F16, "evk_l2norm_bwd: bad dtype");
@@ -284,23 +292,25 @@ extern "C" int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, i
   const bool vec = x_dtype == EVK_DTYPE_F32 && dx_dtype == EVK_DTYPE_F32 && !accumulate && stride_col == 1 &&
                    d % 4 == 0 && d <= 2048 && stride_row % 4 == 0 && ld_g % 4 == 0 && ld_dx % 4 == 0 && part_stride % 4 == 0 &&
                    evk_aligned16(x) && evk_aligned16(g) && evk_aligned16(dx);
+  const bool g16 = g_dtype == EVK_DTYPE_BF16;
   if (vec) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int grid = grid_for_rows(n_out);
     const float* xf = static_cast<const float*>(x);
     float* df = static_cast<float*>(dx);
-    if (d <= 1024)
-      l2norm_bwd_vec_kernel<8><<<grid, kWarpsPerBlock * 32, 0, s>>>(xf, n_out, (int)d, stride_row, gather, norm, g, ld_g,
-                                                                    n_parts, part_stride, scale_dev, scale_host, df, ld_dx);
-    else
-      l2norm_bwd_vec_kernel<16><<<grid, kWarpsPerBlock * 32, 0, s>>>(xf, n_out, (int)d, stride_row, gather, norm, g,
-                                                                     ld_g, n_parts, part_stride, scale_dev, scale_host, df, ld_dx);
+#define EVK_LAUNCH_BWD(IT, B16)                                                                                  \
+  l2norm_bwd_vec_kernel<IT, B16><<<grid, kWarpsPerBlock * 32, 0, s>>>(xf, n_out, (int)d, stride_row, gather, norm, g, \
+                                                                      ld_g, n_parts, part_stride, scale_dev,           \
+                                                                      scale_host, df, ld_dx)
+    if (d <= 1024) { if (g16) EVK_LAUNCH_BWD(8, true); else EVK_LAUNCH_BWD(8, false); }
+    else { if (g16) EVK_LAUNCH_BWD(16, true); else EVK_LAUNCH_BWD(16, false); }
+#undef EVK_LAUNCH_BWD
     EVK_CHECK_LAUNCH("l2norm_bwd_vec");
     return EVK_OK;
   }
   l2norm_bwd_kernel<<<grid_for_rows(n_out), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, x_dtype, n_out, d, stride_row, stride_col, gather, norm, g, ld_g, n_parts, part_stride, scale_dev, scale_host, dx, dx_dtype,
-      ld_dx, accumulate);
+      x, x_dtype, n_out, d, stride_row, stride_col, gather, norm, g, g_dtype, ld_g, n_parts, part_stride, scale_dev, scale_host, dx,
+      dx_dtype, ld_dx, accumulate);
   EVK_CHECK_LAUNCH("l2norm_bwd");
   return EVK_OK;
 }
@@ -309,6 +319,6 @@ extern "C" int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t
                               int64_t stride_col, const int32_t* gather, const float* norm, const float* g,
                               int64_t ld_g, const float* scale_dev, float scale_host, void* dx, int dx_dtype,
                               int64_t ld_dx, int accumulate, evk_stream_t stream) {
-  return evk_l2norm_bwd_parts(x, x_dtype, n_out, d, stride_row, stride_col, gather, norm, g, ld_g, 1, 0, scale_dev,
+  return evk_l2norm_bwd_parts(x, x_dtype, n_out, d, stride_row, stride_col, gather, norm, g, EVK_DTYPE_F32, ld_g, 1, 0, scale_dev,
                               scale_host, dx, dx_dtype, ld_dx, accumulate, stream);
 }

@@ -509,6 +509,7 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
         }
         const CUtensorMap* omap = &p.peer_map[m_warp < p.n_rows ? owner : 0];
         const bool reduce = (p.flags & 0x200) == 0;
+        const bool out16 = (p.flags & 0x2000) != 0;              // bf16 output boxes [32 rows x 64 columns] (store mode only)
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
 #pragma unroll 1
@@ -518,6 +519,34 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait(v);
           if (cc == BN / 64 - 1) release_tmem(as);
+          if (out16) {
+            // two 32-column chunks share one 128-byte-row box; buffers alternate per box
+            const int box = cc >> 1;
+            if ((cc & 1) == 0) {
+              if (lane == 0) tma_store_wait_read<1>();
+              __syncwarp();
+            }
+            const uint32_t row_st = wstg + (box & 1) * 4096 + lane * 128;
+            const int u0 = (cc & 1) * 4;
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+              const uint32_t h0 = pack_bf16x2(p.alpha * v[8 * uu + 0], p.alpha * v[8 * uu + 1]);
+              const uint32_t h1 = pack_bf16x2(p.alpha * v[8 * uu + 2], p.alpha * v[8 * uu + 3]);
+              const uint32_t h2 = pack_bf16x2(p.alpha * v[8 * uu + 4], p.alpha * v[8 * uu + 5]);
+              const uint32_t h3 = pack_bf16x2(p.alpha * v[8 * uu + 6], p.alpha * v[8 * uu + 7]);
+              const uint32_t off = static_cast<uint32_t>(((u0 + uu) ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_st + off), "r"(h0), "r"(h1), "r"(h2),
+                           "r"(h3) : "memory");
+            }
+            if (cc & 1) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0 && m_warp < p.n_rows && !(p.flags & 0x100))
+                tma_store_2d(omap, wstg + (box & 1) * 4096, n0 + (c - 1) * 32, row_in_owner, p.policy_out);
+              if (lane == 0) tma_store_commit();
+            }
+            continue;
+          }
           if (lane == 0) tma_store_wait_read<1>();              // the buffer used two boxes ago has left smem
           __syncwarp();
           const uint32_t row_st = wstg + (cc & 1) * 4096 + lane * 128;
@@ -897,7 +926,8 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
   if (p.rows_per_owner > 0) out = p.out_peer[0];
   EVK_REQUIRE(m > 0 && n > 0 && k > 0 && out, "gemm: empty problem or null output");
   EVK_REQUIRE(m < (1ll << 30) && n < (1ll << 30) && k < (1ll << 30), "gemm: problem too large");
-  EVK_REQUIRE(ld_out >= n && ld_out % 4 == 0 && evk_aligned16(out), "gemm: out needs 16-byte alignment and ld_out %% 4 == 0");
+  EVK_REQUIRE(ld_out >= n && ld_out % ((p.flags & 0x2000) ? 8 : 4) == 0 && evk_aligned16(out),
+              "gemm: out needs 16-byte alignment and 16-byte rows");
   p.num_segs = nsegs;
   p.kb_per_seg = (int)((k + BK - 1) / BK);
   for (int sg = 0; sg < nsegs; ++sg) {
@@ -934,7 +964,8 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
       const int owners = (int)((m + p.rows_per_owner - 1) / p.rows_per_owner);
       for (int o = 0; o < owners; ++o) {
         const int64_t rows_o = (o + 1) * p.rows_per_owner <= m ? p.rows_per_owner : m - o * p.rows_per_owner;
-        rc = make_map_f32_out(&p.peer_map[o], p.out_peer[o], rows_o, n, ld_out);
+        rc = (p.flags & 0x2000) ? make_map_bf16(&p.peer_map[o], p.out_peer[o], rows_o, n, ld_out, 32, 64)
+                                : make_map_f32_out(&p.peer_map[o], p.out_peer[o], rows_o, n, ld_out);
         if (rc != EVK_OK) return rc;
       }
     } else {
@@ -996,6 +1027,10 @@ extern "C" int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int
   }
   p.rows_per_owner = rows_per_owner;
   if (store) p.flags |= 0x200;
+  if (store == 2) {
+    EVK_REQUIRE(use_cta_pairs() && use_tma_epilogue(), "evk_mpce_bwd_gemm_scatter: bf16 partials need the TMA epilogue (CTA pairs)");
+    p.flags |= 0x2000;
+  }
   const void* a_ptrs[3] = {w_hi, w_hi, w_lo};
   const void* b_ptrs[3] = {x_hi, x_lo, x_hi};
   // dKhat partial of this rank's rows: A = W^T (MN-major), K = n_rows; out rows = the n_cols keys

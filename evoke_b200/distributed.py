@@ -18,6 +18,7 @@ checked without a GPU; the product never does.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -173,11 +174,12 @@ class _ShardedGPeer(torch.autograd.Function):
         k_norm = torch.empty(n, dtype=torch.float32, device=dev)
         q_norm = torch.empty(n, dtype=torch.float32, device=dev)
         q_hi = torch.empty((n, pc.ld), dtype=torch.bfloat16, device=dev)
-        dq = torch.empty((n, pc.width), dtype=torch.float32, device=dev) if need_grad else None
+        wq = _round_up(d, 4)
+        dq = torch.empty((n, wq), dtype=torch.float32, device=dev) if need_grad else None
         _lib.call("evk_shard_prologue", text.data_ptr(), text.stride(0), image.data_ptr(), image.stride(0), n, d, world,
                   pc.table("khat"), pc.ld, lo_, k_norm.data_ptr(), q_hi.data_ptr(), q_norm.data_ptr(),
                   row_ids.key.data_ptr(), row_ids.key2.data_ptr() if two else None, pc.table("ids"),
-                  pc.table("ids2") if two else None, None if dq is None else dq.data_ptr(), pc.width, stream)
+                  pc.table("ids2") if two else None, None if dq is None else dq.data_ptr(), wq, stream)
         pc.barrier()
         qn = ops.Normalized(n=n, d=d, norm=q_norm, hi=q_hi, lo=None, ld=pc.ld)
         kn_all = ops.Normalized(n=n_total, d=d, norm=None, hi=pc.khat, lo=None, ld=pc.ld)
@@ -241,7 +243,7 @@ class _ShardedGPeer(torch.autograd.Function):
         # exchange 3, fused: the tiles of this rank's partial dKhat are stored straight into their owners'
         # per-source buffers (posted NVLink stores from the GEMM epilogue; no split-K, no zero fill)
         _lib.call("evk_mpce_bwd_gemm_scatter", e.data_ptr(), None, ld_e, n, n_total, qn.hi.data_ptr(), None, qn.ld, qn.d,
-                  1.0, 0, pc.table("dk_mine"), pc.world, n, pc.width, 1, main.cuda_stream)
+                  1.0, 0, pc.table("dk_mine"), pc.world, n, pc.width, 2 if pc.exchange == "bf16" else 1, main.cuda_stream)
 
         def image_side():
             ops.tc_bwd_gemm(e, None, ld_e, n, n_total, False, kn_all, 0, out=dq)      # dq was zeroed by the prologue
@@ -277,6 +279,9 @@ def peer_eligible(image: torch.Tensor, text: torch.Tensor, precision: str, world
     return (precision == "bf16" and image.is_cuda and world <= 16 and n % 128 == 0 and d % 8 == 0 and d <= 2048
             and text.dtype == torch.float32 and text.stride(1) == 1 and text.stride(0) % 4 == 0
             and text.data_ptr() % 16 == 0)
+
+
+PEER_EXCHANGE = os.environ.get("EVOKE_B200_PEER_EXCHANGE", "bf16")     # dtype of the dKhat partials on NVLink: bf16 | fp32
 
 
 def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local, temp: float, *,
@@ -328,7 +333,7 @@ def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local,
         if peer_eligible(image, text, precision, world):
             from . import peer
             pc = peer.get_context(group, int(image.shape[0]), int(image.shape[1]), image.device,
-                                  two_keys=row_ids.key2 is not None)
+                                  two_keys=row_ids.key2 is not None, exchange=PEER_EXCHANGE)
         if pc is not None:
             return _ShardedGPeer.apply(ops, pc, 1.0 / temp, row_ids, image, text)
         if mode == "peer":

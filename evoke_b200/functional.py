@@ -131,7 +131,7 @@ def l2norm_bwd(x: torch.Tensor, nrm: Normalized, g_hat: torch.Tensor, *, scale_d
         dx = torch.empty(x.shape, dtype=x.dtype, device=x.device)
     n_parts, part_stride = parts if parts is not None else (1, 0)
     _lib.call("evk_l2norm_bwd_parts", _ptr(x), _dtype_code(x), nrm.n, nrm.d, x.stride(0), x.stride(1), _ptr(gather),
-              _ptr(nrm.norm), _ptr(g_hat), g_hat.stride(0), int(n_parts), int(part_stride), _ptr(scale_dev),
+              _ptr(nrm.norm), _ptr(g_hat), _dtype_code(g_hat), g_hat.stride(0), int(n_parts), int(part_stride), _ptr(scale_dev),
               float(scale_host), _ptr(dx), _dtype_code(dx), dx.stride(0), 0, _stream())
     return dx
 

@@ -9,7 +9,7 @@ flag barrier kernel (``evk_peer_barrier``) - no NCCL call sits on the data path:
   khat   [N, ld]  bf16    K1 writes this rank's normalised rows into EVERY rank's copy (all-gather)
   ids    [N] (+ids2 [N])  the id shards, pushed the same way
   slots  [R, N+4] fp32    slot r = rank r's partial column exp-sums + its row-side loss term
-  dk_parts [R, n, D] fp32 this rank's rows of dKhat, one partial per source rank: rank s's K4b epilogue
+  dk_parts [R, n, D] bf16 (or fp32) this rank's rows of dKhat, one partial per source rank: rank s's K4b epilogue
                           stores its tiles for these rows into part s (posted NVLink stores), K1b adds them up
   flags  [16]     uint32  barrier flags (entry r written by rank r only)
 
@@ -41,7 +41,7 @@ class _RawCuda:
 
 class PeerContext:
     def __init__(self, group, n_local: int, d: int, device: torch.device, two_keys: bool = False,
-                 timeout_ms: int = 2000):
+                 timeout_ms: int = 2000, exchange: str = "bf16"):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -53,14 +53,16 @@ class PeerContext:
         self.n_local, self.d = n_local, d
         self.n_total = n_local * self.world
         self.ld = _round_up(d, 8)
-        self.width = _round_up(d, 4)
+        self.exchange = exchange                       # dtype of the dKhat partials that cross NVLink
+        self.width = _round_up(d, 8) if exchange == "bf16" else _round_up(d, 4)
+        esize = 2 if exchange == "bf16" else 4
         self.ld_slot = _round_up(self.n_total + 4, 4)
         self.timeout_ms = timeout_ms
         n, big_n, r = n_local, self.n_total, self.world
         off = 0
         self.off = {}
         for name, nbytes in (("khat", big_n * self.ld * 2), ("ids", big_n * 4), ("ids2", big_n * 4 if two_keys else 0),
-                             ("slots", r * self.ld_slot * 4), ("dk_parts", r * n * self.width * 4), ("flags", 64)):
+                             ("slots", r * self.ld_slot * 4), ("dk_parts", r * n * self.width * esize), ("flags", 64)):
             self.off[name] = off
             off += _round_up(nbytes, _ALIGN)
         self.nbytes = off
@@ -101,12 +103,13 @@ class PeerContext:
         self.ids = self._view("ids", big_n * 4).view(torch.int32)
         self.ids2 = self._view("ids2", big_n * 4).view(torch.int32) if two_keys else None
         self.slots = self._view("slots", r * self.ld_slot * 4).view(torch.float32).view(r, self.ld_slot)
-        self.dk_parts = self._view("dk_parts", r * n * self.width * 4).view(torch.float32).view(r, n, self.width)
+        self.dk_parts = self._view("dk_parts", r * n * self.width * esize).view(
+            torch.bfloat16 if exchange == "bf16" else torch.float32).view(r, n, self.width)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.ptrs = {name: (ctypes.c_uint64 * self.world)(*[b + o for b in self.bases]) for name, o in self.off.items()}
         # where THIS rank's partial for owner t goes: part `rank` of t's dk_parts
-        mine = self.rank * n * self.width * 4
+        mine = self.rank * n * self.width * esize
         self.ptrs["dk_mine"] = (ctypes.c_uint64 * self.world)(*[b + self.off["dk_parts"] + mine for b in self.bases])
         torch.cuda.synchronize(self.device)
 
@@ -144,13 +147,14 @@ class PeerContext:
 _CONTEXTS: dict = {}
 
 
-def get_context(group, n_local: int, d: int, device: torch.device, two_keys: bool = False) -> Optional[PeerContext]:
+def get_context(group, n_local: int, d: int, device: torch.device, two_keys: bool = False,
+                exchange: str = "bf16") -> Optional[PeerContext]:
     """Cached context for (group, shard shape); None if peer mapping is not possible here (the caller
     then uses the NCCL transport).  Collective: every rank must call it with the same arguments."""
-    key = (id(group), n_local, d, torch.device(device).index, two_keys)
+    key = (id(group), n_local, d, torch.device(device).index, two_keys, exchange)
     if key in _CONTEXTS:
         return _CONTEXTS[key]
-    ctx: Optional[PeerContext] = PeerContext(group, n_local, d, device, two_keys)
+    ctx: Optional[PeerContext] = PeerContext(group, n_local, d, device, two_keys, exchange=exchange)
     if ctx.failure is not None:                                  # IPC refused (container policy, no P2P, ...)
         _CONTEXTS["last_error"] = ctx.failure
     # all or nothing; also the barrier after which every rank has mapped every buffer

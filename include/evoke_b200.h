@@ -92,11 +92,11 @@ EVK_API int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t d,
                    void* dx, int dx_dtype, int64_t ld_dx, int accumulate, evk_stream_t stream);
 
 /* Same, with the upstream gradient given as n_parts partial buffers that are summed on the fly (in index
- * order): g_total[r, c] = sum_p g[p * part_stride + r * ld_g + c].  Closes the fused reduce-scatter of
+ * order): g_total[r, c] = sum_p g[p * part_stride + r * ld_g + c] (g_dtype: EVK_DTYPE_F32 or _BF16).  Closes the fused reduce-scatter of
  * evk_mpce_bwd_gemm_scatter(store = 1): part p is what rank p's contraction stored for this rank's rows. */
 EVK_API int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, int64_t d,
                          int64_t stride_row, int64_t stride_col, const int32_t* gather,
-                         const float* norm, const float* g, int64_t ld_g, int n_parts, int64_t part_stride,
+                         const float* norm, const void* g, int g_dtype, int64_t ld_g, int n_parts, int64_t part_stride,
                          const float* scale_dev, float scale_host,
                          void* dx, int dx_dtype, int64_t ld_dx, int accumulate, evk_stream_t stream);
 
@@ -335,7 +335,8 @@ EVK_API int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_sl
  * store != 0: no split-K and plain 128-bit stores instead of red.add - every element of the owners' buffers
  * is written exactly once, so out_ptrs[o] must be a buffer private to THIS source rank (the owner then adds the
  * per-source buffers up: evk_l2norm_bwd_parts) and needs no zero fill.  Posted stores use NVLink far better
- * than 16-byte atomics. */
+ * than 16-byte atomics.  store == 2: the partials are stored as bf16 ([rows_per_owner, ld_out] bf16, ld_out % 8 == 0):
+ * half the NVLink bytes; the owner still adds them up in fp32. */
 EVK_API int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int64_t ld_w,
                               int64_t n_rows, int64_t n_cols,
                               const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d,

@@ -15,6 +15,9 @@ pytestmark = pytest.mark.gpu
 
 def _worker(rank, world, port, n_total, d, tau, precision, mode, out_dir):
     sys.path.insert(0, ROOT)
+    if mode.startswith("peer-"):                     # "peer-fp32": fp32 partials on NVLink instead of bf16
+        os.environ["EVOKE_B200_PEER_EXCHANGE"] = mode.split("-")[1]
+        mode = "peer"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -98,17 +101,17 @@ def test_peer_path_in_a_cuda_graph_on_two_gpus(tmp_path):
             assert np.abs(got[f"d_text{seed}"] - d_t[sl]).max() <= 2e-2 * np.abs(d_t).max()
 
 
-@pytest.mark.parametrize("mode", ["rs", "sym", "peer"])
+@pytest.mark.parametrize("mode", ["rs", "sym", "peer", "peer-fp32"])
 @pytest.mark.parametrize("precision,ltol,gtol", [("fp32", 1e-5, 1e-4), ("bf16", 2e-3, 2e-2)])
 def test_sharded_equals_oracle_on_two_gpus(tmp_path, precision, ltol, gtol, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    if mode == "peer" and precision != "bf16":
+    if mode.startswith("peer") and precision != "bf16":
         pytest.skip("the peer-memory path is a bf16-mode path")
     from evoke_b200 import synth
     from oracle import evoke_oracle as orc
     world, n_total, d, tau = 2, 1536, 256, 0.5
-    port = 29900 + (os.getpid() % 90) + (1 if precision == "fp32" else 0) + (2 if mode == "sym" else 0) + (4 if mode == "peer" else 0)
+    port = 29900 + (os.getpid() % 90) + (1 if precision == "fp32" else 0) + (2 if mode == "sym" else 0) + (4 if mode == "peer" else 0) + (6 if mode == "peer-fp32" else 0)
     mp.spawn(_worker, args=(world, port, n_total, d, tau, precision, mode, str(tmp_path)), nprocs=world, join=True)
     ids = synth.make_study_ids(n_total, seed=31)
     xi = synth.make_embeddings(ids, d, seed=32)
