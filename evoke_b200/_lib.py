@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libevoke_b200.so")
 
 EVK_OK, EVK_ERR_INVALID, EVK_ERR_CUDA, EVK_ERR_UNSUPPORTED = 0, -1, -2, -3
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
-FLAG_EXCLUDE_DIAG, FLAG_NO_COLSUM, FLAG_SPLIT_BF16, FLAG_NO_POS = 1, 2, 4, 8
+FLAG_EXCLUDE_DIAG, FLAG_NO_COLSUM, FLAG_SPLIT_BF16, FLAG_NO_POS, FLAG_AVGPOS = 1, 2, 4, 8, 16
 ABI_VERSION = 2
 
 P, I, L, F, D = c_void_p, c_int, c_int64, c_float, c_double
@@ -28,7 +28,8 @@ SIGNATURES = {
     "evk_l2norm_bwd": [P, I, L, L, L, L, P, P, P, L, P, F, P, I, L, I, P],
     "evk_posmask_build": [P, P, L, P, P, L, L, I, P, L, P, P, I, P],
     "evk_mpce_small_fwd": [P, L, P, L, L, L, L, P, L, F, I, L, P, P, P],
-    "evk_mpce_small_bwd": [P, L, P, L, L, L, L, P, L, P, P, P, F, I, L, P, L, P],
+    "evk_mpce_small_bwd": [P, L, P, L, L, L, L, P, L, P, P, P, F, I, L, P, L, P, P, P],
+    "evk_mpce_finalize_avgpos": [P, P, P, L, F, D, P, P, P, I, P],
     "evk_reduce_partials": [P, L, L, L, P, P, P],
     "evk_mpce_finalize": [P, P, P, L, P, L, L, L, F, F, D, P, P, P, P],
     "evk_mpce_stats_fused": [P, L, L, P, L, L, P, L, P, L, L, L, L, L, F, F, D, P, P, P, P, L, P],
@@ -101,7 +102,7 @@ KERNELS_PER_CALL = {
     "evk_mpce_small_bwd": 1, "evk_reduce_partials": 1, "evk_mpce_finalize": 1, "evk_mpce_stats_fused": 1, "evk_mpce_pos": 1, "evk_mpce_fwd": 1,
     "evk_mpce_bwd_w": 1, "evk_mpce_bwd_gemm": 1, "evk_tc_gemm_probe": 1, "evk_l2norm_fwd_bcast": 1,
     "evk_peer_bcast": 1, "evk_mpce_fwd_store": 1, "evk_mpce_w_from_e": 3, "evk_mpce_pos_logits": 1,
-    "evk_peer_barrier": 1, "evk_shard_prologue": 1, "evk_mpce_shard_stats_push": 1, "evk_l2norm_bwd_parts": 1, "evk_mpce_shard_finish": 1, "evk_mpce_bwd_gemm_scatter": 1,
+    "evk_peer_barrier": 1, "evk_mpce_finalize_avgpos": 1, "evk_shard_prologue": 1, "evk_mpce_shard_stats_push": 1, "evk_l2norm_bwd_parts": 1, "evk_mpce_shard_finish": 1, "evk_mpce_bwd_gemm_scatter": 1,
 }
 launch_count = 0          # running total, read by bench.py ("gpu_launches")
 call_hook = None          # optional callable(name, phase) with phase in {"before", "after"} (bench.py timing)

@@ -24,7 +24,7 @@ small_rows_kernel(const float* __restrict__ q, int64_t ld_q, const float* __rest
                   int64_t ld_words, const int32_t* __restrict__ counts, const float* __restrict__ a_row,
                   const float* __restrict__ b_col, float inv_tau, int flags, int64_t diag_offset,
                   float* __restrict__ row_sum, float* __restrict__ row_pos, float* __restrict__ dq,
-                  int64_t ld_dq) {
+                  int64_t ld_dq, const float* __restrict__ pos_row, const float* __restrict__ pos_col) {
   extern __shared__ __align__(16) float smem[];
   float* qs = smem;                                  // [kTM][d_pad]
   float* kt = qs + (size_t)kTM * d_pad;              // [256][kDK+1]
@@ -35,20 +35,27 @@ small_rows_kernel(const float* __restrict__ q, int64_t ld_q, const float* __rest
   const int64_t r0 = (int64_t)blockIdx.x * kTM;
   const float shift = inv_tau;                       // |S| <= inv_tau for unit rows
   const bool excl = (flags & EVK_FLAG_EXCLUDE_DIAG) != 0;
+  // 'averaged positive logit' rule (PretrainNewMulPos :748-815, :670-708): the positives enter the softmax as ONE
+  // logit, so the exp-sum runs over the negatives only and a positive's weight has no E term
+  const bool avg = (flags & EVK_FLAG_AVGPOS) != 0;
 
   for (int i = t; i < kTM * d_pad; i += kThreads) {
     const int r = i / d_pad, c = i - r * d_pad;
     qs[i] = (r0 + r < n_rows && c < d) ? q[(r0 + r) * ld_q + c] : 0.f;
   }
 
-  float a_i[kTM], neg2_over_c[kTM];
+  float a_i[kTM], neg2_over_c[kTM];             // neg2_over_c: the row's share of a positive's weight in AVGPOS mode
   if (kBwd) {
 #pragma unroll
     for (int r = 0; r < kTM; ++r) {
       const bool ok = r0 + r < n_rows;
       a_i[r] = ok ? a_row[r0 + r] : 0.f;
-      const int c = ok ? counts[r0 + r] : 1;
-      neg2_over_c[r] = -2.f / (float)(c > 0 ? c : 1);
+      if (avg) {
+        neg2_over_c[r] = ok ? pos_row[r0 + r] : 0.f;
+      } else {
+        const int c = ok ? counts[r0 + r] : 1;
+        neg2_over_c[r] = -2.f / (float)(c > 0 ? c : 1);
+      }
     }
   }
 
@@ -102,6 +109,7 @@ small_rows_kernel(const float* __restrict__ q, int64_t ld_q, const float* __rest
       const int64_t j = j0 + t;
       const bool col_ok = j < n_cols;
       const float b_j = (kBwd && col_ok) ? b_col[j] : 0.f;
+      const float p_j = (kBwd && avg && col_ok) ? pos_col[j] : 0.f;
 #pragma unroll
       for (int r = 0; r < kTM; ++r) {
         const int64_t i = r0 + r;
@@ -112,11 +120,12 @@ small_rows_kernel(const float* __restrict__ q, int64_t ld_q, const float* __rest
         const bool pos = ok && ((bits[i * ld_words + (j >> 5)] >> (j & 31)) & 1u);
         if (!kBwd) {
           if (pass == 0) {
-            rs[r] += e;
+            rs[r] += (avg && pos) ? 0.f : e;
             rp[r] += pos ? sv : 0.f;
           }
         } else {
-          float w = e * (a_i[r] + b_j) + (pos ? neg2_over_c[r] : 0.f);
+          float w = avg ? (pos ? neg2_over_c[r] + p_j : e * (a_i[r] + b_j))
+                        : e * (a_i[r] + b_j) + (pos ? neg2_over_c[r] : 0.f);
           if (excl && j == i + diag_offset) w = 0.f;
           ws[t * kTM + r] = w;
         }
@@ -216,7 +225,7 @@ extern "C" int evk_mpce_small_fwd(const float* q, int64_t ld_q, const float* k, 
   const unsigned grid = (unsigned)((n_rows + kTM - 1) / kTM);
   small_rows_kernel<false><<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       q, ld_q, k, ld_k, n_rows, n_cols, (int)d, d_pad, bits, ld_words, nullptr, nullptr, nullptr, inv_tau, flags,
-      diag_offset, row_sum, row_pos, nullptr, 0);
+      diag_offset, row_sum, row_pos, nullptr, 0, nullptr, nullptr);
   EVK_CHECK_LAUNCH("mpce_small_fwd");
   return EVK_OK;
 }
@@ -224,17 +233,20 @@ extern "C" int evk_mpce_small_fwd(const float* q, int64_t ld_q, const float* k, 
 extern "C" int evk_mpce_small_bwd(const float* q, int64_t ld_q, const float* k, int64_t ld_k, int64_t n_rows,
                                   int64_t n_cols, int64_t d, const uint32_t* bits, int64_t ld_words,
                                   const int32_t* counts, const float* a_row, const float* b_col, float inv_tau,
-                                  int flags, int64_t diag_offset, float* dq, int64_t ld_dq, evk_stream_t stream) {
+                                  int flags, int64_t diag_offset, float* dq, int64_t ld_dq, const float* pos_row,
+                                  const float* pos_col, evk_stream_t stream) {
   int rc = small_check(q, k, n_rows, n_cols, d, bits, ld_words, ld_q, ld_k);
   if (rc != EVK_OK) return rc;
-  EVK_REQUIRE(counts && a_row && b_col && dq && ld_dq >= d, "evk_mpce_small_bwd: null pointer or ld_dq < d");
+  EVK_REQUIRE(a_row && b_col && dq && ld_dq >= d, "evk_mpce_small_bwd: null pointer or ld_dq < d");
+  if (flags & EVK_FLAG_AVGPOS) EVK_REQUIRE(pos_row && pos_col, "evk_mpce_small_bwd: EVK_FLAG_AVGPOS needs pos_row and pos_col");
+  else EVK_REQUIRE(counts, "evk_mpce_small_bwd: counts is null");
   const int d_pad = (int)((d + kDK - 1) / kDK * kDK);
   const size_t smem = small_smem_bytes(d_pad);
   EVK_CUDA(cudaFuncSetAttribute(small_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)((n_rows + kTM - 1) / kTM);
   small_rows_kernel<true><<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       q, ld_q, k, ld_k, n_rows, n_cols, (int)d, d_pad, bits, ld_words, counts, a_row, b_col, inv_tau, flags,
-      diag_offset, nullptr, nullptr, dq, ld_dq);
+      diag_offset, nullptr, nullptr, dq, ld_dq, pos_row, pos_col);
   EVK_CHECK_LAUNCH("mpce_small_bwd");
   return EVK_OK;
 }

@@ -61,6 +61,44 @@ finalize_kernel(const float* __restrict__ row_sum, const float* __restrict__ row
   }
 }
 
+// 'Averaged positive logit' rule, one softmax direction (PretrainNewMulPos.global_alignment_loss :783-811,
+// multi_pos_contra_images_v0404 :691-705).  With row_neg[i] = sum over the NEGATIVES of exp(S_ij - shift) and
+// row_pos[i] = sum over the positives of S_ij:
+//   pbar = row_pos/c,  u = exp(pbar - shift),  Z = u + row_neg,  l_i = -pbar + shift + ln Z
+//   a_row[i] = 1/Z (weight of a negative: E_ij/Z),  pos_row[i] = (u/Z - 1)/c (weight of each positive)
+// Rows without positives (c = 0: single-view rows of v0404, :685) contribute nothing and get zero weights.
+__global__ void __launch_bounds__(kFinThreads)
+finalize_avgpos_kernel(const float* __restrict__ row_neg, const float* __restrict__ row_pos,
+                       const int32_t* __restrict__ counts, int64_t n_rows, float shift, double inv_count,
+                       float* __restrict__ a_row, float* __restrict__ pos_row, float* __restrict__ loss_out,
+                       int accumulate) {
+  __shared__ double s_part[kFinThreads / 32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n_rows; i += kFinThreads) {
+    const int c = counts[i];
+    float a = 0.f, pw = 0.f;
+    if (c > 0) {
+      const float pbar = row_pos[i] / (float)c;
+      const float u = expf(pbar - shift);
+      const float z = u + row_neg[i];
+      a = 1.f / z;
+      pw = (u * a - 1.f) / (float)c;
+      acc += (double)shift - (double)pbar + (double)logf(z);
+    }
+    a_row[i] = a;
+    pos_row[i] = pw;
+  }
+  acc = warp_sum_f64(acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kFinThreads / 32; ++w) t += s_part[w];
+    const float l = (float)(t * inv_count);
+    loss_out[0] = accumulate ? loss_out[0] + l : l;
+  }
+}
+
 // Fused single-GPU form: reduce the per-tile partials, emit a_row / b_col and the loss in ONE
 // multi-CTA launch.  Each CTA owns 256 rows (and the same 256 columns), adds its terms in fp64,
 // publishes a per-CTA partial, and the last CTA to finish (atomic ticket) sums the partials in
@@ -248,5 +286,17 @@ extern "C" int evk_mpce_finalize(const float* row_sum, const float* row_pos, con
       row_sum, row_pos, counts, n_rows, col_sum, n_cols, col_lo, col_hi, shift, pos_weight, inv_count, a_row, b_col,
       loss_out);
   EVK_CHECK_LAUNCH("mpce_finalize");
+  return EVK_OK;
+}
+
+extern "C" int evk_mpce_finalize_avgpos(const float* row_neg, const float* row_pos, const int32_t* counts, int64_t n_rows,
+                                        float shift, double inv_count, float* a_row, float* pos_row, float* loss_out,
+                                        int accumulate, evk_stream_t stream) {
+  EVK_REQUIRE(row_neg && row_pos && counts && a_row && pos_row && loss_out && n_rows > 0,
+              "evk_mpce_finalize_avgpos: null pointer or n_rows <= 0");
+  finalize_avgpos_kernel<<<1, kFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(row_neg, row_pos, counts, n_rows, shift,
+                                                                                 inv_count, a_row, pos_row, loss_out,
+                                                                                 accumulate);
+  EVK_CHECK_LAUNCH("mpce_finalize_avgpos");
   return EVK_OK;
 }

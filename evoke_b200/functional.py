@@ -23,7 +23,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (DTYPE_BF16, DTYPE_F16, DTYPE_F32, FLAG_EXCLUDE_DIAG, FLAG_NO_COLSUM, FLAG_NO_POS,
+from ._lib import (DTYPE_BF16, DTYPE_F16, DTYPE_F32, FLAG_AVGPOS, FLAG_EXCLUDE_DIAG, FLAG_NO_COLSUM, FLAG_NO_POS,
                    FLAG_SPLIT_BF16)
 from .ids import DeviceIds
 
@@ -196,12 +196,26 @@ def small_fwd(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int, di
 
 
 def small_bwd(q: Normalized, k: Normalized, bits, counts, a_row, b_col, inv_tau: float, flags: int,
-              diag_offset: int = 0) -> torch.Tensor:
+              diag_offset: int = 0, pos_row=None, pos_col=None) -> torch.Tensor:
     dq = torch.empty((q.n, q.d), dtype=torch.float32, device=q.f32.device)
     _lib.call("evk_mpce_small_bwd", _ptr(q.f32), q.f32.stride(0), _ptr(k.f32), k.f32.stride(0), q.n, k.n, q.d,
               _ptr(bits), bits.stride(0), _ptr(counts), _ptr(a_row), _ptr(b_col), float(inv_tau), flags,
-              diag_offset, _ptr(dq), dq.stride(0), _stream())
+              diag_offset, _ptr(dq), dq.stride(0), _ptr(pos_row), _ptr(pos_col), _stream())
     return dq
+
+
+def finalize_avgpos(row_neg, row_pos, counts, *, shift: float, inv_count: float, loss: Optional[torch.Tensor] = None):
+    """One direction of the averaged-positive rule -> (a_row, pos_row, loss[1]); ``loss`` given: accumulate into it."""
+    n = int(row_neg.shape[0])
+    dev = row_neg.device
+    a_row = torch.empty(n, dtype=torch.float32, device=dev)
+    pos_row = torch.empty(n, dtype=torch.float32, device=dev)
+    acc = loss is not None
+    if loss is None:
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+    _lib.call("evk_mpce_finalize_avgpos", _ptr(row_neg), _ptr(row_pos), _ptr(counts), n, float(shift), float(inv_count),
+              _ptr(a_row), _ptr(pos_row), _ptr(loss), int(acc), _stream())
+    return a_row, pos_row, loss
 
 
 # --- tcgen05 path --------------------------------------------------------------------------
@@ -358,6 +372,7 @@ class LossConfig:
     path: str                       # "small" | "tc"
     row_ids: DeviceIds              # keys of the rows that take part (already truncated / filtered)
     gather: Optional[torch.Tensor] = None   # MPC: int32 indices of the kept rows
+    n_keep: int = 0                 # AMPC: number of multi-view rows (the loss is their mean, :707)
 
 
 def choose_path(path: str, n_rows: int, n_cols: int, d: int) -> str:
@@ -533,3 +548,59 @@ class _MultiPositiveCE(torch.autograd.Function):
 
 def multi_positive_ce(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor]) -> torch.Tensor:
     return _MultiPositiveCE.apply(cfg, image, text)
+
+
+class _AvgPosCE(torch.autograd.Function):
+    """The 'averaged positive logit' objectives of PretrainNewMulPos:
+    kind "AG"   global_alignment_loss :748-815 - both directions, x0.5, / B, shape [1]
+    kind "AMPC" multi_pos_contra_images_v0404 :670-708 - single-view rows leave the QUERIES only (:685), all
+                rows stay keys, diagonal excluded, mean over the multi-view rows, shape [1]
+    fp32 SIMT kernels (the small path): the class is not used by the reference's entry points and its own
+    implementation is a Python loop over rows, so reference-sized batches are what matters here."""
+
+    @staticmethod
+    def forward(ctx, cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor]):
+        ampc = cfg.kind == "AMPC"
+        flags = FLAG_AVGPOS | (FLAG_EXCLUDE_DIAG if ampc else 0)
+        kw = dict(want_f32=True, want_hi=False, want_lo=False)
+        qn = l2norm_fwd(image, **kw)
+        kn = qn if ampc else l2norm_fwd(text, **kw)
+        n = qn.n
+        bits, counts = posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=ampc)
+        row_neg, row_pos = small_fwd(qn, kn, bits, cfg.inv_tau, flags)
+        if ampc:
+            a_row, p_row, loss = finalize_avgpos(row_neg, row_pos, counts, shift=cfg.inv_tau, inv_count=1.0 / cfg.n_keep)
+            b_col, p_col = a_row, p_row                      # (dS + dS^T) in one contraction: S is symmetric
+        else:
+            a_row, p_row, loss = finalize_avgpos(row_neg, row_pos, counts, shift=cfg.inv_tau, inv_count=0.5 / n)
+            col_neg, col_pos = small_fwd(kn, qn, bits, cfg.inv_tau, flags)       # M is symmetric
+            b_col, p_col, loss = finalize_avgpos(col_neg, col_pos, counts, shift=cfg.inv_tau, inv_count=0.5 / n, loss=loss)
+        ctx.cfg, ctx.flags, ctx.qn, ctx.kn = cfg, flags, qn, kn
+        ctx.aux = (bits, a_row, b_col, p_row, p_col)
+        ctx.has_text = text is not None
+        ctx.save_for_backward(image, text) if text is not None else ctx.save_for_backward(image)
+        return loss if image.dtype == torch.float32 else loss.to(image.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out: torch.Tensor):
+        cfg, flags, qn, kn = ctx.cfg, ctx.flags, ctx.qn, ctx.kn
+        bits, a_row, b_col, p_row, p_col = ctx.aux
+        saved = ctx.saved_tensors
+        image = saved[0]
+        text = saved[1] if ctx.has_text else None
+        ampc = cfg.kind == "AMPC"
+        g = grad_out.reshape(1).to(torch.float32).contiguous()
+        scale = cfg.inv_tau / cfg.n_keep if ampc else 0.5 * cfg.inv_tau / qn.n
+        d_image = d_text = None
+        if ctx.needs_input_grad[1]:
+            dq = small_bwd(qn, kn, bits, None, a_row, b_col, cfg.inv_tau, flags, pos_row=p_row, pos_col=p_col)
+            d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale)
+        if not ampc and ctx.needs_input_grad[2]:
+            dk = small_bwd(kn, qn, bits, None, b_col, a_row, cfg.inv_tau, flags, pos_row=p_col, pos_col=p_row)
+            d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
+        return None, d_image, d_text
+
+
+def avgpos_ce(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor]) -> torch.Tensor:
+    return _AvgPosCE.apply(cfg, image, text)

@@ -95,6 +95,47 @@ def multi_pos_contra_images(image: torch.Tensor, patient_ids, temp: float, *,
         return Fn.multi_positive_ce(cfg, image, None)
 
 
+def global_alignment_avgpos(image: torch.Tensor, text: torch.Tensor, patient_ids, temp: float) -> torch.Tensor:
+    """PretrainNewMulPos.global_alignment_loss (reference :748-815): the positives of a row are averaged into ONE
+    logit and a plain cross entropy against the negatives follows; both directions, x0.5, / B.  Returns shape [1]
+    like the reference.  fp32 (small path)."""
+    Fn._require_cuda(image, "global_image_embed")
+    Fn._require_cuda(text, "global_text_embed")
+    if image.shape != text.shape:
+        raise ValueError(f"image/text embedding shapes differ: {tuple(image.shape)} vs {tuple(text.shape)}")
+    b = int(image.shape[0])
+    if b == 0:
+        raise ValueError("empty batch")
+    dev_ids, _ = idmod.to_device_ids(patient_ids, image.device, n=b)
+    if len(dev_ids) < b:
+        raise ValueError(f"patient_ids has {len(dev_ids)} entries for a batch of {b}")
+    cfg = Fn.LossConfig(kind="AG", inv_tau=_inv_tau(temp), precision="fp32", path="small", row_ids=dev_ids)
+    with torch.cuda.device(image.device):
+        return Fn.avgpos_ce(cfg, image, text)
+
+
+def multi_pos_contra_images_avgpos(image: torch.Tensor, patient_ids, temp: float) -> torch.Tensor:
+    """PretrainNewMulPos.multi_pos_contra_images_v0404 (reference :670-708): like v0401 but with the averaged
+    positive logit, and single-view rows are removed from the queries only - every row stays a key (:685).
+    Returns shape [1]; tensor([0.0]) leaf when no study has a second view (:676-677)."""
+    Fn._require_cuda(image, "global_image_embed")
+    m = int(image.shape[0])
+    dev_ids, codes = idmod.to_device_ids(patient_ids, image.device, n=None)
+    if len(dev_ids) != m:
+        raise ValueError(f"patient_ids has {len(dev_ids)} entries for {m} image embeddings")
+    with torch.cuda.device(image.device):
+        if codes is not None:
+            n_keep = len(idmod.multi_view_rows(codes))                   # host ids: no device sync
+        else:
+            _, cnt = Fn.posmask_build(dev_ids, dev_ids, clear_diag=True)
+            n_keep = int((cnt > 0).sum().item())                         # the reference syncs here too (:676)
+        if n_keep == 0:
+            return torch.tensor([0.0], requires_grad=True, device=image.device)
+        cfg = Fn.LossConfig(kind="AMPC", inv_tau=_inv_tau(temp), precision="fp32", path="small", row_ids=dev_ids,
+                            n_keep=n_keep)
+        return Fn.avgpos_ce(cfg, image, None)
+
+
 # ---------------------------------------------------------------- methods with the reference's signatures
 def global_alignment_loss(self, global_image_embed, global_text_embed, patient_ids):
     """Same signature as Pretrain.global_alignment_loss (reference :486)."""
@@ -106,6 +147,28 @@ def multi_pos_contra_images_v0401(self, global_image_embed, patient_ids):
     """Same signature as Pretrain.multi_pos_contra_images_v0401 (reference :421)."""
     return multi_pos_contra_images(global_image_embed, patient_ids, self.args["region_temp"],
                                    precision=getattr(self, "_evoke_b200_precision", DEFAULT_PRECISION))
+
+
+def global_alignment_loss_newmulpos(self, global_image_embed, global_text_embed, patient_ids):
+    """Same signature as PretrainNewMulPos.global_alignment_loss (reference :748)."""
+    return global_alignment_avgpos(global_image_embed, global_text_embed, patient_ids, self.args["instance_temp"])
+
+
+def multi_pos_contra_images_v0404(self, global_image_embed, patient_ids):
+    """Same signature as PretrainNewMulPos.multi_pos_contra_images_v0404 (reference :670)."""
+    return multi_pos_contra_images_avgpos(global_image_embed, patient_ids, self.args["region_temp"])
+
+
+def patch_pretrain_newmulpos(target):
+    """Rebind the two loss methods of a reference ``PretrainNewMulPos`` class or instance (:748, :670)."""
+    if isinstance(target, type):
+        target.global_alignment_loss = global_alignment_loss_newmulpos
+        target.multi_pos_contra_images_v0404 = multi_pos_contra_images_v0404
+    else:
+        import types
+        target.global_alignment_loss = types.MethodType(global_alignment_loss_newmulpos, target)
+        target.multi_pos_contra_images_v0404 = types.MethodType(multi_pos_contra_images_v0404, target)
+    return target
 
 
 def patch_pretrain(target, precision: str = DEFAULT_PRECISION):

@@ -49,6 +49,8 @@ extern "C" {
                                      multi_pos_contra_images_v0401 :438 (fill_diagonal_(-1e9)) */
 #define EVK_FLAG_NO_COLSUM     2  /* skip column sums (symmetric problem: MPC) */
 #define EVK_FLAG_NO_POS        8  /* K3 leaves the positive-logit sums to evk_mpce_pos (bits may be NULL) */
+#define EVK_FLAG_AVGPOS       16  /* 'averaged positive logit' rule of PretrainNewMulPos (:748-815, :670-708): the
+                                     positives of a row enter the softmax as ONE logit, their mean (small path) */
 #define EVK_FLAG_SPLIT_BF16    4  /* operands are (hi, lo) bf16 pairs: S = hi.hi + hi.lo + lo.hi,
                                      ~2^-17 relative, the fp32-parity mode */
 
@@ -122,7 +124,8 @@ EVK_API int evk_posmask_build(const int32_t* ids_row, const int32_t* ids2_row, i
  * forward:  row_sum[i] = sum_j E_ij (diagonal excluded if flagged),
  *           row_pos[i] = sum_j M_ij S_ij
  * replacing the mm + `/temp` + log_softmax of :499-502 / :437-443 for one direction; the
- * caller runs it once per direction.  Nothing of size n_rows x n_cols is ever stored. */
+ * caller runs it once per direction.  Nothing of size n_rows x n_cols is ever stored.
+ * With EVK_FLAG_AVGPOS row_sum[i] runs over the NEGATIVES only. */
 EVK_API int evk_mpce_small_fwd(const float* q, int64_t ld_q, const float* k, int64_t ld_k,
                        int64_t n_rows, int64_t n_cols, int64_t d,
                        const uint32_t* bits, int64_t ld_words,
@@ -132,13 +135,17 @@ EVK_API int evk_mpce_small_fwd(const float* q, int64_t ld_q, const float* k, int
 /* backward for the same rows:  dq[i,:] = sum_j W_ij k[j,:],
  *   W_ij = E_ij (a_i + b_j) - 2 M_ij / c_i      (0 on an excluded diagonal)
  * i.e. N*tau*(dS + its transpose-direction term) of the closed form in oracle/evoke_oracle.py;
- * the 1/(2N tau) (or 1/(M' tau)) factor is applied by evk_l2norm_bwd's scale. */
+ * the 1/(2N tau) (or 1/(M' tau)) factor is applied by evk_l2norm_bwd's scale.
+ * With EVK_FLAG_AVGPOS (then counts may be NULL and pos_row / pos_col are required, else they are ignored):
+ *   W_ij = E_ij (a_i + b_j) for negatives,  pos_row[i] + pos_col[j] for positives,
+ * a / pos_* from evk_mpce_finalize_avgpos of the row resp. column direction. */
 EVK_API int evk_mpce_small_bwd(const float* q, int64_t ld_q, const float* k, int64_t ld_k,
                        int64_t n_rows, int64_t n_cols, int64_t d,
                        const uint32_t* bits, int64_t ld_words, const int32_t* counts,
                        const float* a_row, const float* b_col,
                        float inv_tau, int flags, int64_t diag_offset,
-                       float* dq, int64_t ld_dq, evk_stream_t stream);
+                       float* dq, int64_t ld_dq,
+                       const float* pos_row, const float* pos_col, evk_stream_t stream);
 
 /* ---- statistics -> loss ----------------------------------------------------------------------
  * out[j] = sum_p part[p*ld + j], p < parts: deterministic reduction of per-tile partials;
@@ -158,6 +165,16 @@ EVK_API int evk_mpce_finalize(const float* row_sum, const float* row_pos, const 
                       int64_t col_lo, int64_t col_hi, float shift, float pos_weight,
                       double inv_count, float* a_row, float* b_col, float* loss_out,
                       evk_stream_t stream);
+
+/* One softmax direction of the 'averaged positive logit' rule (PretrainNewMulPos :783-811, v0404 :691-705),
+ * from evk_mpce_small_fwd(EVK_FLAG_AVGPOS)'s row_neg / row_pos:
+ *   pbar_i = row_pos[i]/c_i, u = exp(pbar_i - shift), Z = u + row_neg[i]
+ *   a_row[i] = 1/Z, pos_row[i] = (u/Z - 1)/c_i, loss_out[0] (+)= inv_count * sum_i (shift - pbar_i + ln Z)
+ * rows with c_i = 0 contribute nothing (a = pos = 0).  accumulate != 0 adds to loss_out (second direction). */
+EVK_API int evk_mpce_finalize_avgpos(const float* row_neg, const float* row_pos, const int32_t* counts,
+                             int64_t n_rows, float shift, double inv_count,
+                             float* a_row, float* pos_row, float* loss_out, int accumulate,
+                             evk_stream_t stream);
 
 /* Single-GPU fused form of evk_reduce_partials (x3) + evk_mpce_finalize: takes the per-tile
  * partials of K3 directly (rs_part: [row_parts, ld_row]; rp_part: [pos_parts, ld_pos] - K3's

@@ -185,9 +185,48 @@ def _avgpos_rows(s: np.ndarray, m: np.ndarray) -> np.ndarray:
     return out
 
 
+def _avgpos_rows_grad(s: np.ndarray, m: np.ndarray):
+    """Vectorised per-row loss AND its gradient w.r.t. s (rows with no positive get 0 / 0).
+    dl_i/ds_ij = e^{s_ij}/Z_i for negatives, (e^{pbar_i}/Z_i - 1)/c_i for positives (entries at -inf: 0)."""
+    m = m.astype(bool)
+    c = m.sum(1)
+    ok = c > 0
+    cs = np.where(ok, c, 1)
+    fin = np.isfinite(s)
+    pbar = np.where(m, s, 0.0).sum(1) / cs
+    neg = (~m) & fin
+    mx = np.maximum(pbar, np.where(neg, s, -np.inf).max(1, initial=-np.inf))
+    e = np.where(neg, np.exp(np.where(neg, s, 0.0) - mx[:, None]), 0.0)
+    u = np.exp(pbar - mx)
+    z = u + e.sum(1)
+    loss = np.where(ok, -pbar + mx + np.log(z), 0.0)
+    g = e / z[:, None] + m * ((u / z - 1.0) / cs)[:, None]
+    g[~ok] = 0.0
+    return loss, g
+
+
+def avgpos_g_closed_form(image, text, ids, tau: float):
+    """PretrainNewMulPos.global_alignment_loss (:748-815) with gradients (fp64):
+    -> (loss, d_image, d_text).  Single-positive rows reduce to plain CE (:770-777), so one formula
+    covers both branches; loss = 0.5 * (sum_i l_i + sum_j l'_j) / B (:813)."""
+    image = np.asarray(image, dtype=np.float64)
+    text = np.asarray(text, dtype=np.float64)
+    n = image.shape[0]
+    m = posmask_dense(np.asarray(ids)[:n])
+    ih, _ = l2_normalize(image)
+    th, _ = l2_normalize(text)
+    s = ih @ th.T / tau
+    lr, gr = _avgpos_rows_grad(s, m)
+    lc, gc_ = _avgpos_rows_grad(s.T, m)
+    loss = 0.5 * (lr.sum() + lc.sum()) / n
+    ds = 0.5 / n * (gr + gc_.T)
+    d_ih = ds @ th / tau
+    d_th = ds.T @ ih / tau
+    return float(loss), l2_normalize_bwd(image, d_ih), l2_normalize_bwd(text, d_th)
+
+
 def avgpos_g_loss_closed_form(image, text, ids, tau: float) -> float:
-    """PretrainNewMulPos.global_alignment_loss (:748-815): forward value only (fp64).
-    Single-positive rows reduce to plain CE, so one formula covers both branches."""
+    """Forward value of avgpos_g_closed_form, by the row-by-row restatement of the reference's loop."""
     image = np.asarray(image, dtype=np.float64)
     text = np.asarray(text, dtype=np.float64)
     n = image.shape[0]
@@ -196,6 +235,25 @@ def avgpos_g_loss_closed_form(image, text, ids, tau: float) -> float:
     th, _ = l2_normalize(text)
     s = ih @ th.T / tau
     return float(0.5 * (_avgpos_rows(s, m).sum() + _avgpos_rows(s.T, m).sum()) / n)
+
+
+def avgpos_mpc_grad_closed_form(x, ids, tau: float):
+    """PretrainNewMulPos.multi_pos_contra_images_v0404 (:670-708) with gradient (fp64): -> (loss, dx) or
+    (None, zeros).  Single-view rows are removed from the QUERIES only (:685); every row stays a key."""
+    x = np.asarray(x, dtype=np.float64)
+    ids = np.asarray(ids)
+    idx = mpc_kept_rows(ids)
+    if len(idx) == 0:
+        return None, np.zeros_like(x)
+    m = posmask_dense(ids, clear_diag=True)
+    xh, _ = l2_normalize(x)
+    s = xh @ xh.T / tau
+    np.fill_diagonal(s, -np.inf)
+    l, g = _avgpos_rows_grad(s, m)          # rows without positives contribute 0 / 0
+    loss = l.sum() / len(idx)
+    ds = g / len(idx)
+    d_xh = (ds + ds.T) @ xh / tau
+    return float(loss), l2_normalize_bwd(x, d_xh)
 
 
 def avgpos_mpc_closed_form(x, ids, tau: float):

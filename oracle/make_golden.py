@@ -33,12 +33,14 @@ from oracle import ref_shim  # noqa: E402
 def _run(case: gc.Case, dtype):
     inp = gc.build_inputs(case)
     image = torch.tensor(inp["image"], dtype=dtype, requires_grad=True)
-    if case.kind == "G":
+    if case.kind in ("G", "AG"):
         text = torch.tensor(inp["text"], dtype=dtype, requires_grad=True)
-        out = ref_shim.global_alignment_loss(image, text, inp["ids"], case.tau)
+        fn = ref_shim.global_alignment_loss if case.kind == "G" else ref_shim.avgpos_global_alignment_loss
+        out = fn(image, text, inp["ids"], case.tau)
         out.sum().backward()
         return out, image.grad, text.grad
-    out = ref_shim.multi_pos_contra_images_v0401(image, inp["ids"], case.tau)
+    fn = ref_shim.multi_pos_contra_images_v0401 if case.kind == "MPC" else ref_shim.avgpos_multi_pos_contra_images_v0404
+    out = fn(image, inp["ids"], case.tau)
     if out.grad_fn is None:                     # the [0.0] leaf: nothing flows to the input
         return out, torch.zeros_like(image), None
     out.sum().backward()
@@ -48,10 +50,10 @@ def _run(case: gc.Case, dtype):
 def _reference_mask(case: gc.Case):
     """The label matrix exactly as the reference builds it (numpy ==, :489 / :422-424)."""
     ids = gc.build_inputs(case)["ids"]
-    if case.kind == "G":
+    if case.kind in ("G", "AG"):
         ids = ids[: case.n]
     m = ids.reshape(-1, 1) == ids.reshape(1, -1)
-    if case.kind == "MPC":
+    if case.kind in ("MPC", "AMPC"):
         np.fill_diagonal(m, False)
     n = m.shape[0]
     words = (n + 31) // 32
@@ -88,6 +90,6 @@ def make(case: gc.Case):
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
-    names = sys.argv[1:] or [c.name for c in gc.CASES]
+    names = sys.argv[1:] or [c.name for c in gc.CASES + gc.AVGPOS_CASES]
     for nm in names:
         make(gc.BY_NAME[nm])

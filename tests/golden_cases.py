@@ -22,6 +22,7 @@ SAMPLE_ROWS = 16
 class Case:
     name: str
     kind: str                    # "G" (global_alignment_loss) | "MPC" (multi_pos_contra_images_v0401)
+                                 # "AG" / "AMPC": the PretrainNewMulPos variants (:748-815, v0404 :670-708)
     n: int
     d: int
     tau: float = 0.5
@@ -60,7 +61,20 @@ CASES = [
     Case("mpc_all_same", "MPC", 12, 32, ids="same"),
 ]
 
-BY_NAME = {c.name: c for c in CASES}
+# 'averaged positive logit' variants of PretrainNewMulPos
+AVGPOS_CASES = [
+    Case("ag_n8_d16", "AG", 8, 16, ids="hand8"),
+    Case("ag_cfg1", "AG", 32, 768, ids="twoview", extra_ids=32, string_ids=True),   # all single-positive rows
+    Case("ag_n96_d128", "AG", 96, 128, ids="cfg3", seed=21),
+    Case("ag_n300_d512_t007", "AG", 300, 512, tau=0.07, ids="cfg2"),
+    Case("ag_all_same", "AG", 12, 32, ids="same"),
+    Case("ampc_n8_d16", "AMPC", 8, 16, ids="hand8"),
+    Case("ampc_cfg1", "AMPC", 64, 768, ids="twoview", string_ids=True),
+    Case("ampc_n96_d128", "AMPC", 96, 128, ids="cfg3", seed=21),
+    Case("ampc_all_single", "AMPC", 16, 64, ids="unique"),
+]
+
+BY_NAME = {c.name: c for c in CASES + AVGPOS_CASES}
 
 
 def build_ids(case: Case) -> np.ndarray:
@@ -88,7 +102,7 @@ def build_inputs(case: Case):
     ids = build_ids(case)
     image = synth.make_embeddings(ids[: case.n], case.d, seed=case.seed + 1)
     text = None
-    if case.kind == "G":
+    if case.kind in ("G", "AG"):
         text = synth.make_embeddings(ids[: case.n], case.d, seed=case.seed + 2)
     if case.zero_row >= 0:
         image[case.zero_row] = 0.0

@@ -48,6 +48,33 @@ def test_mpc_closed_form_matches_reference_golden(case):
     assert abs(np.linalg.norm(dx) - gold["d_image_norm64"]) <= 1e-9 * gold["d_image_norm64"]
 
 
+@pytest.mark.parametrize("case", gc.AVGPOS_CASES, ids=lambda c: c.name)
+def test_avgpos_closed_forms_match_reference_golden(case):
+    """PretrainNewMulPos.global_alignment_loss / multi_pos_contra_images_v0404."""
+    inp = gc.build_inputs(case)
+    gold = gc.load_golden(case)
+    rows = gold["rows"]
+    assert tuple(gold["out_shape"]) == (1,)
+    if case.kind == "AG":
+        loss, d_i, d_t = orc.avgpos_g_closed_form(inp["image"], inp["text"], inp["ids"], case.tau)
+        # the reference accumulates this loss in a float32 tensor (torch.tensor([0.0]) :768, :693) whatever the
+        # input dtype, so its value is only fp32-accurate; its gradients are fp64
+        assert abs(loss - gold["loss64"]) <= 2e-6 * max(abs(gold["loss64"]), 1.0)
+        assert abs(orc.avgpos_g_loss_closed_form(inp["image"], inp["text"], inp["ids"], case.tau) - loss) <= 1e-12 * max(abs(loss), 1.0)
+        scale = max(np.abs(gold["d_image64"]).max(), 1e-30)
+        # (the fp32 loss tensor also rounds the 1/B factor of the backward: gradients agree to ~6e-8 relative)
+        assert np.abs(d_i[rows] - gold["d_image64"]).max() <= 3e-7 * scale + 1e-15
+        assert np.abs(d_t[rows] - gold["d_text64"]).max() <= 3e-7 * max(np.abs(gold["d_text64"]).max(), 1e-30) + 1e-15
+        return
+    loss, dx = orc.avgpos_mpc_grad_closed_form(inp["image"], inp["ids"], case.tau)
+    if gold["empty"]:
+        assert loss is None and gold["loss64"] == 0.0 and not dx.any()
+        return
+    assert abs(loss - gold["loss64"]) <= 2e-6 * abs(gold["loss64"])
+    assert abs(orc.avgpos_mpc_closed_form(inp["image"], inp["ids"], case.tau) - loss) <= 1e-12 * abs(loss)
+    assert _rel(dx[rows], gold["d_image64"]) < 3e-7
+
+
 @pytest.mark.parametrize("case", [c for c in gc.CASES if c.n <= 1024], ids=lambda c: c.name)
 def test_packed_mask_bit_exact(case):
     inp = gc.build_inputs(case)
