@@ -32,12 +32,12 @@ def test_avgpos_against_reference_golden(case):
         return
     out.sum().backward()
     rows = gold["rows"]
-    assert abs(out.item() - gold["loss64"]) <= 1e-5 * max(abs(gold["loss64"]), 1e-3)
+    assert abs(out.item() - gold["loss64"]) <= 1e-5 * abs(gold["loss64"]) + 2e-6      # (all-positives case: loss == 0)
     scale_i = max(np.abs(gold["d_image64"]).max(), 1e-12)
-    assert np.abs(image.grad.cpu().numpy()[rows] - gold["d_image64"]).max() <= 1e-4 * scale_i + 1e-10
+    assert np.abs(image.grad.cpu().numpy()[rows] - gold["d_image64"]).max() <= 1e-4 * scale_i + 1e-8
     if text is not None:
         scale_t = max(np.abs(gold["d_text64"]).max(), 1e-12)
-        assert np.abs(text.grad.cpu().numpy()[rows] - gold["d_text64"]).max() <= 1e-4 * scale_t + 1e-10
+        assert np.abs(text.grad.cpu().numpy()[rows] - gold["d_text64"]).max() <= 1e-4 * scale_t + 1e-8
 
 
 def test_avgpos_against_oracle_on_fresh_inputs_and_patched_methods():
