@@ -98,6 +98,7 @@ struct Prologue {
   float* zero; int64_t ld_zero; int zero_width;
   int64_t n, ld, row_offset;
   int d;
+  int* step;                            // optional device counter advanced once per launch (one step = one epoch)
 };
 
 template <int kIters>
@@ -106,11 +107,13 @@ shard_prologue_kernel(const Prologue p) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  if (p.step && blockIdx.x == 0 && threadIdx.x == 0) *p.step += 1;
   // ids: one element per thread, pushed to every rank
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < p.n; t += (int64_t)gridDim.x * blockDim.x) {
     const int32_t v = __ldg(p.ids + t);
     const int32_t v2 = p.ids2 ? __ldg(p.ids2 + t) : 0;
-    for (int q = 0; q < p.khat.n; ++q) {
+    for (int q = 0; q < kMaxPeers; ++q) {
+      if (p.ids_dst[q] == nullptr) break;
       p.ids_dst[q][p.row_offset + t] = v;
       if (p.ids2) p.ids2_dst[q][p.row_offset + t] = v2;
     }
@@ -255,6 +258,65 @@ shard_finish_kernel(const float* __restrict__ slots, int n_slots, int64_t ld_slo
   }
 }
 
+// All-gather that runs NEXT TO the similarity sweep: this rank's shard (already in its own buffer) is copied
+// to the peers one destination at a time, in the order rank+1, rank+2, ... - at any moment every GPU receives
+// from exactly one source at full NVLink rate, so the shards land in a known order - and after each destination
+// the last CTA to finish raises that destination's `landed` flag for this source (epoch = the step counter).
+// K3 consumes the column blocks in the same order and waits per source (tc_engine.cu).
+struct PushArgs {
+  uint4* dst[kMaxPeers];
+  uint32_t* landed[kMaxPeers];          // landed[t] = base of rank t's landed-flag area (entry s: source s)
+  int n, rank;
+};
+
+__global__ void __launch_bounds__(256)
+peer_push_kernel(const uint4* __restrict__ src, int64_t n_vec, PushArgs a, int64_t dst_offset_vec,
+                 const int* __restrict__ step, unsigned int* __restrict__ counters) {
+  __shared__ bool s_last;
+  const uint32_t epoch = (uint32_t)*step;
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.landed[a.rank] + a.rank), "r"(epoch) : "memory");
+  for (int k = 1; k < a.n; ++k) {
+    const int t = (a.rank + k) % a.n;
+    uint4* out = a.dst[t] + dst_offset_vec;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x)
+      out[i] = __ldg(src + i);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int done = atomicAdd(counters + k, 1u);
+      s_last = done == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      counters[k] = 0;                                           // ready for the next step (graph replay)
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.landed[t] + a.rank), "r"(epoch) : "memory");
+    }
+  }
+}
+
+// waits until every source's shard of this step has landed here (side-stream consumers of the gathered rows)
+__global__ void __launch_bounds__(32)
+peer_wait_landed_kernel(const uint32_t* __restrict__ landed, int n, const int* __restrict__ step, int* __restrict__ error,
+                        uint64_t timeout_ns) {
+  const int t = threadIdx.x;
+  if (t < n) {
+    const uint32_t epoch = (uint32_t)*step;
+    const uint64_t t0 = global_timer_ns();
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(landed + t) : "memory");
+      if ((int32_t)(v - epoch) >= 0) break;
+      if (global_timer_ns() - t0 > timeout_ns) {
+        atomicExch(error, 1);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+}
+
 int fill_dst(PeerDst& dst, int n_dst, const uint64_t* hi, const uint64_t* lo) {
   EVK_REQUIRE(n_dst >= 1 && n_dst <= kMaxPeers && hi, "peer destinations: need 1..%d base pointers", kMaxPeers);
   memset(&dst, 0, sizeof(dst));
@@ -391,8 +453,8 @@ extern "C" int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld
 extern "C" int evk_shard_prologue(const float* text, int64_t text_stride, const float* image, int64_t image_stride,
                                   int64_t n_rows, int64_t d, int n_dst, const uint64_t* khat_ptrs, int64_t ld_bf16,
                                   int64_t row_offset, float* k_norm, void* q_hi, float* q_norm, const int32_t* ids,
-                                  const int32_t* ids2, const uint64_t* ids_ptrs, const uint64_t* ids2_ptrs,
-                                  float* zero_buf, int64_t ld_zero, evk_stream_t stream) {
+                                  const int32_t* ids2, int n_ids_dst, const uint64_t* ids_ptrs, const uint64_t* ids2_ptrs,
+                                  float* zero_buf, int64_t ld_zero, int* step_counter, evk_stream_t stream) {
   EVK_REQUIRE(text && image && k_norm && q_hi && q_norm && ids && ids_ptrs && khat_ptrs && n_rows > 0 && d > 0,
               "evk_shard_prologue: null pointer or empty shape");
   EVK_REQUIRE(d % 8 == 0 && d <= 2048 && text_stride % 4 == 0 && image_stride % 4 == 0 && evk_aligned16(text) &&
@@ -404,7 +466,9 @@ extern "C" int evk_shard_prologue(const float* text, int64_t text_stride, const 
   memset(&p, 0, sizeof(p));
   int rc = fill_dst(p.khat, n_dst, khat_ptrs, nullptr);
   if (rc != EVK_OK) return rc;
-  for (int q = 0; q < n_dst; ++q) {
+  EVK_REQUIRE(n_ids_dst >= 1 && n_ids_dst <= kMaxPeers, "evk_shard_prologue: 1..%d id destinations", kMaxPeers);
+  p.step = step_counter;
+  for (int q = 0; q < n_ids_dst; ++q) {
     p.ids_dst[q] = reinterpret_cast<int32_t*>(ids_ptrs[q]);
     p.ids2_dst[q] = ids2_ptrs ? reinterpret_cast<int32_t*>(ids2_ptrs[q]) : nullptr;
     EVK_REQUIRE(p.ids_dst[q] && (!ids2_ptrs || p.ids2_dst[q]), "evk_shard_prologue: null id destination");
@@ -421,5 +485,41 @@ extern "C" int evk_shard_prologue(const float* text, int64_t text_stride, const 
   if (d <= 1024) shard_prologue_kernel<4><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, s>>>(p);
   else shard_prologue_kernel<8><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, s>>>(p);
   EVK_CHECK_LAUNCH("shard_prologue");
+  return EVK_OK;
+}
+
+extern "C" int evk_peer_push_shard(const void* src, int64_t bytes, int n_ranks, int rank, const uint64_t* dst_ptrs,
+                                   int64_t dst_offset_bytes, const uint64_t* landed_ptrs, const int* step,
+                                   void* counters, evk_stream_t stream) {
+  EVK_REQUIRE(src && dst_ptrs && landed_ptrs && step && counters && bytes > 0 && bytes % 16 == 0 &&
+                  dst_offset_bytes >= 0 && dst_offset_bytes % 16 == 0 && evk_aligned16(src),
+              "evk_peer_push_shard: bad arguments (16-byte aligned multiples)");
+  EVK_REQUIRE(n_ranks >= 1 && n_ranks <= kMaxPeers && rank >= 0 && rank < n_ranks, "evk_peer_push_shard: bad rank / world");
+  PushArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n_ranks;
+  a.rank = rank;
+  for (int t = 0; t < n_ranks; ++t) {
+    a.dst[t] = reinterpret_cast<uint4*>(dst_ptrs[t]);
+    a.landed[t] = reinterpret_cast<uint32_t*>(landed_ptrs[t]);
+    EVK_REQUIRE(a.dst[t] && a.landed[t] && evk_aligned16(a.dst[t]), "evk_peer_push_shard: null / misaligned destination");
+  }
+  const int64_t n_vec = bytes / 16;
+  int64_t blocks = (n_vec + 255) / 256;
+  const int64_t cap = evk_sm_count();                // one small CTA per SM: it shares the SMs with the K3 CTAs
+  if (blocks > cap) blocks = cap;
+  peer_push_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(src), n_vec, a, dst_offset_bytes / 16, step, static_cast<unsigned int*>(counters));
+  EVK_CHECK_LAUNCH("peer_push_shard");
+  return EVK_OK;
+}
+
+extern "C" int evk_peer_wait_landed(const void* landed, int n_ranks, const int* step, int* error, int64_t timeout_ms,
+                                    evk_stream_t stream) {
+  EVK_REQUIRE(landed && step && error && n_ranks >= 1 && n_ranks <= kMaxPeers, "evk_peer_wait_landed: bad arguments");
+  const uint64_t timeout_ns = (uint64_t)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
+  peer_wait_landed_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint32_t*>(landed), n_ranks,
+                                                                        step, error, timeout_ns);
+  EVK_CHECK_LAUNCH("peer_wait_landed");
   return EVK_OK;
 }

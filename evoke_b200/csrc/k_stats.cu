@@ -116,21 +116,24 @@ constexpr int kStatThreads = 256;
 constexpr int kStatElems = 32;                       // rows (and columns) per CTA
 constexpr int kStatGroups = kStatThreads / kStatElems;   // partial-sum groups per element
 
-// sum of part[p*ld + i] over p = g, g+G, ... with four independent loads in flight
+// sum of part[p*ld + i] over p = g, g+G, ... with eight independent loads in flight
 __device__ __forceinline__ float strided_partial_sum(const float* __restrict__ part, int64_t parts, int64_t ld,
                                                      int64_t i, int g) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = 0.f;
   int64_t p = g;
-  for (; p + 3 * kStatGroups < parts; p += 4 * kStatGroups) {
-    s0 += part[p * ld + i];
-    s1 += part[(p + kStatGroups) * ld + i];
-    s2 += part[(p + 2 * kStatGroups) * ld + i];
-    s3 += part[(p + 3 * kStatGroups) * ld + i];
+  for (; p + 7 * kStatGroups < parts; p += 8 * kStatGroups) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += part[(p + k * kStatGroups) * ld + i];
   }
-  for (; p < parts; p += kStatGroups) s0 += part[p * ld + i];
-  return (s0 + s1) + (s2 + s3);
+  for (; p < parts; p += kStatGroups) s[0] += part[p * ld + i];
+  return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
+// blockIdx.y selects the statistic a CTA reduces - 0: row exp-sums (a_row, ln R_i), 1: positive-logit sums
+// (- pos_weight pos_i / c_i), 2: column exp-sums (b_col, ln C_j) - the loss terms are additive, so the three
+// run side by side instead of one after the other in the same threads.
 __global__ void __launch_bounds__(kStatThreads)
 stats_fused_kernel(const float* __restrict__ rs_part, int64_t row_parts, int64_t ld_row,
                    const float* __restrict__ rp_part, int64_t pos_parts, int64_t ld_pos,
@@ -139,35 +142,35 @@ stats_fused_kernel(const float* __restrict__ rs_part, int64_t row_parts, int64_t
                    int64_t col_lo, int64_t col_hi, float shift, float pos_weight, double inv_count,
                    float* __restrict__ a_row, float* __restrict__ b_col, float* __restrict__ loss_out,
                    double* __restrict__ cta_partial, unsigned int* __restrict__ ticket, const StatPush push) {
-  __shared__ float s_sum[3][kStatGroups][kStatElems];
+  __shared__ float s_sum[kStatGroups][kStatElems];
   __shared__ double s_part[kStatElems / 32];
   __shared__ bool s_last;
   const int e = threadIdx.x % kStatElems, g = threadIdx.x / kStatElems;
   const int64_t i = (int64_t)blockIdx.x * kStatElems + e;
-  s_sum[0][g][e] = i < n_rows ? strided_partial_sum(rs_part, row_parts, ld_row, i, g) : 0.f;
-  s_sum[1][g][e] = i < n_rows ? strided_partial_sum(rp_part, pos_parts, ld_pos, i, g) : 0.f;
-  s_sum[2][g][e] = (cs_part && i < n_cols) ? strided_partial_sum(cs_part, col_parts, ld_col, i, g) : 0.f;
+  const int which = blockIdx.y;
+  float v = 0.f;
+  if (which == 0 && i < n_rows) v = strided_partial_sum(rs_part, row_parts, ld_row, i, g);
+  if (which == 1 && i < n_rows) v = strided_partial_sum(rp_part, pos_parts, ld_pos, i, g);
+  if (which == 2 && cs_part && i < n_cols) v = strided_partial_sum(cs_part, col_parts, ld_col, i, g);
+  s_sum[g][e] = v;
   __syncthreads();
   if (threadIdx.x < kStatElems) {
     double acc = 0.0;
-    float r = 0.f, pos = 0.f, c = 0.f;
+    float t = 0.f;
 #pragma unroll
-    for (int gg = 0; gg < kStatGroups; ++gg) {          // fixed order: deterministic
-      r += s_sum[0][gg][e];
-      pos += s_sum[1][gg][e];
-      c += s_sum[2][gg][e];
-    }
-    if (i < n_rows) {
+    for (int gg = 0; gg < kStatGroups; ++gg) t += s_sum[gg][e];          // fixed order: deterministic
+    if (which == 0 && i < n_rows) {
+      a_row[i] = 1.f / t;
+      acc = (double)shift + (double)logf(t);
+    } else if (which == 1 && i < n_rows) {
       const int cnt = counts ? counts[i] : 1;
-      a_row[i] = 1.f / r;
-      acc += (double)shift + (double)logf(r) - (double)pos_weight * (cnt > 0 ? (double)pos / (double)cnt : 0.0);
-    }
-    if (cs_part && i < n_cols) {
+      acc = -(double)pos_weight * (cnt > 0 ? (double)t / (double)cnt : 0.0);
+    } else if (which == 2 && cs_part && i < n_cols) {
       if (push.n > 0) {
-        for (int p = 0; p < push.n; ++p) push.dst[p][push.offset + i] = c;
+        for (int p = 0; p < push.n; ++p) push.dst[p][push.offset + i] = t;
       } else {
-        b_col[i] = 1.f / c;
-        if (i >= col_lo && i < col_hi) acc += (double)shift + (double)logf(c);
+        b_col[i] = 1.f / t;
+        if (i >= col_lo && i < col_hi) acc = (double)shift + (double)logf(t);
       }
     }
     acc = warp_sum_f64(acc);
@@ -177,17 +180,18 @@ stats_fused_kernel(const float* __restrict__ rs_part, int64_t row_parts, int64_t
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < kStatElems / 32; ++w) t += s_part[w];
-    cta_partial[blockIdx.x] = t;
+    cta_partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
     __threadfence();
     const unsigned int done = atomicAdd(ticket, 1u);
-    s_last = (done == gridDim.x - 1);
+    s_last = (done == gridDim.x * gridDim.y - 1);
   }
   __syncthreads();
   if (s_last && threadIdx.x < 32) {
     __threadfence();
     // lane l sums partials l, l+32, ... ; lanes are then combined in a fixed butterfly order
     double t = 0.0;
-    for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32) t += reinterpret_cast<volatile double*>(cta_partial)[b];
+    for (unsigned int b = threadIdx.x; b < gridDim.x * gridDim.y; b += 32)
+      t += reinterpret_cast<volatile double*>(cta_partial)[b];
     t = warp_sum_f64(t);
     if (threadIdx.x == 0) {
       const float l = (float)(t * inv_count);
@@ -215,13 +219,13 @@ int stats_fused_impl(const float* rs_part, int64_t row_parts, int64_t ld_row, co
               "evk_mpce_stats_fused: bad column arguments");
   const int64_t n = (cs_part && n_cols > n_rows) ? n_cols : n_rows;
   const int64_t blocks = (n + kStatElems - 1) / kStatElems;
-  EVK_REQUIRE(workspace_bytes >= 16 + 8 * blocks && evk_aligned16(workspace),
-              "evk_mpce_stats_fused: workspace needs %lld bytes, 16-byte aligned", (long long)(16 + 8 * blocks));
+  EVK_REQUIRE(workspace_bytes >= 16 + 24 * blocks && evk_aligned16(workspace),
+              "evk_mpce_stats_fused: workspace needs %lld bytes, 16-byte aligned", (long long)(16 + 24 * blocks));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   unsigned int* ticket = static_cast<unsigned int*>(workspace);
   double* partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + 16);
   EVK_CUDA(cudaMemsetAsync(ticket, 0, 16, s));
-  stats_fused_kernel<<<(unsigned)blocks, kStatThreads, 0, s>>>(rs_part, row_parts, ld_row, rp_part, pos_parts, ld_pos,
+  stats_fused_kernel<<<dim3((unsigned)blocks, 3), kStatThreads, 0, s>>>(rs_part, row_parts, ld_row, rp_part, pos_parts, ld_pos,
                                                               counts, n_rows,
                                                               cs_part, col_parts, ld_col, cs_part ? n_cols : 0, col_lo,
                                                               col_hi, shift, pos_weight, inv_count, a_row, b_col,

@@ -61,6 +61,10 @@ struct alignas(64) TcParams {
   float* row_sum_part; float* row_pos_part; int64_t ld_rowpart;
   float* col_sum_part; int64_t ld_colpart;
   const int32_t* counts; const float* a_row; const float* b_col;
+  // EPI_FWD*, sharded: the key rows arrive per source rank while the sweep runs (evk_peer_push_shard).  The tiles
+  // are then visited column-block-major starting at this rank's own columns (rot_tiles), and the producer waits for
+  // landed[source] >= *step before its first load from a source's columns.
+  const uint32_t* landed; const int* step; int* error; int64_t cols_per_source; int rot_tiles;
   // EPI_GEMM
   float* out; int64_t ld_out; float alpha;
   // EPI_GEMM, reduce-scatter fused into the epilogue: output row i belongs to rank i / rows_per_owner and
@@ -96,11 +100,13 @@ constexpr int smem_bytes_total() {
 //               numbered column-block-major (mb fastest) so that the groups working on the same rows of W
 //               at the same time are the ones with different nb: the strip is read from HBM once.
 struct Sched {
-  int splits, total_kb, m_tiles, n_tiles, num_groups, u, total_units;
+  int splits, total_kb, m_tiles, n_tiles, num_groups, u, total_units, rot;
   int64_t pos, end;
+  // rot_ >= 0 (splits == 1 only): column-block-major order starting at column tile rot_ (sharded K3)
   __device__ __forceinline__ void init(int splits_, int total_kb_, int m_tiles_, int n_tiles_, int group_id,
-                                       int num_groups_) {
+                                       int num_groups_, int rot_ = -1) {
     splits = splits_; total_kb = total_kb_; m_tiles = m_tiles_; n_tiles = n_tiles_; num_groups = num_groups_;
+    rot = rot_;
     u = group_id;
     total_units = m_tiles * n_tiles * (splits > 0 ? splits : 1);
     const int64_t items = (int64_t)m_tiles * n_tiles * total_kb;
@@ -111,7 +117,14 @@ struct Sched {
     if (splits > 0) {
       if (u >= total_units) return false;
       const int tile = u / splits, sp = u - tile * splits;
-      mb = tile / n_tiles; nb = tile - mb * n_tiles;
+      if (rot >= 0) {
+        const int nbi = tile / m_tiles;
+        mb = tile - nbi * m_tiles;
+        nb = nbi + rot;
+        if (nb >= n_tiles) nb -= n_tiles;
+      } else {
+        mb = tile / n_tiles; nb = tile - mb * n_tiles;
+      }
       kb0 = (int)(((int64_t)sp * total_kb) / splits);
       kb1 = (int)(((int64_t)(sp + 1) * total_kb) / splits);
       u += num_groups;
@@ -199,7 +212,8 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
 
   const int total_kb = p.num_segs * p.kb_per_seg;
   Sched sched;
-  sched.init(p.splits, total_kb, p.m_tiles, p.n_tiles, group_id, num_groups);
+  sched.init(p.splits, total_kb, p.m_tiles, p.n_tiles, group_id, num_groups,
+             ((EPI == EPI_FWD || EPI == EPI_FWD_E) && p.landed) ? p.rot_tiles : -1);
   int mb, nb, kb0, kb1;
 
   if (warp == kProducerWarp) {
@@ -207,9 +221,37 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int have_src = -1;
       while (sched.next(mb, nb, kb0, kb1)) {
         const int m0 = mb * (CTA2 ? 2 * BM : BM) + (int)cta_rank * BM;
         const int n0 = nb * BN + (int)cta_rank * kBRows * (CTA2 ? 1 : 0);
+        if ((EPI == EPI_FWD || EPI == EPI_FWD_E) && p.landed) {
+          // first tile of a source's columns: its rows must have landed (both CTAs of a pair wait on their own)
+          const int src_lo = (int)(((int64_t)nb * BN) / p.cols_per_source);
+          int64_t last_col = (int64_t)nb * BN + BN - 1;
+          if (last_col >= p.n_cols) last_col = p.n_cols - 1;
+          const int src_hi = (int)(last_col / p.cols_per_source);
+          for (int src = src_lo; src <= src_hi; ++src) {
+            if (src == have_src) continue;
+            const uint32_t epoch = (uint32_t)*p.step;
+            uint64_t t0 = 0;
+            for (uint32_t spins = 0;; ++spins) {
+              uint32_t v;
+              asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.landed + src) : "memory");
+              if ((int32_t)(v - epoch) >= 0) break;
+              uint64_t now;
+              asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+              if (spins == 0) t0 = now;
+              if (now - t0 > 2000000000ull) {                    // 2 s: a dead peer must not hang the GPU
+                atomicExch(p.error, 1);
+                break;
+              }
+              __nanosleep(128);
+            }
+            have_src = src;
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");       // the landed rows are read by TMA (async proxy)
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           const int seg = kb / p.kb_per_seg, kk = (kb - seg * p.kb_per_seg) * BK;
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -827,7 +869,8 @@ int mpce_fwd_impl(const void* q_hi, const void* q_lo, int64_t ld_q, const void* 
                   int64_t ld_k, int64_t n_rows, int64_t n_cols, int64_t d, const uint32_t* bits,
                   int64_t ld_words, float inv_tau, int flags, int64_t diag_offset, float* row_sum_part,
                   float* row_pos_part, int64_t ld_rowpart, float* col_sum_part, int64_t ld_colpart,
-                  void* e_out, int64_t ld_e, evk_stream_t stream) {
+                  void* e_out, int64_t ld_e, evk_stream_t stream, const uint32_t* landed = nullptr,
+                  const int* step = nullptr, int* error = nullptr, int64_t cols_per_source = 0, int64_t first_col = 0) {
   int rc = check_device();
   if (rc != EVK_OK) return rc;
   const bool cta2 = use_cta_pairs();
@@ -852,6 +895,15 @@ int mpce_fwd_impl(const void* q_hi, const void* q_lo, int64_t ld_q, const void* 
   p.ld_rowpart = ld_rowpart;
   p.col_sum_part = col_sum_part;
   p.ld_colpart = ld_colpart;
+  if (landed) {
+    EVK_REQUIRE(step && error && cols_per_source > 0 && cols_per_source % BN == 0 && first_col >= 0 && first_col % BN == 0 &&
+                    first_col < n_cols, "evk_mpce_fwd_store_gathered: cols_per_source / first_col must be multiples of 256");
+    p.landed = landed;
+    p.step = step;
+    p.error = error;
+    p.cols_per_source = cols_per_source;
+    p.rot_tiles = (int)(first_col / BN);
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (e_out) {
     EVK_REQUIRE((flags & EVK_FLAG_SPLIT_BF16) == 0, "evk_mpce_fwd_store: the E strip is a bf16-mode feature (no split operands)");
@@ -881,6 +933,20 @@ extern "C" int evk_mpce_fwd_store(const void* q_hi, int64_t ld_q, const void* k_
   EVK_REQUIRE(e_out && evk_aligned16(e_out), "evk_mpce_fwd_store: e_out must be a 16-byte aligned device pointer");
   return mpce_fwd_impl(q_hi, nullptr, ld_q, k_hi, nullptr, ld_k, n_rows, n_cols, d, bits, ld_words, inv_tau, flags,
                        diag_offset, row_sum_part, row_pos_part, ld_rowpart, col_sum_part, ld_colpart, e_out, ld_e, stream);
+}
+
+extern "C" int evk_mpce_fwd_store_gathered(const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k, int64_t n_rows,
+                                           int64_t n_cols, int64_t d, const uint32_t* bits, int64_t ld_words,
+                                           float inv_tau, int flags, int64_t diag_offset, float* row_sum_part,
+                                           float* row_pos_part, int64_t ld_rowpart, float* col_sum_part,
+                                           int64_t ld_colpart, void* e_out, int64_t ld_e, const uint32_t* landed,
+                                           const int* step, int* error, int64_t cols_per_source, int64_t first_col,
+                                           evk_stream_t stream) {
+  EVK_REQUIRE(landed && step && error, "evk_mpce_fwd_store_gathered: null flag pointers");
+  EVK_REQUIRE(!e_out || evk_aligned16(e_out), "evk_mpce_fwd_store_gathered: e_out must be 16-byte aligned");
+  return mpce_fwd_impl(q_hi, nullptr, ld_q, k_hi, nullptr, ld_k, n_rows, n_cols, d, bits, ld_words, inv_tau, flags,
+                       diag_offset, row_sum_part, row_pos_part, ld_rowpart, col_sum_part, ld_colpart, e_out, ld_e, stream,
+                       landed, step, error, cols_per_source, first_col);
 }
 
 extern "C" int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi, const void* k_lo,

@@ -170,41 +170,71 @@ class _ShardedGPeer(torch.autograd.Function):
         side = ops._side_stream(dev)
         stream = main.cuda_stream
         two = row_ids.key2 is not None
-        # exchange 1 (one launch): normalised keys + ids into every rank's buffers, local queries, zeroed dQhat
+        # exchange 1: one launch normalises both sides (keys into this rank's own buffer rows), pushes the id shard
+        # to every rank and zeroes dQhat; after the barrier the key rows travel to the peers on the side stream
+        # WHILE K3 runs - K3 visits its own columns first and waits per source for the others (landed flags)
         k_norm = torch.empty(n, dtype=torch.float32, device=dev)
         q_norm = torch.empty(n, dtype=torch.float32, device=dev)
         q_hi = torch.empty((n, pc.ld), dtype=torch.bfloat16, device=dev)
         wq = _round_up(d, 4)
         dq = torch.empty((n, wq), dtype=torch.float32, device=dev) if need_grad else None
-        _lib.call("evk_shard_prologue", text.data_ptr(), text.stride(0), image.data_ptr(), image.stride(0), n, d, world,
-                  pc.table("khat"), pc.ld, lo_, k_norm.data_ptr(), q_hi.data_ptr(), q_norm.data_ptr(),
-                  row_ids.key.data_ptr(), row_ids.key2.data_ptr() if two else None, pc.table("ids"),
-                  pc.table("ids2") if two else None, None if dq is None else dq.data_ptr(), wq, stream)
+        overlap_gather = OVERLAP_GATHER and world > 1
+        _lib.call("evk_shard_prologue", text.data_ptr(), text.stride(0), image.data_ptr(), image.stride(0), n, d,
+                  1 if overlap_gather else world, pc.table("khat_local") if overlap_gather else pc.table("khat"), pc.ld, lo_,
+                  k_norm.data_ptr(), q_hi.data_ptr(), q_norm.data_ptr(),
+                  row_ids.key.data_ptr(), row_ids.key2.data_ptr() if two else None, world, pc.table("ids"),
+                  pc.table("ids2") if two else None, None if dq is None else dq.data_ptr(), wq, pc.step.data_ptr(), stream)
         pc.barrier()
         qn = ops.Normalized(n=n, d=d, norm=q_norm, hi=q_hi, lo=None, ld=pc.ld)
         kn_all = ops.Normalized(n=n_total, d=d, norm=None, hi=pc.khat, lo=None, ld=pc.ld)
         kn_local = ops.Normalized(n=n, d=d, norm=k_norm, hi=pc.khat[lo_:lo_ + n], lo=None, ld=pc.ld)
         ids_all = DeviceIds(pc.ids, pc.ids2 if two else None)
+        if overlap_gather:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                _lib.call("evk_peer_push_shard", pc.khat[lo_:].data_ptr(), n * pc.ld * 2, world, rank, pc.table("khat"),
+                          lo_ * pc.ld * 2, pc.table("landed"), pc.step.data_ptr(), pc.counters.data_ptr(), side.cuda_stream)
+
+        def sweep(bits, store):
+            """K3 over this rank's row block (with the per-source waits when the gather is still in flight)."""
+            n_ct = (n_total + ops.TILE_N - 1) // ops.TILE_N
+            n_rt = (n + ops.TILE_M - 1) // ops.TILE_M
+            if not overlap_gather:
+                return ops.tc_fwd_store(qn, kn_all, bits, inv_tau, 0, lo_) if store else \
+                    ops.tc_fwd_partials(qn, kn_all, bits, inv_tau, 0, lo_) + (None, 0)
+            rs = torch.empty((n_ct * ops.ROW_PARTS, n), dtype=torch.float32, device=dev)
+            rp = torch.empty((n_ct * ops.ROW_PARTS, n), dtype=torch.float32, device=dev)
+            cs = torch.empty((n_rt, n_total), dtype=torch.float32, device=dev)
+            ld_e = _round_up(n_total, 64)
+            e = torch.empty((n, ld_e), dtype=torch.bfloat16, device=dev) if store else None
+            _lib.call("evk_mpce_fwd_store_gathered", q_hi.data_ptr(), pc.ld, pc.khat.data_ptr(), pc.ld, n, n_total, d,
+                      bits.data_ptr(), bits.stride(0), float(inv_tau), 0, lo_, rs.data_ptr(), rp.data_ptr(), n,
+                      cs.data_ptr(), n_total, None if e is None else e.data_ptr(), ld_e, pc.landed.data_ptr(),
+                      pc.step.data_ptr(), pc.error.data_ptr(), n, lo_, stream)
+            return rs, rp, cs, e, (ld_e if store else 0)
+
         pos = None
         if need_grad:
             bits, counts, pos_idx = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_, want_list=True)
-            if overlap:                        # exact positive logits (O(n D)) next to K3
+            if overlap or overlap_gather:      # exact positive logits (O(n D)) next to K3, once every shard has landed
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
+                    if overlap_gather:
+                        _lib.call("evk_peer_wait_landed", pc.landed.data_ptr(), world, pc.step.data_ptr(),
+                                  pc.error.data_ptr(), pc.timeout_ms, side.cuda_stream)
                     pos_dot = ops.pos_logits(qn, kn_all, pos_idx, counts)
                 ops._shared_with(side, q_hi, pos_idx, counts)
             else:
                 pos_dot = ops.pos_logits(qn, kn_all, pos_idx, counts)
             pos = (pos_idx, pos_dot)
-            rs_part, rp_part, cs_part, e, ld_e = ops.tc_fwd_store(qn, kn_all, bits, inv_tau, 0, lo_)
+            rs_part, rp_part, cs_part, e, ld_e = sweep(bits, True)
         else:
             bits, counts = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_)
-            rs_part, rp_part, cs_part = ops.tc_fwd_partials(qn, kn_all, bits, inv_tau, 0, lo_)
-            e, ld_e = None, 0
+            rs_part, rp_part, cs_part, e, ld_e = sweep(bits, False)
         # exchange 2 (one launch): partials -> a_row, and this rank's slot (partial column sums of its rows +
         # its row-side loss term) into every rank's slot buffer
         a_row = torch.empty(n, dtype=torch.float32, device=dev)
-        ws = torch.empty(_round_up(16 + 8 * ((n_total + 31) // 32), 16), dtype=torch.uint8, device=dev)
+        ws = torch.empty(_round_up(16 + 24 * ((n_total + 31) // 32), 16), dtype=torch.uint8, device=dev)
         _lib.call("evk_mpce_shard_stats_push", rs_part.data_ptr(), int(rs_part.shape[0]), n, rp_part.data_ptr(),
                   int(rp_part.shape[0]), n, counts.data_ptr(), n, cs_part.data_ptr(), int(cs_part.shape[0]), n_total,
                   n_total, float(inv_tau), 2.0, 0.5 / n_total, a_row.data_ptr(), pc.table("slots"), world,
@@ -215,9 +245,10 @@ class _ShardedGPeer(torch.autograd.Function):
         ws2 = torch.empty(_round_up(16 + 8 * ((n_total + 255) // 256), 16), dtype=torch.uint8, device=dev)
         _lib.call("evk_mpce_shard_finish", pc.slots.data_ptr(), world, pc.ld_slot, n_total, float(inv_tau), 0.5 / n_total,
                   b_col.data_ptr(), loss.data_ptr(), ws2.data_ptr(), ws2.numel(), stream)
-        if need_grad and overlap:
-            main.wait_stream(side)
-            ops._shared_with(main, pos_dot)
+        if overlap_gather or (need_grad and overlap):
+            main.wait_stream(side)              # the push (and the positives) are part of this step
+            if need_grad:
+                ops._shared_with(main, pos_dot)
         ctx.ops, ctx.pc, ctx.inv_tau = ops, pc, inv_tau
         ctx.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, e, ld_e, dq)
         ctx.pos = pos
@@ -259,12 +290,14 @@ class _ShardedGPeer(torch.autograd.Function):
             ops._shared_with(side, e, dq, g, image, qn.norm)
         else:
             d_image = image_side()
+        if overlap:
+            # the barrier also tells the peers that this rank is done READING its gathered key rows (the local
+            # contraction does), so that they may overwrite them in the next step: join before signalling
+            main.wait_stream(side)
+            ops._shared_with(main, d_image)
         pc.barrier()                           # every rank's partial for these rows has landed
         d_text = ops.l2norm_bwd(text, kn_local, pc.dk_parts[0], scale_dev=g, scale_host=scale,
                                 parts=(pc.world, n * pc.width))
-        if overlap:
-            main.wait_stream(side)
-            ops._shared_with(main, d_image)
         ctx.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, None, 0, None)
         return None, None, None, None, d_image, d_text
 
@@ -282,6 +315,9 @@ def peer_eligible(image: torch.Tensor, text: torch.Tensor, precision: str, world
 
 
 PEER_EXCHANGE = os.environ.get("EVOKE_B200_PEER_EXCHANGE", "bf16")     # dtype of the dKhat partials on NVLink: bf16 | fp32
+# EVOKE_B200_OVERLAP_GATHER=1: the key rows travel on a side stream WHILE K3 runs (per-source landed flags, staggered
+# pushes).  Measured slower on B200 x 8 (0.383 vs 0.321 ms/step: the copy kernel and K2 contend with the sweep), so off.
+OVERLAP_GATHER = os.environ.get("EVOKE_B200_OVERLAP_GATHER", "0") == "1"
 
 
 def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local, temp: float, *,

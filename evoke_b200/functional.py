@@ -301,7 +301,7 @@ def stats_fused(rs_part, rp_part, cs_part, counts, *, shift: float, pos_weight: 
     a_row = torch.empty(n_rows, dtype=torch.float32, device=dev)
     b_col = torch.empty(n_cols, dtype=torch.float32, device=dev) if cs_part is not None else None
     loss = torch.empty(1, dtype=torch.float32, device=dev)
-    ws_bytes = 16 + 8 * ((max(n_rows, n_cols) + 31) // 32)
+    ws_bytes = 16 + 24 * ((max(n_rows, n_cols) + 31) // 32)
     ws = torch.empty(_round_up(ws_bytes, 16), dtype=torch.uint8, device=dev)
     _lib.call("evk_mpce_stats_fused", _ptr(rs_part), int(rs_part.shape[0]), max(int(rs_part.stride(0)), n_rows),
               _ptr(rp_part), int(rp_part.shape[0]), max(int(rp_part.stride(0)), n_rows),

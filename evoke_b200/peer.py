@@ -12,6 +12,7 @@ flag barrier kernel (``evk_peer_barrier``) - no NCCL call sits on the data path:
   dk_parts [R, n, D] bf16 (or fp32) this rank's rows of dKhat, one partial per source rank: rank s's K4b epilogue
                           stores its tiles for these rows into part s (posted NVLink stores), K1b adds them up
   flags  [16]     uint32  barrier flags (entry r written by rank r only)
+  landed [16]     uint32  landed[s] = step in which source s's key rows last arrived here completely
 
 Only torch.distributed's object all-gather is used, once per context, for the handles.
 """
@@ -62,7 +63,7 @@ class PeerContext:
         off = 0
         self.off = {}
         for name, nbytes in (("khat", big_n * self.ld * 2), ("ids", big_n * 4), ("ids2", big_n * 4 if two_keys else 0),
-                             ("slots", r * self.ld_slot * 4), ("dk_parts", r * n * self.width * esize), ("flags", 64)):
+                             ("slots", r * self.ld_slot * 4), ("dk_parts", r * n * self.width * esize), ("flags", 64), ("landed", 64)):
             self.off[name] = off
             off += _round_up(nbytes, _ALIGN)
         self.nbytes = off
@@ -105,11 +106,15 @@ class PeerContext:
         self.slots = self._view("slots", r * self.ld_slot * 4).view(torch.float32).view(r, self.ld_slot)
         self.dk_parts = self._view("dk_parts", r * n * self.width * esize).view(
             torch.bfloat16 if exchange == "bf16" else torch.float32).view(r, n, self.width)
+        self.landed = self._view("landed", 64).view(torch.int32)
+        self.step = torch.zeros(1, dtype=torch.int32, device=self.device)          # advanced by the prologue kernel
+        self.counters = torch.zeros(16, dtype=torch.int32, device=self.device)     # push kernel's per-destination tickets
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.ptrs = {name: (ctypes.c_uint64 * self.world)(*[b + o for b in self.bases]) for name, o in self.off.items()}
         # where THIS rank's partial for owner t goes: part `rank` of t's dk_parts
         mine = self.rank * n * self.width * esize
+        self.ptrs["khat_local"] = (ctypes.c_uint64 * 1)(self.base + self.off["khat"])
         self.ptrs["dk_mine"] = (ctypes.c_uint64 * self.world)(*[b + self.off["dk_parts"] + mine for b in self.bases])
         torch.cuda.synchronize(self.device)
 
@@ -139,7 +144,7 @@ class PeerContext:
                 lib.evk_peer_close(ctypes.c_void_p(b))
         self.bases = []
         if self.base:
-            self._raw = self.khat = self.ids = self.ids2 = self.slots = self.dk_parts = None
+            self._raw = self.khat = self.ids = self.ids2 = self.slots = self.dk_parts = self.landed = None
             lib.evk_peer_free(ctypes.c_void_p(self.base))
             self.base = 0
 

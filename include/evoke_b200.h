@@ -178,7 +178,7 @@ EVK_API int evk_mpce_finalize_avgpos(const float* row_neg, const float* row_pos,
 
 /* Single-GPU fused form of evk_reduce_partials (x3) + evk_mpce_finalize: takes the per-tile
  * partials of K3 directly (rs_part: [row_parts, ld_row]; rp_part: [pos_parts, ld_pos] - K3's
- * partials, or the single row written by evk_mpce_pos; cs_part: [col_parts, ld_col] or NULL), the loss covers all rows and all columns.  workspace: >= 16 + 8*ceil(max(n_rows,n_cols)/32)
+ * partials, or the single row written by evk_mpce_pos; cs_part: [col_parts, ld_col] or NULL), the loss covers all rows and all columns.  workspace: >= 16 + 24*ceil(max(n_rows,n_cols)/32)
  * bytes, 16-byte aligned, contents irrelevant.  Deterministic (fixed summation order). */
 EVK_API int evk_mpce_stats_fused(const float* rs_part, int64_t row_parts, int64_t ld_row,
                          const float* rp_part, int64_t pos_parts, int64_t ld_pos,
@@ -224,6 +224,23 @@ EVK_API int evk_mpce_fwd_store(const void* q_hi, int64_t ld_q, const void* k_hi,
 EVK_API int evk_mpce_pos_logits(const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k,
                         int64_t n_rows, int64_t d, const int32_t* pos_idx, const int32_t* counts, int pos_slots,
                         float* pos_dot, evk_stream_t stream);
+
+/* Sharded K3 that starts before the all-gather of the key rows has finished.  k_hi is this rank's buffer of ALL
+ * key rows, filled by every rank's evk_peer_push_shard while the sweep runs: column c belongs to source
+ * c / cols_per_source, and landed[s] (this rank's landed-flag area) reaches *step once source s's rows are
+ * complete.  The column blocks are visited starting at first_col (this rank's own rows, already in place) and the
+ * TMA producer waits for a source's flag before its first load from that source's columns; if a flag does not
+ * arrive within 2 s *error is set and the sweep continues (a dead peer must not hang the GPU).
+ * e_out may be NULL (statistics only).  Otherwise as evk_mpce_fwd_store. */
+EVK_API int evk_mpce_fwd_store_gathered(const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k,
+                                int64_t n_rows, int64_t n_cols, int64_t d,
+                                const uint32_t* bits, int64_t ld_words,
+                                float inv_tau, int flags, int64_t diag_offset,
+                                float* row_sum_part, float* row_pos_part, int64_t ld_rowpart,
+                                float* col_sum_part, int64_t ld_colpart,
+                                void* e_out, int64_t ld_e,
+                                const uint32_t* landed, const int* step, int* error,
+                                int64_t cols_per_source, int64_t first_col, evk_stream_t stream);
 
 /* K4t, in place over the strip written by evk_mpce_fwd_store (or any row range of it: offset the
  * strip / bits / counts / a_row pointers):  strip[i, j] <- bf16( E_ij (a_row[i] + b_col[j]) - 2 M_ij / c_i ),
@@ -294,12 +311,31 @@ EVK_API int evk_peer_bcast(const void* src, int64_t bytes, int n_dst, const uint
  * into the local q_hi, the id shard(s) pushed to offset row_offset of every rank's id buffer(s), and - if
  * zero_buf != NULL - the zero fill of an fp32 [n_rows, ld_zero] accumulator (the split-K output of the local
  * gradient contraction).  Contiguous fp32 inputs, d % 8 == 0, d <= 2048.  F.normalize of :495-496 for both
- * sides plus what a sharded run must exchange before the similarity sweep. */
+ * sides plus what a sharded run must exchange before the similarity sweep.  n_dst = 1 with only this rank's
+ * own buffer keeps the key rows local (evk_peer_push_shard then moves them next to the sweep); the ids always go
+ * to all n_ids_dst ranks.  step_counter (may be NULL): device int advanced by one per launch - the epoch of the
+ * landed flags. */
 EVK_API int evk_shard_prologue(const float* text, int64_t text_stride, const float* image, int64_t image_stride,
                        int64_t n_rows, int64_t d, int n_dst, const uint64_t* khat_ptrs, int64_t ld_bf16,
                        int64_t row_offset, float* k_norm, void* q_hi, float* q_norm,
-                       const int32_t* ids, const int32_t* ids2, const uint64_t* ids_ptrs, const uint64_t* ids2_ptrs,
-                       float* zero_buf, int64_t ld_zero, evk_stream_t stream);
+                       const int32_t* ids, const int32_t* ids2, int n_ids_dst,
+                       const uint64_t* ids_ptrs, const uint64_t* ids2_ptrs,
+                       float* zero_buf, int64_t ld_zero, int* step_counter, evk_stream_t stream);
+
+/* The all-gather of the key rows, overlapped with the similarity sweep.  Copies this rank's shard (`bytes` at
+ * `src`, normally its own rows inside its own buffer) to byte offset dst_offset_bytes of every OTHER rank's
+ * buffer, one destination at a time in the order rank+1, rank+2, ... (every GPU then receives from one source at
+ * a time, at full NVLink rate, and the shards land in a known order), and after each destination raises that
+ * destination's landed flag for this source: landed_ptrs[t][rank] = *step (release, system scope).  Its own flag
+ * is raised at once.  counters: >= 64 bytes of zeroed device memory owned by the caller (reset by the kernel). */
+EVK_API int evk_peer_push_shard(const void* src, int64_t bytes, int n_ranks, int rank,
+                        const uint64_t* dst_ptrs, int64_t dst_offset_bytes,
+                        const uint64_t* landed_ptrs, const int* step, void* counters, evk_stream_t stream);
+
+/* Waits (one tiny kernel) until landed[s] >= *step for every source s < n_ranks: for consumers of the gathered
+ * rows other than K3.  Sets *error after timeout_ms (<= 0: 2000) instead of hanging. */
+EVK_API int evk_peer_wait_landed(const void* landed, int n_ranks, const int* step, int* error, int64_t timeout_ms,
+                         evk_stream_t stream);
 
 /* Sharded form of evk_mpce_stats_fused: reduces K3's partials of this rank's row block, writes a_row, and
  * stores this rank's statistics slot - the raw partial column sums (n_cols floats) followed by its row-side
