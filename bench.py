@@ -440,6 +440,17 @@ def run_cuda(args):
         cpu_baseline = {"value": N_GLOBAL / (t_cpu * scale), "unit": "pairs/s", "cores": threads, "kind": "port",
                         "sample": sample}
 
+    transport = "none"
+    if world > 1:
+        from evoke_b200 import peer as _peer
+        pcs = [c for c in _peer._CONTEXTS.values() if isinstance(c, _peer.PeerContext)]
+        if pcs:
+            transport = (f"peer memory over NVLink (this library's kernels: all-gather stores, GEMM-epilogue scatter of "
+                         f"{pcs[0].exchange} partials, flag barriers; CUDA IPC)")
+            for c in pcs:
+                c.check()                                  # a barrier that timed out invalidates the run
+        else:
+            transport = "NCCL (all-gather / all-reduce / reduce-scatter)"
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
@@ -447,9 +458,11 @@ def run_cuda(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": N_GLOBAL, "dim": DIM, "rows_per_rank": n_loc,
                        "precision": "bf16 operands, fp32 accumulate/statistics; fp32 inputs and gradients",
-                       "parallelism": (f"dp{world} row shards, shard_mode={args.shard_mode}" if world > 1 else "single GPU"),
-                       "l2": "no explicit flush: each step streams a 0.5 GB bf16 W strip (+0.15 GB operands/grads) "
-                             "through the 126 MB L2, so no timed iteration starts with its inputs cached"},
+                       "parallelism": (f"dp{world} row shards, shard_mode={args.shard_mode}, transport={transport}"
+                                       if world > 1 else "single GPU"),
+                       "l2": "no explicit flush: each step writes, rewrites and reads a bf16 E/W strip of "
+                             f"{n_loc * N_GLOBAL * 2 / 1e6:.0f} MB per GPU (+ operands/gradients) through the 126 MB L2, "
+                             "so no timed iteration starts with its inputs cached"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu_baseline, "loss": loss_val,
             "launch_mode": "cuda_graph" if graphed is not None else "eager",

@@ -168,7 +168,9 @@ l2norm_bwd_kernel(const void* __restrict__ x, int x_dtype, int64_t n_out, int64_
 // One pass: the row of x and g stays in registers between the projection and the update.
 // Algorithmic bytes per row: 4d (x) + 4d (g) read, 4d (dx) written.
 // kBf16G: the partial buffers hold bf16 (the compressed exchange of the sharded path): 4 values = one 64-bit load
-template <int kIters, bool kBf16G>
+// kParts: several partial buffers are summed (kept out of the single-buffer kernel: a runtime loop between the
+// loads of the unrolled iterations serialises them, 27 -> 39 us at the bench shape)
+template <int kIters, bool kBf16G, bool kParts>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t stride_row,
                       const int32_t* __restrict__ gather, const float* __restrict__ norm,
@@ -203,10 +205,27 @@ l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t
       if (c * 4 < d) {
         xv[it] = __ldg(xr + c);
         gv[it] = gload(0, c);
-        for (int p = 1; p < n_parts; ++p) {        // partial dXhat buffers written by the ranks' K4b epilogues
-          const float4 t = gload(p, c);
-          gv[it].x += t.x; gv[it].y += t.y; gv[it].z += t.z; gv[it].w += t.w;
+      }
+    }
+    if (kParts) {
+      for (int p = 1; p < n_parts; ++p) {          // partial dXhat buffers written by the ranks' K4b epilogues:
+        float4 t[kIters];                          // all loads of one part are in flight together
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+          const int c = it * 32 + lane;
+          if (c * 4 < d) t[it] = gload(p, c);
         }
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+          const int c = it * 32 + lane;
+          if (c * 4 < d) { gv[it].x += t[it].x; gv[it].y += t[it].y; gv[it].z += t[it].z; gv[it].w += t[it].w; }
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int c = it * 32 + lane;
+      if (c * 4 < d) {
         xv[it].x *= inv_den; xv[it].y *= inv_den; xv[it].z *= inv_den; xv[it].w *= inv_den;   // xhat (1 ulp of the forward's)
         proj = fmaf(xv[it].x, gv[it].x, proj);
         proj = fmaf(xv[it].y, gv[it].y, proj);
@@ -298,12 +317,18 @@ extern "C" int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, i
     const int grid = grid_for_rows(n_out);
     const float* xf = static_cast<const float*>(x);
     float* df = static_cast<float*>(dx);
-#define EVK_LAUNCH_BWD(IT, B16)                                                                                  \
-  l2norm_bwd_vec_kernel<IT, B16><<<grid, kWarpsPerBlock * 32, 0, s>>>(xf, n_out, (int)d, stride_row, gather, norm, g, \
-                                                                      ld_g, n_parts, part_stride, scale_dev,           \
-                                                                      scale_host, df, ld_dx)
-    if (d <= 1024) { if (g16) EVK_LAUNCH_BWD(8, true); else EVK_LAUNCH_BWD(8, false); }
-    else { if (g16) EVK_LAUNCH_BWD(16, true); else EVK_LAUNCH_BWD(16, false); }
+#define EVK_LAUNCH_BWD(IT, B16, PARTS)                                                                                    \
+  l2norm_bwd_vec_kernel<IT, B16, PARTS><<<grid, kWarpsPerBlock * 32, 0, s>>>(xf, n_out, (int)d, stride_row, gather, norm, g, \
+                                                                             ld_g, n_parts, part_stride, scale_dev,           \
+                                                                             scale_host, df, ld_dx)
+    const bool multi = n_parts > 1;
+    if (d <= 1024) {
+      if (g16) { if (multi) EVK_LAUNCH_BWD(8, true, true); else EVK_LAUNCH_BWD(8, true, false); }
+      else { if (multi) EVK_LAUNCH_BWD(8, false, true); else EVK_LAUNCH_BWD(8, false, false); }
+    } else {
+      if (g16) { if (multi) EVK_LAUNCH_BWD(16, true, true); else EVK_LAUNCH_BWD(16, true, false); }
+      else { if (multi) EVK_LAUNCH_BWD(16, false, true); else EVK_LAUNCH_BWD(16, false, false); }
+    }
 #undef EVK_LAUNCH_BWD
     EVK_CHECK_LAUNCH("l2norm_bwd_vec");
     return EVK_OK;

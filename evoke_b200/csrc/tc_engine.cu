@@ -81,9 +81,9 @@ struct alignas(64) TcParams {
 
 template <int EPI>
 constexpr int epi_smem_bytes() {
-  return EPI == EPI_FWD ? 4 * BN * 4
+  return EPI == EPI_FWD ? 2 * 4 * BN * 4
          : (EPI == EPI_BWD_W ? kEpiWarps * 8192
-            : (EPI == EPI_FWD_E ? 4 * BN * 4 + kEpiWarps * 8192 : (EPI == EPI_GEMM_TMA ? kEpiWarps * 8192 : 0)));
+            : (EPI == EPI_FWD_E ? 2 * 4 * BN * 4 + kEpiWarps * 8192 : (EPI == EPI_GEMM_TMA ? kEpiWarps * 8192 : 0)));
 }
 template <int EPI, int STAGES, bool CTA2>
 constexpr int smem_bytes_total() {
@@ -231,8 +231,9 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
           int64_t last_col = (int64_t)nb * BN + BN - 1;
           if (last_col >= p.n_cols) last_col = p.n_cols - 1;
           const int src_hi = (int)(last_col / p.cols_per_source);
+          const int own = (int)(((int64_t)p.rot_tiles * BN) / p.cols_per_source);   // written by this GPU's prologue
           for (int src = src_lo; src <= src_hi; ++src) {
-            if (src == have_src) continue;
+            if (src == have_src || src == own) continue;
             const uint32_t epoch = (uint32_t)*p.step;
             uint64_t t0 = 0;
             for (uint32_t spins = 0;; ++spins) {
@@ -346,15 +347,29 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
 
       if (EPI == EPI_FWD || EPI == EPI_FWD_E) {
         constexpr bool kStoreE = EPI == EPI_FWD_E;
-        float* colpart = reinterpret_cast<float*>(epi_gen);       // [4][BN]
+        // [2][4][BN]: double-buffered by tile, so one CTA-level barrier per tile is enough (a warp cannot write
+        // buffer b again before every warp has passed the next tile's barrier, i.e. finished reading b)
+        float* colpart = reinterpret_cast<float*>(epi_gen) + (lu & 1) * 4 * BN;
         // EPI_FWD_E: this warp's private staging for its 32 rows x 128 columns of E (bf16), two
         // 128B-swizzled [32 x 64] boxes, stored with its own TMA stores (as in EPI_BWD_W)
-        const uint32_t wstg = epi_base + 4 * BN * 4 + warp * 8192;
+        const uint32_t wstg = epi_base + 2 * 4 * BN * 4 + warp * 8192;
         const bool want_col = (p.flags & EVK_FLAG_NO_COLSUM) == 0;
         const bool want_pos = (p.flags & EVK_FLAG_NO_POS) == 0;   // else evk_mpce_pos supplies the positive sums
         const uint32_t* mrow = want_pos ? p.bits + (row_ok ? i : 0) * p.ld_words + (n0 >> 5) : nullptr;
         const int64_t dcol = i + p.diag_offset - n0;              // diagonal column inside this tile?
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f, rp = 0.f;
+        // the four mask words of this warp's 128 columns: one 128-bit load issued BEFORE the wait for the
+        // accumulator (its latency - the mask streams from HBM - used to be exposed once per 32-column chunk)
+        uint32_t mw4[4] = {0u, 0u, 0u, 0u};
+        if (want_pos && row_ok) {
+          if (p.flags & 0x4000) {
+            const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(mrow + c_lo));
+            mw4[0] = t4.x; mw4[1] = t4.y; mw4[2] = t4.z; mw4[3] = t4.w;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mw4[k] = __ldg(mrow + c_lo + k);
+          }
+        }
         if (kStoreE) {
           if (lane == 0) tma_store_wait_read<0>();                // this warp's previous stores have left smem
           __syncwarp();
@@ -364,7 +379,7 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
 #pragma unroll 1
         for (int cc = 0; cc < BN / 64; ++cc) {
           const int c = c_lo + cc;
-          const uint32_t mword = (want_pos && row_ok) ? __ldg(mrow + c) : 0u;
+          const uint32_t mword = cc == 0 ? mw4[0] : (cc == 1 ? mw4[1] : (cc == 2 ? mw4[2] : mw4[3]));
           float v[32];
           if (p.flags & 0x800) {                                  // bring-up knockout: no TMEM read
 #pragma unroll
@@ -436,7 +451,6 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
           const float s = (colpart[et] + colpart[BN + et]) + (colpart[2 * BN + et] + colpart[3 * BN + et]);
           // each CTA (128-row block) writes its own partial row: index = global 128-row block
           if (n0 + et < p.n_cols && m0 < p.n_rows) p.col_sum_part[(int64_t)(m0 / BM) * p.ld_colpart + n0 + et] = s;
-          named_bar_sync(1, kEpiThreads);                         // colpart reusable
         }
       } else if (EPI == EPI_BWD_W) {
         // Every warp stages and stores its own 32 rows x 128 columns: private 8 KiB staging region,
@@ -887,6 +901,7 @@ int mpce_fwd_impl(const void* q_hi, const void* q_lo, int64_t ld_q, const void* 
   EVK_REQUIRE(inv_tau > 0.f && inv_tau <= 40.f, "evk_mpce_fwd: 1/tau=%g outside (0, 40]: the fixed-shift softmax needs exp(-2/tau) to stay normal in fp32", inv_tau);
   p.inv_tau = inv_tau;
   p.flags = flags;
+  if (bits && evk_aligned16(bits) && ld_words % 4 == 0) p.flags |= 0x4000;     // 128-bit mask loads
   p.diag_offset = diag_offset;
   p.bits = bits;
   p.ld_words = ld_words;
