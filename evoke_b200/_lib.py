@@ -22,6 +22,7 @@ P, I, L, F, D = c_void_p, c_int, c_int64, c_float, c_double
 # name -> argtypes, in header order.  tests/test_abi.py checks this table against the header.
 SIGNATURES = {
     "evk_version": [],
+    "evk_mpce_row_parts": [],
     "evk_last_error": [],
     "evk_device_info": [I, P, P, P],
     "evk_l2norm_fwd": [P, I, L, L, L, L, P, P, L, P, P, L, P, P],

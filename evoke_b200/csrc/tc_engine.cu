@@ -32,10 +32,14 @@ constexpr int kABytes = BM * BK * 2;          // 16 KiB: this CTA's 128 rows of 
 constexpr int kEpiWarps = 8;                  // two per SMSP; warp w reads TMEM lanes 32*(w%4)..+31
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;    // + TMA producer warp + MMA issuer warp
-constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+// K3 (EPI_FWD / EPI_FWD_E) runs SIXTEEN epilogue warps (four per SMSP, 32 rows x 64 columns each): its epilogue
+// - exp, row/column sums, bf16 pack - sets the pace of the kernel (ncu: the MMA waits for TMEM stages, 45% of the
+// epilogue's warp samples are fixed-latency / scoreboard stalls that two warps per scheduler cannot hide).
+constexpr int kEpiWarpsFwd = 16;
+// default number of epilogue warps of an epilogue kind (K3 variants are chosen at launch, see mpce_fwd_impl)
+__host__ __device__ constexpr int epi_warps(int epi) { return kEpiWarps; }
 constexpr int kTmemCols = 512;
 constexpr int kMaxSegs = 3;
-constexpr int kRowParts = kEpiWarps / 4;      // row-statistic partials written per 256-column tile
 
 enum { EPI_FWD = 0, EPI_BWD_W = 1, EPI_GEMM = 2, EPI_FWD_E = 3, EPI_GEMM_TMA = 4 };
 // EPI_FWD_E: K3 that also stores E as bf16.  EPI_GEMM_TMA: K4b whose fp32 tiles leave through shared memory and
@@ -83,11 +87,13 @@ template <int EPI>
 constexpr int epi_smem_bytes() {
   return EPI == EPI_FWD ? 2 * 4 * BN * 4
          : (EPI == EPI_BWD_W ? kEpiWarps * 8192
-            : (EPI == EPI_FWD_E ? 2 * 4 * BN * 4 + kEpiWarps * 8192 : (EPI == EPI_GEMM_TMA ? kEpiWarps * 8192 : 0)));
+            : (EPI == EPI_FWD_E ? 2 * 4 * BN * 4 : (EPI == EPI_GEMM_TMA ? kEpiWarps * 8192 : 0)));
 }
-template <int EPI, int STAGES, bool CTA2>
+// EW epilogue warps, SB staging boxes (4 KiB each) per warp for the E-strip store of EPI_FWD_E
+template <int EPI, int STAGES, bool CTA2, int EW = kEpiWarps, int SB = 2>
 constexpr int smem_bytes_total() {
-  return 1024 /*align slack*/ + STAGES * stage_bytes<CTA2>() + epi_smem_bytes<EPI>() + (2 * STAGES + 4) * 8 + 16;
+  return 1024 /*align slack*/ + STAGES * stage_bytes<CTA2>() + epi_smem_bytes<EPI>() +
+         (EPI == EPI_FWD_E ? EW * SB * 4096 : 0) + (2 * STAGES + 4) * 8 + 16;
 }
 
 // Work decomposition, identical in the three warp roles.
@@ -161,9 +167,13 @@ __device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
 // tcgen05.mma.cta_group::2 (M = 256), which reads A from each CTA and B from both halves, and its
 // commits are multicast to the barriers of both CTAs.  Each CTA's TMEM holds the accumulator of
 // its own 128 rows x 256 columns, so the epilogue is the same code in both modes.
-template <int EPI, bool A_MN, bool B_MN, int STAGES, bool CTA2>
+// EW = epilogue warps, SB = 4 KiB staging boxes per warp for the E-strip store (EPI_FWD_E).
 // (the contraction kernels are capped at 128 registers - bound 512 threads - so that K4t CTAs fit beside them)
-__global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512 : kThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
+template <int EPI, bool A_MN, bool B_MN, int STAGES, bool CTA2, int EW = kEpiWarps, int SB = 2>
+__global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512 : (EW + 2) * 32, 1)
+tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int kEW = EW;                             // epilogue warps of THIS instantiation
+  constexpr int kProducerWarp = kEW, kMmaWarp = kEW + 1;
   constexpr int kStage = stage_bytes<CTA2>();
   constexpr int kBRows = CTA2 ? BN / 2 : BN;          // B rows (tile columns) loaded by this CTA
   extern __shared__ uint8_t smem_raw[];
@@ -171,14 +181,15 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t epi_base = smem_base + STAGES * kStage;
   uint8_t* epi_gen = smem_gen + STAGES * kStage;
-  const uint32_t bar_base = epi_base + epi_smem_bytes<EPI>();
+  constexpr int kEpiBytes = epi_smem_bytes<EPI>() + (EPI == EPI_FWD_E ? EW * SB * 4096 : 0);
+  const uint32_t bar_base = epi_base + kEpiBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(epi_gen + epi_smem_bytes<EPI>() + 8 * (2 * STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(epi_gen + kEpiBytes + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
@@ -197,7 +208,7 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiWarps * (CTA2 ? 2 : 1));
+      mbar_init(tempty_bar(s), kEW * (CTA2 ? 2 : 1));
     }
     fence_mbar_init();
   }
@@ -217,15 +228,15 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
   int mb, nb, kb0, kb1;
 
   if (warp == kProducerWarp) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (whole warp loops, one lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       int have_src = -1;
       while (sched.next(mb, nb, kb0, kb1)) {
         const int m0 = mb * (CTA2 ? 2 * BM : BM) + (int)cta_rank * BM;
         const int n0 = nb * BN + (int)cta_rank * kBRows * (CTA2 ? 1 : 0);
-        if ((EPI == EPI_FWD || EPI == EPI_FWD_E) && p.landed) {
+        if ((EPI == EPI_FWD || EPI == EPI_FWD_E) && p.landed && lane == 0) {
           // first tile of a source's columns: its rows must have landed (both CTAs of a pair wait on their own)
           const int src_lo = (int)(((int64_t)nb * BN) / p.cols_per_source);
           int64_t last_col = (int64_t)nb * BN + BN - 1;
@@ -253,12 +264,14 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
           }
           asm volatile("fence.proxy.async;" ::: "memory");       // the landed rows are read by TMA (async proxy)
         }
+        __syncwarp();
         for (int kb = kb0; kb < kb1; ++kb) {
           const int seg = kb / p.kb_per_seg, kk = (kb - seg * p.kb_per_seg) * BK;
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * kStage, b_dst = a_dst + kABytes;
+          if (elect_one()) {
           // the (leader's) full barrier expects the bytes of every CTA that feeds this stage
           if (leader) mbar_expect_tx(full_bar(stage), kStage * (CTA2 ? 2 : 1));
-          const uint32_t a_dst = smem_base + stage * kStage, b_dst = a_dst + kABytes;
           auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1, uint64_t pol) {
             if (CTA2) tma_load_2d_cta2(dst, m, full_bar(stage), c0, c1, pol);
             else tma_load_2d(dst, m, full_bar(stage), c0, c1, pol);
@@ -275,14 +288,16 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
 #pragma unroll
             for (int b = 0; b < kBRows / 64; ++b) load(b_dst + b * 8192, &p.b_map[seg], n0 + 64 * b, kk, p.policy_b);
           }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
     __syncwarp();
   } else if (warp == kMmaWarp) {
-    // ===================================================================== MMA issuer (leader CTA)
-    if (lane == 0 && leader) {
+    // ===================================================================== MMA issuer (leader CTA; whole warp loops, one lane issues)
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0;
       int lu = 0;
@@ -301,30 +316,34 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
           // descriptors differ from the stage-0 ones only in the 14-bit (address >> 4) field
           const uint64_t ad0 = a_desc0 + (uint64_t)((stage * kStage) >> 4);
           const uint64_t bd0 = b_desc0 + (uint64_t)((stage * kStage) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = ad0 + (uint64_t)(A_MN ? k * (2048 >> 4) : k * (32 >> 4));
-            const uint64_t bd = bd0 + (uint64_t)(B_MN ? k * (2048 >> 4) : k * (32 >> 4));
-            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-            if (CTA2) umma_bf16_cta2(d_tmem, ad, bd, idesc, acc);
-            else umma_bf16(d_tmem, ad, bd, idesc, acc);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = ad0 + (uint64_t)(A_MN ? k * (2048 >> 4) : k * (32 >> 4));
+              const uint64_t bd = bd0 + (uint64_t)(B_MN ? k * (2048 >> 4) : k * (32 >> 4));
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (CTA2) umma_bf16_cta2(d_tmem, ad, bd, idesc, acc);
+              else umma_bf16(d_tmem, ad, bd, idesc, acc);
+            }
+            // smem slot free (in both CTAs) once these MMAs retire
+            if (CTA2) umma_commit_cta2(empty_bar(stage)); else umma_commit(empty_bar(stage));
+            // last k-block of the unit: accumulator ready for the epilogue warps (of both CTAs)
+            if (kb == kb1 - 1) { if (CTA2) umma_commit_cta2(tfull_bar(as)); else umma_commit(tfull_bar(as)); }
           }
-          // smem slot free (in both CTAs) once these MMAs retire
-          if (CTA2) umma_commit_cta2(empty_bar(stage)); else umma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        // accumulator ready for the epilogue warps (of both CTAs)
-        if (CTA2) umma_commit_cta2(tfull_bar(as)); else umma_commit(tfull_bar(as));
       }
     }
     __syncwarp();
   } else {
     // ===================================================================== epilogue warps
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int hh = warp >> 2;                     // which half of the tile's columns this warp owns
+    const int hh = warp >> 2;                     // which part (half / quarter) of the tile's columns this warp owns
+    constexpr int kChunks = BN / 32 / (kEW / 4);  // 32-column chunks per warp: 4 (eight warps) or 2 (sixteen)
     const int row = q * 32 + lane;                // tile row owned by this thread
-    const int et = warp * 32 + lane;              // 0..255
-    const int c_lo = hh * (BN / 64);              // first 32-column chunk of this warp (4 chunks)
+    const int et = warp * 32 + lane;              // 0 .. 32*kEW-1
+    const int c_lo = hh * kChunks;                // first 32-column chunk of this warp
     const float c1 = p.inv_tau * 1.4426950408889634f;    // exp(s/tau - shift) = 2^(s*c1 - c1)
     const bool excl = (p.flags & EVK_FLAG_EXCLUDE_DIAG) != 0;
     auto release_tmem = [&](int as) {
@@ -350,24 +369,29 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
         // [2][4][BN]: double-buffered by tile, so one CTA-level barrier per tile is enough (a warp cannot write
         // buffer b again before every warp has passed the next tile's barrier, i.e. finished reading b)
         float* colpart = reinterpret_cast<float*>(epi_gen) + (lu & 1) * 4 * BN;
-        // EPI_FWD_E: this warp's private staging for its 32 rows x 128 columns of E (bf16), two
+        // EPI_FWD_E: this warp's private staging for its 32 rows x (32 kChunks) columns of E (bf16),
         // 128B-swizzled [32 x 64] boxes, stored with its own TMA stores (as in EPI_BWD_W)
-        const uint32_t wstg = epi_base + 2 * 4 * BN * 4 + warp * 8192;
+        // SB staging buffers per warp: with fewer buffers than boxes a buffer is reused after its store has been read
+        const uint32_t wstg = epi_base + 2 * 4 * BN * 4 + warp * (SB * 4096);
+        const int m_warp = m0 + q * 32;
         const bool want_col = (p.flags & EVK_FLAG_NO_COLSUM) == 0;
         const bool want_pos = (p.flags & EVK_FLAG_NO_POS) == 0;   // else evk_mpce_pos supplies the positive sums
         const uint32_t* mrow = want_pos ? p.bits + (row_ok ? i : 0) * p.ld_words + (n0 >> 5) : nullptr;
         const int64_t dcol = i + p.diag_offset - n0;              // diagonal column inside this tile?
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f, rp = 0.f;
-        // the four mask words of this warp's 128 columns: one 128-bit load issued BEFORE the wait for the
-        // accumulator (its latency - the mask streams from HBM - used to be exposed once per 32-column chunk)
+        // the mask words of this warp's columns: one vector load issued BEFORE the wait for the accumulator
+        // (its latency - the mask streams from HBM - used to be exposed once per 32-column chunk)
         uint32_t mw4[4] = {0u, 0u, 0u, 0u};
         if (want_pos && row_ok) {
-          if (p.flags & 0x4000) {
+          if ((p.flags & 0x4000) && kChunks == 4) {
             const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(mrow + c_lo));
             mw4[0] = t4.x; mw4[1] = t4.y; mw4[2] = t4.z; mw4[3] = t4.w;
+          } else if ((p.flags & 0x4000) && kChunks == 2) {
+            const uint2 t2 = __ldg(reinterpret_cast<const uint2*>(mrow + c_lo));
+            mw4[0] = t2.x; mw4[1] = t2.y;
           } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mw4[k] = __ldg(mrow + c_lo + k);
+            for (int k = 0; k < kChunks; ++k) mw4[k] = __ldg(mrow + c_lo + k);
           }
         }
         if (kStoreE) {
@@ -377,7 +401,7 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 64; ++cc) {
+        for (int cc = 0; cc < kChunks; ++cc) {
           const int c = c_lo + cc;
           const uint32_t mword = cc == 0 ? mw4[0] : (cc == 1 ? mw4[1] : (cc == 2 ? mw4[2] : mw4[3]));
           float v[32];
@@ -412,7 +436,12 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
             rs0 += v[k]; rs1 += v[k + 1]; rs2 += v[k + 2]; rs3 += v[k + 3];
           }
           if (kStoreE) {                                          // E -> bf16 -> swizzled staging (dead entries are 0)
-            const uint32_t row_st = wstg + (cc >> 1) * 4096 + lane * 128;
+            const int box = cc >> 1;
+            if ((cc & 1) == 0 && box >= SB) {                     // buffer reuse within the tile
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+            }
+            const uint32_t row_st = wstg + (box % SB) * 4096 + lane * 128;
             const int u0 = (cc & 1) * 4;
 #pragma unroll
             for (int uu = 0; uu < 4; ++uu) {
@@ -424,6 +453,14 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_st + off), "r"(h0), "r"(h1), "r"(h2),
                            "r"(h3) : "memory");
             }
+            if (cc & 1) {                                         // a [32 x 64] box is complete: store it now
+              fence_proxy_async_smem();                           // generic-proxy writes -> async proxy
+              __syncwarp();
+              if (lane == 0) {                                    // OOB rows / columns are clipped by the map
+                tma_store_2d(&p.out_map[0], wstg + (box % SB) * 4096, n0 + (c - 1) * 32, m_warp, p.policy_out);
+                tma_store_commit();
+              }
+            }
           }
           if (want_col) {
             const float cs = warp_transpose_sum(v, lane);
@@ -431,26 +468,18 @@ __global__ void __launch_bounds__((EPI == EPI_GEMM || EPI == EPI_GEMM_TMA) ? 512
           }
         }
         release_tmem(as);                                         // TMEM stage drained
-        if (kStoreE) {
-          fence_proxy_async_smem();                               // generic-proxy writes -> async proxy
-          __syncwarp();
-          if (lane == 0) {
-            const int cx = n0 + c_lo * 32, m_warp = m0 + q * 32;  // OOB rows / columns are clipped by the map
-            tma_store_2d(&p.out_map[0], wstg, cx, m_warp, p.policy_out);
-            tma_store_2d(&p.out_map[0], wstg + 4096, cx + 64, m_warp, p.policy_out);
-            tma_store_commit();
-          }
-        }
         if (row_ok) {
-          const int64_t po = ((int64_t)nb * kRowParts + hh) * p.ld_rowpart + i;
+          const int64_t po = ((int64_t)nb * (kEW / 4) + hh) * p.ld_rowpart + i;
           p.row_sum_part[po] = (rs0 + rs1) + (rs2 + rs3);
           if (want_pos) p.row_pos_part[po] = rp;
         }
         if (want_col) {
-          named_bar_sync(1, kEpiThreads);
-          const float s = (colpart[et] + colpart[BN + et]) + (colpart[2 * BN + et] + colpart[3 * BN + et]);
-          // each CTA (128-row block) writes its own partial row: index = global 128-row block
-          if (n0 + et < p.n_cols && m0 < p.n_rows) p.col_sum_part[(int64_t)(m0 / BM) * p.ld_colpart + n0 + et] = s;
+          named_bar_sync(1, kEW * 32);
+          if (et < BN) {
+            const float s = (colpart[et] + colpart[BN + et]) + (colpart[2 * BN + et] + colpart[3 * BN + et]);
+            // each CTA (128-row block) writes its own partial row: index = global 128-row block
+            if (n0 + et < p.n_cols && m0 < p.n_rows) p.col_sum_part[(int64_t)(m0 / BM) * p.ld_colpart + n0 + et] = s;
+          }
         }
       } else if (EPI == EPI_BWD_W) {
         // Every warp stages and stores its own 32 rows x 128 columns: private 8 KiB staging region,
@@ -758,6 +787,17 @@ bool use_cta_pairs() {
   return v != 0;
 }
 
+int k3_variant() {
+  // EVK_K3_VARIANT: 0 = 8 epilogue warps, 4 stages (default); 1 = 16 epilogue warps; 2 = 8 warps, 5 stages with
+  // single-buffered E staging.  evk_mpce_row_parts() tells the caller how many row-partial rows K3 writes.
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EVK_K3_VARIANT");
+    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+  }
+  return v;
+}
+
 bool use_stream_k() {
   // EVK_STREAMK=1 selects the stream-K work decomposition of the gradient contractions.  Measured on B200 at
   // the bench shape it is 5% SLOWER than tile x split-K units (322 vs 305 us per contraction: the split-K
@@ -780,11 +820,11 @@ void fill_descs(TcParams& p, bool a_mn, bool b_mn, int variant, bool cta2) {
   p.idesc = umma_idesc_bf16(cta2 ? 2 * BM : BM, BN, a_mn, b_mn);
 }
 
-template <int EPI, bool A_MN, bool B_MN, int STAGES, bool CTA2>
+template <int EPI, bool A_MN, bool B_MN, int STAGES, bool CTA2, int EW = kEpiWarps, int SB = 2>
 int launch(const TcParams& p, cudaStream_t s) {
-  constexpr int smem = smem_bytes_total<EPI, STAGES, CTA2>();
+  constexpr int smem = smem_bytes_total<EPI, STAGES, CTA2, EW, SB>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
-  auto kern = tc_kernel<EPI, A_MN, B_MN, STAGES, CTA2>;
+  auto kern = tc_kernel<EPI, A_MN, B_MN, STAGES, CTA2, EW, SB>;
   static thread_local bool attr_set = false;          // per instantiation, per thread: cheap and race-free
   if (!attr_set) {
     EVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -809,7 +849,7 @@ int launch(const TcParams& p, cudaStream_t s) {
   } else {
     cfg.gridDim = dim3(units < sms ? units : sms);
   }
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3((EW + 2) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   EVK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
@@ -925,11 +965,19 @@ int mpce_fwd_impl(const void* q_hi, const void* q_lo, int64_t ld_q, const void* 
     EVK_REQUIRE(ld_e >= n_cols && ld_e % 8 == 0, "evk_mpce_fwd_store: ld_e=%lld must be >= n_cols and a multiple of 8", (long long)ld_e);
     rc = make_map_bf16(&p.out_map[0], e_out, n_rows, n_cols, ld_e, 32, 64);
     if (rc != EVK_OK) return rc;
-    return cta2 ? launch<EPI_FWD_E, false, false, 4, true>(p, s) : launch<EPI_FWD_E, false, false, 3, false>(p, s);
+    if (!cta2) return launch<EPI_FWD_E, false, false, 3, false>(p, s);
+    switch (k3_variant()) {
+      case 1: return launch<EPI_FWD_E, false, false, 4, true, 16, 1>(p, s);   // 16 epilogue warps, 4 stages
+      case 2: return launch<EPI_FWD_E, false, false, 5, true, 8, 1>(p, s);    // 8 warps, one staging box each, 5 stages
+      default: return launch<EPI_FWD_E, false, false, 4, true, 8, 2>(p, s);   // 8 warps, two boxes each, 4 stages
+    }
   }
+  if (cta2 && k3_variant() == 1) return launch<EPI_FWD, false, false, 6, true, 16, 1>(p, s);
   return cta2 ? launch<EPI_FWD, false, false, 6, true>(p, s) : launch<EPI_FWD, false, false, 4, false>(p, s);
 }
 }  // namespace
+
+extern "C" int evk_mpce_row_parts(void) { return (use_cta_pairs() && k3_variant() == 1) ? 4 : 2; }
 
 extern "C" int evk_mpce_fwd(const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi, const void* k_lo,
                             int64_t ld_k, int64_t n_rows, int64_t n_cols, int64_t d, const uint32_t* bits,

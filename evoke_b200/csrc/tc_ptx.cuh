@@ -44,6 +44,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp.  The single-thread roles (TMA producer, MMA issuer) run their loops with the WHOLE
+// warp and issue under this predicate: the loop state is then warp-uniform, lives in uniform registers, and
+// UTCHMMA / UTMALDG take their operands directly.  With an `if (lane == 0)` role the compiler wraps every such
+// instruction in an ELECT / R2UR.BROADCAST waterfall loop (~19 instructions per MMA): the issuing warp, not the
+// tensor pipe, then sets the pace of the kernel.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- clusters (CTA pairs)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

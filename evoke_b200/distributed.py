@@ -202,8 +202,8 @@ class _ShardedGPeer(torch.autograd.Function):
             if not overlap_gather:
                 return ops.tc_fwd_store(qn, kn_all, bits, inv_tau, 0, lo_) if store else \
                     ops.tc_fwd_partials(qn, kn_all, bits, inv_tau, 0, lo_) + (None, 0)
-            rs = torch.empty((n_ct * ops.ROW_PARTS, n), dtype=torch.float32, device=dev)
-            rp = torch.empty((n_ct * ops.ROW_PARTS, n), dtype=torch.float32, device=dev)
+            rs = torch.empty((n_ct * ops._row_parts(), n), dtype=torch.float32, device=dev)
+            rp = torch.empty((n_ct * ops._row_parts(), n), dtype=torch.float32, device=dev)
             cs = torch.empty((n_rt, n_total), dtype=torch.float32, device=dev)
             ld_e = _round_up(n_total, 64)
             e = torch.empty((n, ld_e), dtype=torch.bfloat16, device=dev) if store else None

@@ -29,11 +29,18 @@ from .ids import DeviceIds
 
 SMALL_PATH_MAX = int(os.environ.get("EVOKE_B200_SMALL_MAX", "512"))   # rows/cols up to which the SIMT path is used
 TILE_M, TILE_N = 128, 256
-ROW_PARTS = 2          # row-statistic partials per 256-column tile (two epilogue warps share a row)
+ROW_PARTS = 2          # row-statistic partials per 256-column tile (epilogue warps sharing a row); see _row_parts()
 OVERLAP_STREAMS = os.environ.get("EVOKE_B200_OVERLAP", "0") == "1"   # side-stream overlap outside graph capture too
 # bf16 mode: K3 stores E = exp(S - 1/tau) as a bf16 row strip and the backward turns it into W in place
 # (HBM-bound K4t) instead of recomputing the similarity tiles (K4a): 6 N^2 D executed FLOP instead of 8.
 E_STRIP = os.environ.get("EVOKE_B200_ESTRIP", "1") == "1"
+
+
+def _row_parts() -> int:
+    """Row-partial rows K3 writes per 256-column tile (asked from the library: it depends on the kernel variant)."""
+    global ROW_PARTS
+    ROW_PARTS = int(_lib.load().evk_mpce_row_parts())
+    return ROW_PARTS
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -226,8 +233,8 @@ def tc_fwd_partials(q: Normalized, k: Normalized, bits, inv_tau: float, flags: i
     n_rt = (q.n + TILE_M - 1) // TILE_M
     want_col = not (flags & FLAG_NO_COLSUM)
     want_pos = not (flags & FLAG_NO_POS)
-    rs_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev)
-    rp_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev) if want_pos else None
+    rs_part = torch.empty((n_ct * _row_parts(), q.n), dtype=torch.float32, device=dev)
+    rp_part = torch.empty((n_ct * _row_parts(), q.n), dtype=torch.float32, device=dev) if want_pos else None
     cs_part = torch.empty((n_rt, k.n), dtype=torch.float32, device=dev) if want_col else None
     _lib.call("evk_mpce_fwd", _ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, q.n, k.n, q.d,
               _ptr(bits) if want_pos else None, bits.stride(0) if want_pos else 0, float(inv_tau), flags, diag_offset,
@@ -242,8 +249,8 @@ def tc_fwd_store(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int,
     n_rt = (q.n + TILE_M - 1) // TILE_M
     want_col = not (flags & FLAG_NO_COLSUM)
     want_pos = not (flags & FLAG_NO_POS)
-    rs_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev)
-    rp_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev) if want_pos else None
+    rs_part = torch.empty((n_ct * _row_parts(), q.n), dtype=torch.float32, device=dev)
+    rp_part = torch.empty((n_ct * _row_parts(), q.n), dtype=torch.float32, device=dev) if want_pos else None
     cs_part = torch.empty((n_rt, k.n), dtype=torch.float32, device=dev) if want_col else None
     ld_e = _round_up(k.n, 64)
     e = torch.empty((q.n, ld_e), dtype=torch.bfloat16, device=dev)
@@ -318,14 +325,14 @@ def tc_fwd(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int, diag_
     n_ct = (k.n + TILE_N - 1) // TILE_N
     n_rt = (q.n + TILE_M - 1) // TILE_M
     want_col = not (flags & FLAG_NO_COLSUM)
-    rs_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev)
-    rp_part = torch.empty((n_ct * ROW_PARTS, q.n), dtype=torch.float32, device=dev)
+    rs_part = torch.empty((n_ct * _row_parts(), q.n), dtype=torch.float32, device=dev)
+    rp_part = torch.empty((n_ct * _row_parts(), q.n), dtype=torch.float32, device=dev)
     cs_part = torch.empty((n_rt, k.n), dtype=torch.float32, device=dev) if want_col else None
     _lib.call("evk_mpce_fwd", _ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, q.n, k.n, q.d,
               _ptr(bits), bits.stride(0), float(inv_tau), flags, diag_offset,
               _ptr(rs_part), _ptr(rp_part), q.n, _ptr(cs_part), k.n, _stream())
-    row_sum = reduce_partials(rs_part, n_ct * ROW_PARTS, q.n)
-    row_pos = reduce_partials(rp_part, n_ct * ROW_PARTS, q.n)
+    row_sum = reduce_partials(rs_part, n_ct * _row_parts(), q.n)
+    row_pos = reduce_partials(rp_part, n_ct * _row_parts(), q.n)
     col_sum = reduce_partials(cs_part, n_rt, k.n) if want_col else None
     return row_sum, row_pos, col_sum
 

@@ -194,9 +194,12 @@ EVK_API int evk_mpce_stats_fused(const float* rs_part, int64_t row_parts, int64_
  * With EVK_FLAG_SPLIT_BF16 the *_lo pointers carry the low halves written by K1.
  *
  * K3 forward (flash-style: S tiles live only in TMEM):
- *   row_sum_part[cb, i] / row_pos_part[cb, i] : partial over column block cb (256 columns)
+ *   row_sum_part[P*cb + part, i] / row_pos_part[...] : partial over part `part` of column block cb (256 columns),
+ *                                               P = evk_mpce_row_parts() (one per epilogue warp sharing a row):
+ *                                               P * ceil(n_cols/256) partial rows
  *   col_sum_part[rb, j]                       : partial over row block rb (128 rows)
  * pitches: ld_rowpart >= n_rows, ld_colpart >= n_cols.  Reduce with evk_reduce_partials. */
+EVK_API int evk_mpce_row_parts(void);
 EVK_API int evk_mpce_fwd(const void* q_hi, const void* q_lo, int64_t ld_q,
                  const void* k_hi, const void* k_lo, int64_t ld_k,
                  int64_t n_rows, int64_t n_cols, int64_t d,
