@@ -24,7 +24,19 @@ small_rows_kernel(const float* __restrict__ q, int64_t ld_q, const float* __rest
                   int64_t ld_words, const int32_t* __restrict__ counts, const float* __restrict__ a_row,
                   const float* __restrict__ b_col, float inv_tau, int flags, int64_t diag_offset,
                   float* __restrict__ row_sum, float* __restrict__ row_pos, float* __restrict__ dq,
-                  int64_t ld_dq, const float* __restrict__ pos_row, const float* __restrict__ pos_col) {
+                  int64_t ld_dq, const float* __restrict__ pos_row, const float* __restrict__ pos_col,
+                  int64_t bs_q, int64_t bs_k, int64_t bs_vec, int64_t bs_dq) {
+  // blockIdx.y = batch entry (independent problems of the same shape sharing mask and counts: the per-sample
+  // token-level InfoNCE of local_text_token_alignment_loss :518-525); all strides are 0 for a single problem
+  q += blockIdx.y * bs_q;
+  k += blockIdx.y * bs_k;
+  if (a_row) a_row += blockIdx.y * bs_vec;
+  if (b_col) b_col += blockIdx.y * bs_vec;
+  if (row_sum) row_sum += blockIdx.y * bs_vec;
+  if (row_pos) row_pos += blockIdx.y * bs_vec;
+  if (dq) dq += blockIdx.y * bs_dq;
+  if (pos_row) pos_row += blockIdx.y * bs_vec;
+  if (pos_col) pos_col += blockIdx.y * bs_vec;
   extern __shared__ __align__(16) float smem[];
   float* qs = smem;                                  // [kTM][d_pad]
   float* kt = qs + (size_t)kTM * d_pad;              // [256][kDK+1]
@@ -212,41 +224,82 @@ int small_check(const float* q, const float* k, int64_t n_rows, int64_t n_cols, 
 
 }  // namespace
 
+namespace {
+int small_fwd_impl(const float* q, int64_t ld_q, const float* k, int64_t ld_k, int64_t n_rows,
+                   int64_t n_cols, int64_t d, const uint32_t* bits, int64_t ld_words, float inv_tau,
+                   int flags, int64_t diag_offset, float* row_sum, float* row_pos, int64_t batch, int64_t bs_q,
+                   int64_t bs_k, int64_t bs_vec, evk_stream_t stream) {
+  int rc = small_check(q, k, n_rows, n_cols, d, bits, ld_words, ld_q, ld_k);
+  if (rc != EVK_OK) return rc;
+  EVK_REQUIRE(row_sum && row_pos, "evk_mpce_small_fwd: null output");
+  EVK_REQUIRE(batch >= 1 && batch <= 65535, "evk_mpce_small_fwd: batch must be in 1..65535");
+  const int d_pad = (int)((d + kDK - 1) / kDK * kDK);
+  const size_t smem = small_smem_bytes(d_pad);
+  EVK_CUDA(cudaFuncSetAttribute(small_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const dim3 grid((unsigned)((n_rows + kTM - 1) / kTM), (unsigned)batch);
+  small_rows_kernel<false><<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      q, ld_q, k, ld_k, n_rows, n_cols, (int)d, d_pad, bits, ld_words, nullptr, nullptr, nullptr, inv_tau, flags,
+      diag_offset, row_sum, row_pos, nullptr, 0, nullptr, nullptr, bs_q, bs_k, bs_vec, 0);
+  EVK_CHECK_LAUNCH("mpce_small_fwd");
+  return EVK_OK;
+}
+}  // namespace
+
 extern "C" int evk_mpce_small_fwd(const float* q, int64_t ld_q, const float* k, int64_t ld_k, int64_t n_rows,
                                   int64_t n_cols, int64_t d, const uint32_t* bits, int64_t ld_words, float inv_tau,
                                   int flags, int64_t diag_offset, float* row_sum, float* row_pos,
                                   evk_stream_t stream) {
-  int rc = small_check(q, k, n_rows, n_cols, d, bits, ld_words, ld_q, ld_k);
-  if (rc != EVK_OK) return rc;
-  EVK_REQUIRE(row_sum && row_pos, "evk_mpce_small_fwd: null output");
-  const int d_pad = (int)((d + kDK - 1) / kDK * kDK);
-  const size_t smem = small_smem_bytes(d_pad);
-  EVK_CUDA(cudaFuncSetAttribute(small_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = (unsigned)((n_rows + kTM - 1) / kTM);
-  small_rows_kernel<false><<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      q, ld_q, k, ld_k, n_rows, n_cols, (int)d, d_pad, bits, ld_words, nullptr, nullptr, nullptr, inv_tau, flags,
-      diag_offset, row_sum, row_pos, nullptr, 0, nullptr, nullptr);
-  EVK_CHECK_LAUNCH("mpce_small_fwd");
-  return EVK_OK;
+  return small_fwd_impl(q, ld_q, k, ld_k, n_rows, n_cols, d, bits, ld_words, inv_tau, flags, diag_offset, row_sum, row_pos,
+                        1, 0, 0, 0, stream);
 }
 
-extern "C" int evk_mpce_small_bwd(const float* q, int64_t ld_q, const float* k, int64_t ld_k, int64_t n_rows,
-                                  int64_t n_cols, int64_t d, const uint32_t* bits, int64_t ld_words,
-                                  const int32_t* counts, const float* a_row, const float* b_col, float inv_tau,
-                                  int flags, int64_t diag_offset, float* dq, int64_t ld_dq, const float* pos_row,
-                                  const float* pos_col, evk_stream_t stream) {
+extern "C" int evk_mpce_small_fwd_batched(const float* q, int64_t ld_q, int64_t bs_q, const float* k, int64_t ld_k,
+                                          int64_t bs_k, int64_t batch, int64_t n_rows, int64_t n_cols, int64_t d,
+                                          const uint32_t* bits, int64_t ld_words, float inv_tau, int flags,
+                                          float* row_sum, float* row_pos, int64_t bs_vec, evk_stream_t stream) {
+  return small_fwd_impl(q, ld_q, k, ld_k, n_rows, n_cols, d, bits, ld_words, inv_tau, flags, 0, row_sum, row_pos, batch,
+                        bs_q, bs_k, bs_vec, stream);
+}
+
+namespace {
+int small_bwd_impl(const float* q, int64_t ld_q, const float* k, int64_t ld_k, int64_t n_rows,
+                   int64_t n_cols, int64_t d, const uint32_t* bits, int64_t ld_words,
+                   const int32_t* counts, const float* a_row, const float* b_col, float inv_tau,
+                   int flags, int64_t diag_offset, float* dq, int64_t ld_dq, const float* pos_row,
+                   const float* pos_col, int64_t batch, int64_t bs_q, int64_t bs_k, int64_t bs_vec, int64_t bs_dq,
+                   evk_stream_t stream) {
   int rc = small_check(q, k, n_rows, n_cols, d, bits, ld_words, ld_q, ld_k);
   if (rc != EVK_OK) return rc;
+  EVK_REQUIRE(batch >= 1 && batch <= 65535, "evk_mpce_small_bwd: batch must be in 1..65535");
   EVK_REQUIRE(a_row && b_col && dq && ld_dq >= d, "evk_mpce_small_bwd: null pointer or ld_dq < d");
   if (flags & EVK_FLAG_AVGPOS) EVK_REQUIRE(pos_row && pos_col, "evk_mpce_small_bwd: EVK_FLAG_AVGPOS needs pos_row and pos_col");
   else EVK_REQUIRE(counts, "evk_mpce_small_bwd: counts is null");
   const int d_pad = (int)((d + kDK - 1) / kDK * kDK);
   const size_t smem = small_smem_bytes(d_pad);
   EVK_CUDA(cudaFuncSetAttribute(small_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = (unsigned)((n_rows + kTM - 1) / kTM);
+  const dim3 grid((unsigned)((n_rows + kTM - 1) / kTM), (unsigned)batch);
   small_rows_kernel<true><<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       q, ld_q, k, ld_k, n_rows, n_cols, (int)d, d_pad, bits, ld_words, counts, a_row, b_col, inv_tau, flags,
-      diag_offset, nullptr, nullptr, dq, ld_dq, pos_row, pos_col);
+      diag_offset, nullptr, nullptr, dq, ld_dq, pos_row, pos_col, bs_q, bs_k, bs_vec, bs_dq);
   EVK_CHECK_LAUNCH("mpce_small_bwd");
   return EVK_OK;
+}
+}  // namespace
+
+extern "C" int evk_mpce_small_bwd(const float* q, int64_t ld_q, const float* k, int64_t ld_k, int64_t n_rows,
+                                  int64_t n_cols, int64_t d, const uint32_t* bits, int64_t ld_words,
+                                  const int32_t* counts, const float* a_row, const float* b_col, float inv_tau,
+                                  int flags, int64_t diag_offset, float* dq, int64_t ld_dq, const float* pos_row,
+                                  const float* pos_col, evk_stream_t stream) {
+  return small_bwd_impl(q, ld_q, k, ld_k, n_rows, n_cols, d, bits, ld_words, counts, a_row, b_col, inv_tau, flags,
+                        diag_offset, dq, ld_dq, pos_row, pos_col, 1, 0, 0, 0, 0, stream);
+}
+
+extern "C" int evk_mpce_small_bwd_batched(const float* q, int64_t ld_q, int64_t bs_q, const float* k, int64_t ld_k,
+                                          int64_t bs_k, int64_t batch, int64_t n_rows, int64_t n_cols, int64_t d,
+                                          const uint32_t* bits, int64_t ld_words, const int32_t* counts,
+                                          const float* a_row, const float* b_col, int64_t bs_vec, float inv_tau,
+                                          int flags, float* dq, int64_t ld_dq, int64_t bs_dq, evk_stream_t stream) {
+  return small_bwd_impl(q, ld_q, k, ld_k, n_rows, n_cols, d, bits, ld_words, counts, a_row, b_col, inv_tau, flags, 0, dq,
+                        ld_dq, nullptr, nullptr, batch, bs_q, bs_k, bs_vec, bs_dq, stream);
 }

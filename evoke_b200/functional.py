@@ -611,3 +611,85 @@ class _AvgPosCE(torch.autograd.Function):
 
 def avgpos_ce(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor]) -> torch.Tensor:
     return _AvgPosCE.apply(cfg, image, text)
+
+
+# ------------------------------------------------------------------------------------- f1: local token alignment
+class _LocalTokenAlign(torch.autograd.Function):
+    """Pretrain.local_text_token_alignment_loss (reference :506-526): text tokens attend over their sample's patch
+    tokens (K `local_attend`), both sides are L2-normalised (K1) and an L x L token-level InfoNCE with identity targets
+    is taken in both directions over all B*L rows - per sample that is the G loss with identity ids, so it runs on the
+    batched small-path kernels with a shared identity mask.  fp32 throughout (the reference's sizes are tiny:
+    B=32, L~99, P=49)."""
+
+    @staticmethod
+    def forward(ctx, inv_tau: float, image: torch.Tensor, text: torch.Tensor):
+        b, p, d = (int(x) for x in image.shape)
+        l = int(text.shape[1])
+        dev = image.device
+        v = image.detach().to(torch.float32).contiguous()
+        t = text.detach().to(torch.float32).contiguous()
+        att = torch.empty((b, l, p), dtype=torch.float32, device=dev)
+        o = torch.empty((b, l, d), dtype=torch.float32, device=dev)
+        _lib.call("evk_local_attend_fwd", _ptr(t), _ptr(v), b, l, p, d, _ptr(att), _ptr(o), _stream())
+        t2, o2 = t.view(b * l, d), o.view(b * l, d)
+        tn = l2norm_fwd(t2, want_f32=True, want_hi=False, want_lo=False)
+        on = l2norm_fwd(o2, want_f32=True, want_hi=False, want_lo=False)
+        eye_ids = DeviceIds(torch.arange(l, dtype=torch.int32, device=dev))
+        bits, counts = posmask_build(eye_ids, eye_ids, clear_diag=False)          # identity targets (:520), c_i = 1
+        n = b * l
+
+        def fwd(q, k):
+            rs = torch.empty(n, dtype=torch.float32, device=dev)
+            rp = torch.empty(n, dtype=torch.float32, device=dev)
+            _lib.call("evk_mpce_small_fwd_batched", _ptr(q.f32), q.f32.stride(0), l * q.f32.stride(0), _ptr(k.f32),
+                      k.f32.stride(0), l * k.f32.stride(0), b, l, l, d, _ptr(bits), bits.stride(0), float(inv_tau), 0,
+                      _ptr(rs), _ptr(rp), l, _stream())
+            return rs, rp
+
+        row_sum, row_pos = fwd(tn, on)            # rows = text tokens (word_sim_1, :519-521)
+        col_sum, _ = fwd(on, tn)                  # rows = attended tokens (word_sim_2, :523-524)
+        ones = torch.ones(n, dtype=torch.int32, device=dev)
+        a_row, b_col, loss = finalize(row_sum, row_pos, ones, col_sum, col_lo=0, col_hi=n, shift=inv_tau, pos_weight=2.0,
+                                      inv_count=0.5 / n)
+        ctx.inv_tau, ctx.shape = inv_tau, (b, l, p, d)
+        ctx.aux = (v, t, att, o2, tn, on, bits, counts, a_row, b_col)
+        ctx.in_dtypes = (image.dtype, text.dtype)
+        out = loss.reshape(())
+        return out if image.dtype == torch.float32 else out.to(image.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out: torch.Tensor):
+        b, l, p, d = ctx.shape
+        v, t, att, o2, tn, on, bits, counts, a_row, b_col = ctx.aux
+        dev = v.device
+        inv_tau = ctx.inv_tau
+        g = grad_out.reshape(1).to(torch.float32).contiguous()
+        scale = 0.5 * inv_tau / (b * l)
+
+        def bwd(q, k, a, bc):
+            dq = torch.empty((b * l, d), dtype=torch.float32, device=dev)
+            _lib.call("evk_mpce_small_bwd_batched", _ptr(q.f32), q.f32.stride(0), l * q.f32.stride(0), _ptr(k.f32),
+                      k.f32.stride(0), l * k.f32.stride(0), b, l, l, d, _ptr(bits), bits.stride(0), _ptr(counts), _ptr(a),
+                      _ptr(bc), l, float(inv_tau), 0, _ptr(dq), dq.stride(0), l * dq.stride(0), _stream())
+            return dq
+
+        d_th = bwd(tn, on, a_row, b_col)
+        d_oh = bwd(on, tn, b_col, a_row)
+        d_t = l2norm_bwd(t.view(b * l, d), tn, d_th, scale_dev=g, scale_host=scale)     # through F.normalize (:515)
+        d_o = l2norm_bwd(o2, on, d_oh, scale_dev=g, scale_host=scale)                   # through F.normalize (:514)
+        ds = torch.empty((b, l, p), dtype=torch.float32, device=dev)
+        d_v = torch.empty((b, p, d), dtype=torch.float32, device=dev)
+        _lib.call("evk_local_attend_bwd", _ptr(t), _ptr(v), _ptr(att), _ptr(d_o), b, l, p, d, _ptr(ds), _ptr(d_t), _ptr(d_v),
+                  _stream())
+        d_image = d_v if ctx.needs_input_grad[1] else None
+        d_text = d_t.view(b, l, d) if ctx.needs_input_grad[2] else None
+        if d_image is not None and ctx.in_dtypes[0] != torch.float32:
+            d_image = d_image.to(ctx.in_dtypes[0])
+        if d_text is not None and ctx.in_dtypes[1] != torch.float32:
+            d_text = d_text.to(ctx.in_dtypes[1])
+        return None, d_image, d_text
+
+
+def local_token_align(inv_tau: float, image: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
+    return _LocalTokenAlign.apply(inv_tau, image, text)

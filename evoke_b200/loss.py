@@ -136,6 +136,22 @@ def multi_pos_contra_images_avgpos(image: torch.Tensor, patient_ids, temp: float
         return Fn.avgpos_ce(cfg, image, None)
 
 
+def local_text_token_alignment(local_image: torch.Tensor, local_text: torch.Tensor, temp: float) -> torch.Tensor:
+    """Pretrain.local_text_token_alignment_loss (reference :506-526): local_image [B, P, D] patch tokens, local_text
+    [B, L, D] text tokens (any strides / float dtype) -> 0-dim loss.  fp32 kernels; P <= 1024, D <= 4096."""
+    for name, x in (("local_image_embed", local_image), ("local_text_embed", local_text)):
+        if not x.is_cuda:
+            raise RuntimeError(f"evoke_b200: `{name}` lives on {x.device}; this library only runs on a CUDA (sm_100a) device")
+        if x.dim() != 3:
+            raise ValueError(f"evoke_b200: `{name}` must be 3-D [B, tokens, D], got shape {tuple(x.shape)}")
+    if local_image.shape[0] != local_text.shape[0] or local_image.shape[2] != local_text.shape[2]:
+        raise ValueError(f"patch / text token shapes do not match: {tuple(local_image.shape)} vs {tuple(local_text.shape)}")
+    if local_text.shape[1] > 4096 or local_image.shape[1] > 1024 or local_image.shape[2] > 4096:
+        raise ValueError("local_text_token_alignment supports up to 4096 text tokens, 1024 patches and D <= 4096")
+    with torch.cuda.device(local_image.device):
+        return Fn.local_token_align(_inv_tau(temp), local_image, local_text)
+
+
 # ---------------------------------------------------------------- methods with the reference's signatures
 def global_alignment_loss(self, global_image_embed, global_text_embed, patient_ids):
     """Same signature as Pretrain.global_alignment_loss (reference :486)."""
@@ -171,20 +187,29 @@ def patch_pretrain_newmulpos(target):
     return target
 
 
-def patch_pretrain(target, precision: str = DEFAULT_PRECISION):
-    """Rebind the two loss methods on a reference ``Pretrain`` class (affects every instance) or
-    on a single instance.  Works for all six model files because only the method names and
+def local_text_token_alignment_loss(self, local_image_embed, local_text_embed):
+    """Same signature as Pretrain.local_text_token_alignment_loss (reference :506)."""
+    return local_text_token_alignment(local_image_embed, local_text_embed, self.args["region_temp"])
+
+
+def patch_pretrain(target, precision: str = DEFAULT_PRECISION, local_tokens: bool = False):
+    """Rebind the two loss methods (and, with ``local_tokens=True``, ``local_text_token_alignment_loss`` :506) on a
+    reference ``Pretrain`` class (affects every instance) or on a single instance.  Works for all six model files because only the method names and
     ``self.args`` are relied upon.  Returns ``target``."""
     if precision not in ("fp32", "bf16"):
         raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
     if isinstance(target, type):
         target.global_alignment_loss = global_alignment_loss
         target.multi_pos_contra_images_v0401 = multi_pos_contra_images_v0401
+        if local_tokens:
+            target.local_text_token_alignment_loss = local_text_token_alignment_loss
         target._evoke_b200_precision = precision
     else:
         import types
         target.global_alignment_loss = types.MethodType(global_alignment_loss, target)
         target.multi_pos_contra_images_v0401 = types.MethodType(multi_pos_contra_images_v0401, target)
+        if local_tokens:
+            target.local_text_token_alignment_loss = types.MethodType(local_text_token_alignment_loss, target)
         target._evoke_b200_precision = precision
     return target
 

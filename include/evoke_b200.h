@@ -147,6 +147,32 @@ EVK_API int evk_mpce_small_bwd(const float* q, int64_t ld_q, const float* k, int
                        float* dq, int64_t ld_dq,
                        const float* pos_row, const float* pos_col, evk_stream_t stream);
 
+/* Batched forms (independent problems of one shape, e.g. one per sample): problem b uses q + b*bs_q, k + b*bs_k
+ * and the row / column vectors (row_sum, row_pos, a_row, b_col) at offset b*bs_vec, dq at b*bs_dq; the mask and
+ * counts are shared by all problems.  Used for the per-sample token-level InfoNCE of
+ * Pretrain.local_text_token_alignment_loss (:518-525), which is the G loss with identity ids on every sample. */
+EVK_API int evk_mpce_small_fwd_batched(const float* q, int64_t ld_q, int64_t bs_q, const float* k, int64_t ld_k, int64_t bs_k,
+                               int64_t batch, int64_t n_rows, int64_t n_cols, int64_t d,
+                               const uint32_t* bits, int64_t ld_words, float inv_tau, int flags,
+                               float* row_sum, float* row_pos, int64_t bs_vec, evk_stream_t stream);
+EVK_API int evk_mpce_small_bwd_batched(const float* q, int64_t ld_q, int64_t bs_q, const float* k, int64_t ld_k, int64_t bs_k,
+                               int64_t batch, int64_t n_rows, int64_t n_cols, int64_t d,
+                               const uint32_t* bits, int64_t ld_words, const int32_t* counts,
+                               const float* a_row, const float* b_col, int64_t bs_vec,
+                               float inv_tau, int flags, float* dq, int64_t ld_dq, int64_t bs_dq, evk_stream_t stream);
+
+/* ---- f1: Pretrain.local_text_token_alignment_loss (:506-526), the parameter-free cross-attention ------------
+ * text [batch, l, d], image [batch, p, d], contiguous fp32.  Forward (:509-511):
+ *   att[b, i, :] = softmax_p( text[b, i] . image[b, p] / sqrt(d) ),   out[b, i] = sum_p att[b, i, p] image[b, p]
+ * Backward, given d_out = dL/d out: d_image is written, d_text is ACCUMULATED into (it already holds the gradient
+ * that reaches the text tokens through their own normalisation, :515); ds is a [batch, l, p] workspace.
+ * fp32 SIMT, one CTA per (token, sample); deterministic.  p <= 1024, d <= 8192. */
+EVK_API int evk_local_attend_fwd(const float* text, const float* image, int64_t batch, int64_t l, int64_t p, int64_t d,
+                         float* att, float* out, evk_stream_t stream);
+EVK_API int evk_local_attend_bwd(const float* text, const float* image, const float* att, const float* d_out,
+                         int64_t batch, int64_t l, int64_t p, int64_t d,
+                         float* ds, float* d_text, float* d_image, evk_stream_t stream);
+
 /* ---- statistics -> loss ----------------------------------------------------------------------
  * out[j] = sum_p part[p*ld + j], p < parts: deterministic reduction of per-tile partials;
  * if divisor != NULL the sum is divided by divisor[j] (0 where divisor[j] <= 0): pos_j / c_j. */

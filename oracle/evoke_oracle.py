@@ -36,6 +36,8 @@ Y=M/c_i, S = Ihat That^T / tau.
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 EPS = 1e-12  # F.normalize default eps
@@ -269,6 +271,50 @@ def avgpos_mpc_closed_form(x, ids, tau: float):
     s = xh @ xh.T / tau
     np.fill_diagonal(s, -np.inf)
     return float(_avgpos_rows(s[idx], m[idx]).sum() / len(idx))
+
+
+# ----------------------------------------------------------------------------- f1 (next row)
+def local_token_alignment_closed_form(local_image, local_text, tau: float):
+    """Pretrain.local_text_token_alignment_loss (:506-526), fp64, with gradients: -> (loss, d_image, d_text).
+
+    local_image [B, P, D] patch tokens, local_text [B, L, D] text tokens.  Per sample: the text tokens attend over
+    the patches (softmax(T V^T / sqrt(D)) V, :509-511), both sides are L2-normalised (:514-515), and an L x L
+    token-level InfoNCE with identity targets is taken in both directions over all B*L rows (:518-525).
+    Not yet built in CUDA; this pins the oracle for it."""
+    v = np.asarray(local_image, dtype=np.float64)
+    t = np.asarray(local_text, dtype=np.float64)
+    b, l, d = t.shape
+    s1 = np.einsum("bld,bpd->blp", t, v) / math.sqrt(d)
+    s1 = s1 - s1.max(-1, keepdims=True)
+    a = np.exp(s1)
+    a /= a.sum(-1, keepdims=True)
+    o = np.einsum("blp,bpd->bld", a, v)
+    on = np.maximum(np.linalg.norm(o, axis=-1, keepdims=True), 1e-12)
+    tn = np.maximum(np.linalg.norm(t, axis=-1, keepdims=True), 1e-12)
+    oh, th = o / on, t / tn
+    sim = np.einsum("bld,bmd->blm", th, oh) / tau               # [b, n1 (text), n2 (attended)]
+    lse_r = _lse(sim, 2)
+    lse_c = _lse(sim, 1)
+    diag = np.einsum("bll->bl", sim)
+    n_rows = b * l
+    loss = 0.5 * ((lse_r - diag).sum() + (lse_c - diag).sum()) / n_rows
+    # d loss / d sim
+    p_r = np.exp(sim - lse_r[:, :, None])
+    p_c = np.exp(sim - lse_c[:, None, :])
+    eye = np.eye(l)[None]
+    dsim = 0.5 / n_rows * ((p_r - eye) + (p_c - eye))
+    d_th = np.einsum("blm,bmd->bld", dsim, oh) / tau
+    d_oh = np.einsum("blm,bld->bmd", dsim, th) / tau
+    # through the normalisations (no clamp in these cases)
+    d_o = (d_oh - oh * (oh * d_oh).sum(-1, keepdims=True)) / on
+    d_t = (d_th - th * (th * d_th).sum(-1, keepdims=True)) / tn
+    # through the attention
+    d_a = np.einsum("bld,bpd->blp", d_o, v)
+    d_v = np.einsum("blp,bld->bpd", a, d_o)
+    d_s1 = a * (d_a - (d_a * a).sum(-1, keepdims=True)) / math.sqrt(d)
+    d_t = d_t + np.einsum("blp,bpd->bld", d_s1, v)
+    d_v = d_v + np.einsum("blp,bld->bpd", d_s1, t)
+    return float(loss), d_v, d_t
 
 
 # ----------------------------------------------------------------------------- torch ports

@@ -88,8 +88,34 @@ def make(case: gc.Case):
           f"rows={len(rows)} -> {os.path.getsize(gc.golden_path(case))} B")
 
 
+LOCAL_CASES = {"local_b3_l7_p5_d16": (3, 7, 5, 16, 0.5, 41), "local_b4_l99_p49_d64": (4, 99, 49, 64, 0.5, 42),
+               "local_b2_l20_p49_d768_t02": (2, 20, 49, 768, 0.2, 43)}
+
+
+def local_inputs(name):
+    b, l, p, d, tau, seed = LOCAL_CASES[name]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return rng.standard_normal((b, p, d)).astype(np.float32), rng.standard_normal((b, l, d)).astype(np.float32), tau
+
+
+def make_local(name):
+    """f1: Pretrain.local_text_token_alignment_loss on seeded token tensors (fp64 run of the reference)."""
+    v, t, tau = local_inputs(name)
+    vi = torch.tensor(v, dtype=torch.float64, requires_grad=True)
+    ti = torch.tensor(t, dtype=torch.float64, requires_grad=True)
+    out = ref_shim.local_text_token_alignment_loss(vi, ti, tau)
+    out.backward()
+    path = os.path.join(gc.GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, loss64=np.float64(out.item()), d_image64=vi.grad.numpy()[:, :4], d_text64=ti.grad.numpy()[:, :4],
+                        d_image_norm64=np.float64(vi.grad.norm().item()), d_text_norm64=np.float64(ti.grad.norm().item()))
+    print(f"{name:28s} loss64={out.item():.12f} -> {os.path.getsize(path)} B")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
-    names = sys.argv[1:] or [c.name for c in gc.CASES + gc.AVGPOS_CASES]
+    names = sys.argv[1:] or ([c.name for c in gc.CASES + gc.AVGPOS_CASES] + list(LOCAL_CASES))
     for nm in names:
-        make(gc.BY_NAME[nm])
+        if nm in LOCAL_CASES:
+            make_local(nm)
+        else:
+            make(gc.BY_NAME[nm])

@@ -71,3 +71,8 @@ def avgpos_global_alignment_loss(image, text, ids, temp: float = 0.5):
 
 def avgpos_multi_pos_contra_images_v0404(x, ids, temp: float = 0.5):
     return load().PretrainNewMulPos.multi_pos_contra_images_v0404(fake_self(region_temp=temp), x, ids)
+
+
+def local_text_token_alignment_loss(local_image, local_text, temp: float = 0.5):
+    """Pretrain.local_text_token_alignment_loss (:506-526): the next row of the hot path."""
+    return load().Pretrain.local_text_token_alignment_loss(fake_self(region_temp=temp), local_image, local_text)

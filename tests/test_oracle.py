@@ -160,3 +160,20 @@ def test_avgpos_variants_against_live_reference():
     assert abs(orc.avgpos_g_loss_closed_form(x, t, ids, 0.5) - ref.item()) < 2e-6
     ref2 = ref_shim.avgpos_multi_pos_contra_images_v0404(torch.tensor(x), ids, 0.5)
     assert abs(orc.avgpos_mpc_closed_form(x, ids, 0.5) - ref2.item()) < 2e-6
+
+
+@pytest.mark.parametrize("name", ["local_b3_l7_p5_d16", "local_b4_l99_p49_d64", "local_b2_l20_p49_d768_t02"])
+def test_local_token_alignment_closed_form_matches_reference_golden(name):
+    """SURVEY.md §8 f1 (next row): the oracle of Pretrain.local_text_token_alignment_loss (:506-526), pinned to
+    golden vectors recorded from the reference (inputs are regenerated from the seeds in oracle/make_golden.py)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import make_golden as mg
+    v, t, tau = mg.local_inputs(name)
+    gold = np.load(os.path.join(gc.GOLDEN_DIR, name + ".npz"))
+    loss, d_v, d_t = orc.local_token_alignment_closed_form(v, t, tau)
+    assert abs(loss - gold["loss64"]) <= 1e-11 * abs(gold["loss64"])
+    assert _rel(d_v[:, :4], gold["d_image64"]) < 1e-9 and _rel(d_t[:, :4], gold["d_text64"]) < 1e-9
+    assert abs(np.linalg.norm(d_v) - gold["d_image_norm64"]) <= 1e-9 * gold["d_image_norm64"]
+    assert abs(np.linalg.norm(d_t) - gold["d_text_norm64"]) <= 1e-9 * gold["d_text_norm64"]
