@@ -614,6 +614,21 @@ def avgpos_ce(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor]
 
 
 # ------------------------------------------------------------------------------------- f1: local token alignment
+_IDENTITY_CACHE: dict = {}
+
+
+def _identity_targets(l: int, n: int, dev: torch.device):
+    """Identity mask [l, ld_words] with its counts, and n ones (constants of f1, built once per shape and device)."""
+    key = (l, n, dev.index if dev.index is not None else torch.cuda.current_device())
+    hit = _IDENTITY_CACHE.get(key)
+    if hit is None:
+        eye_ids = DeviceIds(torch.arange(l, dtype=torch.int32, device=dev))
+        bits, counts = posmask_build(eye_ids, eye_ids, clear_diag=False)
+        hit = (bits, counts, torch.ones(n, dtype=torch.int32, device=dev))
+        _IDENTITY_CACHE[key] = hit
+    return hit
+
+
 class _LocalTokenAlign(torch.autograd.Function):
     """Pretrain.local_text_token_alignment_loss (reference :506-526): text tokens attend over their sample's patch
     tokens (K `local_attend`), both sides are L2-normalised (K1) and an L x L token-level InfoNCE with identity targets
@@ -634,9 +649,8 @@ class _LocalTokenAlign(torch.autograd.Function):
         t2, o2 = t.view(b * l, d), o.view(b * l, d)
         tn = l2norm_fwd(t2, want_f32=True, want_hi=False, want_lo=False)
         on = l2norm_fwd(o2, want_f32=True, want_hi=False, want_lo=False)
-        eye_ids = DeviceIds(torch.arange(l, dtype=torch.int32, device=dev))
-        bits, counts = posmask_build(eye_ids, eye_ids, clear_diag=False)          # identity targets (:520), c_i = 1
         n = b * l
+        bits, counts, ones = _identity_targets(l, n, dev)                          # identity targets (:520), c_i = 1
 
         def fwd(q, k):
             rs = torch.empty(n, dtype=torch.float32, device=dev)
@@ -648,7 +662,6 @@ class _LocalTokenAlign(torch.autograd.Function):
 
         row_sum, row_pos = fwd(tn, on)            # rows = text tokens (word_sim_1, :519-521)
         col_sum, _ = fwd(on, tn)                  # rows = attended tokens (word_sim_2, :523-524)
-        ones = torch.ones(n, dtype=torch.int32, device=dev)
         a_row, b_col, loss = finalize(row_sum, row_pos, ones, col_sum, col_lo=0, col_hi=n, shift=inv_tau, pos_weight=2.0,
                                       inv_count=0.5 / n)
         ctx.inv_tau, ctx.shape = inv_tau, (b, l, p, d)

@@ -166,7 +166,7 @@ EVK_API int evk_mpce_small_bwd_batched(const float* q, int64_t ld_q, int64_t bs_
  *   att[b, i, :] = softmax_p( text[b, i] . image[b, p] / sqrt(d) ),   out[b, i] = sum_p att[b, i, p] image[b, p]
  * Backward, given d_out = dL/d out: d_image is written, d_text is ACCUMULATED into (it already holds the gradient
  * that reaches the text tokens through their own normalisation, :515); ds is a [batch, l, p] workspace.
- * fp32 SIMT, one CTA per (token, sample); deterministic.  p <= 1024, d <= 8192. */
+ * fp32 SIMT, one CTA per (8 tokens, sample); deterministic.  p <= 1024, d <= 4096, 8 (d + p) floats of shared memory. */
 EVK_API int evk_local_attend_fwd(const float* text, const float* image, int64_t batch, int64_t l, int64_t p, int64_t d,
                          float* att, float* out, evk_stream_t stream);
 EVK_API int evk_local_attend_bwd(const float* text, const float* image, const float* att, const float* d_out,
