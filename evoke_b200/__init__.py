@@ -10,12 +10,12 @@ from .loss import (ContrastiveObjective, global_alignment, global_alignment_avgp
                    multi_pos_contra_images, multi_pos_contra_images_avgpos, multi_pos_contra_images_v0401,
                    multi_pos_contra_images_v0404, patch_pretrain, patch_pretrain_newmulpos)
 from .lm_loss import LanguageModelCriterion, compute_lm_loss
-from .graphs import GraphedGlobalAlignment
+from .graphs import GraphedGlobalAlignment, GraphedLocalTokenAlign
 
 __all__ = [
     "ContrastiveObjective", "global_alignment", "global_alignment_loss", "multi_pos_contra_images",
     "multi_pos_contra_images_v0401", "patch_pretrain", "global_alignment_avgpos", "multi_pos_contra_images_avgpos",
     "multi_pos_contra_images_v0404", "patch_pretrain_newmulpos", "local_text_token_alignment",
-    "local_text_token_alignment_loss", "GraphedGlobalAlignment", "LanguageModelCriterion", "compute_lm_loss",
+    "local_text_token_alignment_loss", "GraphedGlobalAlignment", "GraphedLocalTokenAlign", "LanguageModelCriterion", "compute_lm_loss",
 ]
 __version__ = "0.1.0"

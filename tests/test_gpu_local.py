@@ -57,3 +57,18 @@ def test_local_token_alignment_reference_shapes_strided_inputs_and_patched_metho
     assert abs(loss.item() - want) <= 1e-5 * abs(want)
     assert rel_max(head_v.grad.permute(0, 2, 1).cpu().numpy(), 2.0 * d_v) <= 1e-4
     assert rel_max(head_t.grad.permute(0, 2, 1).cpu().numpy(), 2.0 * d_t) <= 1e-4
+
+
+def test_local_token_alignment_cuda_graph_tracks_new_inputs():
+    b, p, l, d, tau = 4, 49, 30, 128, 0.5
+    g = evoke_b200.GraphedLocalTokenAlign(b, p, l, d, tau).capture()
+    rng = np.random.default_rng(3)
+    for _ in range(2):
+        v = rng.standard_normal((b, p, d)).astype(np.float32)
+        t = rng.standard_normal((b, l, d)).astype(np.float32)
+        g.load(torch.tensor(v, device=DEV), torch.tensor(t, device=DEV))
+        loss = g.step()
+        want, d_v, d_t = orc.local_token_alignment_closed_form(v, t, tau)
+        assert abs(loss.item() - want) <= 1e-5 * abs(want)
+        assert rel_max(g.image.grad.cpu().numpy(), d_v) <= 1e-4
+        assert rel_max(g.text.grad.cpu().numpy(), d_t) <= 1e-4

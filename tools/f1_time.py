@@ -47,3 +47,16 @@ def timed(fn, reps=30):
 
 print("torch eager fwd+bwd  us/step, loss:", timed(ref))
 print("evoke_b200 fwd+bwd   us/step, loss:", timed(ours))
+
+g = evoke_b200.GraphedLocalTokenAlign(b, p, l, d, tau).capture()
+g.load(v.detach(), t.detach())
+for _ in range(5):
+    g.step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(100):
+    loss = g.step()
+e1.record()
+torch.cuda.synchronize()
+print("evoke_b200 CUDA graph us/step, loss:", (e0.elapsed_time(e1) / 100 * 1e3, loss.item()))
