@@ -18,7 +18,7 @@ constexpr int kDK = 32;              // feature chunk staged through shared memo
 constexpr int kMaxSlots = 8;         // backward: feature columns per thread per pass (8*256 = 2048)
 
 template <bool kBwd>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kBwd ? 2 : 3)
 small_rows_kernel(const float* __restrict__ q, int64_t ld_q, const float* __restrict__ k, int64_t ld_k,
                   int64_t n_rows, int64_t n_cols, int d, int d_pad, const uint32_t* __restrict__ bits,
                   int64_t ld_words, const int32_t* __restrict__ counts, const float* __restrict__ a_row,
@@ -44,6 +44,8 @@ small_rows_kernel(const float* __restrict__ q, int64_t ld_q, const float* __rest
 
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
+  // 128-bit loads of the key rows need 16-byte aligned rows in every batch entry
+  const bool k_vec = ((reinterpret_cast<uintptr_t>(k) & 15u) == 0) && (ld_k % 4 == 0);
   const int64_t r0 = (int64_t)blockIdx.x * kTM;
   const float shift = inv_tau;                       // |S| <= inv_tau for unit rows
   const bool excl = (flags & EVK_FLAG_EXCLUDE_DIAG) != 0;
@@ -93,12 +95,37 @@ small_rows_kernel(const float* __restrict__ q, int64_t ld_q, const float* __rest
       for (int r = 0; r < kTM; ++r) s[r] = 0.f;
       for (int dk0 = 0; dk0 < d_pad; dk0 += kDK) {
         __syncthreads();                             // kt (and, first time, qs) hazards
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-          const int row = warp * 32 + i;
-          const int64_t j = j0 + row;
-          const int c = dk0 + lane;
-          kt[row * (kDK + 1) + lane] = (j < n_cols && c < d) ? __ldg(k + j * ld_k + c) : 0.f;
+        {
+          // a warp fills its 32 rows x 32 floats with eight 128-bit loads per lane, four in flight at a time (the
+          // tile load is latency-bound): lane -> (row lane>>3 of a group of four, 16-byte piece lane&7)
+          const int piece = (lane & 7) * 4;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {                 // two rounds of four loads: registers vs loads in flight
+            float4 tmp[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = warp * 32 + (half * 4 + i) * 4 + (lane >> 3);
+              const int64_t j = j0 + row;
+              const int c = dk0 + piece;
+              tmp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (j < n_cols) {
+                const float* src = k + j * ld_k + c;
+                if (k_vec && c + 3 < d) {
+                  tmp[i] = __ldg(reinterpret_cast<const float4*>(src));
+                } else {
+                  if (c < d) tmp[i].x = __ldg(src);
+                  if (c + 1 < d) tmp[i].y = __ldg(src + 1);
+                  if (c + 2 < d) tmp[i].z = __ldg(src + 2);
+                  if (c + 3 < d) tmp[i].w = __ldg(src + 3);
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float* dst = kt + (warp * 32 + (half * 4 + i) * 4 + (lane >> 3)) * (kDK + 1) + piece;
+              dst[0] = tmp[i].x; dst[1] = tmp[i].y; dst[2] = tmp[i].z; dst[3] = tmp[i].w;
+            }
+          }
         }
         __syncthreads();
 #pragma unroll
