@@ -42,7 +42,7 @@ class _RawCuda:
 
 class PeerContext:
     def __init__(self, group, n_local: int, d: int, device: torch.device, two_keys: bool = False,
-                 timeout_ms: int = 2000, exchange: str = "bf16"):
+                 timeout_ms: int = 10000, exchange: str = "bf16"):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
