@@ -33,6 +33,8 @@ SIGNATURES = {
     "evk_mpce_finalize_avgpos": [P, P, P, L, F, D, P, P, P, I, P],
     "evk_mpce_small_fwd_batched": [P, L, L, P, L, L, L, L, L, L, P, L, F, I, P, P, L, P],
     "evk_mpce_small_bwd_batched": [P, L, L, P, L, L, L, L, L, L, P, L, P, P, P, L, F, I, P, L, L, P],
+    "evk_token_sim_fwd": [P, P, L, L, L, F, P, P, P, P, P],
+    "evk_token_sim_bwd": [P, P, P, P, P, L, L, L, P, P, P],
     "evk_local_attend_fwd": [P, P, L, L, L, L, P, P, P],
     "evk_local_attend_bwd": [P, P, P, P, L, L, L, L, P, P, P, P],
     "evk_reduce_partials": [P, L, L, L, P, P, P],
@@ -111,7 +113,7 @@ KERNELS_PER_CALL = {
     "evk_mpce_bwd_w": 1, "evk_mpce_bwd_gemm": 1, "evk_tc_gemm_probe": 1, "evk_l2norm_fwd_bcast": 1,
     "evk_peer_bcast": 1, "evk_mpce_fwd_store": 1, "evk_mpce_w_from_e": 3, "evk_mpce_pos_logits": 1,
     "evk_peer_barrier": 1, "evk_mpce_small_fwd_batched": 1, "evk_mpce_small_bwd_batched": 1,
-    "evk_local_attend_fwd": 1, "evk_local_attend_bwd": 2, "evk_peer_push_shard": 1, "evk_peer_wait_landed": 1, "evk_mpce_fwd_store_gathered": 1, "evk_mpce_finalize_avgpos": 1, "evk_shard_prologue": 1, "evk_mpce_shard_stats_push": 1, "evk_l2norm_bwd_parts": 1, "evk_mpce_shard_finish": 1, "evk_mpce_bwd_gemm_scatter": 1,
+    "evk_local_attend_fwd": 1, "evk_local_attend_bwd": 2, "evk_token_sim_fwd": 1, "evk_token_sim_bwd": 1, "evk_peer_push_shard": 1, "evk_peer_wait_landed": 1, "evk_mpce_fwd_store_gathered": 1, "evk_mpce_finalize_avgpos": 1, "evk_shard_prologue": 1, "evk_mpce_shard_stats_push": 1, "evk_l2norm_bwd_parts": 1, "evk_mpce_shard_finish": 1, "evk_mpce_bwd_gemm_scatter": 1,
 }
 launch_count = 0          # running total, read by bench.py ("gpu_launches")
 call_hook = None          # optional callable(name, phase) with phase in {"before", "after"} (bench.py timing)

@@ -182,6 +182,160 @@ local_attend_bwd_patch_kernel(const float* __restrict__ text, const float* __res
   }
 }
 
+// ---- per-sample token-level InfoNCE (:518-525) for L <= 128: register-blocked fp32 kernels, one sample per CTA (row) ----
+constexpr int kTS = 128;                       // tokens per sample held by one CTA
+constexpr int kKC = 16;                        // feature chunk of the similarity product
+
+// E[b, i, j] = exp(That_i . Ohat_j / tau - 1/tau), its row sums, column sums and the diagonal logits.
+// 256 threads = 16 x 16; thread (ty, tx) owns rows 8 ty .. 8 ty + 7 and columns tx, tx + 16, .. (interleaved: the
+// shared-memory reads of the column operand and the stores of E are then conflict-free / coalesced).
+__global__ void __launch_bounds__(kThreads)
+token_sim_fwd_kernel(const float* __restrict__ th, const float* __restrict__ oh, int l, int d, float inv_tau,
+                     float* __restrict__ e_out, float* __restrict__ row_sum, float* __restrict__ row_pos,
+                     float* __restrict__ col_sum) {
+  __shared__ float as[kKC][kTS + 4];
+  __shared__ float bs[kKC][kTS + 4];
+  __shared__ float colp[16][kTS];
+  const int b = blockIdx.x;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const float* a_base = th + (int64_t)b * l * d;
+  const float* b_base = oh + (int64_t)b * l * d;
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+  for (int k0 = 0; k0 < d; k0 += kKC) {
+#pragma unroll
+    for (int i = 0; i < (kTS * kKC) / kThreads; ++i) {           // 8 elements per thread and operand
+      const int idx = t + kThreads * i;
+      const int row = idx / kKC, kk = idx - row * kKC;
+      const bool ok = row < l && k0 + kk < d;
+      as[kk][row] = ok ? __ldg(a_base + (int64_t)row * d + k0 + kk) : 0.f;
+      bs[kk][row] = ok ? __ldg(b_base + (int64_t)row * d + k0 + kk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kKC; ++kk) {
+      float av[8], bv[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) av[r] = as[kk][ty * 8 + r];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) bv[c] = bs[kk][tx + 16 * c];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+  const float shift = inv_tau;
+  float cs[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) cs[c] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = ty * 8 + r;
+    float rs = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = tx + 16 * c;
+      const bool ok = i < l && j < l;
+      const float sv = acc[r][c] * inv_tau;
+      const float e = ok ? expf(sv - shift) : 0.f;
+      if (ok) e_out[((int64_t)b * l + i) * l + j] = e;
+      if (ok && i == j) row_pos[(int64_t)b * l + i] = sv;
+      rs += e;
+      cs[c] += e;
+    }
+    // the 16 threads of a row group are 16 consecutive lanes
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (tx == 0 && i < l) row_sum[(int64_t)b * l + i] = rs;
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) colp[ty][tx + 16 * c] = cs[c];
+  __syncthreads();
+  if (t < l) {
+    float sum = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) sum += colp[g][t];               // fixed order: deterministic
+    col_sum[(int64_t)b * l + t] = sum;
+  }
+}
+
+// d_th[b, i, c] = sum_j W_ij Ohat[j, c],  d_oh[b, j, c] = sum_i W_ij That[i, c],  W = E (a_i + b_j) - 2 [i == j]
+// (identity targets: c_i = 1).  CTA = (64 feature columns, sample); W, the Ohat and That column slabs in shared memory.
+constexpr int kDC = 64;
+__global__ void __launch_bounds__(kThreads)
+token_sim_bwd_kernel(const float* __restrict__ th, const float* __restrict__ oh, const float* __restrict__ e_in,
+                     const float* __restrict__ a_row, const float* __restrict__ b_col, int l, int d,
+                     float* __restrict__ d_th, float* __restrict__ d_oh) {
+  extern __shared__ float sm[];
+  float* w = sm;                                 // [kTS][kTS + 1]
+  float* oc = w + kTS * (kTS + 1);               // [kTS][kDC]
+  float* tc = oc + kTS * kDC;                    // [kTS][kDC]
+  const int c0 = blockIdx.x * kDC, b = blockIdx.y;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const int64_t base = (int64_t)b * l;
+  for (int idx = t; idx < kTS * kTS; idx += kThreads) {
+    const int i = idx / kTS, j = idx - i * kTS;
+    float v = 0.f;
+    if (i < l && j < l) v = e_in[(base + i) * l + j] * (__ldg(a_row + base + i) + __ldg(b_col + base + j)) - (i == j ? 2.f : 0.f);
+    w[i * (kTS + 1) + j] = v;
+  }
+  for (int idx = t; idx < kTS * kDC; idx += kThreads) {
+    const int j = idx / kDC, c = idx - j * kDC;
+    const bool ok = j < l && c0 + c < d;
+    oc[idx] = ok ? __ldg(oh + (base + j) * d + c0 + c) : 0.f;
+    tc[idx] = ok ? __ldg(th + (base + j) * d + c0 + c) : 0.f;
+  }
+  __syncthreads();
+  float acc[8][4];
+  // rows of W
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  for (int j = 0; j < l; ++j) {
+    const float4 o4 = *reinterpret_cast<const float4*>(oc + j * kDC + tx * 4);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float wv = w[(ty * 8 + r) * (kTS + 1) + j];
+      acc[r][0] = fmaf(wv, o4.x, acc[r][0]); acc[r][1] = fmaf(wv, o4.y, acc[r][1]);
+      acc[r][2] = fmaf(wv, o4.z, acc[r][2]); acc[r][3] = fmaf(wv, o4.w, acc[r][3]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = ty * 8 + r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (i < l && c0 + tx * 4 + c < d) d_th[(base + i) * d + c0 + tx * 4 + c] = acc[r][c];
+  }
+  // columns of W
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  for (int i = 0; i < l; ++i) {
+    const float4 t4 = *reinterpret_cast<const float4*>(tc + i * kDC + tx * 4);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float wv = w[i * (kTS + 1) + ty * 8 + r];
+      acc[r][0] = fmaf(wv, t4.x, acc[r][0]); acc[r][1] = fmaf(wv, t4.y, acc[r][1]);
+      acc[r][2] = fmaf(wv, t4.z, acc[r][2]); acc[r][3] = fmaf(wv, t4.w, acc[r][3]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int j = ty * 8 + r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (j < l && c0 + tx * 4 + c < d) d_oh[(base + j) * d + c0 + tx * 4 + c] = acc[r][c];
+  }
+}
+
 int check_shape(int64_t batch, int64_t l, int64_t p, int64_t d) {
   EVK_REQUIRE(batch >= 1 && batch <= 65535 && l >= 1 && p >= 1 && d >= 1, "evk_local_attend: empty shape or batch > 65535");
   EVK_REQUIRE(p <= kMaxP && l <= 4096 && d <= 4096, "evk_local_attend: supports p <= %d patches, l <= 4096 tokens, d <= 4096", kMaxP);
@@ -223,5 +377,27 @@ extern "C" int evk_local_attend_bwd(const float* text, const float* image, const
   local_attend_bwd_patch_kernel<<<dim3((unsigned)((p + kTile - 1) / kTile), (unsigned)batch), kThreads, smem2, s>>>(text, att, ds, d_out, (int)l, (int)p,
                                                                                           (int)d, d_image);
   EVK_CHECK_LAUNCH("local_attend_bwd_patch");
+  return EVK_OK;
+}
+
+extern "C" int evk_token_sim_fwd(const float* th, const float* oh, int64_t batch, int64_t l, int64_t d, float inv_tau,
+                                 float* e_out, float* row_sum, float* row_pos, float* col_sum, evk_stream_t stream) {
+  EVK_REQUIRE(th && oh && e_out && row_sum && row_pos && col_sum, "evk_token_sim_fwd: null pointer");
+  EVK_REQUIRE(batch >= 1 && l >= 1 && l <= kTS && d >= 1 && inv_tau > 0.f, "evk_token_sim_fwd: needs 1 <= l <= %d tokens per sample", kTS);
+  token_sim_fwd_kernel<<<(unsigned)batch, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(th, oh, (int)l, (int)d, inv_tau, e_out,
+                                                                                         row_sum, row_pos, col_sum);
+  EVK_CHECK_LAUNCH("token_sim_fwd");
+  return EVK_OK;
+}
+
+extern "C" int evk_token_sim_bwd(const float* th, const float* oh, const float* e_in, const float* a_row, const float* b_col,
+                                 int64_t batch, int64_t l, int64_t d, float* d_th, float* d_oh, evk_stream_t stream) {
+  EVK_REQUIRE(th && oh && e_in && a_row && b_col && d_th && d_oh, "evk_token_sim_bwd: null pointer");
+  EVK_REQUIRE(batch >= 1 && batch <= 65535 && l >= 1 && l <= kTS && d >= 1, "evk_token_sim_bwd: needs 1 <= l <= %d tokens per sample", kTS);
+  const size_t smem = sizeof(float) * (size_t)(kTS * (kTS + 1) + 2 * kTS * kDC);
+  EVK_CUDA(cudaFuncSetAttribute(token_sim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  token_sim_bwd_kernel<<<dim3((unsigned)((d + kDC - 1) / kDC), (unsigned)batch), kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      th, oh, e_in, a_row, b_col, (int)l, (int)d, d_th, d_oh);
+  EVK_CHECK_LAUNCH("token_sim_bwd");
   return EVK_OK;
 }

@@ -614,6 +614,7 @@ def avgpos_ce(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor]
 
 
 # ------------------------------------------------------------------------------------- f1: local token alignment
+F1_TOKEN_SIM = os.environ.get("EVOKE_B200_F1_TOKEN_SIM", "1") == "1"   # per-sample token-similarity kernels (l <= 128)
 _IDENTITY_CACHE: dict = {}
 
 
@@ -652,6 +653,17 @@ class _LocalTokenAlign(torch.autograd.Function):
         n = b * l
         bits, counts, ones = _identity_targets(l, n, dev)                          # identity targets (:520), c_i = 1
 
+        # l <= 128: register-blocked per-sample kernels (E kept for the backward: B*l*l floats); else the batched
+        # small-path kernels
+        token_sim = F1_TOKEN_SIM and l <= 128
+        if token_sim:
+            e = torch.empty((b, l, l), dtype=torch.float32, device=dev)
+            row_sum = torch.empty(n, dtype=torch.float32, device=dev)
+            row_pos = torch.empty(n, dtype=torch.float32, device=dev)
+            col_sum = torch.empty(n, dtype=torch.float32, device=dev)
+            _lib.call("evk_token_sim_fwd", _ptr(tn.f32), _ptr(on.f32), b, l, d, float(inv_tau), _ptr(e), _ptr(row_sum),
+                      _ptr(row_pos), _ptr(col_sum), _stream())
+
         def fwd(q, k):
             rs = torch.empty(n, dtype=torch.float32, device=dev)
             rp = torch.empty(n, dtype=torch.float32, device=dev)
@@ -660,12 +672,14 @@ class _LocalTokenAlign(torch.autograd.Function):
                       _ptr(rs), _ptr(rp), l, _stream())
             return rs, rp
 
-        row_sum, row_pos = fwd(tn, on)            # rows = text tokens (word_sim_1, :519-521)
-        col_sum, _ = fwd(on, tn)                  # rows = attended tokens (word_sim_2, :523-524)
+        if not token_sim:
+            e = None
+            row_sum, row_pos = fwd(tn, on)        # rows = text tokens (word_sim_1, :519-521)
+            col_sum, _ = fwd(on, tn)              # rows = attended tokens (word_sim_2, :523-524)
         a_row, b_col, loss = finalize(row_sum, row_pos, ones, col_sum, col_lo=0, col_hi=n, shift=inv_tau, pos_weight=2.0,
                                       inv_count=0.5 / n)
         ctx.inv_tau, ctx.shape = inv_tau, (b, l, p, d)
-        ctx.aux = (v, t, att, o2, tn, on, bits, counts, a_row, b_col)
+        ctx.aux = (v, t, att, o2, tn, on, bits, counts, a_row, b_col, e)
         ctx.in_dtypes = (image.dtype, text.dtype)
         out = loss.reshape(())
         return out if image.dtype == torch.float32 else out.to(image.dtype)
@@ -674,7 +688,7 @@ class _LocalTokenAlign(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out: torch.Tensor):
         b, l, p, d = ctx.shape
-        v, t, att, o2, tn, on, bits, counts, a_row, b_col = ctx.aux
+        v, t, att, o2, tn, on, bits, counts, a_row, b_col, e = ctx.aux
         dev = v.device
         inv_tau = ctx.inv_tau
         g = grad_out.reshape(1).to(torch.float32).contiguous()
@@ -687,8 +701,14 @@ class _LocalTokenAlign(torch.autograd.Function):
                       _ptr(bc), l, float(inv_tau), 0, _ptr(dq), dq.stride(0), l * dq.stride(0), _stream())
             return dq
 
-        d_th = bwd(tn, on, a_row, b_col)
-        d_oh = bwd(on, tn, b_col, a_row)
+        if e is not None:
+            d_th = torch.empty((b * l, d), dtype=torch.float32, device=dev)
+            d_oh = torch.empty((b * l, d), dtype=torch.float32, device=dev)
+            _lib.call("evk_token_sim_bwd", _ptr(tn.f32), _ptr(on.f32), _ptr(e), _ptr(a_row), _ptr(b_col), b, l, d, _ptr(d_th),
+                      _ptr(d_oh), _stream())
+        else:
+            d_th = bwd(tn, on, a_row, b_col)
+            d_oh = bwd(on, tn, b_col, a_row)
         d_t = l2norm_bwd(t.view(b * l, d), tn, d_th, scale_dev=g, scale_host=scale)     # through F.normalize (:515)
         d_o = l2norm_bwd(o2, on, d_oh, scale_dev=g, scale_host=scale)                   # through F.normalize (:514)
         ds = torch.empty((b, l, p), dtype=torch.float32, device=dev)

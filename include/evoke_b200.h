@@ -173,6 +173,16 @@ EVK_API int evk_local_attend_bwd(const float* text, const float* image, const fl
                          int64_t batch, int64_t l, int64_t p, int64_t d,
                          float* ds, float* d_text, float* d_image, evk_stream_t stream);
 
+/* Per-sample token-level InfoNCE of f1 (:518-525) for l <= 128 tokens, register-blocked fp32, one sample per CTA:
+ *   e_out[b, i, j] = exp(th[b,i] . oh[b,j] * inv_tau - inv_tau),  row_sum / col_sum = its row / column sums per sample
+ *   (vectors of batch*l), row_pos[b*l + i] = the diagonal logit (identity targets :520).
+ * th / oh: the L2-normalised text / attended tokens, contiguous [batch*l, d].  evk_mpce_finalize turns the sums into
+ * a_row / b_col / loss; the backward then is d_th = W oh, d_oh = W^T th with W = E (a_i + b_j) - 2 [i == j]. */
+EVK_API int evk_token_sim_fwd(const float* th, const float* oh, int64_t batch, int64_t l, int64_t d, float inv_tau,
+                      float* e_out, float* row_sum, float* row_pos, float* col_sum, evk_stream_t stream);
+EVK_API int evk_token_sim_bwd(const float* th, const float* oh, const float* e_in, const float* a_row, const float* b_col,
+                      int64_t batch, int64_t l, int64_t d, float* d_th, float* d_oh, evk_stream_t stream);
+
 /* ---- statistics -> loss ----------------------------------------------------------------------
  * out[j] = sum_p part[p*ld + j], p < parts: deterministic reduction of per-tile partials;
  * if divisor != NULL the sum is divided by divisor[j] (0 where divisor[j] <= 0): pos_j / c_j. */

@@ -59,6 +59,23 @@ def test_local_token_alignment_reference_shapes_strided_inputs_and_patched_metho
     assert rel_max(head_t.grad.permute(0, 2, 1).cpu().numpy(), 2.0 * d_t) <= 1e-4
 
 
+def test_local_token_alignment_batched_small_path_and_long_sequences(monkeypatch):
+    """The fallback (batched small-path kernels) on the same inputs, and l > 128 which always takes it."""
+    from evoke_b200 import functional as Fn
+    rng = np.random.default_rng(5)
+    for (b, l, p, d, force) in ((3, 40, 20, 96, True), (2, 150, 49, 64, False)):
+        monkeypatch.setattr(Fn, "F1_TOKEN_SIM", not force)
+        v = rng.standard_normal((b, p, d)).astype(np.float32)
+        t = rng.standard_normal((b, l, d)).astype(np.float32)
+        image = torch.tensor(v, device=DEV, requires_grad=True)
+        text = torch.tensor(t, device=DEV, requires_grad=True)
+        loss = evoke_b200.local_text_token_alignment(image, text, 0.5)
+        loss.backward()
+        want, d_v, d_t = orc.local_token_alignment_closed_form(v, t, 0.5)
+        assert abs(loss.item() - want) <= 1e-5 * abs(want)
+        assert rel_max(image.grad.cpu().numpy(), d_v) <= 1e-4 and rel_max(text.grad.cpu().numpy(), d_t) <= 1e-4
+
+
 def test_local_token_alignment_cuda_graph_tracks_new_inputs():
     b, p, l, d, tau = 4, 49, 30, 128, 0.5
     g = evoke_b200.GraphedLocalTokenAlign(b, p, l, d, tau).capture()
