@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libevoke_b200.so")
 EVK_OK, EVK_ERR_INVALID, EVK_ERR_CUDA, EVK_ERR_UNSUPPORTED = 0, -1, -2, -3
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 FLAG_EXCLUDE_DIAG, FLAG_NO_COLSUM, FLAG_SPLIT_BF16, FLAG_NO_POS, FLAG_AVGPOS = 1, 2, 4, 8, 16
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 P, I, L, F, D = c_void_p, c_int, c_int64, c_float, c_double
 
@@ -25,6 +25,12 @@ SIGNATURES = {
     "evk_mpce_row_parts": [],
     "evk_last_error": [],
     "evk_device_info": [I, P, P, P],
+    "evk_stats_workspace_bytes": [L, L],
+    "evk_shard_finish_workspace_bytes": [L],
+    "evk_posmask_ld_words": [L],
+    "evk_mpce_rowpart_rows": [L],
+    "evk_mpce_colpart_rows": [L],
+    "evk_mpce_strip_ld": [L],
     "evk_l2norm_fwd": [P, I, L, L, L, L, P, P, L, P, P, L, P, P],
     "evk_l2norm_bwd": [P, I, L, L, L, L, P, P, P, L, P, F, P, I, L, I, P],
     "evk_posmask_build": [P, P, L, P, P, L, L, I, P, L, P, P, I, P],
@@ -49,7 +55,7 @@ SIGNATURES = {
     "evk_mpce_pos_logits": [P, L, P, L, L, L, P, P, I, P, P],
     "evk_l2norm_fwd_bcast": [P, I, L, L, L, L, I, P, P, L, L, P, P],
     "evk_peer_bcast": [P, L, I, P, L, P],
-    "evk_shard_prologue": [P, L, P, L, L, L, I, P, L, L, P, P, P, P, P, I, P, P, P, L, P, P],
+    "evk_shard_prologue": [P, I, L, L, P, I, L, L, L, L, I, P, L, L, P, P, P, P, P, I, P, P, P, L, P, P, P],
     "evk_peer_push_shard": [P, L, I, I, P, L, P, P, P, P],
     "evk_peer_wait_landed": [P, I, P, P, L, P],
     "evk_mpce_fwd_store_gathered": [P, L, P, L, L, L, L, P, L, F, I, L, P, P, L, P, L, P, L, P, P, P, L, L, P],
@@ -59,12 +65,16 @@ SIGNATURES = {
     "evk_peer_export": [P, P],
     "evk_peer_open": [P, P],
     "evk_peer_close": [P],
-    "evk_peer_barrier": [P, I, I, P, P, L, P],
-    "evk_mpce_shard_finish": [P, I, L, L, F, D, P, P, P, L, P],
+    "evk_peer_barrier": [P, I, I, P, P, P, L, P],
+    "evk_mpce_shard_finish": [P, I, L, L, F, D, P, P, P, L, P, P],
     "evk_mpce_bwd_gemm_scatter": [P, P, L, L, L, P, P, L, L, F, I, P, I, L, L, I, P],
-    "evk_l2norm_bwd_parts": [P, I, L, L, L, L, P, P, P, I, L, I, L, P, F, P, I, L, I, P],
+    "evk_l2norm_bwd_parts": [P, I, L, L, L, L, P, P, P, I, L, I, L, P, F, P, I, L, I, P, P],
     "evk_tc_gemm_probe": [P, L, I, P, L, I, L, L, L, P, L, I, I, P],
 }
+
+# host helpers that return a size instead of a status code
+INT64_RESULT = {"evk_stats_workspace_bytes", "evk_shard_finish_workspace_bytes", "evk_posmask_ld_words",
+                "evk_mpce_rowpart_rows", "evk_mpce_colpart_rows", "evk_mpce_strip_ld"}
 
 _lib = None
 
@@ -85,7 +95,7 @@ def load() -> ctypes.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = ABI mismatch, fail loudly
         fn.argtypes = argtypes
-        fn.restype = c_char_p if name == "evk_last_error" else c_int
+        fn.restype = c_char_p if name == "evk_last_error" else (c_int64 if name in INT64_RESULT else c_int)
     ver = lib.evk_version()
     if ver != ABI_VERSION:
         raise EvokeLibraryError(f"libevoke_b200.so ABI version {ver} != expected {ABI_VERSION}; rebuild")
@@ -117,6 +127,14 @@ KERNELS_PER_CALL = {
 }
 launch_count = 0          # running total, read by bench.py ("gpu_launches")
 call_hook = None          # optional callable(name, phase) with phase in {"before", "after"} (bench.py timing)
+
+
+def size(name: str, *args) -> int:
+    """A buffer-size helper of the C ABI (evk_*_bytes / _ld_* / _rows): the library is the single source of the layouts."""
+    v = int(getattr(load(), name)(*args))
+    if v <= 0:
+        raise ValueError(f"{name}{args}: bad arguments")
+    return v
 
 
 def call(name: str, *args) -> None:

@@ -42,6 +42,35 @@ int evk_version(void) { return EVK_ABI_VERSION; }
 
 const char* evk_last_error(void) { return g_err; }
 
+// ---- sizes of caller-owned buffers: the single source of truth for the layouts the kernels assume ------------
+int64_t evk_stats_workspace_bytes(int64_t n_rows, int64_t n_cols) {
+  if (n_rows <= 0 || n_cols < 0) return 0;
+  const int64_t n = n_cols > n_rows ? n_cols : n_rows;
+  const int64_t b = 16 + 24 * ((n + 31) / 32);          // ticket + 3 statistics x one fp64 partial per 32-element CTA
+  return (b + 15) / 16 * 16;
+}
+
+int64_t evk_shard_finish_workspace_bytes(int64_t n_cols) {
+  if (n_cols <= 0) return 0;
+  const int64_t b = 16 + 8 * ((n_cols + 255) / 256);
+  return (b + 15) / 16 * 16;
+}
+
+int64_t evk_posmask_ld_words(int64_t n_cols) {
+  if (n_cols <= 0) return 0;
+  const int64_t w = (n_cols + 255) / 256 * 8;           // whole 256-column tiles
+  return (w + 7) / 8 * 8;
+}
+
+int64_t evk_mpce_rowpart_rows(int64_t n_cols) {
+  if (n_cols <= 0) return 0;
+  return (n_cols + 255) / 256 * (int64_t)evk_mpce_row_parts();
+}
+
+int64_t evk_mpce_colpart_rows(int64_t n_rows) { return n_rows <= 0 ? 0 : (n_rows + 127) / 128; }
+
+int64_t evk_mpce_strip_ld(int64_t n_cols) { return n_cols <= 0 ? 0 : (n_cols + 63) / 64 * 64; }
+
 int evk_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
   int v = 0;
   if (sm_count) {

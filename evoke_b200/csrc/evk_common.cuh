@@ -10,7 +10,7 @@
 
 #include "../../include/evoke_b200.h"
 
-#define EVK_ABI_VERSION 2
+#define EVK_ABI_VERSION 3
 #define EVK_NORM_EPS 1e-12f       // F.normalize default eps
 
 // ---- error state (thread local; see evk_api.cu) ------------------------------------------

@@ -124,11 +124,13 @@ l2norm_bwd_kernel(const void* __restrict__ x, int x_dtype, int64_t n_out, int64_
                   int64_t stride_col, const int32_t* __restrict__ gather, const float* __restrict__ norm,
                   const void* __restrict__ g, int g_dtype, int64_t ld_g, int n_parts, int64_t part_stride,
                   const float* __restrict__ scale_dev,
-                  float scale_host, void* __restrict__ dx, int dx_dtype, int64_t ld_dx, int accumulate) {
+                  float scale_host, void* __restrict__ dx, int dx_dtype, int64_t ld_dx, int accumulate,
+                  const int* __restrict__ error) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-  const float scale = scale_host * (scale_dev ? __ldg(scale_dev) : 1.f);
+  float scale = scale_host * (scale_dev ? __ldg(scale_dev) : 1.f);
+  if (error && *reinterpret_cast<const volatile int*>(error) != 0) scale = __int_as_float(0x7fc00000);   // poisoned step
   for (int64_t r = warp0; r < n_out; r += nwarps) {
     const int64_t src = gather ? (int64_t)gather[r] : r;
     const int64_t base = src * stride_row;
@@ -176,11 +178,13 @@ l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t
                       const int32_t* __restrict__ gather, const float* __restrict__ norm,
                       const void* __restrict__ g, int64_t ld_g, int n_parts, int64_t part_stride,
                       const float* __restrict__ scale_dev,
-                      float scale_host, float* __restrict__ dx, int64_t ld_dx) {
+                      float scale_host, float* __restrict__ dx, int64_t ld_dx, const int* __restrict__ error) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-  const float scale = scale_host * (scale_dev ? __ldg(scale_dev) : 1.f);
+  float scale = scale_host * (scale_dev ? __ldg(scale_dev) : 1.f);
+  // sharded path: a cross-GPU barrier of this step timed out -> NaN gradients instead of silently wrong ones
+  if (error && *reinterpret_cast<const volatile int*>(error) != 0) scale = __int_as_float(0x7fc00000);
   for (int64_t r = warp0; r < n_out; r += nwarps) {
     const int64_t src = gather ? (int64_t)gather[r] : r;
     const float4* xr = reinterpret_cast<const float4*>(x + src * stride_row);
@@ -299,7 +303,7 @@ extern "C" int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, i
                                     int64_t stride_col, const int32_t* gather, const float* norm, const void* g,
                                     int g_dtype, int64_t ld_g, int n_parts, int64_t part_stride, const float* scale_dev,
                                     float scale_host, void* dx, int dx_dtype, int64_t ld_dx, int accumulate,
-                                    evk_stream_t stream) {
+                                    const int* error, evk_stream_t stream) {
   EVK_REQUIRE(x && norm && g && dx, "evk_l2norm_bwd: null pointer");
   EVK_REQUIRE(n_parts >= 1 && (n_parts == 1 || part_stride >= n_out * ld_g), "evk_l2norm_bwd_parts: bad partial-buffer layout");
   EVK_REQUIRE(g_dtype == EVK_DTYPE_F32 || g_dtype == EVK_DTYPE_BF16, "evk_l2norm_bwd_parts: partial buffers must be fp32 or bf16");
@@ -320,7 +324,7 @@ extern "C" int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, i
 #define EVK_LAUNCH_BWD(IT, B16, PARTS)                                                                                    \
   l2norm_bwd_vec_kernel<IT, B16, PARTS><<<grid, kWarpsPerBlock * 32, 0, s>>>(xf, n_out, (int)d, stride_row, gather, norm, g, \
                                                                              ld_g, n_parts, part_stride, scale_dev,           \
-                                                                             scale_host, df, ld_dx)
+                                                                             scale_host, df, ld_dx, error)
     const bool multi = n_parts > 1;
     if (d <= 1024) {
       if (g16) { if (multi) EVK_LAUNCH_BWD(8, true, true); else EVK_LAUNCH_BWD(8, true, false); }
@@ -335,7 +339,7 @@ extern "C" int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, i
   }
   l2norm_bwd_kernel<<<grid_for_rows(n_out), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       x, x_dtype, n_out, d, stride_row, stride_col, gather, norm, g, g_dtype, ld_g, n_parts, part_stride, scale_dev, scale_host, dx,
-      dx_dtype, ld_dx, accumulate);
+      dx_dtype, ld_dx, accumulate, error);
   EVK_CHECK_LAUNCH("l2norm_bwd");
   return EVK_OK;
 }
@@ -345,5 +349,5 @@ extern "C" int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t
                               int64_t ld_g, const float* scale_dev, float scale_host, void* dx, int dx_dtype,
                               int64_t ld_dx, int accumulate, evk_stream_t stream) {
   return evk_l2norm_bwd_parts(x, x_dtype, n_out, d, stride_row, stride_col, gather, norm, g, EVK_DTYPE_F32, ld_g, 1, 0, scale_dev,
-                              scale_host, dx, dx_dtype, ld_dx, accumulate, stream);
+                              scale_host, dx, dx_dtype, ld_dx, accumulate, nullptr, stream);
 }

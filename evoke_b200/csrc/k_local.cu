@@ -383,7 +383,8 @@ extern "C" int evk_local_attend_bwd(const float* text, const float* image, const
 extern "C" int evk_token_sim_fwd(const float* th, const float* oh, int64_t batch, int64_t l, int64_t d, float inv_tau,
                                  float* e_out, float* row_sum, float* row_pos, float* col_sum, evk_stream_t stream) {
   EVK_REQUIRE(th && oh && e_out && row_sum && row_pos && col_sum, "evk_token_sim_fwd: null pointer");
-  EVK_REQUIRE(batch >= 1 && l >= 1 && l <= kTS && d >= 1 && inv_tau > 0.f, "evk_token_sim_fwd: needs 1 <= l <= %d tokens per sample", kTS);
+  EVK_REQUIRE(batch >= 1 && l >= 1 && l <= kTS && d >= 1, "evk_token_sim_fwd: needs 1 <= l <= %d tokens per sample", kTS);
+  EVK_REQUIRE(inv_tau > 0.f && inv_tau <= EVK_MAX_INV_TAU, "evk_token_sim_fwd: 1/tau=%g outside (0, %g] (fixed-shift softmax)", inv_tau, EVK_MAX_INV_TAU);
   token_sim_fwd_kernel<<<(unsigned)batch, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(th, oh, (int)l, (int)d, inv_tau, e_out,
                                                                                          row_sum, row_pos, col_sum);
   EVK_CHECK_LAUNCH("token_sim_fwd");

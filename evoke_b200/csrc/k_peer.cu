@@ -88,8 +88,11 @@ l2norm_fwd_bcast_kernel(const float* __restrict__ x, int64_t n_rows, int d, int6
 // (all-gather), K1 of the query rows (image) kept local, the id shard pushed to every rank, and the zero fill
 // of the split-K accumulator of the local gradient contraction (same [n, D] shape as the query rows).
 struct Prologue {
-  const float* text; int64_t text_stride;
-  const float* image; int64_t image_stride;
+  // the embeddings as the caller holds them: fp32 / bf16 / fp16, any row and feature strides (the reference hands over
+  // [:,0,:] views of the permuted projection-head output: feature stride 1 + P, v0520.py:484,399).  `*_fast`: fp32,
+  // unit feature stride, 16-byte aligned rows -> 128-bit loads.
+  const void* text; int64_t text_stride, text_cs; int text_dtype, text_fast;
+  const void* image; int64_t image_stride, image_cs; int image_dtype, image_fast;
   PeerDst khat;                         // destinations of the normalised key rows
   __nv_bfloat16* q_hi;                  // local normalised query rows
   float* k_norm; float* q_norm;
@@ -99,6 +102,7 @@ struct Prologue {
   int64_t n, ld, row_offset;
   int d;
   int* step;                            // optional device counter advanced once per launch (one step = one epoch)
+  const int* error;                     // optional: sticky failure flag of the transport (a barrier timed out)
 };
 
 template <int kIters>
@@ -107,6 +111,9 @@ shard_prologue_kernel(const Prologue p) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  // a peer missed a barrier earlier: its buffers may still be in use, so nothing is written into peer memory any
+  // more (the step's loss and gradients are poisoned downstream, the host raises at its next entry)
+  if (p.error && *reinterpret_cast<const volatile int*>(p.error) != 0) return;
   if (p.step && blockIdx.x == 0 && threadIdx.x == 0) *p.step += 1;
   // ids: one element per thread, pushed to every rank
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < p.n; t += (int64_t)gridDim.x * blockDim.x) {
@@ -121,17 +128,26 @@ shard_prologue_kernel(const Prologue p) {
   for (int64_t rr = warp0; rr < 2 * p.n; rr += nwarps) {
     const bool is_text = rr < p.n;
     const int64_t r = is_text ? rr : rr - p.n;
-    const float* xr = is_text ? p.text + r * p.text_stride : p.image + r * p.image_stride;
+    const void* xb = is_text ? p.text : p.image;
+    const int64_t rs = is_text ? p.text_stride : p.image_stride, cs = is_text ? p.text_cs : p.image_cs;
+    const int dt = is_text ? p.text_dtype : p.image_dtype;
+    const bool fast = (is_text ? p.text_fast : p.image_fast) != 0;
     float v[kIters][8];
     float ss = 0.f;
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
       const int c = (it * 32 + lane) * 8;
       if (c < p.d) {
-        const float4 p0 = __ldg(reinterpret_cast<const float4*>(xr + c));
-        const float4 p1 = __ldg(reinterpret_cast<const float4*>(xr + c + 4));
-        v[it][0] = p0.x; v[it][1] = p0.y; v[it][2] = p0.z; v[it][3] = p0.w;
-        v[it][4] = p1.x; v[it][5] = p1.y; v[it][6] = p1.z; v[it][7] = p1.w;
+        if (fast) {
+          const float* xr = static_cast<const float*>(xb) + r * rs;
+          const float4 p0 = __ldg(reinterpret_cast<const float4*>(xr + c));
+          const float4 p1 = __ldg(reinterpret_cast<const float4*>(xr + c + 4));
+          v[it][0] = p0.x; v[it][1] = p0.y; v[it][2] = p0.z; v[it][3] = p0.w;
+          v[it][4] = p1.x; v[it][5] = p1.y; v[it][6] = p1.z; v[it][7] = p1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[it][e] = load_as_float(xb, dt, r * rs + (int64_t)(c + e) * cs);
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) ss = fmaf(v[it][e], v[it][e], ss);
       }
@@ -188,7 +204,8 @@ struct PeerFlags {
 };
 
 __global__ void __launch_bounds__(32)
-peer_barrier_kernel(PeerFlags pf, uint32_t* __restrict__ epoch, int* __restrict__ error, uint64_t timeout_ns) {
+peer_barrier_kernel(PeerFlags pf, uint32_t* __restrict__ epoch, int* __restrict__ error, int* __restrict__ error_host,
+                    uint64_t timeout_ns) {
   const int t = threadIdx.x;
   const uint32_t e = *epoch + 1u;
   __syncwarp();
@@ -202,7 +219,10 @@ peer_barrier_kernel(PeerFlags pf, uint32_t* __restrict__ epoch, int* __restrict_
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
       if ((int32_t)(v - e) >= 0) break;
       if (global_timer_ns() - t0 > timeout_ns) {
+        // sticky: the consumers of this step (evk_mpce_shard_finish, evk_l2norm_bwd_parts) turn it into NaN loss /
+        // gradients, the prologue stops writing into peer memory, and the host sees the mirror without a sync
         atomicExch(error, 1);
+        if (error_host) *reinterpret_cast<volatile int*>(error_host) = 1;
         break;
       }
       __nanosleep(64);
@@ -221,15 +241,17 @@ constexpr int kFinishThreads = 256;
 __global__ void __launch_bounds__(kFinishThreads)
 shard_finish_kernel(const float* __restrict__ slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
                     double inv_count, float* __restrict__ b_col, float* __restrict__ loss_out,
-                    double* __restrict__ cta_partial, unsigned int* __restrict__ ticket) {
+                    double* __restrict__ cta_partial, unsigned int* __restrict__ ticket, const int* __restrict__ error) {
   __shared__ double s_part[kFinishThreads / 32];
   __shared__ bool s_last;
   const int64_t j = (int64_t)blockIdx.x * kFinishThreads + threadIdx.x;
+  // a barrier of this step timed out: some slot / key rows may be stale -> the result must not look valid
+  const bool poisoned = error && *reinterpret_cast<const volatile int*>(error) != 0;
   double acc = 0.0;
   if (j < n_cols) {
     float c = 0.f;
     for (int r = 0; r < n_slots; ++r) c += slots[r * ld_slot + j];
-    b_col[j] = 1.f / c;
+    b_col[j] = poisoned ? __int_as_float(0x7fc00000) : 1.f / c;
     acc = (double)shift + (double)logf(c);
   }
 #pragma unroll
@@ -253,7 +275,7 @@ shard_finish_kernel(const float* __restrict__ slots, int n_slots, int64_t ld_slo
     if (threadIdx.x == 0) {
       t *= inv_count;
       for (int r = 0; r < n_slots; ++r) t += (double)slots[r * ld_slot + n_cols];
-      loss_out[0] = (float)t;
+      loss_out[0] = poisoned ? __int_as_float(0x7fc00000) : (float)t;
     }
   }
 }
@@ -415,7 +437,7 @@ extern "C" int evk_peer_close(void* ptr) {
 }
 
 extern "C" int evk_peer_barrier(const uint64_t* flag_ptrs, int n_ranks, int rank, uint32_t* epoch, int* error,
-                                int64_t timeout_ms, evk_stream_t stream) {
+                                int* error_host, int64_t timeout_ms, evk_stream_t stream) {
   EVK_REQUIRE(flag_ptrs && epoch && error && n_ranks >= 1 && n_ranks <= kMaxPeers && rank >= 0 && rank < n_ranks,
               "evk_peer_barrier: bad arguments (1..%d ranks)", kMaxPeers);
   PeerFlags pf;
@@ -427,14 +449,14 @@ extern "C" int evk_peer_barrier(const uint64_t* flag_ptrs, int n_ranks, int rank
     EVK_REQUIRE(pf.flags[t], "evk_peer_barrier: null flag area");
   }
   const uint64_t timeout_ns = (uint64_t)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
-  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, epoch, error, timeout_ns);
+  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, epoch, error, error_host, timeout_ns);
   EVK_CHECK_LAUNCH("peer_barrier");
   return EVK_OK;
 }
 
 extern "C" int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
                                      double inv_count, float* b_col, float* loss_out, void* workspace,
-                                     int64_t workspace_bytes, evk_stream_t stream) {
+                                     int64_t workspace_bytes, const int* error, evk_stream_t stream) {
   EVK_REQUIRE(slots && b_col && loss_out && n_slots >= 1 && n_cols > 0 && ld_slot > n_cols,
               "evk_mpce_shard_finish: bad arguments (ld_slot must exceed n_cols: the loss term follows the column sums)");
   const int64_t blocks = (n_cols + kFinishThreads - 1) / kFinishThreads;
@@ -445,21 +467,27 @@ extern "C" int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld
   double* partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + 16);
   EVK_CUDA(cudaMemsetAsync(ticket, 0, 16, s));
   shard_finish_kernel<<<(unsigned)blocks, kFinishThreads, 0, s>>>(slots, n_slots, ld_slot, n_cols, shift, inv_count, b_col,
-                                                                 loss_out, partial, ticket);
+                                                                 loss_out, partial, ticket, error);
   EVK_CHECK_LAUNCH("shard_finish");
   return EVK_OK;
 }
 
-extern "C" int evk_shard_prologue(const float* text, int64_t text_stride, const float* image, int64_t image_stride,
+extern "C" int evk_shard_prologue(const void* text, int text_dtype, int64_t text_stride, int64_t text_col_stride,
+                                  const void* image, int image_dtype, int64_t image_stride, int64_t image_col_stride,
                                   int64_t n_rows, int64_t d, int n_dst, const uint64_t* khat_ptrs, int64_t ld_bf16,
                                   int64_t row_offset, float* k_norm, void* q_hi, float* q_norm, const int32_t* ids,
                                   const int32_t* ids2, int n_ids_dst, const uint64_t* ids_ptrs, const uint64_t* ids2_ptrs,
-                                  float* zero_buf, int64_t ld_zero, int* step_counter, evk_stream_t stream) {
+                                  float* zero_buf, int64_t ld_zero, int* step_counter, const int* error,
+                                  evk_stream_t stream) {
   EVK_REQUIRE(text && image && k_norm && q_hi && q_norm && ids && ids_ptrs && khat_ptrs && n_rows > 0 && d > 0,
               "evk_shard_prologue: null pointer or empty shape");
-  EVK_REQUIRE(d % 8 == 0 && d <= 2048 && text_stride % 4 == 0 && image_stride % 4 == 0 && evk_aligned16(text) &&
-                  evk_aligned16(image) && evk_aligned16(q_hi) && ld_bf16 >= d && ld_bf16 % 8 == 0 && row_offset >= 0,
-              "evk_shard_prologue: needs contiguous fp32 rows, d %% 8 == 0, d <= 2048, 16-byte aligned buffers");
+  EVK_REQUIRE(text_dtype >= EVK_DTYPE_F32 && text_dtype <= EVK_DTYPE_F16 && image_dtype >= EVK_DTYPE_F32 &&
+                  image_dtype <= EVK_DTYPE_F16, "evk_shard_prologue: bad dtype");
+  EVK_REQUIRE(d % 8 == 0 && d <= 2048 && evk_aligned16(q_hi) && ld_bf16 >= d && ld_bf16 % 8 == 0 && row_offset >= 0,
+              "evk_shard_prologue: needs d %% 8 == 0, d <= 2048, 16-byte aligned bf16 outputs");
+  auto fast = [](const void* x, int dt, int64_t rs, int64_t cs) {
+    return dt == EVK_DTYPE_F32 && cs == 1 && rs % 4 == 0 && evk_aligned16(x);
+  };
   EVK_REQUIRE((ids2 == nullptr) == (ids2_ptrs == nullptr), "evk_shard_prologue: ids2 / ids2_ptrs must both be set or both null");
   EVK_REQUIRE(!zero_buf || (ld_zero % 4 == 0 && ld_zero >= d && evk_aligned16(zero_buf)), "evk_shard_prologue: bad zero buffer");
   Prologue p;
@@ -468,12 +496,16 @@ extern "C" int evk_shard_prologue(const float* text, int64_t text_stride, const 
   if (rc != EVK_OK) return rc;
   EVK_REQUIRE(n_ids_dst >= 1 && n_ids_dst <= kMaxPeers, "evk_shard_prologue: 1..%d id destinations", kMaxPeers);
   p.step = step_counter;
+  p.error = error;
   for (int q = 0; q < n_ids_dst; ++q) {
     p.ids_dst[q] = reinterpret_cast<int32_t*>(ids_ptrs[q]);
     p.ids2_dst[q] = ids2_ptrs ? reinterpret_cast<int32_t*>(ids2_ptrs[q]) : nullptr;
     EVK_REQUIRE(p.ids_dst[q] && (!ids2_ptrs || p.ids2_dst[q]), "evk_shard_prologue: null id destination");
   }
-  p.text = text; p.text_stride = text_stride; p.image = image; p.image_stride = image_stride;
+  p.text = text; p.text_stride = text_stride; p.text_cs = text_col_stride; p.text_dtype = text_dtype;
+  p.text_fast = fast(text, text_dtype, text_stride, text_col_stride) ? 1 : 0;
+  p.image = image; p.image_stride = image_stride; p.image_cs = image_col_stride; p.image_dtype = image_dtype;
+  p.image_fast = fast(image, image_dtype, image_stride, image_col_stride) ? 1 : 0;
   p.q_hi = static_cast<__nv_bfloat16*>(q_hi); p.k_norm = k_norm; p.q_norm = q_norm;
   p.ids = ids; p.ids2 = ids2;
   p.zero = zero_buf; p.ld_zero = ld_zero; p.zero_width = (int)(((d + 3) / 4) * 4);

@@ -239,8 +239,12 @@ size_t small_smem_bytes(int d_pad) {
 }
 
 int small_check(const float* q, const float* k, int64_t n_rows, int64_t n_cols, int64_t d, const uint32_t* bits,
-                int64_t ld_words, int64_t ld_q, int64_t ld_k) {
+                int64_t ld_words, int64_t ld_q, int64_t ld_k, float inv_tau) {
   EVK_REQUIRE(q && k && bits, "evk_mpce_small: null pointer");
+  // same domain as the tcgen05 path: with the fixed shift E = exp(S - 1/tau) >= exp(-2/tau) must stay a normal
+  // fp32 number, or a row of weakly aligned pairs could sum to 0 (ln 0, 1/0)
+  EVK_REQUIRE(inv_tau > 0.f && inv_tau <= EVK_MAX_INV_TAU, "evk_mpce_small: 1/tau=%g outside (0, %g] (temperature >= %g)",
+              inv_tau, EVK_MAX_INV_TAU, 1.0 / EVK_MAX_INV_TAU);
   EVK_REQUIRE(n_rows > 0 && n_cols > 0 && d > 0, "evk_mpce_small: empty problem (%lld x %lld x %lld)",
               (long long)n_rows, (long long)n_cols, (long long)d);
   EVK_REQUIRE(d <= 4096, "evk_mpce_small: d=%lld > 4096 is not supported by the small path", (long long)d);
@@ -256,7 +260,8 @@ int small_fwd_impl(const float* q, int64_t ld_q, const float* k, int64_t ld_k, i
                    int64_t n_cols, int64_t d, const uint32_t* bits, int64_t ld_words, float inv_tau,
                    int flags, int64_t diag_offset, float* row_sum, float* row_pos, int64_t batch, int64_t bs_q,
                    int64_t bs_k, int64_t bs_vec, evk_stream_t stream) {
-  int rc = small_check(q, k, n_rows, n_cols, d, bits, ld_words, ld_q, ld_k);
+  flags &= EVK_FLAG_PUBLIC_MASK;
+  int rc = small_check(q, k, n_rows, n_cols, d, bits, ld_words, ld_q, ld_k, inv_tau);
   if (rc != EVK_OK) return rc;
   EVK_REQUIRE(row_sum && row_pos, "evk_mpce_small_fwd: null output");
   EVK_REQUIRE(batch >= 1 && batch <= 65535, "evk_mpce_small_fwd: batch must be in 1..65535");
@@ -295,7 +300,8 @@ int small_bwd_impl(const float* q, int64_t ld_q, const float* k, int64_t ld_k, i
                    int flags, int64_t diag_offset, float* dq, int64_t ld_dq, const float* pos_row,
                    const float* pos_col, int64_t batch, int64_t bs_q, int64_t bs_k, int64_t bs_vec, int64_t bs_dq,
                    evk_stream_t stream) {
-  int rc = small_check(q, k, n_rows, n_cols, d, bits, ld_words, ld_q, ld_k);
+  flags &= EVK_FLAG_PUBLIC_MASK;
+  int rc = small_check(q, k, n_rows, n_cols, d, bits, ld_words, ld_q, ld_k, inv_tau);
   if (rc != EVK_OK) return rc;
   EVK_REQUIRE(batch >= 1 && batch <= 65535, "evk_mpce_small_bwd: batch must be in 1..65535");
   EVK_REQUIRE(a_row && b_col && dq && ld_dq >= d, "evk_mpce_small_bwd: null pointer or ld_dq < d");

@@ -47,6 +47,14 @@ constexpr int kTmemCols = 512;
 constexpr int kMaxSegs = 3;
 
 enum { EPI_FWD = 0, EPI_BWD_W = 1, EPI_GEMM = 2, EPI_FWD_E = 3, EPI_GEMM_TMA = 4 };
+// Bits of TcParams::flags above the public EVK_FLAG_* set.  They are set by this file only: every extern "C" entry
+// point masks the caller's flags with EVK_FLAG_PUBLIC_MASK first.
+enum {
+  kIntDropOut = 0x100,   // evk_tc_gemm_probe(variant & 8): run the main loop, drop the output (main-loop rate probe)
+  kIntStore = 0x200,     // gradient contraction: whole-K units, plain stores instead of reduce-add
+  kIntBf16Out = 0x2000,  // gradient contraction, store mode: bf16 [32 x 64] output boxes
+  kIntVecMask = 0x4000,  // K3: the mask rows allow 128-bit loads
+};
 // EPI_FWD_E: K3 that also stores E as bf16.  EPI_GEMM_TMA: K4b whose fp32 tiles leave through shared memory and
 // TMA (store, or reduce-add in L2): whole 128-byte lines per request instead of 16-byte red.add / st per lane,
 // which is what peer memory over NVLink needs and also takes the accumulation off the epilogue warps.
@@ -388,10 +396,10 @@ tc_kernel(const __grid_constant__ TcParams p) {
         // (its latency - the mask streams from HBM - used to be exposed once per 32-column chunk)
         uint32_t mw4[4] = {0u, 0u, 0u, 0u};
         if (want_pos && row_ok) {
-          if ((p.flags & 0x4000) && kChunks == 4) {
+          if ((p.flags & kIntVecMask) && kChunks == 4) {
             const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(mrow + c_lo));
             mw4[0] = t4.x; mw4[1] = t4.y; mw4[2] = t4.z; mw4[3] = t4.w;
-          } else if ((p.flags & 0x4000) && kChunks == 2) {
+          } else if ((p.flags & kIntVecMask) && kChunks == 2) {
             const uint2 t2 = __ldg(reinterpret_cast<const uint2*>(mrow + c_lo));
             mw4[0] = t2.x; mw4[1] = t2.y;
           } else {
@@ -410,13 +418,8 @@ tc_kernel(const __grid_constant__ TcParams p) {
           const int c = c_lo + cc;
           const uint32_t mword = cc == 0 ? mw4[0] : (cc == 1 ? mw4[1] : (cc == 2 ? mw4[2] : mw4[3]));
           float v[32];
-          if (p.flags & 0x800) {                                  // bring-up knockout: no TMEM read
-#pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = 0.f;
-          } else {
-            tmem_ld_32x32(taddr + c * 32, v);
-            tmem_ld_wait(v);
-          }
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait(v);
           const int cbase = n0 + c * 32;
           uint32_t live = (cbase + 32 <= p.n_cols) ? 0xffffffffu
                           : (cbase >= p.n_cols ? 0u : ((1u << (int)(p.n_cols - cbase)) - 1u));
@@ -428,10 +431,8 @@ tc_kernel(const __grid_constant__ TcParams p) {
             for (int k = 0; k < 32; ++k)
               if ((m >> k) & 1u) rp = fmaf(v[k], p.inv_tau, rp);
           }
-          if (!(p.flags & 0x400)) {                               // (0x400: bring-up knockout of the exp)
 #pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = ex2_approx(fmaf(v[k], c1, -c1));
-          }
+          for (int k = 0; k < 32; ++k) v[k] = ex2_approx(fmaf(v[k], c1, -c1));
           if (live != 0xffffffffu) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = ((live >> k) & 1u) ? v[k] : 0.f;
@@ -512,7 +513,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
             float v[32];
             tmem_ld_32x32(taddr + c * 32, v);
             tmem_ld_wait(v);
-            if (!(p.flags & 0x400)) {                             // (0x400: bring-up knockout of the math)
+            {
               const int cbase = n0 + c * 32;
               if (cbase + 32 <= p.n_cols) {
                 const float4* bp = reinterpret_cast<const float4*>(p.b_col + cbase);   // warp-uniform: broadcast loads
@@ -554,7 +555,6 @@ tc_kernel(const __grid_constant__ TcParams p) {
               uint32_t h2 = pack_bf16x2(v[8 * uu + 4], v[8 * uu + 5]);
               uint32_t h3 = pack_bf16x2(v[8 * uu + 6], v[8 * uu + 7]);
               const uint32_t off = static_cast<uint32_t>(((u0 + uu) ^ (lane & 7)) << 4);
-              if (!(p.flags & 0x1000))
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + off), "r"(h0), "r"(h1), "r"(h2),
                            "r"(h3) : "memory");
               if (split) {
@@ -575,7 +575,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
           if (r == rounds - 1) release_tmem(as);
           fence_proxy_async_smem();                               // generic-proxy writes -> async proxy
           __syncwarp();
-          if (lane == 0 && !(p.flags & 0x3000)) {
+          if (lane == 0) {
             const int cx = n0 + (c_lo + r * per_round) * 32;      // first column of this round
             if (split) {
               tma_store_2d(&p.out_map[0], wstg, cx, m_warp, p.policy_out);
@@ -598,8 +598,8 @@ tc_kernel(const __grid_constant__ TcParams p) {
           row_in_owner = (int)(m_warp - (int64_t)owner * p.rows_per_owner);
         }
         const CUtensorMap* omap = &p.peer_map[m_warp < p.n_rows ? owner : 0];
-        const bool reduce = (p.flags & 0x200) == 0;
-        const bool out16 = (p.flags & 0x2000) != 0;              // bf16 output boxes [32 rows x 64 columns] (store mode only)
+        const bool reduce = (p.flags & kIntStore) == 0;
+        const bool out16 = (p.flags & kIntBf16Out) != 0;              // bf16 output boxes [32 rows x 64 columns] (store mode only)
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
 #pragma unroll 1
@@ -631,7 +631,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
             if (cc & 1) {
               fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0 && m_warp < p.n_rows && !(p.flags & 0x100))
+              if (lane == 0 && m_warp < p.n_rows && !(p.flags & kIntDropOut))
                 tma_store_2d(omap, wstg + (box & 1) * 4096, n0 + (c - 1) * 32, row_in_owner, p.policy_out);
               if (lane == 0) tma_store_commit();
             }
@@ -648,7 +648,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && m_warp < p.n_rows && !(p.flags & 0x100)) {
+          if (lane == 0 && m_warp < p.n_rows && !(p.flags & kIntDropOut)) {
             // rows / columns beyond the output are clipped by the tensor map
             if (reduce) tma_reduce_add_2d(omap, wstg + (cc & 1) * 4096, n0 + c * 32, row_in_owner);
             else tma_store_2d(omap, wstg + (cc & 1) * 4096, n0 + c * 32, row_in_owner, p.policy_out);
@@ -672,8 +672,8 @@ tc_kernel(const __grid_constant__ TcParams p) {
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait(v);
           const int cbase = n0 + c * 32;
-          if (row_ok && !(p.flags & 0x100)) {
-            if (p.flags & 0x200) {                               // whole-K units: plain (posted) stores, no accumulation
+          if (row_ok && !(p.flags & kIntDropOut)) {
+            if (p.flags & kIntStore) {                            // whole-K units: plain (posted) stores, no accumulation
               if (cbase + 32 <= p.n_cols) {
 #pragma unroll
                 for (int k = 0; k < 32; k += 4)
@@ -830,10 +830,14 @@ int launch(const TcParams& p, cudaStream_t s) {
   constexpr int smem = smem_bytes_total<EPI, STAGES, CTA2, EW, SB>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
   auto kern = tc_kernel<EPI, A_MN, B_MN, STAGES, CTA2, EW, SB>;
-  static thread_local bool attr_set = false;          // per instantiation, per thread: cheap and race-free
-  if (!attr_set) {
+  // per instantiation, per thread AND per device (the attribute belongs to the function on one device; a host
+  // thread that drives several GPUs must opt in on each of them)
+  static thread_local uint64_t attr_set = 0;
+  int dev = 0;
+  EVK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !((attr_set >> dev) & 1ull)) {
     EVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set |= 1ull << dev;
   }
   const int sms = evk_sm_count();
   // stream-K (splits == 0): every group gets a range; a range should hold at least a few k-blocks
@@ -865,10 +869,12 @@ int launch(const TcParams& p, cudaStream_t s) {
 int check_device() {
   // cuTensorMapEncodeTiled is a driver call: it needs the primary context bound to THIS thread.
   // autograd runs backward on its own thread, whose first CUDA activity may be this library.
-  static thread_local bool ctx_bound = false;
-  if (!ctx_bound) {
+  static thread_local uint64_t ctx_bound = 0;         // per device: the thread may switch devices between calls
+  int dev = 0;
+  EVK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !((ctx_bound >> dev) & 1ull)) {
     EVK_CUDA(cudaFree(nullptr));
-    ctx_bound = true;
+    if (dev >= 0 && dev < 64) ctx_bound |= 1ull << dev;
   }
   if (!evk_is_sm100())
     return evk_set_error(EVK_ERR_UNSUPPORTED, "the tcgen05 path needs an sm_100 (B200) device; there is no fallback");
@@ -930,6 +936,7 @@ int mpce_fwd_impl(const void* q_hi, const void* q_lo, int64_t ld_q, const void* 
                   float* row_pos_part, int64_t ld_rowpart, float* col_sum_part, int64_t ld_colpart,
                   void* e_out, int64_t ld_e, evk_stream_t stream, const uint32_t* landed = nullptr,
                   const int* step = nullptr, int* error = nullptr, int64_t cols_per_source = 0, int64_t first_col = 0) {
+  flags &= EVK_FLAG_PUBLIC_MASK;
   int rc = check_device();
   if (rc != EVK_OK) return rc;
   const bool cta2 = use_cta_pairs();
@@ -943,10 +950,10 @@ int mpce_fwd_impl(const void* q_hi, const void* q_lo, int64_t ld_q, const void* 
   EVK_REQUIRE(!want_pos || ld_words >= (int64_t)p.n_tiles * (BN / 32), "evk_mpce_fwd: ld_words=%lld must cover whole 256-column tiles (>= %lld)",
               (long long)ld_words, (long long)p.n_tiles * (BN / 32));
   EVK_REQUIRE(ld_rowpart >= n_rows && (!want_col || ld_colpart >= n_cols), "evk_mpce_fwd: partial pitches too small");
-  EVK_REQUIRE(inv_tau > 0.f && inv_tau <= 40.f, "evk_mpce_fwd: 1/tau=%g outside (0, 40]: the fixed-shift softmax needs exp(-2/tau) to stay normal in fp32", inv_tau);
+  EVK_REQUIRE(inv_tau > 0.f && inv_tau <= EVK_MAX_INV_TAU, "evk_mpce_fwd: 1/tau=%g outside (0, 40]: the fixed-shift softmax needs exp(-2/tau) to stay normal in fp32", inv_tau);
   p.inv_tau = inv_tau;
   p.flags = flags;
-  if (bits && evk_aligned16(bits) && ld_words % 4 == 0) p.flags |= 0x4000;     // 128-bit mask loads
+  if (bits && evk_aligned16(bits) && ld_words % 4 == 0) p.flags |= kIntVecMask;     // 128-bit mask loads
   p.diag_offset = diag_offset;
   p.bits = bits;
   p.ld_words = ld_words;
@@ -1022,6 +1029,7 @@ extern "C" int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q, 
                               int64_t ld_words, const int32_t* counts, const float* a_row, const float* b_col,
                               float inv_tau, int flags, int64_t diag_offset, void* w_hi, void* w_lo, int64_t ld_w,
                               evk_stream_t stream) {
+  flags &= EVK_FLAG_PUBLIC_MASK;
   int rc = check_device();
   if (rc != EVK_OK) return rc;
   const bool cta2 = use_cta_pairs();
@@ -1034,7 +1042,7 @@ extern "C" int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q, 
   EVK_REQUIRE(evk_aligned16(b_col), "evk_mpce_bwd_w: b_col must be 16-byte aligned");
   EVK_REQUIRE(ld_words >= (int64_t)p.n_tiles * (BN / 32), "evk_mpce_bwd_w: ld_words must cover whole 256-column tiles");
   EVK_REQUIRE(ld_w >= n_cols && ld_w % 8 == 0, "evk_mpce_bwd_w: ld_w=%lld must be >= n_cols and a multiple of 8", (long long)ld_w);
-  EVK_REQUIRE(inv_tau > 0.f && inv_tau <= 40.f, "evk_mpce_bwd_w: 1/tau=%g outside (0, 40]", inv_tau);
+  EVK_REQUIRE(inv_tau > 0.f && inv_tau <= EVK_MAX_INV_TAU, "evk_mpce_bwd_w: 1/tau=%g outside (0, 40]", inv_tau);
   rc = make_map_bf16(&p.out_map[0], w_hi, n_rows, n_cols, ld_w, 32, 64);
   if (rc != EVK_OK) return rc;
   if (split) {
@@ -1060,7 +1068,7 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
   if (p.rows_per_owner > 0) out = p.out_peer[0];
   EVK_REQUIRE(m > 0 && n > 0 && k > 0 && out, "gemm: empty problem or null output");
   EVK_REQUIRE(m < (1ll << 30) && n < (1ll << 30) && k < (1ll << 30), "gemm: problem too large");
-  EVK_REQUIRE(ld_out >= n && ld_out % ((p.flags & 0x2000) ? 8 : 4) == 0 && evk_aligned16(out),
+  EVK_REQUIRE(ld_out >= n && ld_out % ((p.flags & kIntBf16Out) ? 8 : 4) == 0 && evk_aligned16(out),
               "gemm: out needs 16-byte alignment and 16-byte rows");
   p.num_segs = nsegs;
   p.kb_per_seg = (int)((k + BK - 1) / BK);
@@ -1078,7 +1086,7 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
   const int total_kb = p.num_segs * p.kb_per_seg;
   const int groups = cta2 ? evk_sm_count() / 2 : evk_sm_count();
   p.splits = force_splits > 0 ? force_splits : (use_stream_k() ? 0 : choose_splits(p.m_tiles * p.n_tiles, total_kb, groups));
-  if (p.flags & 0x200) p.splits = 1;      // store epilogue: every output element is written by exactly one unit
+  if (p.flags & kIntStore) p.splits = 1;      // store epilogue: every output element is written by exactly one unit
   if (p.splits > total_kb) p.splits = total_kb;
   p.out = out;
   p.ld_out = ld_out;
@@ -1090,7 +1098,7 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
     if (e[0] == '0') p.policy_a = p.policy_b = kEvictNormal;
   }
   fill_descs(p, a_mn, b_mn, variant, cta2);
-  if (variant & 8) p.flags |= 0x100;      // bring-up: run the main loop, drop the output
+  if (variant & 8) p.flags |= kIntDropOut;      // bring-up: run the main loop, drop the output
   if (cta2 && use_tma_epilogue() && !(variant & 16) && (b_mn) ) {
     // output tiles leave through TMA (store, or reduce-add when units are split along K)
     int rc;
@@ -1098,7 +1106,7 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
       const int owners = (int)((m + p.rows_per_owner - 1) / p.rows_per_owner);
       for (int o = 0; o < owners; ++o) {
         const int64_t rows_o = (o + 1) * p.rows_per_owner <= m ? p.rows_per_owner : m - o * p.rows_per_owner;
-        rc = (p.flags & 0x2000) ? make_map_bf16(&p.peer_map[o], p.out_peer[o], rows_o, n, ld_out, 32, 64)
+        rc = (p.flags & kIntBf16Out) ? make_map_bf16(&p.peer_map[o], p.out_peer[o], rows_o, n, ld_out, 32, 64)
                                 : make_map_f32_out(&p.peer_map[o], p.out_peer[o], rows_o, n, ld_out);
         if (rc != EVK_OK) return rc;
       }
@@ -1125,6 +1133,7 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
 extern "C" int evk_mpce_bwd_gemm(const void* w_hi, const void* w_lo, int64_t ld_w, int64_t n_rows, int64_t n_cols,
                                  int transpose_w, const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d,
                                  float alpha, int flags, float* out, int64_t ld_out, evk_stream_t stream) {
+  flags &= EVK_FLAG_PUBLIC_MASK;
   int rc = check_device();
   if (rc != EVK_OK) return rc;
   const bool split = (flags & EVK_FLAG_SPLIT_BF16) != 0;
@@ -1145,6 +1154,7 @@ extern "C" int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int
                                          const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d, float alpha,
                                          int flags, const uint64_t* out_ptrs, int n_owners, int64_t rows_per_owner,
                                          int64_t ld_out, int store, evk_stream_t stream) {
+  flags &= EVK_FLAG_PUBLIC_MASK;
   int rc = check_device();
   if (rc != EVK_OK) return rc;
   const bool split = (flags & EVK_FLAG_SPLIT_BF16) != 0;
@@ -1160,10 +1170,10 @@ extern "C" int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int
     EVK_REQUIRE(p.out_peer[r] && evk_aligned16(p.out_peer[r]), "evk_mpce_bwd_gemm_scatter: owner buffers must be 16-byte aligned");
   }
   p.rows_per_owner = rows_per_owner;
-  if (store) p.flags |= 0x200;
+  if (store) p.flags |= kIntStore;
   if (store == 2) {
     EVK_REQUIRE(use_cta_pairs() && use_tma_epilogue(), "evk_mpce_bwd_gemm_scatter: bf16 partials need the TMA epilogue (CTA pairs)");
-    p.flags |= 0x2000;
+    p.flags |= kIntBf16Out;
   }
   const void* a_ptrs[3] = {w_hi, w_hi, w_lo};
   const void* b_ptrs[3] = {x_hi, x_lo, x_hi};

@@ -164,6 +164,7 @@ class _ShardedGPeer(torch.autograd.Function):
         n, n_total, d = pc.n_local, pc.n_total, pc.d
         lo_ = rank * n
         dev = image.device
+        pc.raise_if_failed()                     # a barrier of an earlier step timed out (pinned mirror: no device sync)
         need_grad = any(ctx.needs_input_grad[4:])
         overlap = ops.OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
         main = torch.cuda.current_stream()
@@ -179,11 +180,14 @@ class _ShardedGPeer(torch.autograd.Function):
         wq = _round_up(d, 4)
         dq = torch.empty((n, wq), dtype=torch.float32, device=dev) if need_grad else None
         overlap_gather = OVERLAP_GATHER and world > 1
-        _lib.call("evk_shard_prologue", text.data_ptr(), text.stride(0), image.data_ptr(), image.stride(0), n, d,
+        # inputs as the caller holds them (strided [:,0,:] head views, bf16/fp16): the prologue's loader honours them
+        _lib.call("evk_shard_prologue", text.data_ptr(), ops._dtype_code(text), text.stride(0), text.stride(1),
+                  image.data_ptr(), ops._dtype_code(image), image.stride(0), image.stride(1), n, d,
                   1 if overlap_gather else world, pc.table("khat_local") if overlap_gather else pc.table("khat"), pc.ld, lo_,
                   k_norm.data_ptr(), q_hi.data_ptr(), q_norm.data_ptr(),
                   row_ids.key.data_ptr(), row_ids.key2.data_ptr() if two else None, world, pc.table("ids"),
-                  pc.table("ids2") if two else None, None if dq is None else dq.data_ptr(), wq, pc.step.data_ptr(), stream)
+                  pc.table("ids2") if two else None, None if dq is None else dq.data_ptr(), wq, pc.step.data_ptr(),
+                  pc.error.data_ptr(), stream)
         pc.barrier()
         qn = ops.Normalized(n=n, d=d, norm=q_norm, hi=q_hi, lo=None, ld=pc.ld)
         kn_all = ops.Normalized(n=n_total, d=d, norm=None, hi=pc.khat, lo=None, ld=pc.ld)
@@ -234,7 +238,7 @@ class _ShardedGPeer(torch.autograd.Function):
         # exchange 2 (one launch): partials -> a_row, and this rank's slot (partial column sums of its rows +
         # its row-side loss term) into every rank's slot buffer
         a_row = torch.empty(n, dtype=torch.float32, device=dev)
-        ws = torch.empty(_round_up(16 + 24 * ((n_total + 31) // 32), 16), dtype=torch.uint8, device=dev)
+        ws = torch.empty(_lib.size("evk_stats_workspace_bytes", n, n_total), dtype=torch.uint8, device=dev)
         _lib.call("evk_mpce_shard_stats_push", rs_part.data_ptr(), int(rs_part.shape[0]), n, rp_part.data_ptr(),
                   int(rp_part.shape[0]), n, counts.data_ptr(), n, cs_part.data_ptr(), int(cs_part.shape[0]), n_total,
                   n_total, float(inv_tau), 2.0, 0.5 / n_total, a_row.data_ptr(), pc.table("slots"), world,
@@ -242,9 +246,9 @@ class _ShardedGPeer(torch.autograd.Function):
         pc.barrier()
         b_col = torch.empty(n_total, dtype=torch.float32, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
-        ws2 = torch.empty(_round_up(16 + 8 * ((n_total + 255) // 256), 16), dtype=torch.uint8, device=dev)
+        ws2 = torch.empty(_lib.size("evk_shard_finish_workspace_bytes", n_total), dtype=torch.uint8, device=dev)
         _lib.call("evk_mpce_shard_finish", pc.slots.data_ptr(), world, pc.ld_slot, n_total, float(inv_tau), 0.5 / n_total,
-                  b_col.data_ptr(), loss.data_ptr(), ws2.data_ptr(), ws2.numel(), stream)
+                  b_col.data_ptr(), loss.data_ptr(), ws2.data_ptr(), ws2.numel(), pc.error.data_ptr(), stream)
         if overlap_gather or (need_grad and overlap):
             main.wait_stream(side)              # the push (and the positives) are part of this step
             if need_grad:
@@ -278,7 +282,7 @@ class _ShardedGPeer(torch.autograd.Function):
 
         def image_side():
             ops.tc_bwd_gemm(e, None, ld_e, n, n_total, False, kn_all, 0, out=dq)      # dq was zeroed by the prologue
-            return ops.l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale)
+            return ops.l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, error=pc.error)
 
         if overlap:
             # the local contraction fills the SMs as the scattering one drains (it may be NVLink-bound)
@@ -297,7 +301,7 @@ class _ShardedGPeer(torch.autograd.Function):
             ops._shared_with(main, d_image)
         pc.barrier()                           # every rank's partial for these rows has landed
         d_text = ops.l2norm_bwd(text, kn_local, pc.dk_parts[0], scale_dev=g, scale_host=scale,
-                                parts=(pc.world, n * pc.width))
+                                parts=(pc.world, n * pc.width), error=pc.error)
         ctx.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, None, 0, None)
         return None, None, None, None, d_image, d_text
 
@@ -306,12 +310,16 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+_FLOAT_DTYPES = (torch.float32, torch.bfloat16, torch.float16)
+
+
 def peer_eligible(image: torch.Tensor, text: torch.Tensor, precision: str, world: int) -> bool:
-    """Static conditions of the peer-memory path (identical on every rank for equal shapes/dtypes)."""
+    """Conditions of the peer-memory path.  They depend on shapes, dtypes and the precision mode only - never on
+    strides or pointer alignment, which may differ between ranks: every rank must pick the same transport (the
+    context set-up is collective), and the prologue kernel reads any strides / fp32, bf16, fp16 inputs itself."""
     n, d = int(image.shape[0]), int(image.shape[1])
-    return (precision == "bf16" and image.is_cuda and world <= 16 and n % 128 == 0 and d % 8 == 0 and d <= 2048
-            and text.dtype == torch.float32 and text.stride(1) == 1 and text.stride(0) % 4 == 0
-            and text.data_ptr() % 16 == 0)
+    return (precision == "bf16" and image.is_cuda and text.is_cuda and world <= 16 and n % 128 == 0 and d % 8 == 0
+            and d <= 2048 and image.dtype == text.dtype and image.dtype in _FLOAT_DTYPES)
 
 
 PEER_EXCHANGE = os.environ.get("EVOKE_B200_PEER_EXCHANGE", "bf16")     # dtype of the dKhat partials on NVLink: bf16 | fp32
@@ -343,8 +351,12 @@ def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local,
         from . import functional as ops  # the CUDA kernels
         ops._require_cuda(image, "image")
         ops._require_cuda(text, "text")
+        if image.dtype not in _FLOAT_DTYPES:
+            raise TypeError(f"embeddings must be float32, bfloat16 or float16, got {image.dtype}")
     if image.shape != text.shape:
         raise ValueError(f"image/text shapes differ: {tuple(image.shape)} vs {tuple(text.shape)}")
+    if image.dtype != text.dtype:
+        raise TypeError(f"image/text embedding dtypes differ: {image.dtype} vs {text.dtype}")
     if precision not in ("fp32", "bf16"):
         raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
     from . import ids as idmod
@@ -358,9 +370,8 @@ def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local,
             # rank-local factorisation would give inconsistent codes: keep the raw integers (exact two-word keys)
             ids_local = torch.from_numpy(np.ascontiguousarray(ids_local.astype(np.int64)))
         row_ids, _ = idmod.to_device_ids(ids_local, image.device, n=int(image.shape[0]))
-    temp = float(temp)
-    if not temp > 0:
-        raise ValueError("temperature must be positive")
+    from .loss import _inv_tau
+    inv_tau = _inv_tau(temp)
     if mode not in ("auto", "rs", "sym", "peer"):
         raise ValueError(f"mode must be 'auto', 'rs', 'sym' or 'peer', got {mode!r}")
     world = dist.get_world_size(group)
@@ -371,9 +382,9 @@ def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local,
             pc = peer.get_context(group, int(image.shape[0]), int(image.shape[1]), image.device,
                                   two_keys=row_ids.key2 is not None, exchange=PEER_EXCHANGE)
         if pc is not None:
-            return _ShardedGPeer.apply(ops, pc, 1.0 / temp, row_ids, image, text)
+            return _ShardedGPeer.apply(ops, pc, inv_tau, row_ids, image, text)
         if mode == "peer":
-            raise RuntimeError("evoke_b200: mode='peer' needs bf16 precision, contiguous fp32 text rows, n_local % 128 == 0, "
-                               "d % 8 == 0 and CUDA-IPC peer mapping between the ranks' GPUs")
+            raise RuntimeError("evoke_b200: mode='peer' needs bf16 precision, n_local % 128 == 0, d % 8 == 0, d <= 2048 "
+                               "and CUDA-IPC peer mapping between the ranks' GPUs")
     sym = mode == "sym" or (mode in ("auto", "peer") and world >= 8)
-    return _ShardedG.apply(ops, group, 1.0 / temp, precision, sym, row_ids, image, text)
+    return _ShardedG.apply(ops, group, inv_tau, precision, sym, row_ids, image, text)

@@ -129,9 +129,11 @@ def l2norm_fwd(x: torch.Tensor, *, want_f32: bool, want_hi: bool, want_lo: bool,
 
 
 def l2norm_bwd(x: torch.Tensor, nrm: Normalized, g_hat: torch.Tensor, *, scale_dev: Optional[torch.Tensor],
-               scale_host: float, gather: Optional[torch.Tensor] = None, parts=None) -> torch.Tensor:
+               scale_host: float, gather: Optional[torch.Tensor] = None, parts=None,
+               error: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Backward of K1 fused with the loss scale; returns dx with x's shape and dtype.
-    parts = (n_parts, stride_in_elements): g_hat is the first of n_parts partial buffers to be summed."""
+    parts = (n_parts, stride_in_elements): g_hat is the first of n_parts partial buffers to be summed.
+    error: the sharded transport's failure flag (device int32): non-zero -> the gradients are NaN."""
     if gather is not None:
         dx = torch.zeros(x.shape, dtype=x.dtype, device=x.device)       # filtered rows get zero gradient
     else:
@@ -139,7 +141,7 @@ def l2norm_bwd(x: torch.Tensor, nrm: Normalized, g_hat: torch.Tensor, *, scale_d
     n_parts, part_stride = parts if parts is not None else (1, 0)
     _lib.call("evk_l2norm_bwd_parts", _ptr(x), _dtype_code(x), nrm.n, nrm.d, x.stride(0), x.stride(1), _ptr(gather),
               _ptr(nrm.norm), _ptr(g_hat), _dtype_code(g_hat), g_hat.stride(0), int(n_parts), int(part_stride), _ptr(scale_dev),
-              float(scale_host), _ptr(dx), _dtype_code(dx), dx.stride(0), 0, _stream())
+              float(scale_host), _ptr(dx), _dtype_code(dx), dx.stride(0), 0, _ptr(error), _stream())
     return dx
 
 
@@ -151,7 +153,7 @@ def posmask_build(rows: DeviceIds, cols: DeviceIds, *, clear_diag: bool, diag_of
     (+ pos_idx [n_rows, POS_SLOTS], the first positives of every row, with want_list)."""
     n_rows, n_cols = len(rows), len(cols)
     dev = rows.key.device
-    ld_words = _round_up(_round_up(n_cols, TILE_N) // 32, 8)             # whole 256-column tiles
+    ld_words = _lib.size("evk_posmask_ld_words", n_cols)                 # whole 256-column tiles
     bits = torch.empty((n_rows, ld_words), dtype=torch.int32, device=dev)
     counts = torch.empty(n_rows, dtype=torch.int32, device=dev)
     pos_idx = torch.empty((n_rows, POS_SLOTS), dtype=torch.int32, device=dev) if want_list else None
@@ -226,16 +228,22 @@ def finalize_avgpos(row_neg, row_pos, counts, *, shift: float, inv_count: float,
 
 
 # --- tcgen05 path --------------------------------------------------------------------------
+def alloc_partials(n_rows: int, n_cols: int, dev, want_pos: bool = True, want_col: bool = True):
+    """K3's per-tile partial statistics (rs_part, rp_part | None, cs_part | None); the library states their row counts."""
+    rows = _lib.size("evk_mpce_rowpart_rows", n_cols)
+    rs_part = torch.empty((rows, n_rows), dtype=torch.float32, device=dev)
+    rp_part = torch.empty((rows, n_rows), dtype=torch.float32, device=dev) if want_pos else None
+    cs_part = torch.empty((_lib.size("evk_mpce_colpart_rows", n_rows), n_cols), dtype=torch.float32,
+                          device=dev) if want_col else None
+    return rs_part, rp_part, cs_part
+
+
 def tc_fwd_partials(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int, diag_offset: int = 0):
     """K3.  Returns the per-tile partials (rs_part, rp_part, cs_part | None) and their counts."""
     dev = q.hi.device
-    n_ct = (k.n + TILE_N - 1) // TILE_N
-    n_rt = (q.n + TILE_M - 1) // TILE_M
     want_col = not (flags & FLAG_NO_COLSUM)
     want_pos = not (flags & FLAG_NO_POS)
-    rs_part = torch.empty((n_ct * _row_parts(), q.n), dtype=torch.float32, device=dev)
-    rp_part = torch.empty((n_ct * _row_parts(), q.n), dtype=torch.float32, device=dev) if want_pos else None
-    cs_part = torch.empty((n_rt, k.n), dtype=torch.float32, device=dev) if want_col else None
+    rs_part, rp_part, cs_part = alloc_partials(q.n, k.n, dev, want_pos, want_col)
     _lib.call("evk_mpce_fwd", _ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, q.n, k.n, q.d,
               _ptr(bits) if want_pos else None, bits.stride(0) if want_pos else 0, float(inv_tau), flags, diag_offset,
               _ptr(rs_part), _ptr(rp_part), q.n, _ptr(cs_part), k.n, _stream())
@@ -245,14 +253,10 @@ def tc_fwd_partials(q: Normalized, k: Normalized, bits, inv_tau: float, flags: i
 def tc_fwd_store(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int, diag_offset: int = 0):
     """K3 that also writes the bf16 E strip [q.n, ld_e].  Returns (rs_part, rp_part, cs_part | None, e, ld_e)."""
     dev = q.hi.device
-    n_ct = (k.n + TILE_N - 1) // TILE_N
-    n_rt = (q.n + TILE_M - 1) // TILE_M
     want_col = not (flags & FLAG_NO_COLSUM)
     want_pos = not (flags & FLAG_NO_POS)
-    rs_part = torch.empty((n_ct * _row_parts(), q.n), dtype=torch.float32, device=dev)
-    rp_part = torch.empty((n_ct * _row_parts(), q.n), dtype=torch.float32, device=dev) if want_pos else None
-    cs_part = torch.empty((n_rt, k.n), dtype=torch.float32, device=dev) if want_col else None
-    ld_e = _round_up(k.n, 64)
+    rs_part, rp_part, cs_part = alloc_partials(q.n, k.n, dev, want_pos, want_col)
+    ld_e = _lib.size("evk_mpce_strip_ld", k.n)
     e = torch.empty((q.n, ld_e), dtype=torch.bfloat16, device=dev)
     _lib.call("evk_mpce_fwd_store", _ptr(q.hi), q.ld, _ptr(k.hi), k.ld, q.n, k.n, q.d,
               _ptr(bits) if want_pos else None, bits.stride(0) if want_pos else 0, float(inv_tau), flags, diag_offset,
@@ -308,8 +312,7 @@ def stats_fused(rs_part, rp_part, cs_part, counts, *, shift: float, pos_weight: 
     a_row = torch.empty(n_rows, dtype=torch.float32, device=dev)
     b_col = torch.empty(n_cols, dtype=torch.float32, device=dev) if cs_part is not None else None
     loss = torch.empty(1, dtype=torch.float32, device=dev)
-    ws_bytes = 16 + 24 * ((max(n_rows, n_cols) + 31) // 32)
-    ws = torch.empty(_round_up(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    ws = torch.empty(_lib.size("evk_stats_workspace_bytes", n_rows, n_cols), dtype=torch.uint8, device=dev)
     _lib.call("evk_mpce_stats_fused", _ptr(rs_part), int(rs_part.shape[0]), max(int(rs_part.stride(0)), n_rows),
               _ptr(rp_part), int(rp_part.shape[0]), max(int(rp_part.stride(0)), n_rows),
               _ptr(counts), n_rows, _ptr(cs_part), 0 if cs_part is None else int(cs_part.shape[0]),
@@ -322,18 +325,14 @@ def stats_fused(rs_part, rp_part, cs_part, counts, *, shift: float, pos_weight: 
 def tc_fwd(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int, diag_offset: int = 0):
     """K3 + partial reduction (sharded path).  Returns (row_sum, row_pos, col_sum | None)."""
     dev = q.hi.device
-    n_ct = (k.n + TILE_N - 1) // TILE_N
-    n_rt = (q.n + TILE_M - 1) // TILE_M
     want_col = not (flags & FLAG_NO_COLSUM)
-    rs_part = torch.empty((n_ct * _row_parts(), q.n), dtype=torch.float32, device=dev)
-    rp_part = torch.empty((n_ct * _row_parts(), q.n), dtype=torch.float32, device=dev)
-    cs_part = torch.empty((n_rt, k.n), dtype=torch.float32, device=dev) if want_col else None
+    rs_part, rp_part, cs_part = alloc_partials(q.n, k.n, dev, True, want_col)
     _lib.call("evk_mpce_fwd", _ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, q.n, k.n, q.d,
               _ptr(bits), bits.stride(0), float(inv_tau), flags, diag_offset,
               _ptr(rs_part), _ptr(rp_part), q.n, _ptr(cs_part), k.n, _stream())
-    row_sum = reduce_partials(rs_part, n_ct * _row_parts(), q.n)
-    row_pos = reduce_partials(rp_part, n_ct * _row_parts(), q.n)
-    col_sum = reduce_partials(cs_part, n_rt, k.n) if want_col else None
+    row_sum = reduce_partials(rs_part, int(rs_part.shape[0]), q.n)
+    row_pos = reduce_partials(rp_part, int(rp_part.shape[0]), q.n)
+    col_sum = reduce_partials(cs_part, int(cs_part.shape[0]), k.n) if want_col else None
     return row_sum, row_pos, col_sum
 
 
@@ -341,7 +340,7 @@ def tc_bwd_w(q: Normalized, k: Normalized, bits, counts, a_row, b_col, inv_tau: 
              diag_offset: int = 0):
     """K4a.  Returns the bf16 W strip (hi, lo|None, ld_w)."""
     dev = q.hi.device
-    ld_w = _round_up(k.n, 64)
+    ld_w = _lib.size("evk_mpce_strip_ld", k.n)
     w_hi = torch.empty((q.n, ld_w), dtype=torch.bfloat16, device=dev)
     w_lo = torch.empty((q.n, ld_w), dtype=torch.bfloat16, device=dev) if (flags & FLAG_SPLIT_BF16) else None
     _lib.call("evk_mpce_bwd_w", _ptr(q.hi), _ptr(q.lo), q.ld, _ptr(k.hi), _ptr(k.lo), k.ld, q.n, k.n, q.d,

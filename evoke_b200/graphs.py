@@ -81,6 +81,12 @@ class GraphedGlobalAlignment:
     def step(self) -> torch.Tensor:
         if self.graph is None:
             self.capture()
+        if self.sharded:
+            # a replayed graph never re-enters the Python forward: poll the transport's failure mirror here
+            from . import peer
+            for c in peer._CONTEXTS.values():
+                if isinstance(c, peer.PeerContext):
+                    c.raise_if_failed()
         self.graph.replay()
         return self.loss
 

@@ -27,10 +27,20 @@ from . import ids as idmod
 DEFAULT_PRECISION = "fp32"      # the reference computes in fp32; "bf16" is the throughput mode
 
 
+MAX_INV_TAU = 40.0        # EVK_MAX_INV_TAU of include/evoke_b200.h
+
+
 def _inv_tau(temp: float) -> float:
+    """1/temperature, inside the domain of the fixed-shift softmax: the kernels use E = exp(S - 1/tau) (|S| <= 1/tau
+    for unit rows), and exp(-2/tau) must stay a normal fp32 number or a row of weakly aligned pairs could sum to
+    zero.  The reference (F.cross_entropy's running max) accepts any temperature; this library raises below
+    tau = 0.025 instead of returning inf/NaN.  EVOKE trains with 0.5 (config/finetune_config.yaml:73-74)."""
     temp = float(temp)
     if not temp > 0.0:
         raise ValueError(f"temperature must be positive, got {temp}")
+    if 1.0 / temp > MAX_INV_TAU:
+        raise ValueError(f"evoke_b200: temperature {temp} is below the supported minimum {1.0 / MAX_INV_TAU} "
+                         "(fixed-shift softmax: exp(-2/tau) must stay normal in fp32)")
     return 1.0 / temp
 
 

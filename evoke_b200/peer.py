@@ -19,6 +19,7 @@ Only torch.distributed's object all-gather is used, once per context, for the ha
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -110,7 +111,11 @@ class PeerContext:
         self.step = torch.zeros(1, dtype=torch.int32, device=self.device)          # advanced by the prologue kernel
         self.counters = torch.zeros(16, dtype=torch.int32, device=self.device)     # push kernel's per-destination tickets
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # failure flag of the transport (a peer missed a barrier): sticky device int read by the step's closing kernels
+        # (NaN loss / gradients), mirrored by the barrier kernel into pinned HOST memory so that the next step's entry
+        # can raise without synchronising the device
         self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.error_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.ptrs = {name: (ctypes.c_uint64 * self.world)(*[b + o for b in self.bases]) for name, o in self.off.items()}
         # where THIS rank's partial for owner t goes: part `rank` of t's dk_parts
         mine = self.rank * n * self.width * esize
@@ -129,12 +134,22 @@ class PeerContext:
     def barrier(self) -> None:
         """Enqueue the cross-GPU barrier on the current stream."""
         _lib.call("evk_peer_barrier", self.ptrs["flags"], self.world, self.rank, self.epoch.data_ptr(),
-                  self.error.data_ptr(), self.timeout_ms, torch.cuda.current_stream().cuda_stream)
+                  self.error.data_ptr(), self.error_host.data_ptr(), self.timeout_ms,
+                  torch.cuda.current_stream().cuda_stream)
+
+    FAILED = ("evoke_b200: a peer did not reach a cross-GPU barrier within {:.1f} s; the loss and gradients of that step "
+              "are NaN and this transport context is dead (the peers' buffers may be out of step): tear the process "
+              "group down")
+
+    def raise_if_failed(self) -> None:
+        """Host-side check WITHOUT a device sync (reads the pinned mirror): called at the entry of every step."""
+        if int(self.error_host[0]) != 0:
+            raise RuntimeError(self.FAILED.format(self.timeout_ms / 1e3))
 
     def check(self) -> None:
         """Raise if a barrier timed out (synchronises the device)."""
-        if int(self.error.item()) != 0:
-            raise RuntimeError("evoke_b200: a peer did not reach a cross-GPU barrier in time; the sharded result is invalid")
+        if int(self.error.item()) != 0 or int(self.error_host[0]) != 0:
+            raise RuntimeError(self.FAILED.format(self.timeout_ms / 1e3))
 
     def close(self) -> None:
         lib = _lib.load()
@@ -153,13 +168,15 @@ _CONTEXTS: dict = {}
 
 
 def get_context(group, n_local: int, d: int, device: torch.device, two_keys: bool = False,
-                exchange: str = "bf16") -> Optional[PeerContext]:
+                exchange: str = "bf16", timeout_ms: Optional[int] = None) -> Optional[PeerContext]:
     """Cached context for (group, shard shape); None if peer mapping is not possible here (the caller
     then uses the NCCL transport).  Collective: every rank must call it with the same arguments."""
     key = (id(group), n_local, d, torch.device(device).index, two_keys, exchange)
     if key in _CONTEXTS:
         return _CONTEXTS[key]
-    ctx: Optional[PeerContext] = PeerContext(group, n_local, d, device, two_keys, exchange=exchange)
+    if timeout_ms is None:
+        timeout_ms = int(os.environ.get("EVOKE_B200_PEER_TIMEOUT_MS", "10000"))
+    ctx: Optional[PeerContext] = PeerContext(group, n_local, d, device, two_keys, timeout_ms=timeout_ms, exchange=exchange)
     if ctx.failure is not None:                                  # IPC refused (container policy, no P2P, ...)
         _CONTEXTS["last_error"] = ctx.failure
     # all or nothing; also the barrier after which every rank has mapped every buffer

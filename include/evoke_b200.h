@@ -14,8 +14,9 @@
  *  - Plain pointers and sizes only.  Every pointer is a DEVICE pointer unless it says host.
  *  - The library never allocates, frees or retains device memory, never synchronises the
  *    device, and enqueues on the caller's `stream` (a cudaStream_t passed as void*): calls
- *    are CUDA-graph capturable and re-entrant.  Workspaces are sized by the *_bytes helpers
- *    and owned by the caller.
+ *    are CUDA-graph capturable and re-entrant.  Workspaces are sized by the evk_*_bytes helpers
+ *    below and owned by the caller.  (One exception, stated there: evk_peer_alloc, because
+ *    CUDA-IPC handles name whole cudaMalloc allocations.)
  *  - Return value: EVK_OK or a negative code; evk_last_error() returns a thread-local,
  *    human-readable message for the last failing call on this thread.  Launch errors are
  *    picked up with cudaGetLastError(), without a device sync.
@@ -48,11 +49,15 @@ extern "C" {
 #define EVK_FLAG_EXCLUDE_DIAG  1  /* column (row + diag_offset) is removed from the softmax:
                                      multi_pos_contra_images_v0401 :438 (fill_diagonal_(-1e9)) */
 #define EVK_FLAG_NO_COLSUM     2  /* skip column sums (symmetric problem: MPC) */
+#define EVK_FLAG_SPLIT_BF16    4  /* operands are (hi, lo) bf16 pairs: S = hi.hi + hi.lo + lo.hi,
+                                     ~2^-17 relative, the fp32-parity mode */
 #define EVK_FLAG_NO_POS        8  /* K3 leaves the positive-logit sums to evk_mpce_pos (bits may be NULL) */
 #define EVK_FLAG_AVGPOS       16  /* 'averaged positive logit' rule of PretrainNewMulPos (:748-815, :670-708): the
                                      positives of a row enter the softmax as ONE logit, their mean (small path) */
-#define EVK_FLAG_SPLIT_BF16    4  /* operands are (hi, lo) bf16 pairs: S = hi.hi + hi.lo + lo.hi,
-                                     ~2^-17 relative, the fp32-parity mode */
+#define EVK_FLAG_PUBLIC_MASK  31  /* every entry point ignores bits outside the EVK_FLAG_* set */
+/* Every loss entry point requires 0 < inv_tau <= EVK_MAX_INV_TAU (tau >= 0.025): the softmax uses the fixed
+ * shift 1/tau (unit rows: |S| <= 1/tau) and exp(-2/tau) must stay a normal fp32 number. */
+#define EVK_MAX_INV_TAU     40.0f
 
 typedef void* evk_stream_t;
 
@@ -66,6 +71,21 @@ EVK_API int         evk_version(void);                 /* ABI version, bumped on
 EVK_API const char* evk_last_error(void);
 /* host query; sm_count / cc may be NULL */
 EVK_API int         evk_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- sizes of caller-owned buffers (host functions; <= 0 means bad arguments) ------------------------------
+ * workspace of evk_mpce_stats_fused / evk_mpce_shard_stats_push for n_rows rows and n_cols columns (0 if no
+ * column statistics) */
+EVK_API int64_t evk_stats_workspace_bytes(int64_t n_rows, int64_t n_cols);
+/* workspace of evk_mpce_shard_finish */
+EVK_API int64_t evk_shard_finish_workspace_bytes(int64_t n_cols);
+/* row pitch (uint32 words) of the K2 mask the tcgen05 entry points expect: whole 256-column tiles, 16-byte rows */
+EVK_API int64_t evk_posmask_ld_words(int64_t n_cols);
+/* rows of the row-statistic partial buffers (rs_part / rp_part) K3 writes for n_cols key columns */
+EVK_API int64_t evk_mpce_rowpart_rows(int64_t n_cols);
+/* rows of the column-statistic partial buffer (cs_part) K3 writes for n_rows query rows */
+EVK_API int64_t evk_mpce_colpart_rows(int64_t n_rows);
+/* row pitch (bf16 elements) of the E / W strip for n_cols key columns */
+EVK_API int64_t evk_mpce_strip_ld(int64_t n_cols);
 
 /* ---- K1: fused L2-normalise (+ bf16 hi/lo split, + row gather) --------------------------
  * Replaces F.normalize(x, dim=-1, p=2) at :495-496 and :436: xhat = x / max(||x||_2, 1e-12).
@@ -95,12 +115,15 @@ EVK_API int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t d,
 
 /* Same, with the upstream gradient given as n_parts partial buffers that are summed on the fly (in index
  * order): g_total[r, c] = sum_p g[p * part_stride + r * ld_g + c] (g_dtype: EVK_DTYPE_F32 or _BF16).  Closes the fused reduce-scatter of
- * evk_mpce_bwd_gemm_scatter(store = 1): part p is what rank p's contraction stored for this rank's rows. */
+ * evk_mpce_bwd_gemm_scatter(store = 1): part p is what rank p's contraction stored for this rank's rows.
+ * error (may be NULL): device int; when it is non-zero (a cross-GPU barrier of this step timed out,
+ * evk_peer_barrier) every gradient written is NaN instead of a silently wrong value. */
 EVK_API int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, int64_t d,
                          int64_t stride_row, int64_t stride_col, const int32_t* gather,
                          const float* norm, const void* g, int g_dtype, int64_t ld_g, int n_parts, int64_t part_stride,
                          const float* scale_dev, float scale_host,
-                         void* dx, int dx_dtype, int64_t ld_dx, int accumulate, evk_stream_t stream);
+                         void* dx, int dx_dtype, int64_t ld_dx, int accumulate, const int* error,
+                         evk_stream_t stream);
 
 /* ---- K2: positive-mask builder -------------------------------------------------------------
  * Replaces (ids.reshape(-1,1) == ids.reshape(1,-1)) + .float().to(device) + rowsum at
@@ -349,17 +372,22 @@ EVK_API int evk_peer_bcast(const void* src, int64_t bytes, int n_dst, const uint
  * row_offset.. of EVERY rank's key buffer (khat_ptrs: host table, n_dst entries), K1 of its query rows (image)
  * into the local q_hi, the id shard(s) pushed to offset row_offset of every rank's id buffer(s), and - if
  * zero_buf != NULL - the zero fill of an fp32 [n_rows, ld_zero] accumulator (the split-K output of the local
- * gradient contraction).  Contiguous fp32 inputs, d % 8 == 0, d <= 2048.  F.normalize of :495-496 for both
+ * gradient contraction).  text / image: fp32, bf16 or fp16 with arbitrary element strides (the reference's
+ * [:,0,:] head views, :484/:399; contiguous 16-byte aligned fp32 rows take 128-bit loads); d % 8 == 0,
+ * d <= 2048.  F.normalize of :495-496 for both
  * sides plus what a sharded run must exchange before the similarity sweep.  n_dst = 1 with only this rank's
  * own buffer keeps the key rows local (evk_peer_push_shard then moves them next to the sweep); the ids always go
  * to all n_ids_dst ranks.  step_counter (may be NULL): device int advanced by one per launch - the epoch of the
- * landed flags. */
-EVK_API int evk_shard_prologue(const float* text, int64_t text_stride, const float* image, int64_t image_stride,
+ * landed flags.  error (may be NULL): the transport's sticky failure flag (evk_peer_barrier); once set the
+ * kernel writes nothing, in particular nothing into peer memory. */
+EVK_API int evk_shard_prologue(const void* text, int text_dtype, int64_t text_stride, int64_t text_col_stride,
+                       const void* image, int image_dtype, int64_t image_stride, int64_t image_col_stride,
                        int64_t n_rows, int64_t d, int n_dst, const uint64_t* khat_ptrs, int64_t ld_bf16,
                        int64_t row_offset, float* k_norm, void* q_hi, float* q_norm,
                        const int32_t* ids, const int32_t* ids2, int n_ids_dst,
                        const uint64_t* ids_ptrs, const uint64_t* ids2_ptrs,
-                       float* zero_buf, int64_t ld_zero, int* step_counter, evk_stream_t stream);
+                       float* zero_buf, int64_t ld_zero, int* step_counter, const int* error,
+                       evk_stream_t stream);
 
 /* The all-gather of the key rows, overlapped with the similarity sweep.  Copies this rank's shard (`bytes` at
  * `src`, normally its own rows inside its own buffer) to byte offset dst_offset_bytes of every OTHER rank's
@@ -389,8 +417,8 @@ EVK_API int evk_mpce_shard_stats_push(const float* rs_part, int64_t row_parts, i
                               const uint64_t* slot_ptrs, int n_dst, int64_t slot_offset,
                               void* workspace, int64_t workspace_bytes, evk_stream_t stream);
 
-/* Symmetric buffers for that transport.  evk_peer_alloc is the one place the library allocates device
- * memory (cudaMalloc, zero-filled): CUDA-IPC handles name whole allocations, so the exchanged buffers
+/* Symmetric buffers for that transport.  evk_peer_alloc is the ONE place the library allocates device
+ * memory (cudaMalloc + cudaMemset, i.e. it also synchronises; called once per transport context, never per step): CUDA-IPC handles name whole allocations, so the exchanged buffers
  * cannot come out of a caching allocator.  The caller frees them with evk_peer_free.  evk_peer_export
  * writes the 64-byte IPC handle of such a buffer to HOST memory; evk_peer_open maps a peer's handle
  * (received through any host channel, e.g. torch.distributed) into this process; evk_peer_close unmaps. */
@@ -405,19 +433,23 @@ EVK_API int evk_peer_close(void* ptr);
  * start, peer-mapped).  epoch: this rank's device-resident uint32 counter (zeroed at start; advanced by the
  * kernel).  Everything this rank wrote to peer memory in earlier kernels of the stream is visible to the peers
  * once they pass.  If a peer does not arrive within timeout_ms (<= 0: 2000) *error (device int) is set to 1
- * and the kernel returns: a dead peer must not hang the GPU. */
+ * and the kernel returns: a dead peer must not hang the GPU.  The flag is sticky and is what makes the failure
+ * loud without a host sync: evk_mpce_shard_finish then writes a NaN loss, evk_l2norm_bwd_parts NaN gradients,
+ * evk_shard_prologue stops writing into peer memory, and error_host (may be NULL; an int in pinned, device-
+ * accessible HOST memory) is set as well, so the host can poll it before its next step and raise. */
 EVK_API int evk_peer_barrier(const uint64_t* flag_ptrs, int n_ranks, int rank, uint32_t* epoch, int* error,
-                     int64_t timeout_ms, evk_stream_t stream);
+                     int* error_host, int64_t timeout_ms, evk_stream_t stream);
 
 /* Closes the sharded forward after the statistics exchange.  slots: [n_slots, ld_slot] fp32, slot r = rank r's
  * partial column exp-sums over its own rows (n_cols floats) followed by its row-side loss term
  * inv_count * sum_{i in rows of r} (shift + ln R_i - 2 pos_i / c_i) at index n_cols.
  *   b_col[j] = 1 / sum_r slots[r][j];   loss_out[0] = sum_r slots[r][n_cols] + inv_count * sum_j (shift + ln C_j)
  * (:501-503 on the concatenated batch).  Fixed summation order: every rank computes identical bits.
- * workspace: >= 16 + 8*ceil(n_cols/256) bytes, 16-byte aligned, contents irrelevant. */
+ * workspace: evk_shard_finish_workspace_bytes(n_cols) bytes, 16-byte aligned, contents irrelevant.
+ * error (may be NULL): when *error != 0 (a barrier timed out) loss and b_col are NaN. */
 EVK_API int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
                           double inv_count, float* b_col, float* loss_out,
-                          void* workspace, int64_t workspace_bytes, evk_stream_t stream);
+                          void* workspace, int64_t workspace_bytes, const int* error, evk_stream_t stream);
 
 /* K4b with the reduce-scatter fused into its epilogue: the partial dKhat of this rank's row block,
  *   out_owner(j)[j % rows_per_owner, :] += alpha * sum_i W[i, j] x[i, :],   owner(j) = j / rows_per_owner,
