@@ -200,12 +200,12 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // A peer that never arrives does not hang the GPU: after timeout_ns the kernel raises *error and returns.
 struct PeerFlags {
   uint32_t* flags[kMaxPeers];      // flags[t] = base of rank t's flag area (kMaxPeers uint32 slots)
+  int* err[kMaxPeers];             // err[t] = rank t's failure flag (symmetric memory; err[rank] is this rank's own)
   int n, rank;
 };
 
 __global__ void __launch_bounds__(32)
-peer_barrier_kernel(PeerFlags pf, uint32_t* __restrict__ epoch, int* __restrict__ error, int* __restrict__ error_host,
-                    uint64_t timeout_ns) {
+peer_barrier_kernel(PeerFlags pf, uint32_t* __restrict__ epoch, int* __restrict__ error_host, uint64_t timeout_ns) {
   const int t = threadIdx.x;
   const uint32_t e = *epoch + 1u;
   __syncwarp();
@@ -219,9 +219,12 @@ peer_barrier_kernel(PeerFlags pf, uint32_t* __restrict__ epoch, int* __restrict_
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
       if ((int32_t)(v - e) >= 0) break;
       if (global_timer_ns() - t0 > timeout_ns) {
-        // sticky: the consumers of this step (evk_mpce_shard_finish, evk_l2norm_bwd_parts) turn it into NaN loss /
-        // gradients, the prologue stops writing into peer memory, and the host sees the mirror without a sync
-        atomicExch(error, 1);
+        // Sticky, and raised on EVERY rank (the late peer passes its own barriers at once - this rank is ahead of it -
+        // and would otherwise consume this rank's out-of-step buffers without noticing).  The consumers of the step
+        // (evk_mpce_shard_finish, evk_l2norm_bwd_parts) turn the flag into NaN loss / gradients, the prologue stops
+        // writing into peer memory, and the host sees the mirror without a sync.
+        for (int q = 0; q < pf.n; ++q)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.err[q]), "r"(1) : "memory");
         if (error_host) *reinterpret_cast<volatile int*>(error_host) = 1;
         break;
       }
@@ -241,12 +244,14 @@ constexpr int kFinishThreads = 256;
 __global__ void __launch_bounds__(kFinishThreads)
 shard_finish_kernel(const float* __restrict__ slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
                     double inv_count, float* __restrict__ b_col, float* __restrict__ loss_out,
-                    double* __restrict__ cta_partial, unsigned int* __restrict__ ticket, const int* __restrict__ error) {
+                    double* __restrict__ cta_partial, unsigned int* __restrict__ ticket, const int* __restrict__ error,
+                    int* __restrict__ error_host) {
   __shared__ double s_part[kFinishThreads / 32];
   __shared__ bool s_last;
   const int64_t j = (int64_t)blockIdx.x * kFinishThreads + threadIdx.x;
   // a barrier of this step timed out: some slot / key rows may be stale -> the result must not look valid
   const bool poisoned = error && *reinterpret_cast<const volatile int*>(error) != 0;
+  if (poisoned && error_host && blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile int*>(error_host) = 1;
   double acc = 0.0;
   if (j < n_cols) {
     float c = 0.f;
@@ -436,9 +441,9 @@ extern "C" int evk_peer_close(void* ptr) {
   return EVK_OK;
 }
 
-extern "C" int evk_peer_barrier(const uint64_t* flag_ptrs, int n_ranks, int rank, uint32_t* epoch, int* error,
-                                int* error_host, int64_t timeout_ms, evk_stream_t stream) {
-  EVK_REQUIRE(flag_ptrs && epoch && error && n_ranks >= 1 && n_ranks <= kMaxPeers && rank >= 0 && rank < n_ranks,
+extern "C" int evk_peer_barrier(const uint64_t* flag_ptrs, const uint64_t* error_ptrs, int n_ranks, int rank,
+                                uint32_t* epoch, int* error_host, int64_t timeout_ms, evk_stream_t stream) {
+  EVK_REQUIRE(flag_ptrs && error_ptrs && epoch && n_ranks >= 1 && n_ranks <= kMaxPeers && rank >= 0 && rank < n_ranks,
               "evk_peer_barrier: bad arguments (1..%d ranks)", kMaxPeers);
   PeerFlags pf;
   memset(&pf, 0, sizeof(pf));
@@ -446,17 +451,18 @@ extern "C" int evk_peer_barrier(const uint64_t* flag_ptrs, int n_ranks, int rank
   pf.rank = rank;
   for (int t = 0; t < n_ranks; ++t) {
     pf.flags[t] = reinterpret_cast<uint32_t*>(flag_ptrs[t]);
-    EVK_REQUIRE(pf.flags[t], "evk_peer_barrier: null flag area");
+    pf.err[t] = reinterpret_cast<int*>(error_ptrs[t]);
+    EVK_REQUIRE(pf.flags[t] && pf.err[t], "evk_peer_barrier: null flag area");
   }
   const uint64_t timeout_ns = (uint64_t)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
-  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, epoch, error, error_host, timeout_ns);
+  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, epoch, error_host, timeout_ns);
   EVK_CHECK_LAUNCH("peer_barrier");
   return EVK_OK;
 }
 
 extern "C" int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
                                      double inv_count, float* b_col, float* loss_out, void* workspace,
-                                     int64_t workspace_bytes, const int* error, evk_stream_t stream) {
+                                     int64_t workspace_bytes, const int* error, int* error_host, evk_stream_t stream) {
   EVK_REQUIRE(slots && b_col && loss_out && n_slots >= 1 && n_cols > 0 && ld_slot > n_cols,
               "evk_mpce_shard_finish: bad arguments (ld_slot must exceed n_cols: the loss term follows the column sums)");
   const int64_t blocks = (n_cols + kFinishThreads - 1) / kFinishThreads;
@@ -467,7 +473,7 @@ extern "C" int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld
   double* partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + 16);
   EVK_CUDA(cudaMemsetAsync(ticket, 0, 16, s));
   shard_finish_kernel<<<(unsigned)blocks, kFinishThreads, 0, s>>>(slots, n_slots, ld_slot, n_cols, shift, inv_count, b_col,
-                                                                 loss_out, partial, ticket, error);
+                                                                 loss_out, partial, ticket, error, error_host);
   EVK_CHECK_LAUNCH("shard_finish");
   return EVK_OK;
 }

@@ -147,6 +147,156 @@ class _ShardedG(torch.autograd.Function):
         return None, None, None, None, None, None, d_image, d_text
 
 
+def peer_forward(ops, pc, inv_tau: float, row_ids: DeviceIds, image: torch.Tensor, text: torch.Tensor, need_grad: bool = True):
+    """Forward kernel sequence of the peer-memory sharded G loss.  Returns (loss [1] fp32, state)."""
+    from . import _lib
+    world, rank = pc.world, pc.rank
+    n, n_total, d = pc.n_local, pc.n_total, pc.d
+    lo_ = rank * n
+    dev = image.device
+    pc.raise_if_failed()                     # a barrier of an earlier step timed out (pinned mirror: no device sync)
+    overlap = ops.OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
+    main = torch.cuda.current_stream()
+    side = ops._side_stream(dev)
+    stream = main.cuda_stream
+    two = row_ids.key2 is not None
+    # exchange 1: one launch normalises both sides (keys into this rank's own buffer rows), pushes the id shard
+    # to every rank and zeroes dQhat; after the barrier the key rows travel to the peers on the side stream
+    # WHILE K3 runs - K3 visits its own columns first and waits per source for the others (landed flags)
+    k_norm = torch.empty(n, dtype=torch.float32, device=dev)
+    q_norm = torch.empty(n, dtype=torch.float32, device=dev)
+    q_hi = torch.empty((n, pc.ld), dtype=torch.bfloat16, device=dev)
+    wq = _round_up(d, 4)
+    dq = torch.empty((n, wq), dtype=torch.float32, device=dev) if need_grad else None
+    overlap_gather = OVERLAP_GATHER and world > 1
+    # inputs as the caller holds them (strided [:,0,:] head views, bf16/fp16): the prologue's loader honours them
+    _lib.call("evk_shard_prologue", text.data_ptr(), ops._dtype_code(text), text.stride(0), text.stride(1),
+              image.data_ptr(), ops._dtype_code(image), image.stride(0), image.stride(1), n, d,
+              1 if overlap_gather else world, pc.table("khat_local") if overlap_gather else pc.table("khat"), pc.ld, lo_,
+              k_norm.data_ptr(), q_hi.data_ptr(), q_norm.data_ptr(),
+              row_ids.key.data_ptr(), row_ids.key2.data_ptr() if two else None, world, pc.table("ids"),
+              pc.table("ids2") if two else None, None if dq is None else dq.data_ptr(), wq, pc.step.data_ptr(),
+              pc.error.data_ptr(), stream)
+    pc.barrier()
+    qn = ops.Normalized(n=n, d=d, norm=q_norm, hi=q_hi, lo=None, ld=pc.ld)
+    kn_all = ops.Normalized(n=n_total, d=d, norm=None, hi=pc.khat, lo=None, ld=pc.ld)
+    kn_local = ops.Normalized(n=n, d=d, norm=k_norm, hi=pc.khat[lo_:lo_ + n], lo=None, ld=pc.ld)
+    ids_all = DeviceIds(pc.ids, pc.ids2 if two else None)
+    if overlap_gather:
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _lib.call("evk_peer_push_shard", pc.khat[lo_:].data_ptr(), n * pc.ld * 2, world, rank, pc.table("khat"),
+                      lo_ * pc.ld * 2, pc.table("landed"), pc.step.data_ptr(), pc.counters.data_ptr(), side.cuda_stream)
+
+    def sweep(bits, store):
+        """K3 over this rank's row block (with the per-source waits when the gather is still in flight)."""
+        n_ct = (n_total + ops.TILE_N - 1) // ops.TILE_N
+        n_rt = (n + ops.TILE_M - 1) // ops.TILE_M
+        if not overlap_gather:
+            return ops.tc_fwd_store(qn, kn_all, bits, inv_tau, 0, lo_) if store else \
+                ops.tc_fwd_partials(qn, kn_all, bits, inv_tau, 0, lo_) + (None, 0)
+        rs = torch.empty((n_ct * ops._row_parts(), n), dtype=torch.float32, device=dev)
+        rp = torch.empty((n_ct * ops._row_parts(), n), dtype=torch.float32, device=dev)
+        cs = torch.empty((n_rt, n_total), dtype=torch.float32, device=dev)
+        ld_e = _round_up(n_total, 64)
+        e = torch.empty((n, ld_e), dtype=torch.bfloat16, device=dev) if store else None
+        _lib.call("evk_mpce_fwd_store_gathered", q_hi.data_ptr(), pc.ld, pc.khat.data_ptr(), pc.ld, n, n_total, d,
+                  bits.data_ptr(), bits.stride(0), float(inv_tau), 0, lo_, rs.data_ptr(), rp.data_ptr(), n,
+                  cs.data_ptr(), n_total, None if e is None else e.data_ptr(), ld_e, pc.landed.data_ptr(),
+                  pc.step.data_ptr(), pc.error.data_ptr(), n, lo_, stream)
+        return rs, rp, cs, e, (ld_e if store else 0)
+
+    pos = None
+    if need_grad:
+        bits, counts, pos_idx = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_, want_list=True)
+        if overlap or overlap_gather:      # exact positive logits (O(n D)) next to K3, once every shard has landed
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                if overlap_gather:
+                    _lib.call("evk_peer_wait_landed", pc.landed.data_ptr(), world, pc.step.data_ptr(),
+                              pc.error.data_ptr(), pc.timeout_ms, side.cuda_stream)
+                pos_dot = ops.pos_logits(qn, kn_all, pos_idx, counts)
+            ops._shared_with(side, q_hi, pos_idx, counts)
+        else:
+            pos_dot = ops.pos_logits(qn, kn_all, pos_idx, counts)
+        pos = (pos_idx, pos_dot)
+        rs_part, rp_part, cs_part, e, ld_e = sweep(bits, True)
+    else:
+        bits, counts = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_)
+        rs_part, rp_part, cs_part, e, ld_e = sweep(bits, False)
+    # exchange 2 (one launch): partials -> a_row, and this rank's slot (partial column sums of its rows +
+    # its row-side loss term) into every rank's slot buffer
+    a_row = torch.empty(n, dtype=torch.float32, device=dev)
+    ws = torch.empty(_lib.size("evk_stats_workspace_bytes", n, n_total), dtype=torch.uint8, device=dev)
+    _lib.call("evk_mpce_shard_stats_push", rs_part.data_ptr(), int(rs_part.shape[0]), n, rp_part.data_ptr(),
+              int(rp_part.shape[0]), n, counts.data_ptr(), n, cs_part.data_ptr(), int(cs_part.shape[0]), n_total,
+              n_total, float(inv_tau), 2.0, 0.5 / n_total, a_row.data_ptr(), pc.table("slots"), world,
+              rank * pc.ld_slot, ws.data_ptr(), ws.numel(), stream)
+    pc.barrier()
+    b_col = torch.empty(n_total, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    ws2 = torch.empty(_lib.size("evk_shard_finish_workspace_bytes", n_total), dtype=torch.uint8, device=dev)
+    _lib.call("evk_mpce_shard_finish", pc.slots.data_ptr(), world, pc.ld_slot, n_total, float(inv_tau), 0.5 / n_total,
+              b_col.data_ptr(), loss.data_ptr(), ws2.data_ptr(), ws2.numel(), pc.error.data_ptr(),
+              pc.error_host.data_ptr(), stream)
+    if overlap_gather or (need_grad and overlap):
+        main.wait_stream(side)              # the push (and the positives) are part of this step
+        if need_grad:
+            ops._shared_with(main, pos_dot)
+    st = ops._State()
+    st.ops, st.pc, st.inv_tau = ops, pc, inv_tau
+    st.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, e, ld_e, dq)
+    st.pos = pos
+    st.image, st.text = image, text
+    return loss, st
+
+
+
+def peer_backward(st, g: torch.Tensor):
+    """Backward kernel sequence; g = upstream gradient, fp32 [1] on the device.  Returns (d_image, d_text)."""
+    from . import _lib
+    ops, pc, inv_tau = st.ops, st.pc, st.inv_tau
+    qn, kn_local, kn_all, bits, counts, a_row, b_col, e, ld_e, dq = st.sv
+    if e is None:
+        raise RuntimeError("evoke_b200: backward called twice on the sharded loss (the E strip was consumed)")
+    image, text = st.image, st.text
+    n, n_total = pc.n_local, pc.n_total
+    scale = 0.5 * inv_tau / n_total
+    overlap = ops.OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
+    main = torch.cuda.current_stream()
+    ops.tc_w_from_e(e, ld_e, n_total, bits, counts, a_row, b_col, qn, kn_all, inv_tau, pos=st.pos)
+    # exchange 3, fused: the tiles of this rank's partial dKhat are stored straight into their owners'
+    # per-source buffers (posted NVLink stores from the GEMM epilogue; no split-K, no zero fill)
+    _lib.call("evk_mpce_bwd_gemm_scatter", e.data_ptr(), None, ld_e, n, n_total, qn.hi.data_ptr(), None, qn.ld, qn.d,
+              1.0, 0, pc.table("dk_mine"), pc.world, n, pc.width, 2 if pc.exchange == "bf16" else 1, main.cuda_stream)
+
+    def image_side():
+        ops.tc_bwd_gemm(e, None, ld_e, n, n_total, False, kn_all, 0, out=dq)      # dq was zeroed by the prologue
+        return ops.l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, error=pc.error)
+
+    if overlap:
+        # the local contraction fills the SMs as the scattering one drains (it may be NVLink-bound)
+        side = ops._side_stream(image.device)
+        w_ready = main.record_event()
+        with torch.cuda.stream(side):
+            side.wait_event(w_ready)
+            d_image = image_side()
+        ops._shared_with(side, e, dq, g, image, qn.norm)
+    else:
+        d_image = image_side()
+    if overlap:
+        # the barrier also tells the peers that this rank is done READING its gathered key rows (the local
+        # contraction does), so that they may overwrite them in the next step: join before signalling
+        main.wait_stream(side)
+        ops._shared_with(main, d_image)
+    pc.barrier()                           # every rank's partial for these rows has landed
+    d_text = ops.l2norm_bwd(text, kn_local, pc.dk_parts[0], scale_dev=g, scale_host=scale,
+                            parts=(pc.world, n * pc.width), error=pc.error)
+    if not torch.cuda.is_current_stream_capturing():
+        st.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, None, 0, None)
+    return d_image, d_text
+
+
 class _ShardedGPeer(torch.autograd.Function):
     """Peer-memory form (bf16 mode): the three exchange steps are done by this library's own kernels over
     NVLink - the prologue kernel stores the normalised key rows and the ids into every rank's buffers
@@ -159,150 +309,14 @@ class _ShardedGPeer(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ops, pc, inv_tau: float, row_ids: DeviceIds, image: torch.Tensor, text: torch.Tensor):
-        from . import _lib
-        world, rank = pc.world, pc.rank
-        n, n_total, d = pc.n_local, pc.n_total, pc.d
-        lo_ = rank * n
-        dev = image.device
-        pc.raise_if_failed()                     # a barrier of an earlier step timed out (pinned mirror: no device sync)
-        need_grad = any(ctx.needs_input_grad[4:])
-        overlap = ops.OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
-        main = torch.cuda.current_stream()
-        side = ops._side_stream(dev)
-        stream = main.cuda_stream
-        two = row_ids.key2 is not None
-        # exchange 1: one launch normalises both sides (keys into this rank's own buffer rows), pushes the id shard
-        # to every rank and zeroes dQhat; after the barrier the key rows travel to the peers on the side stream
-        # WHILE K3 runs - K3 visits its own columns first and waits per source for the others (landed flags)
-        k_norm = torch.empty(n, dtype=torch.float32, device=dev)
-        q_norm = torch.empty(n, dtype=torch.float32, device=dev)
-        q_hi = torch.empty((n, pc.ld), dtype=torch.bfloat16, device=dev)
-        wq = _round_up(d, 4)
-        dq = torch.empty((n, wq), dtype=torch.float32, device=dev) if need_grad else None
-        overlap_gather = OVERLAP_GATHER and world > 1
-        # inputs as the caller holds them (strided [:,0,:] head views, bf16/fp16): the prologue's loader honours them
-        _lib.call("evk_shard_prologue", text.data_ptr(), ops._dtype_code(text), text.stride(0), text.stride(1),
-                  image.data_ptr(), ops._dtype_code(image), image.stride(0), image.stride(1), n, d,
-                  1 if overlap_gather else world, pc.table("khat_local") if overlap_gather else pc.table("khat"), pc.ld, lo_,
-                  k_norm.data_ptr(), q_hi.data_ptr(), q_norm.data_ptr(),
-                  row_ids.key.data_ptr(), row_ids.key2.data_ptr() if two else None, world, pc.table("ids"),
-                  pc.table("ids2") if two else None, None if dq is None else dq.data_ptr(), wq, pc.step.data_ptr(),
-                  pc.error.data_ptr(), stream)
-        pc.barrier()
-        qn = ops.Normalized(n=n, d=d, norm=q_norm, hi=q_hi, lo=None, ld=pc.ld)
-        kn_all = ops.Normalized(n=n_total, d=d, norm=None, hi=pc.khat, lo=None, ld=pc.ld)
-        kn_local = ops.Normalized(n=n, d=d, norm=k_norm, hi=pc.khat[lo_:lo_ + n], lo=None, ld=pc.ld)
-        ids_all = DeviceIds(pc.ids, pc.ids2 if two else None)
-        if overlap_gather:
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                _lib.call("evk_peer_push_shard", pc.khat[lo_:].data_ptr(), n * pc.ld * 2, world, rank, pc.table("khat"),
-                          lo_ * pc.ld * 2, pc.table("landed"), pc.step.data_ptr(), pc.counters.data_ptr(), side.cuda_stream)
-
-        def sweep(bits, store):
-            """K3 over this rank's row block (with the per-source waits when the gather is still in flight)."""
-            n_ct = (n_total + ops.TILE_N - 1) // ops.TILE_N
-            n_rt = (n + ops.TILE_M - 1) // ops.TILE_M
-            if not overlap_gather:
-                return ops.tc_fwd_store(qn, kn_all, bits, inv_tau, 0, lo_) if store else \
-                    ops.tc_fwd_partials(qn, kn_all, bits, inv_tau, 0, lo_) + (None, 0)
-            rs = torch.empty((n_ct * ops._row_parts(), n), dtype=torch.float32, device=dev)
-            rp = torch.empty((n_ct * ops._row_parts(), n), dtype=torch.float32, device=dev)
-            cs = torch.empty((n_rt, n_total), dtype=torch.float32, device=dev)
-            ld_e = _round_up(n_total, 64)
-            e = torch.empty((n, ld_e), dtype=torch.bfloat16, device=dev) if store else None
-            _lib.call("evk_mpce_fwd_store_gathered", q_hi.data_ptr(), pc.ld, pc.khat.data_ptr(), pc.ld, n, n_total, d,
-                      bits.data_ptr(), bits.stride(0), float(inv_tau), 0, lo_, rs.data_ptr(), rp.data_ptr(), n,
-                      cs.data_ptr(), n_total, None if e is None else e.data_ptr(), ld_e, pc.landed.data_ptr(),
-                      pc.step.data_ptr(), pc.error.data_ptr(), n, lo_, stream)
-            return rs, rp, cs, e, (ld_e if store else 0)
-
-        pos = None
-        if need_grad:
-            bits, counts, pos_idx = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_, want_list=True)
-            if overlap or overlap_gather:      # exact positive logits (O(n D)) next to K3, once every shard has landed
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    if overlap_gather:
-                        _lib.call("evk_peer_wait_landed", pc.landed.data_ptr(), world, pc.step.data_ptr(),
-                                  pc.error.data_ptr(), pc.timeout_ms, side.cuda_stream)
-                    pos_dot = ops.pos_logits(qn, kn_all, pos_idx, counts)
-                ops._shared_with(side, q_hi, pos_idx, counts)
-            else:
-                pos_dot = ops.pos_logits(qn, kn_all, pos_idx, counts)
-            pos = (pos_idx, pos_dot)
-            rs_part, rp_part, cs_part, e, ld_e = sweep(bits, True)
-        else:
-            bits, counts = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_)
-            rs_part, rp_part, cs_part, e, ld_e = sweep(bits, False)
-        # exchange 2 (one launch): partials -> a_row, and this rank's slot (partial column sums of its rows +
-        # its row-side loss term) into every rank's slot buffer
-        a_row = torch.empty(n, dtype=torch.float32, device=dev)
-        ws = torch.empty(_lib.size("evk_stats_workspace_bytes", n, n_total), dtype=torch.uint8, device=dev)
-        _lib.call("evk_mpce_shard_stats_push", rs_part.data_ptr(), int(rs_part.shape[0]), n, rp_part.data_ptr(),
-                  int(rp_part.shape[0]), n, counts.data_ptr(), n, cs_part.data_ptr(), int(cs_part.shape[0]), n_total,
-                  n_total, float(inv_tau), 2.0, 0.5 / n_total, a_row.data_ptr(), pc.table("slots"), world,
-                  rank * pc.ld_slot, ws.data_ptr(), ws.numel(), stream)
-        pc.barrier()
-        b_col = torch.empty(n_total, dtype=torch.float32, device=dev)
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
-        ws2 = torch.empty(_lib.size("evk_shard_finish_workspace_bytes", n_total), dtype=torch.uint8, device=dev)
-        _lib.call("evk_mpce_shard_finish", pc.slots.data_ptr(), world, pc.ld_slot, n_total, float(inv_tau), 0.5 / n_total,
-                  b_col.data_ptr(), loss.data_ptr(), ws2.data_ptr(), ws2.numel(), pc.error.data_ptr(), stream)
-        if overlap_gather or (need_grad and overlap):
-            main.wait_stream(side)              # the push (and the positives) are part of this step
-            if need_grad:
-                ops._shared_with(main, pos_dot)
-        ctx.ops, ctx.pc, ctx.inv_tau = ops, pc, inv_tau
-        ctx.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, e, ld_e, dq)
-        ctx.pos = pos
-        ctx.save_for_backward(image, text)
+        loss, ctx.st = peer_forward(ops, pc, inv_tau, row_ids, image.detach(), text.detach(), any(ctx.needs_input_grad[4:]))
         out = loss.reshape(())
         return out if image.dtype == torch.float32 else out.to(image.dtype)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        from . import _lib
-        ops, pc, inv_tau = ctx.ops, ctx.pc, ctx.inv_tau
-        qn, kn_local, kn_all, bits, counts, a_row, b_col, e, ld_e, dq = ctx.sv
-        if e is None:
-            raise RuntimeError("evoke_b200: backward called twice on the sharded loss (the E strip was consumed)")
-        image, text = ctx.saved_tensors
-        n, n_total = pc.n_local, pc.n_total
-        g = grad_out.reshape(1).to(torch.float32).contiguous()
-        scale = 0.5 * inv_tau / n_total
-        overlap = ops.OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
-        main = torch.cuda.current_stream()
-        ops.tc_w_from_e(e, ld_e, n_total, bits, counts, a_row, b_col, qn, kn_all, inv_tau, pos=ctx.pos)
-        # exchange 3, fused: the tiles of this rank's partial dKhat are stored straight into their owners'
-        # per-source buffers (posted NVLink stores from the GEMM epilogue; no split-K, no zero fill)
-        _lib.call("evk_mpce_bwd_gemm_scatter", e.data_ptr(), None, ld_e, n, n_total, qn.hi.data_ptr(), None, qn.ld, qn.d,
-                  1.0, 0, pc.table("dk_mine"), pc.world, n, pc.width, 2 if pc.exchange == "bf16" else 1, main.cuda_stream)
-
-        def image_side():
-            ops.tc_bwd_gemm(e, None, ld_e, n, n_total, False, kn_all, 0, out=dq)      # dq was zeroed by the prologue
-            return ops.l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, error=pc.error)
-
-        if overlap:
-            # the local contraction fills the SMs as the scattering one drains (it may be NVLink-bound)
-            side = ops._side_stream(image.device)
-            w_ready = main.record_event()
-            with torch.cuda.stream(side):
-                side.wait_event(w_ready)
-                d_image = image_side()
-            ops._shared_with(side, e, dq, g, image, qn.norm)
-        else:
-            d_image = image_side()
-        if overlap:
-            # the barrier also tells the peers that this rank is done READING its gathered key rows (the local
-            # contraction does), so that they may overwrite them in the next step: join before signalling
-            main.wait_stream(side)
-            ops._shared_with(main, d_image)
-        pc.barrier()                           # every rank's partial for these rows has landed
-        d_text = ops.l2norm_bwd(text, kn_local, pc.dk_parts[0], scale_dev=g, scale_host=scale,
-                                parts=(pc.world, n * pc.width), error=pc.error)
-        ctx.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, None, 0, None)
+        d_image, d_text = peer_backward(ctx.st, grad_out.reshape(1).to(torch.float32).contiguous())
         return None, None, None, None, d_image, d_text
 
 
@@ -329,7 +343,8 @@ OVERLAP_GATHER = os.environ.get("EVOKE_B200_OVERLAP_GATHER", "0") == "1"
 
 
 def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local, temp: float, *,
-                             group=None, precision: str = "bf16", mode: str = "auto", ops=None) -> torch.Tensor:
+                             group=None, precision: str = "bf16", mode: str = "auto", ops=None,
+                             graph: Optional[bool] = None) -> torch.Tensor:
     """G loss of the GLOBAL batch from this rank's shard (same row count on every rank).
 
     image, text: [n_local, D] on this rank's device; ids_local: the n_local ids of these rows
@@ -338,6 +353,8 @@ def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local,
     Returns the global loss (identical on every rank); .backward() yields d(global loss)/d(local
     shard), so a DDP-style gradient average over ranks must not be applied to it twice.
 
+    graph: peer transport only - replay the step from the CUDA-graph cache (see evoke_b200.loss.global_alignment;
+    None: the EVOKE_B200_GRAPHS default, on).
     mode: "peer" - exchanges done by this library's kernels over peer-mapped memory (NVLink): K1 stores into every
                   rank's key buffer, K4b's epilogue red.adds into the owner's dKhat (6 nND FLOP per rank); bf16 mode;
           "rs"  - partial dKhat for all N keys + reduce-scatter (8 nND FLOP per rank, N*D fp32 exchanged);
@@ -382,6 +399,14 @@ def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local,
             pc = peer.get_context(group, int(image.shape[0]), int(image.shape[1]), image.device,
                                   two_keys=row_ids.key2 is not None, exchange=PEER_EXCHANGE)
         if pc is not None:
+            from . import graphs
+            use_graph = graphs.DROPIN_GRAPHS if graph is None else bool(graph)
+            if use_graph and not torch.cuda.is_current_stream_capturing():
+                # collective: every rank captures at the same call (same shapes on every rank); the warm-up and the
+                # captured sequences contain the flag barriers
+                def fwd(im, tx, ids, need):
+                    return peer_forward(ops, pc, inv_tau, ids, im, tx, any(need))
+                return graphs.graphed_call(("Gpeer", id(pc), inv_tau), fwd, peer_backward, image, text, row_ids)
             return _ShardedGPeer.apply(ops, pc, inv_tau, row_ids, image, text)
         if mode == "peer":
             raise RuntimeError("evoke_b200: mode='peer' needs bf16 precision, n_local % 128 == 0, d % 8 == 0, d <= 2048 "

@@ -389,166 +389,185 @@ def choose_path(path: str, n_rows: int, n_cols: int, d: int) -> str:
     return "small" if (max(n_rows, n_cols) <= SMALL_PATH_MAX and d <= 4096) else "tc"
 
 
+class _State:
+    """What the backward needs from the forward (the role autograd's ctx plays; a plain object so that the same two
+    functions can also be captured into CUDA graphs, evoke_b200/graphs.py)."""
+    pass
+
+
+def mpce_forward(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor], need_grad=(True, True)):
+    """Forward kernel sequence of the G / MPC loss.  Returns (loss [1] fp32, state).  need_grad = (image, text)."""
+    st = _State()
+    st.e_strip = None
+    st.pos = None
+    small = cfg.path == "small"
+    split = (not small) and cfg.precision == "fp32"
+    flags = FLAG_SPLIT_BF16 if split else 0
+    kw = dict(want_f32=small, want_hi=not small, want_lo=split)
+    mpc = cfg.kind == "MPC"
+    if mpc:
+        flags |= FLAG_EXCLUDE_DIAG | FLAG_NO_COLSUM
+    if small:
+        qn = l2norm_fwd(image, gather=cfg.gather, **kw)
+        kn = qn if mpc else l2norm_fwd(text, **kw)
+        n = qn.n
+        pos_weight, inv_count = (1.0, 1.0 / n) if mpc else (2.0, 0.5 / n)
+        bits, counts = posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc)
+        row_sum, row_pos = small_fwd(qn, kn, bits, cfg.inv_tau, flags)
+        col_sum = None if mpc else small_fwd(kn, qn, bits, cfg.inv_tau, flags)[0]
+        a_row, b_col, loss = finalize(row_sum, row_pos, counts, col_sum, col_lo=0, col_hi=0 if mpc else n,
+                                      shift=cfg.inv_tau, pos_weight=pos_weight, inv_count=inv_count)
+    else:
+        # K2 (integer-ALU bound) runs on a side stream next to the two HBM-bound K1 launches
+        # when the sequence is being captured into a CUDA graph.  The positive-logit sums stay
+        # in the K3 epilogue: ln R_i and pos_i must come from the same tensor-core accumulators
+        # for their rounding to cancel in the loss (cold temperatures, see DESIGN.md §3).
+        overlap = OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
+        use_strip = E_STRIP and not split and any(need_grad)
+        pos_idx = pos_dot = None
+
+        def build_mask():
+            if use_strip:
+                return posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc, want_list=True)
+            return posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc) + (None,)
+
+        if overlap:
+            main = torch.cuda.current_stream()
+            side = _side_stream(image.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                bits, counts, pos_idx = build_mask()
+        else:
+            bits, counts, pos_idx = build_mask()
+        qn = l2norm_fwd(image, gather=cfg.gather, **kw)
+        kn = qn if mpc else l2norm_fwd(text, **kw)
+        n = qn.n
+        pos_weight, inv_count = (1.0, 1.0 / n) if mpc else (2.0, 0.5 / n)
+        if overlap:
+            main.wait_stream(side)
+            _shared_with(main, bits, counts, pos_idx)
+        if use_strip:
+            # exact logits of the listed positives (O(N*D)), next to K3 on the side stream; the backward's
+            # K4t needs them for the entries where softmax and target cancel
+            if overlap:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    pos_dot = pos_logits(qn, kn, pos_idx, counts)
+                _shared_with(side, qn.hi, kn.hi, pos_idx, counts)
+            else:
+                pos_dot = pos_logits(qn, kn, pos_idx, counts)
+            rs_part, rp_part, cs_part, e_strip, ld_e = tc_fwd_store(qn, kn, bits, cfg.inv_tau, flags)
+            st.e_strip = (e_strip, ld_e)
+            st.pos = (pos_idx, pos_dot)
+        else:
+            rs_part, rp_part, cs_part = tc_fwd_partials(qn, kn, bits, cfg.inv_tau, flags)
+        a_row, b_col, loss = stats_fused(rs_part, rp_part, cs_part, counts, shift=cfg.inv_tau,
+                                         pos_weight=pos_weight, inv_count=inv_count)
+        if use_strip and overlap:
+            main.wait_stream(side)
+            _shared_with(main, pos_dot)
+    if mpc:
+        b_col = a_row
+    st.cfg, st.flags, st.qn, st.kn = cfg, flags, qn, kn
+    st.aux = (bits, counts, a_row, b_col)
+    st.image, st.text = image, text
+    st.need_grad = (bool(need_grad[0]), bool(need_grad[1]) if text is not None else False)
+    return loss, st
+
+
+def mpce_backward(st: _State, g: torch.Tensor):
+    """Backward kernel sequence; g = upstream gradient, fp32 [1] on the device.  Returns (d_image, d_text)."""
+    cfg, flags, qn, kn = st.cfg, st.flags, st.qn, st.kn
+    bits, counts, a_row, b_col = st.aux
+    image, text = st.image, st.text
+    mpc = cfg.kind == "MPC"
+    n = qn.n
+    scale = cfg.inv_tau / n if mpc else 0.5 * cfg.inv_tau / n
+    need_q = st.need_grad[0]
+    need_k = (not mpc) and st.need_grad[1]
+    d_image = d_text = None
+    if cfg.path == "small":
+        if need_q:
+            dq = small_bwd(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
+            d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
+        if need_k:
+            dk = small_bwd(kn, qn, bits, counts, b_col, a_row, cfg.inv_tau, flags)   # M is symmetric
+            d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
+    elif need_q or need_k:
+        dev = image.device
+        width = _round_up(qn.d, 4)
+        overlap = OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
+        strip = st.e_strip
+        if strip is not None:
+            if strip[0] is None:
+                raise RuntimeError("evoke_b200: backward called twice: the E strip saved by the forward is turned "
+                                   "into W in place (set EVOKE_B200_ESTRIP=0 if the graph must be retained)")
+
+        def weights():
+            """W strip for the whole row block: K4t over the saved E strip, or K4a (recompute)."""
+            if strip is None:
+                return tc_bwd_w(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
+            e, ld_e = strip
+            tc_w_from_e(e, ld_e, kn.n, bits, counts, a_row, b_col, qn, kn, cfg.inv_tau, pos=st.pos)
+            return e, None, ld_e
+
+        if not overlap:
+            w_hi, w_lo, ld_w = weights()
+            if need_q:
+                dq = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, False, kn, flags)
+                d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
+            if need_k:
+                dk = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, True, qn, flags)
+                d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
+        else:
+            main = torch.cuda.current_stream()
+            side = _side_stream(dev)
+            # zero-filled split-K accumulators: filled on the side stream while K4a / K4t runs
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dq = torch.zeros((qn.n, width), dtype=torch.float32, device=dev) if need_q else None
+                dk = torch.zeros((kn.n, width), dtype=torch.float32, device=dev) if need_k else None
+                filled = side.record_event()
+            w_hi, w_lo, ld_w = weights()
+            main.wait_event(filled)
+            _shared_with(main, dq, dk)
+            if need_q:
+                tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, False, kn, flags, out=dq)
+            if need_k:
+                # second contraction + its normalise-backward on the side stream: its CTAs take
+                # over the SMs as the first contraction drains, and the image-side K1b overlaps it
+                w_ready = main.record_event()
+                with torch.cuda.stream(side):
+                    side.wait_event(w_ready)
+                    tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, True, qn, flags, out=dk)
+                    d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
+                _shared_with(side, w_hi, w_lo, qn.hi, qn.lo, g, text, kn.norm)
+            if need_q:
+                d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
+            if need_k:
+                main.wait_stream(side)
+                _shared_with(main, d_text)
+        if strip is not None and not torch.cuda.is_current_stream_capturing():
+            st.e_strip = (None, 0)                  # drop the N^2 buffer as soon as it has been consumed
+    return d_image, d_text
+
+
 class _MultiPositiveCE(torch.autograd.Function):
     """loss = f(image[, text]); cfg carries the non-differentiable pieces."""
 
     @staticmethod
     def forward(ctx, cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor]):
-        ctx.e_strip = None
-        ctx.pos = None
-        small = cfg.path == "small"
-        split = (not small) and cfg.precision == "fp32"
-        flags = FLAG_SPLIT_BF16 if split else 0
-        kw = dict(want_f32=small, want_hi=not small, want_lo=split)
-        mpc = cfg.kind == "MPC"
-        if mpc:
-            flags |= FLAG_EXCLUDE_DIAG | FLAG_NO_COLSUM
-        if small:
-            qn = l2norm_fwd(image, gather=cfg.gather, **kw)
-            kn = qn if mpc else l2norm_fwd(text, **kw)
-            n = qn.n
-            pos_weight, inv_count = (1.0, 1.0 / n) if mpc else (2.0, 0.5 / n)
-            bits, counts = posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc)
-            row_sum, row_pos = small_fwd(qn, kn, bits, cfg.inv_tau, flags)
-            col_sum = None if mpc else small_fwd(kn, qn, bits, cfg.inv_tau, flags)[0]
-            a_row, b_col, loss = finalize(row_sum, row_pos, counts, col_sum, col_lo=0, col_hi=0 if mpc else n,
-                                          shift=cfg.inv_tau, pos_weight=pos_weight, inv_count=inv_count)
-        else:
-            # K2 (integer-ALU bound) runs on a side stream next to the two HBM-bound K1 launches
-            # when the sequence is being captured into a CUDA graph.  The positive-logit sums stay
-            # in the K3 epilogue: ln R_i and pos_i must come from the same tensor-core accumulators
-            # for their rounding to cancel in the loss (cold temperatures, see DESIGN.md §3).
-            overlap = OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
-            use_strip = E_STRIP and not split and any(ctx.needs_input_grad[1:])
-            pos_idx = pos_dot = None
-
-            def build_mask():
-                if use_strip:
-                    return posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc, want_list=True)
-                return posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc) + (None,)
-
-            if overlap:
-                main = torch.cuda.current_stream()
-                side = _side_stream(image.device)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    bits, counts, pos_idx = build_mask()
-            else:
-                bits, counts, pos_idx = build_mask()
-            qn = l2norm_fwd(image, gather=cfg.gather, **kw)
-            kn = qn if mpc else l2norm_fwd(text, **kw)
-            n = qn.n
-            pos_weight, inv_count = (1.0, 1.0 / n) if mpc else (2.0, 0.5 / n)
-            if overlap:
-                main.wait_stream(side)
-                _shared_with(main, bits, counts, pos_idx)
-            if use_strip:
-                # exact logits of the listed positives (O(N*D)), next to K3 on the side stream; the backward's
-                # K4t needs them for the entries where softmax and target cancel
-                if overlap:
-                    side.wait_stream(main)
-                    with torch.cuda.stream(side):
-                        pos_dot = pos_logits(qn, kn, pos_idx, counts)
-                    _shared_with(side, qn.hi, kn.hi, pos_idx, counts)
-                else:
-                    pos_dot = pos_logits(qn, kn, pos_idx, counts)
-                rs_part, rp_part, cs_part, e_strip, ld_e = tc_fwd_store(qn, kn, bits, cfg.inv_tau, flags)
-                ctx.e_strip = (e_strip, ld_e)
-                ctx.pos = (pos_idx, pos_dot)
-            else:
-                rs_part, rp_part, cs_part = tc_fwd_partials(qn, kn, bits, cfg.inv_tau, flags)
-            a_row, b_col, loss = stats_fused(rs_part, rp_part, cs_part, counts, shift=cfg.inv_tau,
-                                             pos_weight=pos_weight, inv_count=inv_count)
-            if use_strip and overlap:
-                main.wait_stream(side)
-                _shared_with(main, pos_dot)
-        if mpc:
-            b_col = a_row
-        ctx.cfg, ctx.flags, ctx.qn, ctx.kn = cfg, flags, qn, kn
-        ctx.aux = (bits, counts, a_row, b_col)
-        ctx.has_text = text is not None
-        ctx.save_for_backward(image, text) if text is not None else ctx.save_for_backward(image)
+        need = (ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        loss, st = mpce_forward(cfg, image.detach(), None if text is None else text.detach(), need)
+        ctx.st = st
         out = loss.reshape(())
         return out if image.dtype == torch.float32 else out.to(image.dtype)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out: torch.Tensor):
-        cfg, flags, qn, kn = ctx.cfg, ctx.flags, ctx.qn, ctx.kn
-        bits, counts, a_row, b_col = ctx.aux
-        saved = ctx.saved_tensors
-        image = saved[0]
-        text = saved[1] if ctx.has_text else None
-        mpc = cfg.kind == "MPC"
-        n = qn.n
         g = grad_out.reshape(1).to(torch.float32).contiguous()
-        scale = cfg.inv_tau / n if mpc else 0.5 * cfg.inv_tau / n
-        need_q = ctx.needs_input_grad[1]
-        need_k = (not mpc) and ctx.needs_input_grad[2]
-        d_image = d_text = None
-        if cfg.path == "small":
-            if need_q:
-                dq = small_bwd(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
-                d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
-            if need_k:
-                dk = small_bwd(kn, qn, bits, counts, b_col, a_row, cfg.inv_tau, flags)   # M is symmetric
-                d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
-        elif need_q or need_k:
-            dev = image.device
-            width = _round_up(qn.d, 4)
-            overlap = OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
-            strip = ctx.e_strip
-            if strip is not None:
-                if strip[0] is None:
-                    raise RuntimeError("evoke_b200: backward called twice: the E strip saved by the forward is turned "
-                                       "into W in place (set EVOKE_B200_ESTRIP=0 if the graph must be retained)")
-
-            def weights():
-                """W strip for the whole row block: K4t over the saved E strip, or K4a (recompute)."""
-                if strip is None:
-                    return tc_bwd_w(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
-                e, ld_e = strip
-                tc_w_from_e(e, ld_e, kn.n, bits, counts, a_row, b_col, qn, kn, cfg.inv_tau, pos=ctx.pos)
-                return e, None, ld_e
-
-            if not overlap:
-                w_hi, w_lo, ld_w = weights()
-                if need_q:
-                    dq = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, False, kn, flags)
-                    d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
-                if need_k:
-                    dk = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, True, qn, flags)
-                    d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
-            else:
-                main = torch.cuda.current_stream()
-                side = _side_stream(dev)
-                # zero-filled split-K accumulators: filled on the side stream while K4a / K4t runs
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    dq = torch.zeros((qn.n, width), dtype=torch.float32, device=dev) if need_q else None
-                    dk = torch.zeros((kn.n, width), dtype=torch.float32, device=dev) if need_k else None
-                    filled = side.record_event()
-                w_hi, w_lo, ld_w = weights()
-                main.wait_event(filled)
-                _shared_with(main, dq, dk)
-                if need_q:
-                    tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, False, kn, flags, out=dq)
-                if need_k:
-                    # second contraction + its normalise-backward on the side stream: its CTAs take
-                    # over the SMs as the first contraction drains, and the image-side K1b overlaps it
-                    w_ready = main.record_event()
-                    with torch.cuda.stream(side):
-                        side.wait_event(w_ready)
-                        tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, True, qn, flags, out=dk)
-                        d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
-                    _shared_with(side, w_hi, w_lo, qn.hi, qn.lo, g, text, kn.norm)
-                if need_q:
-                    d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
-                if need_k:
-                    main.wait_stream(side)
-                    _shared_with(main, d_text)
-            if strip is not None:
-                ctx.e_strip = (None, 0)                  # drop the N^2 buffer as soon as it has been consumed
+        d_image, d_text = mpce_backward(ctx.st, g)
         return None, d_image, d_text
 
 

@@ -141,3 +141,120 @@ class GraphedLocalTokenAlign:
             self.capture()
         self.graph.replay()
         return self.loss
+
+
+# ------------------------------------------------------------------------------------- drop-in graph cache
+import os as _os
+from collections import OrderedDict as _OrderedDict
+
+DROPIN_GRAPHS = _os.environ.get("EVOKE_B200_GRAPHS", "1") == "1"     # default of the reference-signature calls
+_MAX_CACHED = int(_os.environ.get("EVOKE_B200_GRAPH_CACHE", "6"))
+_CACHE: "_OrderedDict[tuple, GraphedStep]" = _OrderedDict()
+
+
+class GraphedStep:
+    """Forward and backward of one loss call, captured as TWO CUDA graphs over static buffers, so that the
+    reference-signature call (``model.global_alignment_loss(image, text, ids)`` ... ``all_loss.backward()``) costs two
+    graph launches instead of ~20 kernel launches: the forward graph is replayed inside the autograd Function's
+    forward, the backward graph - which reads the upstream gradient from a static device scalar - inside its
+    backward.  Semantics are those of ``torch.cuda.make_graphed_callables``: the returned gradients are static
+    buffers, valid until the next call with the same signature; a backward must follow its own forward
+    (a stale or repeated backward raises).
+
+    fwd(image, text, ids, need) -> (loss [1] fp32, state);  bwd(state, g) -> (d_image, d_text | None)."""
+
+    def __init__(self, fwd, bwd, image: torch.Tensor, text: Optional[torch.Tensor], ids: DeviceIds, need, warmup: int = 3):
+        dev = image.device
+        self.image = torch.empty(image.shape, dtype=image.dtype, device=dev)
+        self.text = None if text is None else torch.empty(text.shape, dtype=text.dtype, device=dev)
+        self.key = torch.empty_like(ids.key)
+        self.key2 = None if ids.key2 is None else torch.empty_like(ids.key2)
+        self.ids = DeviceIds(self.key, self.key2)
+        self.g = torch.ones(1, dtype=torch.float32, device=dev)
+        self.need = (bool(need[0]), bool(need[1]))
+        self.gen = 0               # forward generation; a backward must present the generation it belongs to
+        self.bwd_gen = -1
+        self._load(image, text, ids)
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):                    # first-call work (kernel attributes, context binding) before capture
+                loss, st = fwd(self.image, self.text, self.ids, self.need)
+                if any(self.need):
+                    bwd(st, self.g)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph_f = torch.cuda.CUDAGraph()
+        # thread_local: other host threads (a DataLoader's pin-memory thread ...) may keep calling CUDA during capture
+        with torch.no_grad(), torch.cuda.graph(self.graph_f, capture_error_mode="thread_local"):
+            self.loss, self.state = fwd(self.image, self.text, self.ids, self.need)
+        self.graph_b = None
+        self.d_image = self.d_text = None
+        if any(self.need):
+            self.graph_b = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(self.graph_b, pool=self.graph_f.pool(), capture_error_mode="thread_local"):
+                self.d_image, self.d_text = bwd(self.state, self.g)
+            # the capture itself ran neither graph: the E strip of `state` is produced by the first replay
+
+    def _load(self, image, text, ids: DeviceIds):
+        with torch.no_grad():
+            self.image.copy_(image, non_blocking=True)             # also gathers strided [:,0,:] views
+            if self.text is not None:
+                self.text.copy_(text, non_blocking=True)
+            self.key.copy_(ids.key, non_blocking=True)
+            if self.key2 is not None:
+                self.key2.copy_(ids.key2, non_blocking=True)
+
+    def run_forward(self, image, text, ids: DeviceIds) -> int:
+        self._load(image, text, ids)
+        self.graph_f.replay()
+        self.gen += 1
+        return self.gen
+
+    def run_backward(self, gen: int, grad_out: torch.Tensor):
+        if gen != self.gen:
+            raise RuntimeError("evoke_b200: backward of a stale graphed loss call: another forward with the same signature "
+                               "ran in between (set EVOKE_B200_GRAPHS=0 or graph=False to keep several calls alive)")
+        if self.bwd_gen == gen:
+            raise RuntimeError("evoke_b200: backward called twice on a graphed loss call (the E strip was consumed)")
+        self.bwd_gen = gen
+        with torch.no_grad():
+            self.g.copy_(grad_out.reshape(1), non_blocking=True)
+        self.graph_b.replay()
+        return self.d_image, self.d_text
+
+
+class _GraphedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gs: GraphedStep, ids: DeviceIds, image: torch.Tensor, text: Optional[torch.Tensor]):
+        ctx.gs = gs
+        ctx.gen = gs.run_forward(image, text, ids)
+        out = gs.loss.clone().reshape(())
+        return out if image.dtype == torch.float32 else out.to(image.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        d_image, d_text = ctx.gs.run_backward(ctx.gen, grad_out.to(torch.float32))
+        return None, None, d_image if ctx.needs_input_grad[2] else None, d_text if ctx.needs_input_grad[3] else None
+
+
+def graphed_call(key: tuple, fwd, bwd, image: torch.Tensor, text: Optional[torch.Tensor], ids: DeviceIds) -> torch.Tensor:
+    """Run one loss call through the graph cache (capturing on first use of this signature)."""
+    need = (image.requires_grad and torch.is_grad_enabled(),
+            text is not None and text.requires_grad and torch.is_grad_enabled())
+    key = key + (tuple(image.shape), image.dtype, image.device.index, ids.key2 is not None, need)
+    gs = _CACHE.get(key)
+    if gs is None:
+        gs = GraphedStep(fwd, bwd, image.detach(), None if text is None else text.detach(), ids, need)
+        _CACHE[key] = gs
+        while len(_CACHE) > _MAX_CACHED:
+            _CACHE.popitem(last=False)                # least recently used: frees its graphs and their memory pool
+    else:
+        _CACHE.move_to_end(key)
+    return _GraphedLoss.apply(gs, ids, image, text)
+
+
+def clear_graph_cache() -> None:
+    _CACHE.clear()

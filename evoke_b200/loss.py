@@ -45,12 +45,16 @@ def _inv_tau(temp: float) -> float:
 
 
 def global_alignment(image: torch.Tensor, text: torch.Tensor, patient_ids, temp: float, *,
-                     precision: str = DEFAULT_PRECISION, path: str = "auto") -> torch.Tensor:
+                     precision: str = DEFAULT_PRECISION, path: str = "auto", graph: Optional[bool] = None) -> torch.Tensor:
     """Multi-positive image<->text InfoNCE in both directions (reference :486-504).
 
     image, text: [B, D] projected embeddings (any strides; fp32/bf16/fp16) on a CUDA device.
     patient_ids: what the reference passes (numpy array of str/int, length >= B; only the first B
     are used, :488), a (patient, study) pair, or an integer tensor already on the device.
+    graph: replay the call from the CUDA-graph cache (evoke_b200.graphs.GraphedStep: one graph for the forward,
+    one for the backward, captured on first use of a (shape, dtype, precision, temperature) signature; the returned
+    gradients are static buffers, as with torch.cuda.make_graphed_callables).  None: EVOKE_B200_GRAPHS (default on),
+    never inside an outer capture.
     """
     Fn._require_cuda(image, "global_image_embed")
     Fn._require_cuda(text, "global_text_embed")
@@ -66,9 +70,18 @@ def global_alignment(image: torch.Tensor, text: torch.Tensor, patient_ids, temp:
     dev_ids, _ = idmod.to_device_ids(patient_ids, image.device, n=b)
     if len(dev_ids) < b:
         raise ValueError(f"patient_ids has {len(dev_ids)} entries for a batch of {b}")
-    cfg = Fn.LossConfig(kind="G", inv_tau=_inv_tau(temp), precision=precision,
-                        path=Fn.choose_path(path, b, b, d), row_ids=dev_ids)
+    inv_tau = _inv_tau(temp)
+    path = Fn.choose_path(path, b, b, d)
     with torch.cuda.device(image.device):
+        from . import graphs
+        use_graph = graphs.DROPIN_GRAPHS if graph is None else bool(graph)
+        if use_graph and not torch.cuda.is_current_stream_capturing():
+            def fwd(im, tx, ids, need):
+                return Fn.mpce_forward(Fn.LossConfig(kind="G", inv_tau=inv_tau, precision=precision, path=path,
+                                                     row_ids=ids), im, tx, need)
+            key = ("G", inv_tau, precision, path, Fn.E_STRIP, Fn.OVERLAP_STREAMS)
+            return graphs.graphed_call(key, fwd, Fn.mpce_backward, image, text, dev_ids)
+        cfg = Fn.LossConfig(kind="G", inv_tau=inv_tau, precision=precision, path=path, row_ids=dev_ids)
         return Fn.multi_positive_ce(cfg, image, text)
 
 
@@ -166,7 +179,8 @@ def local_text_token_alignment(local_image: torch.Tensor, local_text: torch.Tens
 def global_alignment_loss(self, global_image_embed, global_text_embed, patient_ids):
     """Same signature as Pretrain.global_alignment_loss (reference :486)."""
     return global_alignment(global_image_embed, global_text_embed, patient_ids, self.args["instance_temp"],
-                            precision=getattr(self, "_evoke_b200_precision", DEFAULT_PRECISION))
+                            precision=getattr(self, "_evoke_b200_precision", DEFAULT_PRECISION),
+                            graph=getattr(self, "_evoke_b200_graphs", None))
 
 
 def multi_pos_contra_images_v0401(self, global_image_embed, patient_ids):
@@ -202,10 +216,11 @@ def local_text_token_alignment_loss(self, local_image_embed, local_text_embed):
     return local_text_token_alignment(local_image_embed, local_text_embed, self.args["region_temp"])
 
 
-def patch_pretrain(target, precision: str = DEFAULT_PRECISION, local_tokens: bool = False):
+def patch_pretrain(target, precision: str = DEFAULT_PRECISION, local_tokens: bool = False, graphs: Optional[bool] = None):
     """Rebind the two loss methods (and, with ``local_tokens=True``, ``local_text_token_alignment_loss`` :506) on a
     reference ``Pretrain`` class (affects every instance) or on a single instance.  Works for all six model files because only the method names and
-    ``self.args`` are relied upon.  Returns ``target``."""
+    ``self.args`` are relied upon.  ``graphs``: run ``global_alignment_loss`` from the CUDA-graph cache (None: the
+    EVOKE_B200_GRAPHS default, on).  Returns ``target``."""
     if precision not in ("fp32", "bf16"):
         raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
     if isinstance(target, type):
@@ -214,6 +229,7 @@ def patch_pretrain(target, precision: str = DEFAULT_PRECISION, local_tokens: boo
         if local_tokens:
             target.local_text_token_alignment_loss = local_text_token_alignment_loss
         target._evoke_b200_precision = precision
+        target._evoke_b200_graphs = graphs
     else:
         import types
         target.global_alignment_loss = types.MethodType(global_alignment_loss, target)
@@ -221,6 +237,7 @@ def patch_pretrain(target, precision: str = DEFAULT_PRECISION, local_tokens: boo
         if local_tokens:
             target.local_text_token_alignment_loss = types.MethodType(local_text_token_alignment_loss, target)
         target._evoke_b200_precision = precision
+        target._evoke_b200_graphs = graphs
     return target
 
 

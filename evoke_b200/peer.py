@@ -12,6 +12,7 @@ flag barrier kernel (``evk_peer_barrier``) - no NCCL call sits on the data path:
   dk_parts [R, n, D] bf16 (or fp32) this rank's rows of dKhat, one partial per source rank: rank s's K4b epilogue
                           stores its tiles for these rows into part s (posted NVLink stores), K1b adds them up
   flags  [16]     uint32  barrier flags (entry r written by rank r only)
+  err    [1]      int32   failure flag: a barrier that times out on ANY rank raises it on EVERY rank
   landed [16]     uint32  landed[s] = step in which source s's key rows last arrived here completely
 
 Only torch.distributed's object all-gather is used, once per context, for the handles.
@@ -64,7 +65,7 @@ class PeerContext:
         off = 0
         self.off = {}
         for name, nbytes in (("khat", big_n * self.ld * 2), ("ids", big_n * 4), ("ids2", big_n * 4 if two_keys else 0),
-                             ("slots", r * self.ld_slot * 4), ("dk_parts", r * n * self.width * esize), ("flags", 64), ("landed", 64)):
+                             ("slots", r * self.ld_slot * 4), ("dk_parts", r * n * self.width * esize), ("flags", 64), ("landed", 64), ("err", 64)):
             self.off[name] = off
             off += _round_up(nbytes, _ALIGN)
         self.nbytes = off
@@ -114,7 +115,7 @@ class PeerContext:
         # failure flag of the transport (a peer missed a barrier): sticky device int read by the step's closing kernels
         # (NaN loss / gradients), mirrored by the barrier kernel into pinned HOST memory so that the next step's entry
         # can raise without synchronising the device
-        self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.error = self._view("err", 64).view(torch.int32)[:1]       # in symmetric memory: any rank's barrier may raise it
         self.error_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.ptrs = {name: (ctypes.c_uint64 * self.world)(*[b + o for b in self.bases]) for name, o in self.off.items()}
         # where THIS rank's partial for owner t goes: part `rank` of t's dk_parts
@@ -133,9 +134,8 @@ class PeerContext:
 
     def barrier(self) -> None:
         """Enqueue the cross-GPU barrier on the current stream."""
-        _lib.call("evk_peer_barrier", self.ptrs["flags"], self.world, self.rank, self.epoch.data_ptr(),
-                  self.error.data_ptr(), self.error_host.data_ptr(), self.timeout_ms,
-                  torch.cuda.current_stream().cuda_stream)
+        _lib.call("evk_peer_barrier", self.ptrs["flags"], self.ptrs["err"], self.world, self.rank, self.epoch.data_ptr(),
+                  self.error_host.data_ptr(), self.timeout_ms, torch.cuda.current_stream().cuda_stream)
 
     FAILED = ("evoke_b200: a peer did not reach a cross-GPU barrier within {:.1f} s; the loss and gradients of that step "
               "are NaN and this transport context is dead (the peers' buffers may be out of step): tear the process "
@@ -159,7 +159,7 @@ class PeerContext:
                 lib.evk_peer_close(ctypes.c_void_p(b))
         self.bases = []
         if self.base:
-            self._raw = self.khat = self.ids = self.ids2 = self.slots = self.dk_parts = self.landed = None
+            self._raw = self.khat = self.ids = self.ids2 = self.slots = self.dk_parts = self.landed = self.error = None
             lib.evk_peer_free(ctypes.c_void_p(self.base))
             self.base = 0
 

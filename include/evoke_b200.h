@@ -432,13 +432,16 @@ EVK_API int evk_peer_close(void* ptr);
  * flag_ptrs: HOST array of n_ranks device addresses, entry t = rank t's flag area (>= 16 uint32, zeroed at
  * start, peer-mapped).  epoch: this rank's device-resident uint32 counter (zeroed at start; advanced by the
  * kernel).  Everything this rank wrote to peer memory in earlier kernels of the stream is visible to the peers
- * once they pass.  If a peer does not arrive within timeout_ms (<= 0: 2000) *error (device int) is set to 1
- * and the kernel returns: a dead peer must not hang the GPU.  The flag is sticky and is what makes the failure
- * loud without a host sync: evk_mpce_shard_finish then writes a NaN loss, evk_l2norm_bwd_parts NaN gradients,
- * evk_shard_prologue stops writing into peer memory, and error_host (may be NULL; an int in pinned, device-
- * accessible HOST memory) is set as well, so the host can poll it before its next step and raise. */
-EVK_API int evk_peer_barrier(const uint64_t* flag_ptrs, int n_ranks, int rank, uint32_t* epoch, int* error,
-                     int* error_host, int64_t timeout_ms, evk_stream_t stream);
+ * once they pass.  error_ptrs: HOST array of n_ranks device addresses, entry t = rank t's failure flag (an int in
+ * the same symmetric, peer-mapped memory; zeroed at start).  If a peer does not arrive within timeout_ms
+ * (<= 0: 2000) the failure flag of EVERY rank is set to 1 and the kernel returns: a dead peer must not hang the
+ * GPU, and the late peer - which will pass its own barriers at once - must not trust this rank's buffers either.
+ * The flag is sticky and is what makes the failure loud without a host sync: evk_mpce_shard_finish then writes a
+ * NaN loss, evk_l2norm_bwd_parts NaN gradients, evk_shard_prologue stops writing into peer memory, and
+ * error_host (may be NULL; an int in pinned, device-accessible HOST memory) is set as well, so the host can poll
+ * it before its next step and raise. */
+EVK_API int evk_peer_barrier(const uint64_t* flag_ptrs, const uint64_t* error_ptrs, int n_ranks, int rank,
+                     uint32_t* epoch, int* error_host, int64_t timeout_ms, evk_stream_t stream);
 
 /* Closes the sharded forward after the statistics exchange.  slots: [n_slots, ld_slot] fp32, slot r = rank r's
  * partial column exp-sums over its own rows (n_cols floats) followed by its row-side loss term
@@ -446,10 +449,12 @@ EVK_API int evk_peer_barrier(const uint64_t* flag_ptrs, int n_ranks, int rank, u
  *   b_col[j] = 1 / sum_r slots[r][j];   loss_out[0] = sum_r slots[r][n_cols] + inv_count * sum_j (shift + ln C_j)
  * (:501-503 on the concatenated batch).  Fixed summation order: every rank computes identical bits.
  * workspace: evk_shard_finish_workspace_bytes(n_cols) bytes, 16-byte aligned, contents irrelevant.
- * error (may be NULL): when *error != 0 (a barrier timed out) loss and b_col are NaN. */
+ * error (may be NULL): when *error != 0 (a barrier timed out, here or on a peer) loss and b_col are NaN and
+ * error_host (may be NULL, pinned host int) is set. */
 EVK_API int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
                           double inv_count, float* b_col, float* loss_out,
-                          void* workspace, int64_t workspace_bytes, const int* error, evk_stream_t stream);
+                          void* workspace, int64_t workspace_bytes, const int* error, int* error_host,
+                          evk_stream_t stream);
 
 /* K4b with the reduce-scatter fused into its epilogue: the partial dKhat of this rank's row block,
  *   out_owner(j)[j % rows_per_owner, :] += alpha * sum_i W[i, j] x[i, :],   owner(j) = j / rows_per_owner,

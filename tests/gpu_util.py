@@ -10,7 +10,7 @@ DEV = "cuda"
 # tolerances stated by BASELINE.json north_star
 TOL = {
     "fp32": dict(loss=1e-5, grad=1e-4),
-    "bf16": dict(loss=2e-3, grad=2e-2),     # loss in bf16 mode: not stated upstream; 2e-3 rel used here
+    "bf16": dict(loss=2e-5, grad=2e-2),     # loss in bf16 mode: not stated upstream; achieved ~1e-7 .. 5e-6
 }
 
 
@@ -63,3 +63,81 @@ def check_against_golden(case, precision, path):
 def oracle_g(image, text, ids, tau):
     loss, d_i, d_t, _ = orc.g_loss_closed_form(image, text, ids, tau)
     return loss, d_i, d_t
+
+
+# ------------------------------------------------------------------------------------- full-size reference
+def row_rel_l2(got, want):
+    """Per-row relative L2 error ||g_i - w_i|| / ||w_i|| (max over rows whose reference gradient is not tiny):
+    stricter than the max-norm metric for rows with small gradients."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    nw = np.linalg.norm(want, axis=1)
+    ok = nw > 1e-3 * nw.max()
+    return float((np.linalg.norm(got - want, axis=1)[ok] / nw[ok]).max())
+
+
+def g_loss_fp64_gpu(image, text, key, tau, key2=None, block=4096):
+    """TEST INFRASTRUCTURE: the closed form of oracle.g_loss_closed_form (reference :486-504) evaluated in fp64 with
+    torch on the GPU, in row blocks, for sizes the numpy oracle does not finish in seconds (N = 16384, 32768).
+    tests/test_gpu_fullsize.py pins it to the numpy oracle at a small size before using it.
+    image/text: numpy or torch [N, D]; key (, key2): integer ids (two-component key = patient AND study).
+    Returns (loss, d_image, d_text) as float / numpy fp64."""
+    dev = torch.device(DEV)
+    x = torch.as_tensor(image).to(dev, torch.float64)
+    y = torch.as_tensor(text).to(dev, torch.float64)
+    n = x.shape[0]
+    k1 = torch.as_tensor(np.asarray(key)).to(dev).long()[:n]
+    k2 = None if key2 is None else torch.as_tensor(np.asarray(key2)).to(dev).long()[:n]
+    nx = x.norm(dim=1, keepdim=True)
+    ny = y.norm(dim=1, keepdim=True)
+    xh = x / nx.clamp_min(1e-12)
+    yh = y / ny.clamp_min(1e-12)
+
+    def mask(r0, r1):
+        m = k1[r0:r1, None] == k1[None, :]
+        if k2 is not None:
+            m &= k2[r0:r1, None] == k2[None, :]
+        return m
+
+    # pass 1: row LSE, positive sums, counts; column LSE by streaming log-sum-exp over the row blocks
+    lse_r = torch.empty(n, dtype=torch.float64, device=dev)
+    pos = torch.empty(n, dtype=torch.float64, device=dev)
+    cnt = torch.empty(n, dtype=torch.float64, device=dev)
+    col_m = torch.full((n,), -float("inf"), dtype=torch.float64, device=dev)
+    col_s = torch.zeros(n, dtype=torch.float64, device=dev)
+    for r0 in range(0, n, block):
+        r1 = min(n, r0 + block)
+        s = xh[r0:r1] @ yh.T / tau
+        m = mask(r0, r1)
+        lse_r[r0:r1] = torch.logsumexp(s, dim=1)
+        pos[r0:r1] = (s * m).sum(1)
+        cnt[r0:r1] = m.sum(1)
+        bm = s.max(dim=0).values
+        new_m = torch.maximum(col_m, bm)
+        col_s = col_s * torch.exp(col_m - new_m) + torch.exp(s - new_m[None, :]).sum(0)
+        col_m = new_m
+    lse_c = col_m + col_s.log()
+    # symmetric mask: sum_i Y_ji S_ij over column j equals sum over the row-side positives of the transposed problem;
+    # M_ij = 1 implies c_i = c_j, so sum_j (1/c_j) sum_i M_ij S_ij = sum_i pos_i / c_i
+    loss = 0.5 * ((lse_r - pos / cnt).mean() + (lse_c.mean() - (pos / cnt).mean()))
+    # pass 2: dS block -> gradients
+    d_xh = torch.empty_like(xh)
+    d_yh = torch.zeros_like(yh)
+    for r0 in range(0, n, block):
+        r1 = min(n, r0 + block)
+        s = xh[r0:r1] @ yh.T / tau
+        m = mask(r0, r1).to(torch.float64)
+        ds = torch.exp(s - lse_r[r0:r1, None]) + torch.exp(s - lse_c[None, :])
+        ds -= m / cnt[r0:r1, None]
+        ds -= m / cnt[None, :]
+        ds /= 2.0 * n
+        d_xh[r0:r1] = ds @ yh / tau
+        d_yh += ds.T @ xh[r0:r1] / tau
+
+    def through_normalize(v, vh, nv, g):
+        out = (g - vh * (vh * g).sum(1, keepdim=True)) / nv.clamp_min(1e-12)
+        return torch.where(nv < 1e-12, g / 1e-12, out)
+
+    d_x = through_normalize(x, xh, nx, d_xh)
+    d_y = through_normalize(y, yh, ny, d_yh)
+    return float(loss.item()), d_x.cpu().numpy(), d_y.cpu().numpy()

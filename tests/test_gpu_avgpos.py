@@ -32,12 +32,15 @@ def test_avgpos_against_reference_golden(case):
         return
     out.sum().backward()
     rows = gold["rows"]
-    assert abs(out.item() - gold["loss64"]) <= 1e-5 * abs(gold["loss64"]) + 2e-6      # (all-positives case: loss == 0)
+    # absolute floors only for the degenerate all-positives case (loss == 0 and zero gradients in exact arithmetic)
+    degenerate = case.name == "ag_all_same"
+    floor_l, floor_g = (2e-6, 1e-8) if degenerate else (0.0, 0.0)
+    assert abs(out.item() - gold["loss64"]) <= 1e-5 * abs(gold["loss64"]) + floor_l
     scale_i = max(np.abs(gold["d_image64"]).max(), 1e-12)
-    assert np.abs(image.grad.cpu().numpy()[rows] - gold["d_image64"]).max() <= 1e-4 * scale_i + 1e-8
+    assert np.abs(image.grad.cpu().numpy()[rows] - gold["d_image64"]).max() <= 1e-4 * scale_i + floor_g
     if text is not None:
         scale_t = max(np.abs(gold["d_text64"]).max(), 1e-12)
-        assert np.abs(text.grad.cpu().numpy()[rows] - gold["d_text64"]).max() <= 1e-4 * scale_t + 1e-8
+        assert np.abs(text.grad.cpu().numpy()[rows] - gold["d_text64"]).max() <= 1e-4 * scale_t + floor_g
 
 
 def test_avgpos_against_oracle_on_fresh_inputs_and_patched_methods():

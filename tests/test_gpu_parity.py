@@ -171,3 +171,53 @@ def test_cuda_graph_step_matches_eager_and_tracks_new_inputs():
         assert abs(loss.item() - want) <= 1e-5 * abs(want)
         assert rel_max(g.image.grad.cpu().numpy(), d_i) <= 1e-4
         assert rel_max(g.text.grad.cpu().numpy(), d_t) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------- drop-in graph cache
+@pytest.mark.parametrize("precision,path,n,d", [("bf16", "tc", 1536, 256), ("fp32", "tc", 700, 128), ("fp32", "small", 64, 768)])
+def test_graph_cached_call_equals_the_eager_launch_sequence(precision, path, n, d):
+    """global_alignment(graph=True) replays two captured graphs over static buffers; the kernels and their order are
+    those of the eager call, so loss and gradients must be bit-identical - on fresh data of the same signature too,
+    with strided inputs, and under no_grad."""
+    from evoke_b200 import graphs
+    graphs.clear_graph_cache()
+    for seed in (1, 2, 3):
+        ids = synth.make_study_ids(n, seed=seed)
+        xi = synth.make_embeddings(ids, d, seed=seed + 10)
+        xt = synth.make_embeddings(ids, d, seed=seed + 20)
+        res = []
+        for graph in (False, True):
+            if seed == 3:      # strided head views
+                full_i = torch.zeros((n, d, 3), device=DEV)
+                full_i[:, :, 0] = torch.tensor(xi, device=DEV)
+                full_i.requires_grad_(True)
+                image, leaf_i = full_i.permute(0, 2, 1)[:, 0, :], full_i
+            else:
+                image = leaf_i = torch.tensor(xi, device=DEV, requires_grad=True)
+            text = torch.tensor(xt, device=DEV, requires_grad=True)
+            out = evoke_b200.global_alignment(image, text, ids, 0.5, precision=precision, path=path, graph=graph)
+            (out * 3.0).backward()                                  # a non-unit upstream gradient
+            gi = leaf_i.grad[:, :, 0] if seed == 3 else leaf_i.grad
+            res.append((out.item(), gi.clone(), text.grad.clone()))
+        assert res[0][0] == res[1][0]
+        assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    assert len(graphs._CACHE) == 1                                  # contiguous and strided inputs share one signature
+    with torch.no_grad():                                           # forward-only entry
+        a = evoke_b200.global_alignment(image.detach(), text.detach(), ids, 0.5, precision=precision, path=path, graph=True)
+    assert a.item() == res[1][0] and not a.requires_grad and len(graphs._CACHE) == 2
+
+
+def test_graph_cached_call_rejects_a_stale_backward():
+    from evoke_b200 import graphs
+    graphs.clear_graph_cache()
+    n, d = 1024, 128
+    ids = synth.make_study_ids(n, seed=5)
+    x = torch.tensor(synth.make_embeddings(ids, d, seed=1), device=DEV, requires_grad=True)
+    y = torch.tensor(synth.make_embeddings(ids, d, seed=2), device=DEV, requires_grad=True)
+    first = evoke_b200.global_alignment(x, y, ids, 0.5, precision="bf16", path="tc", graph=True)
+    second = evoke_b200.global_alignment(x, y, ids, 0.5, precision="bf16", path="tc", graph=True)
+    with pytest.raises(RuntimeError, match="stale"):
+        first.backward()
+    second.backward()
+    with pytest.raises(RuntimeError):
+        second.backward()

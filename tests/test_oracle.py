@@ -177,3 +177,46 @@ def test_local_token_alignment_closed_form_matches_reference_golden(name):
     assert _rel(d_v[:, :4], gold["d_image64"]) < 1e-9 and _rel(d_t[:, :4], gold["d_text64"]) < 1e-9
     assert abs(np.linalg.norm(d_v) - gold["d_image_norm64"]) <= 1e-9 * gold["d_image_norm64"]
     assert abs(np.linalg.norm(d_t) - gold["d_text_norm64"]) <= 1e-9 * gold["d_text_norm64"]
+
+
+def test_blockwise_fingerprint_form_equals_the_plain_closed_form():
+    """oracle/make_fingerprints.py evaluates the G loss in row blocks (so that N = 32768 fits in memory); it must be
+    the same function as g_loss_closed_form, for one-component and two-component keys."""
+    import numpy as np
+    from evoke_b200 import synth
+    from oracle import evoke_oracle as orc
+    from oracle import make_fingerprints as mf
+    n, d, tau = 700, 48, 0.3
+    ids = synth.make_study_ids(n, seed=3)
+    xi = synth.make_embeddings(ids, d, seed=4)
+    xt = synth.make_embeddings(ids, d, seed=5)
+    xi[5] = 0.0
+    want, w_i, w_t, _ = orc.g_loss_closed_form(xi, xt, ids, tau)
+    loss, d_i, d_t = mf.g_loss_blockwise(xi, xt, ids, tau, block=97)
+    assert abs(loss - want) <= 1e-7 * abs(want)                  # the plain form reproduces the fp32 rounding of 1/c (3e-8)
+    assert np.abs(d_i - w_i).max() <= 1e-6 * np.abs(w_i).max() and np.abs(d_t - w_t).max() <= 1e-6 * np.abs(w_t).max()
+    pat, stu = synth.make_patient_study_ids(n, seed=6)
+    skey = np.array([f"p{p}_s{s}" for p, s in zip(pat, stu)])
+    want, w_i, w_t, _ = orc.g_loss_closed_form(xi, xt, skey, tau)
+    loss, d_i, d_t = mf.g_loss_blockwise(xi, xt, pat, tau, key2=stu)
+    assert abs(loss - want) <= 1e-7 * abs(want)
+    assert np.abs(d_i - w_i).max() <= 1e-6 * np.abs(w_i).max()
+    fp = mf.fingerprint(loss, d_i, d_t)
+    assert len(fp["rows"]) == 16 and len(set(fp["rows"])) == 16
+
+
+def test_committed_fingerprints_belong_to_the_bench_workloads():
+    """The golden fingerprints bench.py compares against are those of ITS workloads (cheap check: cfg2 recomputed)."""
+    import json
+    import os
+    from oracle import make_fingerprints as mf
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    xi, xt, key, key2, tau = mf.workload("cfg2")
+    loss, d_i, d_t = mf.g_loss_blockwise(xi, xt, key, tau, key2)
+    got = mf.fingerprint(loss, d_i, d_t)
+    want = json.load(open(os.path.join(root, "tests", "golden", "fingerprint_cfg2.json")))
+    assert abs(got["loss"] - want["loss"]) <= 1e-12 * abs(want["loss"])
+    assert got["rows"] == want["rows"]
+    assert max(abs(a - b) for a, b in zip(got["d_image_row_norms"], want["d_image_row_norms"])) <= 1e-12
+    for cfg in ("cfg3", "cfg4"):
+        assert os.path.isfile(os.path.join(root, "tests", "golden", f"fingerprint_{cfg}.json"))
