@@ -67,7 +67,7 @@ SIGNATURES = {
     "evk_peer_close": [P],
     "evk_peer_barrier": [P, P, I, I, P, P, L, P],
     "evk_mpce_shard_finish": [P, I, L, L, F, D, P, P, P, L, P, P, P],
-    "evk_mpce_bwd_gemm_scatter": [P, P, L, L, L, P, P, L, L, F, I, P, I, L, L, I, P],
+    "evk_mpce_bwd_gemm_scatter": [P, P, L, L, L, P, P, L, L, F, I, P, I, L, L, I, I, P],
     "evk_l2norm_bwd_parts": [P, I, L, L, L, L, P, P, P, I, L, I, L, P, F, P, I, L, I, P, P],
     "evk_tc_gemm_probe": [P, L, I, P, L, I, L, L, L, P, L, I, I, P],
 }

@@ -82,6 +82,7 @@ struct alignas(64) TcParams {
   // are then visited column-block-major starting at this rank's own columns (rot_tiles), and the producer waits for
   // landed[source] >= *step before its first load from a source's columns.
   const uint32_t* landed; const int* step; int* error; int64_t cols_per_source; int rot_tiles;
+  int rot_m_tiles;               // EPI_GEMM_TMA scatter: first row block (pair tile) to visit, see Sched
   // EPI_GEMM
   float* out; int64_t ld_out; float alpha;
   // EPI_GEMM, reduce-scatter fused into the epilogue: output row i belongs to rank i / rows_per_owner and
@@ -119,13 +120,15 @@ constexpr int smem_bytes_total() {
 //               numbered column-block-major (mb fastest) so that the groups working on the same rows of W
 //               at the same time are the ones with different nb: the strip is read from HBM once.
 struct Sched {
-  int splits, total_kb, m_tiles, n_tiles, num_groups, u, total_units, rot;
+  int splits, total_kb, m_tiles, n_tiles, num_groups, u, total_units, rot, rot_m;
   int64_t pos, end;
   // rot_ >= 0 (splits == 1 only): column-block-major order starting at column tile rot_ (sharded K3)
+  // rot_m_ > 0 (row-block-major order only): the row blocks are visited starting at row block rot_m_ (fused
+  // reduce-scatter: every rank starts with a different owner, so no GPU is the destination of all ranks at once)
   __device__ __forceinline__ void init(int splits_, int total_kb_, int m_tiles_, int n_tiles_, int group_id,
-                                       int num_groups_, int rot_ = -1) {
+                                       int num_groups_, int rot_ = -1, int rot_m_ = 0) {
     splits = splits_; total_kb = total_kb_; m_tiles = m_tiles_; n_tiles = n_tiles_; num_groups = num_groups_;
-    rot = rot_;
+    rot = rot_; rot_m = rot_m_;
     u = group_id;
     total_units = m_tiles * n_tiles * (splits > 0 ? splits : 1);
     const int64_t items = (int64_t)m_tiles * n_tiles * total_kb;
@@ -143,6 +146,8 @@ struct Sched {
         if (nb >= n_tiles) nb -= n_tiles;
       } else {
         mb = tile / n_tiles; nb = tile - mb * n_tiles;
+        mb += rot_m;
+        if (mb >= m_tiles) mb -= m_tiles;
       }
       kb0 = (int)(((int64_t)sp * total_kb) / splits);
       kb1 = (int)(((int64_t)(sp + 1) * total_kb) / splits);
@@ -237,7 +242,8 @@ tc_kernel(const __grid_constant__ TcParams p) {
   const int total_kb = p.num_segs * p.kb_per_seg;
   Sched sched;
   sched.init(p.splits, total_kb, p.m_tiles, p.n_tiles, group_id, num_groups,
-             ((EPI == EPI_FWD || EPI == EPI_FWD_E) && p.landed) ? p.rot_tiles : -1);
+             ((EPI == EPI_FWD || EPI == EPI_FWD_E) && p.landed) ? p.rot_tiles : -1,
+             (EPI == EPI_GEMM_TMA || EPI == EPI_GEMM) ? p.rot_m_tiles : 0);
   int mb, nb, kb0, kb1;
 
   if (warp == kProducerWarp) {
@@ -873,7 +879,9 @@ int check_device() {
   int dev = 0;
   EVK_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !((ctx_bound >> dev) & 1ull)) {
-    EVK_CUDA(cudaFree(nullptr));
+    // cudaSetDevice initialises the primary context and makes it current on this thread; unlike cudaFree(nullptr)
+    // it is legal while another thread's stream is being captured
+    EVK_CUDA(cudaSetDevice(dev));
     if (dev >= 0 && dev < 64) ctx_bound |= 1ull << dev;
   }
   if (!evk_is_sm100())
@@ -1153,7 +1161,7 @@ extern "C" int evk_mpce_bwd_gemm(const void* w_hi, const void* w_lo, int64_t ld_
 extern "C" int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int64_t ld_w, int64_t n_rows, int64_t n_cols,
                                          const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d, float alpha,
                                          int flags, const uint64_t* out_ptrs, int n_owners, int64_t rows_per_owner,
-                                         int64_t ld_out, int store, evk_stream_t stream) {
+                                         int64_t ld_out, int store, int first_owner, evk_stream_t stream) {
   flags &= EVK_FLAG_PUBLIC_MASK;
   int rc = check_device();
   if (rc != EVK_OK) return rc;
@@ -1170,6 +1178,12 @@ extern "C" int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int
     EVK_REQUIRE(p.out_peer[r] && evk_aligned16(p.out_peer[r]), "evk_mpce_bwd_gemm_scatter: owner buffers must be 16-byte aligned");
   }
   p.rows_per_owner = rows_per_owner;
+  EVK_REQUIRE(first_owner >= 0 && first_owner < n_owners, "evk_mpce_bwd_gemm_scatter: first_owner out of range");
+  {
+    // the row blocks (keys) of owner `first_owner` are computed - and sent - first
+    const int64_t tile_m = use_cta_pairs() ? 2 * BM : BM;
+    p.rot_m_tiles = (int)(((int64_t)first_owner * rows_per_owner) / tile_m);
+  }
   if (store) p.flags |= kIntStore;
   if (store == 2) {
     EVK_REQUIRE(use_cta_pairs() && use_tma_epilogue(), "evk_mpce_bwd_gemm_scatter: bf16 partials need the TMA epilogue (CTA pairs)");

@@ -268,7 +268,8 @@ def peer_backward(st, g: torch.Tensor):
     # exchange 3, fused: the tiles of this rank's partial dKhat are stored straight into their owners'
     # per-source buffers (posted NVLink stores from the GEMM epilogue; no split-K, no zero fill)
     _lib.call("evk_mpce_bwd_gemm_scatter", e.data_ptr(), None, ld_e, n, n_total, qn.hi.data_ptr(), None, qn.ld, qn.d,
-              1.0, 0, pc.table("dk_mine"), pc.world, n, pc.width, 2 if pc.exchange == "bf16" else 1, main.cuda_stream)
+              1.0, 0, pc.table("dk_mine"), pc.world, n, pc.width, 2 if pc.exchange == "bf16" else 1,
+              SCATTER_FIRST_OWNER(pc), main.cuda_stream)
 
     def image_side():
         ops.tc_bwd_gemm(e, None, ld_e, n, n_total, False, kn_all, 0, out=dq)      # dq was zeroed by the prologue
@@ -334,6 +335,13 @@ def peer_eligible(image: torch.Tensor, text: torch.Tensor, precision: str, world
     n, d = int(image.shape[0]), int(image.shape[1])
     return (precision == "bf16" and image.is_cuda and text.is_cuda and world <= 16 and n % 128 == 0 and d % 8 == 0
             and d <= 2048 and image.dtype == text.dtype and image.dtype in _FLOAT_DTYPES)
+
+
+def SCATTER_FIRST_OWNER(pc) -> int:
+    """Owner whose rows the fused reduce-scatter contraction computes (and sends) first: rank + 1, so that at any
+    moment every GPU is the destination of about one sender (EVOKE_B200_SCATTER_ROTATE=0: owner 0 on every rank, the
+    round-1 order, kept for A/B measurements)."""
+    return (pc.rank + 1) % pc.world if os.environ.get("EVOKE_B200_SCATTER_ROTATE", "1") == "1" else 0
 
 
 PEER_EXCHANGE = os.environ.get("EVOKE_B200_PEER_EXCHANGE", "bf16")     # dtype of the dKhat partials on NVLink: bf16 | fp32

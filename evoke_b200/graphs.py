@@ -44,10 +44,10 @@ class GraphedGlobalAlignment:
         if self.sharded:
             from .distributed import global_alignment_sharded
             out = global_alignment_sharded(self.image, self.text, self._ids, self.temp, group=self.group,
-                                           precision=self.precision, mode=self.shard_mode)
+                                           precision=self.precision, mode=self.shard_mode, graph=False)
         else:
             out = _loss.global_alignment(self.image, self.text, self._ids, self.temp, precision=self.precision,
-                                         path=self.path)
+                                         path=self.path, graph=False)     # this object IS the graph
         out.backward()
         return out
 

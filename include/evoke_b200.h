@@ -465,13 +465,17 @@ EVK_API int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_sl
  * is written exactly once, so out_ptrs[o] must be a buffer private to THIS source rank (the owner then adds the
  * per-source buffers up: evk_l2norm_bwd_parts) and needs no zero fill.  Posted stores use NVLink far better
  * than 16-byte atomics.  store == 2: the partials are stored as bf16 ([rows_per_owner, ld_out] bf16, ld_out % 8 == 0):
- * half the NVLink bytes; the owner still adds them up in fp32. */
+ * half the NVLink bytes; the owner still adds them up in fp32.
+ * first_owner: the tiles of this owner's rows are computed and sent first, then first_owner + 1, ... (wrapping).
+ * Every rank should pass a different value ((rank + 1) % n_owners): with the same order on every rank all GPUs
+ * would store into the same owner at the same time and its NVLink ingress (not the sum over GPUs) would bound
+ * the exchange. */
 EVK_API int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int64_t ld_w,
                               int64_t n_rows, int64_t n_cols,
                               const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d,
                               float alpha, int flags,
                               const uint64_t* out_ptrs, int n_owners, int64_t rows_per_owner, int64_t ld_out,
-                              int store, evk_stream_t stream);
+                              int store, int first_owner, evk_stream_t stream);
 
 /* Debug/bring-up: plain C[m,n] = A[m,k] B[n,k]^T (or MN-major operands) through the same
  * tcgen05 main loop, fp32 out.  a_major/b_major: 0 = K contiguous, 1 = M/N contiguous

@@ -24,8 +24,8 @@ from oracle import evoke_oracle as orc
 pytestmark = pytest.mark.gpu
 
 LOSS_TOL = {"fp32": 1e-5, "bf16": 1e-5}
-GRAD_TOL = {"fp32": 1e-4, "bf16": 2e-2}          # max-norm relative (north_star)
-ROW_TOL = {"fp32": 2e-4, "bf16": 2e-2}           # per-row relative L2
+GRAD_TOL = {"fp32": 1e-4, "bf16": 1e-2}          # max-norm relative (north_star: 1e-4 / 2e-2; achieved 4e-5 / 4e-3)
+ROW_TOL = {"fp32": 1e-4, "bf16": 1e-2}           # per-row relative L2 (achieved 4e-5 / 3e-3)
 
 
 def _record(name, **vals):
@@ -122,7 +122,7 @@ def test_cfg4_two_key_mid_size_against_the_numpy_oracle(n, d, tau, precision, pa
     assert got_str[0] == got_host[0]
     # patient-only positives are a DIFFERENT objective: the two-key mask must not degrade to it
     p_loss = orc.g_loss_closed_form(xi, xt, pat, tau)[0]
-    assert abs(p_loss - w_loss) > 1e-3 * abs(w_loss)
+    assert abs(p_loss - w_loss) > 2e-5 * abs(w_loss)             # well outside the 1e-5 loss tolerance
 
 
 def test_cfg4_full_size_two_key_bf16():
