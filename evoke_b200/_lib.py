@@ -33,7 +33,7 @@ SIGNATURES = {
     "evk_mpce_strip_ld": [L],
     "evk_l2norm_fwd": [P, I, L, L, L, L, P, P, L, P, P, L, P, P],
     "evk_l2norm_bwd": [P, I, L, L, L, L, P, P, P, L, P, F, P, I, L, I, P],
-    "evk_posmask_build": [P, P, L, P, P, L, L, I, P, L, P, P, I, P],
+    "evk_posmask_build": [P, P, L, P, P, L, L, I, P, L, P, P, I, I, P, P],
     "evk_mpce_small_fwd": [P, L, P, L, L, L, L, P, L, F, I, L, P, P, P],
     "evk_mpce_small_bwd": [P, L, P, L, L, L, L, P, L, P, P, P, F, I, L, P, L, P, P, P],
     "evk_mpce_finalize_avgpos": [P, P, P, L, F, D, P, P, P, I, P],
@@ -51,24 +51,25 @@ SIGNATURES = {
     "evk_mpce_bwd_w": [P, P, L, P, P, L, L, L, L, P, L, P, P, P, F, I, L, P, P, L, P],
     "evk_mpce_bwd_gemm": [P, P, L, L, L, I, P, P, L, L, F, I, P, L, P],
     "evk_mpce_fwd_store": [P, L, P, L, L, L, L, P, L, F, I, L, P, P, L, P, L, P, L, P],
-    "evk_mpce_w_from_e": [P, L, L, L, P, L, P, P, P, P, L, P, L, L, F, P, P, I, P],
+    "evk_mpce_w_from_e": [P, L, L, L, P, L, P, P, P, P, L, P, L, L, F, P, P, I, P, P, P, P, L, I, P],
     "evk_mpce_pos_logits": [P, L, P, L, L, L, P, P, I, P, P],
+    "evk_mpce_pos_from_lists": [P, L, P, L, L, L, L, P, P, P, P, L, I, P, P, I, F, P, P],
     "evk_l2norm_fwd_bcast": [P, I, L, L, L, L, I, P, P, L, L, P, P],
     "evk_peer_bcast": [P, L, I, P, L, P],
-    "evk_shard_prologue": [P, I, L, L, P, I, L, L, L, L, I, P, L, L, P, P, P, P, P, I, P, P, P, L, P, P, P],
+    "evk_shard_prologue": [P, I, L, L, P, I, L, L, L, L, I, P, L, L, P, P, P, P, P, I, P, P, P, L, P, L, P, P, P],
     "evk_peer_push_shard": [P, L, I, I, P, L, P, P, P, P],
     "evk_peer_wait_landed": [P, I, P, P, L, P],
     "evk_mpce_fwd_store_gathered": [P, L, P, L, L, L, L, P, L, F, I, L, P, P, L, P, L, P, L, P, P, P, L, L, P],
-    "evk_mpce_shard_stats_push": [P, L, L, P, L, L, P, L, P, L, L, L, F, F, D, P, P, I, L, P, L, P],
+    "evk_mpce_shard_stats_push": [P, L, L, P, L, L, P, L, P, L, L, L, F, F, D, P, P, I, L, P, L, I, P],
     "evk_peer_alloc": [L, P],
     "evk_peer_free": [P],
     "evk_peer_export": [P, P],
     "evk_peer_open": [P, P],
     "evk_peer_close": [P],
     "evk_peer_barrier": [P, P, I, I, P, P, L, P],
-    "evk_mpce_shard_finish": [P, I, L, L, F, D, P, P, P, L, P, P, P],
+    "evk_mpce_shard_finish": [P, I, L, L, F, D, P, P, P, L, I, P, P, P, P],
     "evk_mpce_bwd_gemm_scatter": [P, P, L, L, L, P, P, L, L, F, I, P, I, L, L, I, I, P],
-    "evk_l2norm_bwd_parts": [P, I, L, L, L, L, P, P, P, I, L, I, L, P, F, P, I, L, I, P, P],
+    "evk_l2norm_bwd_parts": [P, I, L, L, L, L, P, P, P, I, L, I, L, P, F, P, I, L, I, P, P, P],
     "evk_tc_gemm_probe": [P, L, I, P, L, I, L, L, L, P, L, I, I, P],
 }
 
@@ -77,6 +78,13 @@ INT64_RESULT = {"evk_stats_workspace_bytes", "evk_shard_finish_workspace_bytes",
                 "evk_mpce_rowpart_rows", "evk_mpce_colpart_rows", "evk_mpce_strip_ld"}
 
 _lib = None
+
+
+class PeerSync(ctypes.Structure):
+    """evk_peer_sync_t of include/evoke_b200.h (host struct, passed by pointer)."""
+    _fields_ = [("flag_ptrs", ctypes.c_uint64 * 16), ("err_ptrs", ctypes.c_uint64 * 16), ("err_host", c_void_p),
+                ("step", c_void_p), ("n_ranks", c_int), ("rank", c_int), ("index", c_int), ("per_step", c_int),
+                ("timeout_ms", c_int64)]
 
 
 class EvokeLibraryError(RuntimeError):
@@ -121,7 +129,7 @@ KERNELS_PER_CALL = {
     "evk_l2norm_fwd": 1, "evk_l2norm_bwd": 1, "evk_posmask_build": 1, "evk_mpce_small_fwd": 1,
     "evk_mpce_small_bwd": 1, "evk_reduce_partials": 1, "evk_mpce_finalize": 1, "evk_mpce_stats_fused": 1, "evk_mpce_pos": 1, "evk_mpce_fwd": 1,
     "evk_mpce_bwd_w": 1, "evk_mpce_bwd_gemm": 1, "evk_tc_gemm_probe": 1, "evk_l2norm_fwd_bcast": 1,
-    "evk_peer_bcast": 1, "evk_mpce_fwd_store": 1, "evk_mpce_w_from_e": 3, "evk_mpce_pos_logits": 1,
+    "evk_peer_bcast": 1, "evk_mpce_fwd_store": 1, "evk_mpce_w_from_e": 3, "evk_mpce_pos_logits": 1, "evk_mpce_pos_from_lists": 1,
     "evk_peer_barrier": 1, "evk_mpce_small_fwd_batched": 1, "evk_mpce_small_bwd_batched": 1,
     "evk_local_attend_fwd": 1, "evk_local_attend_bwd": 2, "evk_token_sim_fwd": 1, "evk_token_sim_bwd": 1, "evk_peer_push_shard": 1, "evk_peer_wait_landed": 1, "evk_mpce_fwd_store_gathered": 1, "evk_mpce_finalize_avgpos": 1, "evk_shard_prologue": 1, "evk_mpce_shard_stats_push": 1, "evk_l2norm_bwd_parts": 1, "evk_mpce_shard_finish": 1, "evk_mpce_bwd_gemm_scatter": 1,
 }

@@ -6,6 +6,7 @@
 // the scale pass, 128-bit bf16 stores.  Algorithmic bytes per row (fp32 in, bf16 hi out):
 // 4*d + 2*d (+2*d with the lo half, +4*d with the fp32 copy).
 #include "evk_common.cuh"
+#include "peer_sync.cuh"
 
 namespace {
 
@@ -125,7 +126,8 @@ l2norm_bwd_kernel(const void* __restrict__ x, int x_dtype, int64_t n_out, int64_
                   const void* __restrict__ g, int g_dtype, int64_t ld_g, int n_parts, int64_t part_stride,
                   const float* __restrict__ scale_dev,
                   float scale_host, void* __restrict__ dx, int dx_dtype, int64_t ld_dx, int accumulate,
-                  const int* __restrict__ error) {
+                  const int* __restrict__ error, const PeerSyncDev sync) {
+  peer_sync_block(sync, blockIdx.x == 0);
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
@@ -178,7 +180,9 @@ l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t
                       const int32_t* __restrict__ gather, const float* __restrict__ norm,
                       const void* __restrict__ g, int64_t ld_g, int n_parts, int64_t part_stride,
                       const float* __restrict__ scale_dev,
-                      float scale_host, float* __restrict__ dx, int64_t ld_dx, const int* __restrict__ error) {
+                      float scale_host, float* __restrict__ dx, int64_t ld_dx, const int* __restrict__ error,
+                      const PeerSyncDev sync) {
+  peer_sync_block(sync, blockIdx.x == 0);         // sharded: the partial buffers were stored by the peers' contractions
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
@@ -212,8 +216,27 @@ l2norm_bwd_vec_kernel(const float* __restrict__ x, int64_t n_out, int d, int64_t
       }
     }
     if (kParts) {
-      for (int p = 1; p < n_parts; ++p) {          // partial dXhat buffers written by the ranks' K4b epilogues:
-        float4 t[kIters];                          // all loads of one part are in flight together
+      // partial dXhat buffers written by the ranks' K4b epilogues, summed in index order.  The loads of TWO parts
+      // are in flight together (the round trips, not the bytes, bound this loop: 7 dependent rounds at 8 ranks)
+      int p = 1;
+      for (; p + 1 < n_parts; p += 2) {
+        float4 t0[kIters], t1[kIters];
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+          const int c = it * 32 + lane;
+          if (c * 4 < d) { t0[it] = gload(p, c); t1[it] = gload(p + 1, c); }
+        }
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+          const int c = it * 32 + lane;
+          if (c * 4 < d) {
+            gv[it].x = (gv[it].x + t0[it].x) + t1[it].x; gv[it].y = (gv[it].y + t0[it].y) + t1[it].y;
+            gv[it].z = (gv[it].z + t0[it].z) + t1[it].z; gv[it].w = (gv[it].w + t0[it].w) + t1[it].w;
+          }
+        }
+      }
+      for (; p < n_parts; ++p) {
+        float4 t[kIters];
 #pragma unroll
         for (int it = 0; it < kIters; ++it) {
           const int c = it * 32 + lane;
@@ -303,14 +326,20 @@ extern "C" int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, i
                                     int64_t stride_col, const int32_t* gather, const float* norm, const void* g,
                                     int g_dtype, int64_t ld_g, int n_parts, int64_t part_stride, const float* scale_dev,
                                     float scale_host, void* dx, int dx_dtype, int64_t ld_dx, int accumulate,
-                                    const int* error, evk_stream_t stream) {
+                                    const int* error, const evk_peer_sync_t* sync, evk_stream_t stream) {
   EVK_REQUIRE(x && norm && g && dx, "evk_l2norm_bwd: null pointer");
+  PeerSyncDev ps;
+  {
+    int rc = peer_sync_from_host(sync, ps);
+    if (rc != EVK_OK) return rc;
+  }
   EVK_REQUIRE(n_parts >= 1 && (n_parts == 1 || part_stride >= n_out * ld_g), "evk_l2norm_bwd_parts: bad partial-buffer layout");
   EVK_REQUIRE(g_dtype == EVK_DTYPE_F32 || g_dtype == EVK_DTYPE_BF16, "evk_l2norm_bwd_parts: partial buffers must be fp32 or bf16");
   EVK_REQUIRE(n_out >= 0 && d > 0 && ld_g >= d && ld_dx >= d, "evk_l2norm_bwd: bad shape");
   EVK_REQUIRE(x_dtype >= EVK_DTYPE_F32 && x_dtype <= EVK_DTYPE_F16 && dx_dtype >= EVK_DTYPE_F32 &&
                   dx_dtype <= EVK_DTYPE_F16, "evk_l2norm_bwd: bad dtype");
   EVK_REQUIRE(!accumulate || dx_dtype == EVK_DTYPE_F32, "evk_l2norm_bwd: accumulate needs fp32 dx");
+  EVK_REQUIRE(n_out > 0 || !sync, "evk_l2norm_bwd_parts: a folded sync needs at least one row");
   if (n_out == 0) return EVK_OK;
   const bool vec = x_dtype == EVK_DTYPE_F32 && dx_dtype == EVK_DTYPE_F32 && !accumulate && stride_col == 1 &&
                    d % 4 == 0 && d <= 2048 && stride_row % 4 == 0 && ld_g % 4 == 0 && ld_dx % 4 == 0 && part_stride % 4 == 0 &&
@@ -324,7 +353,7 @@ extern "C" int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, i
 #define EVK_LAUNCH_BWD(IT, B16, PARTS)                                                                                    \
   l2norm_bwd_vec_kernel<IT, B16, PARTS><<<grid, kWarpsPerBlock * 32, 0, s>>>(xf, n_out, (int)d, stride_row, gather, norm, g, \
                                                                              ld_g, n_parts, part_stride, scale_dev,           \
-                                                                             scale_host, df, ld_dx, error)
+                                                                             scale_host, df, ld_dx, error, ps)
     const bool multi = n_parts > 1;
     if (d <= 1024) {
       if (g16) { if (multi) EVK_LAUNCH_BWD(8, true, true); else EVK_LAUNCH_BWD(8, true, false); }
@@ -339,7 +368,7 @@ extern "C" int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, i
   }
   l2norm_bwd_kernel<<<grid_for_rows(n_out), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       x, x_dtype, n_out, d, stride_row, stride_col, gather, norm, g, g_dtype, ld_g, n_parts, part_stride, scale_dev, scale_host, dx,
-      dx_dtype, ld_dx, accumulate, error);
+      dx_dtype, ld_dx, accumulate, error, ps);
   EVK_CHECK_LAUNCH("l2norm_bwd");
   return EVK_OK;
 }
@@ -349,5 +378,5 @@ extern "C" int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t
                               int64_t ld_g, const float* scale_dev, float scale_host, void* dx, int dx_dtype,
                               int64_t ld_dx, int accumulate, evk_stream_t stream) {
   return evk_l2norm_bwd_parts(x, x_dtype, n_out, d, stride_row, stride_col, gather, norm, g, EVK_DTYPE_F32, ld_g, 1, 0, scale_dev,
-                              scale_host, dx, dx_dtype, ld_dx, accumulate, nullptr, stream);
+                              scale_host, dx, dx_dtype, ld_dx, accumulate, nullptr, nullptr, stream);
 }

@@ -15,10 +15,14 @@
 // Degenerate inputs (every key equal) degrade gracefully to one compare per pair.  Exact: keys are
 // compared in full, the hash only picks the starting slot.
 //
+// bits == NULL builds counts and lists only: the bf16 mode of the large path needs nothing of size N^2 from the ids
+// (positive sums and exact W entries come from the lists; rows with more positives than slots are handled by an id
+// scan, see evk_mpce_pos_from_lists / evk_mpce_w_from_e).
 // Optional second output: pos_idx[r, s] = column of the s-th positive of row r (s < pos_slots; the order
 // within a row is unspecified, rows with more positives keep only the first pos_slots - counts[r] tells).
 // The O(N) consumers of the positives (exact W entries, K4t) then need no scan of the N^2/8-byte mask.
 #include "evk_common.cuh"
+#include "peer_sync.cuh"
 
 namespace {
 
@@ -42,7 +46,8 @@ __global__ void __launch_bounds__(kThreads)
 posmask_kernel(const int32_t* __restrict__ ids_row, const int32_t* __restrict__ ids2_row, int64_t n_rows,
                const int32_t* __restrict__ ids_col, const int32_t* __restrict__ ids2_col, int64_t n_cols,
                int64_t diag_offset, int clear_diag, uint32_t* __restrict__ bits, int64_t ld_words,
-               int32_t* __restrict__ counts, int vec_ok, int32_t* __restrict__ pos_idx, int pos_slots) {
+               int32_t* __restrict__ counts, int vec_ok, int32_t* __restrict__ pos_idx, int pos_slots,
+               const PeerSyncDev sync) {
   __shared__ int32_t t_col[kSlots];                      // column (0..1023) held by the slot, -1 = empty
   __shared__ int32_t t_key[kSlots];
   __shared__ int32_t t_key2[kTwoKeys ? kSlots : 1];
@@ -52,6 +57,7 @@ posmask_kernel(const int32_t* __restrict__ ids_row, const int32_t* __restrict__ 
   const int64_t w0 = c0 >> 5;
   const int64_t r_cta = (int64_t)blockIdx.y * kRowsPerCta;
 
+  peer_sync_block(sync, blockIdx.x == 0 && blockIdx.y == 0);     // sharded: the column ids come from the peers
   for (int s = threadIdx.x; s < kSlots; s += kThreads) t_col[s] = -1;
   for (int k = lane; k < 32 * kTilePitch; k += 32) tile[warp][k] = 0u;
   __syncthreads();
@@ -79,7 +85,7 @@ posmask_kernel(const int32_t* __restrict__ ids_row, const int32_t* __restrict__ 
         const int32_t c = t_col[s];
         if (c < 0) break;
         if (t_key[s] == key && (!kTwoKeys || t_key2[s] == key2) && (int64_t)c != diag) {
-          my[lane * kTilePitch + (c >> 5)] |= 1u << (c & 31);
+          if (bits) my[lane * kTilePitch + (c >> 5)] |= 1u << (c & 31);
           // positives are rare: one atomic each; its return value is the entry's slot in the row's list
           const int slot = atomicAdd(counts + r, 1);
           if (pos_idx && slot < pos_slots) pos_idx[r * pos_slots + slot] = (int32_t)(c0 + c);
@@ -88,6 +94,7 @@ posmask_kernel(const int32_t* __restrict__ ids_row, const int32_t* __restrict__ 
       }
     }
     __syncwarp();
+    if (!bits) continue;                         // list-only build: nothing of size N^2 is written
     // stream the 32 x 8-word tile out (and clear it for the next row group): 32 bytes per row
     if (vec_ok) {
 #pragma unroll
@@ -116,25 +123,30 @@ posmask_kernel(const int32_t* __restrict__ ids_row, const int32_t* __restrict__ 
 extern "C" int evk_posmask_build(const int32_t* ids_row, const int32_t* ids2_row, int64_t n_rows,
                                  const int32_t* ids_col, const int32_t* ids2_col, int64_t n_cols,
                                  int64_t diag_offset, int clear_diag, uint32_t* bits, int64_t ld_words,
-                                 int32_t* counts, int32_t* pos_idx, int pos_slots, evk_stream_t stream) {
-  EVK_REQUIRE(ids_row && ids_col && bits && counts, "evk_posmask_build: null pointer");
+                                 int32_t* counts, int32_t* pos_idx, int pos_slots, int counts_zeroed,
+                                 const evk_peer_sync_t* sync, evk_stream_t stream) {
+  EVK_REQUIRE(ids_row && ids_col && counts && (bits || pos_idx), "evk_posmask_build: null pointer (bits may be NULL only with pos_idx)");
   EVK_REQUIRE((ids2_row == nullptr) == (ids2_col == nullptr), "evk_posmask_build: ids2_row/ids2_col must both be set or both null");
   EVK_REQUIRE(n_rows >= 0 && n_cols >= 0, "evk_posmask_build: negative size");
+  if (!bits) ld_words = (n_cols + 31) / 32;      // list-only build: ld_words only sizes the grid
   EVK_REQUIRE(ld_words >= (n_cols + 31) / 32, "evk_posmask_build: ld_words=%lld < ceil(n_cols/32)", (long long)ld_words);
   EVK_REQUIRE(!pos_idx || (pos_slots >= 1 && pos_slots <= 64), "evk_posmask_build: pos_slots must be in 1..64");
   if (n_rows == 0) return EVK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  EVK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_rows, s));
+  PeerSyncDev ps;
+  int rc = peer_sync_from_host(sync, ps);
+  if (rc != EVK_OK) return rc;
+  if (!counts_zeroed) EVK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_rows, s));
   if (ld_words == 0) return EVK_OK;
   const dim3 grid((unsigned)((ld_words * 32 + kColsPerCta - 1) / kColsPerCta), (unsigned)((n_rows + kRowsPerCta - 1) / kRowsPerCta));
   EVK_REQUIRE(grid.y <= 65535u, "evk_posmask_build: n_rows=%lld too large for one launch", (long long)n_rows);
-  const int vec_ok = (ld_words % 4 == 0 && evk_aligned16(bits)) ? 1 : 0;
+  const int vec_ok = (bits && ld_words % 4 == 0 && evk_aligned16(bits)) ? 1 : 0;
   if (ids2_row)
     posmask_kernel<true><<<grid, kThreads, 0, s>>>(ids_row, ids2_row, n_rows, ids_col, ids2_col, n_cols, diag_offset,
-                                                   clear_diag, bits, ld_words, counts, vec_ok, pos_idx, pos_slots);
+                                                   clear_diag, bits, ld_words, counts, vec_ok, pos_idx, pos_slots, ps);
   else
     posmask_kernel<false><<<grid, kThreads, 0, s>>>(ids_row, ids2_row, n_rows, ids_col, ids2_col, n_cols, diag_offset,
-                                                    clear_diag, bits, ld_words, counts, vec_ok, pos_idx, pos_slots);
+                                                    clear_diag, bits, ld_words, counts, vec_ok, pos_idx, pos_slots, ps);
   EVK_CHECK_LAUNCH("posmask");
   return EVK_OK;
 }

@@ -11,6 +11,7 @@
 // pointers; the local one included).  Cross-rank ordering (all shards landed / buffers free again) is
 // the caller's job: a symmetric-memory barrier between producer and consumer kernels.
 #include "evk_common.cuh"
+#include "peer_sync.cuh"
 
 #include <string.h>
 
@@ -99,6 +100,7 @@ struct Prologue {
   const int32_t* ids; const int32_t* ids2;
   int32_t* ids_dst[kMaxPeers]; int32_t* ids2_dst[kMaxPeers];
   float* zero; int64_t ld_zero; int zero_width;
+  int32_t* zero_i32; int64_t n_zero_i32;  // K2's counts (K2 then needs no memset node)
   int64_t n, ld, row_offset;
   int d;
   int* step;                            // optional device counter advanced once per launch (one step = one epoch)
@@ -115,6 +117,8 @@ shard_prologue_kernel(const Prologue p) {
   // more (the step's loss and gradients are poisoned downstream, the host raises at its next entry)
   if (p.error && *reinterpret_cast<const volatile int*>(p.error) != 0) return;
   if (p.step && blockIdx.x == 0 && threadIdx.x == 0) *p.step += 1;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < p.n_zero_i32; t += (int64_t)gridDim.x * blockDim.x)
+    p.zero_i32[t] = 0;
   // ids: one element per thread, pushed to every rank
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < p.n; t += (int64_t)gridDim.x * blockDim.x) {
     const int32_t v = __ldg(p.ids + t);
@@ -245,9 +249,10 @@ __global__ void __launch_bounds__(kFinishThreads)
 shard_finish_kernel(const float* __restrict__ slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
                     double inv_count, float* __restrict__ b_col, float* __restrict__ loss_out,
                     double* __restrict__ cta_partial, unsigned int* __restrict__ ticket, const int* __restrict__ error,
-                    int* __restrict__ error_host) {
+                    int* __restrict__ error_host, const PeerSyncDev sync) {
   __shared__ double s_part[kFinishThreads / 32];
   __shared__ bool s_last;
+  peer_sync_block(sync, blockIdx.x == 0);          // the slots were stored by the peers' statistics kernels
   const int64_t j = (int64_t)blockIdx.x * kFinishThreads + threadIdx.x;
   // a barrier of this step timed out: some slot / key rows may be stale -> the result must not look valid
   const bool poisoned = error && *reinterpret_cast<const volatile int*>(error) != 0;
@@ -281,6 +286,7 @@ shard_finish_kernel(const float* __restrict__ slots, int n_slots, int64_t ld_slo
       t *= inv_count;
       for (int r = 0; r < n_slots; ++r) t += (double)slots[r * ld_slot + n_cols];
       loss_out[0] = poisoned ? __int_as_float(0x7fc00000) : (float)t;
+      *ticket = 0u;                                  // a persistent workspace is ready for the next call
     }
   }
 }
@@ -462,7 +468,13 @@ extern "C" int evk_peer_barrier(const uint64_t* flag_ptrs, const uint64_t* error
 
 extern "C" int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
                                      double inv_count, float* b_col, float* loss_out, void* workspace,
-                                     int64_t workspace_bytes, const int* error, int* error_host, evk_stream_t stream) {
+                                     int64_t workspace_bytes, int workspace_persistent, const int* error, int* error_host,
+                                     const evk_peer_sync_t* sync, evk_stream_t stream) {
+  PeerSyncDev ps;
+  {
+    int rc = peer_sync_from_host(sync, ps);
+    if (rc != EVK_OK) return rc;
+  }
   EVK_REQUIRE(slots && b_col && loss_out && n_slots >= 1 && n_cols > 0 && ld_slot > n_cols,
               "evk_mpce_shard_finish: bad arguments (ld_slot must exceed n_cols: the loss term follows the column sums)");
   const int64_t blocks = (n_cols + kFinishThreads - 1) / kFinishThreads;
@@ -471,9 +483,9 @@ extern "C" int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   unsigned int* ticket = static_cast<unsigned int*>(workspace);
   double* partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + 16);
-  EVK_CUDA(cudaMemsetAsync(ticket, 0, 16, s));
+  if (!workspace_persistent) EVK_CUDA(cudaMemsetAsync(ticket, 0, 16, s));
   shard_finish_kernel<<<(unsigned)blocks, kFinishThreads, 0, s>>>(slots, n_slots, ld_slot, n_cols, shift, inv_count, b_col,
-                                                                 loss_out, partial, ticket, error, error_host);
+                                                                 loss_out, partial, ticket, error, error_host, ps);
   EVK_CHECK_LAUNCH("shard_finish");
   return EVK_OK;
 }
@@ -483,8 +495,8 @@ extern "C" int evk_shard_prologue(const void* text, int text_dtype, int64_t text
                                   int64_t n_rows, int64_t d, int n_dst, const uint64_t* khat_ptrs, int64_t ld_bf16,
                                   int64_t row_offset, float* k_norm, void* q_hi, float* q_norm, const int32_t* ids,
                                   const int32_t* ids2, int n_ids_dst, const uint64_t* ids_ptrs, const uint64_t* ids2_ptrs,
-                                  float* zero_buf, int64_t ld_zero, int* step_counter, const int* error,
-                                  evk_stream_t stream) {
+                                  float* zero_buf, int64_t ld_zero, int32_t* zero_i32, int64_t n_zero_i32,
+                                  int* step_counter, const int* error, evk_stream_t stream) {
   EVK_REQUIRE(text && image && k_norm && q_hi && q_norm && ids && ids_ptrs && khat_ptrs && n_rows > 0 && d > 0,
               "evk_shard_prologue: null pointer or empty shape");
   EVK_REQUIRE(text_dtype >= EVK_DTYPE_F32 && text_dtype <= EVK_DTYPE_F16 && image_dtype >= EVK_DTYPE_F32 &&
@@ -515,6 +527,7 @@ extern "C" int evk_shard_prologue(const void* text, int text_dtype, int64_t text
   p.q_hi = static_cast<__nv_bfloat16*>(q_hi); p.k_norm = k_norm; p.q_norm = q_norm;
   p.ids = ids; p.ids2 = ids2;
   p.zero = zero_buf; p.ld_zero = ld_zero; p.zero_width = (int)(((d + 3) / 4) * 4);
+  p.zero_i32 = zero_i32; p.n_zero_i32 = zero_i32 ? n_zero_i32 : 0;
   p.n = n_rows; p.ld = ld_bf16; p.row_offset = row_offset; p.d = (int)d;
   int64_t blocks = (2 * n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int64_t cap = (int64_t)evk_sm_count() * 8;

@@ -105,7 +105,85 @@ pos_logits_kernel(const __nv_bfloat16* __restrict__ q_hi, int64_t ld_q, const __
   }
 }
 
+// Positive-logit sums WITHOUT the dense mask: row_pos[i] = inv_tau * sum over the positives of row i of q_i . k_j.
+// Rows whose positives all fit the K2 list (counts[i] <= pos_slots: every row of a realistic batch) just add up
+// their pos_dot entries; a row with more positives finds them by scanning the column ids (4-8 bytes per column
+// instead of one mask bit, but only for such rows) and computes the dot products itself.  One warp per row.
+template <int kQVec>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+pos_from_lists_kernel(const __nv_bfloat16* __restrict__ q_hi, int64_t ld_q, const __nv_bfloat16* __restrict__ k_hi,
+                      int64_t ld_k, int64_t n_rows, int64_t n_cols, int d_vec, const int32_t* __restrict__ ids_row,
+                      const int32_t* __restrict__ ids2_row, const int32_t* __restrict__ ids_col,
+                      const int32_t* __restrict__ ids2_col, int64_t diag_offset, int clear_diag,
+                      const int32_t* __restrict__ counts, const float* __restrict__ pos_dot, int pos_slots, float inv_tau,
+                      float* __restrict__ row_pos) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (i >= n_rows) return;
+  const int c = __ldg(counts + i);
+  if (c <= pos_slots) {
+    float v = lane < c ? __ldg(pos_dot + i * pos_slots + lane) : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) row_pos[i] = v * inv_tau;
+    return;
+  }
+  const int32_t key = __ldg(ids_row + i);
+  const int32_t key2 = ids2_row ? __ldg(ids2_row + i) : 0;
+  const int64_t diag = clear_diag ? i + diag_offset : -1;
+  const uint4* qa = reinterpret_cast<const uint4*>(q_hi + i * ld_q);
+  uint4 qv[kQVec];
+#pragma unroll
+  for (int t = 0; t < kQVec; ++t) qv[t] = (lane + 32 * t < d_vec) ? __ldg(qa + lane + 32 * t) : make_uint4(0u, 0u, 0u, 0u);
+  float acc = 0.f;
+  for (int64_t j0 = 0; j0 < n_cols; j0 += 32) {
+    const int64_t j = j0 + lane;
+    bool hit = j < n_cols && __ldg(ids_col + j) == key && j != diag;
+    if (hit && ids2_col) hit = __ldg(ids2_col + j) == key2;
+    uint32_t any = __ballot_sync(0xffffffffu, hit);
+    while (any) {
+      const int b = __ffs(any) - 1;
+      any &= any - 1;
+      const uint4* kb = reinterpret_cast<const uint4*>(k_hi + (j0 + b) * ld_k);
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < kQVec; ++t)
+        if (lane + 32 * t < d_vec) s += dot8_bf16(qv[t], __ldg(kb + lane + 32 * t));
+      acc += s;
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) row_pos[i] = acc * inv_tau;
+}
+
 }  // namespace
+
+extern "C" int evk_mpce_pos_from_lists(const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k, int64_t n_rows,
+                                       int64_t n_cols, int64_t d, const int32_t* ids_row, const int32_t* ids2_row,
+                                       const int32_t* ids_col, const int32_t* ids2_col, int64_t diag_offset, int clear_diag,
+                                       const int32_t* counts, const float* pos_dot, int pos_slots, float inv_tau,
+                                       float* row_pos, evk_stream_t stream) {
+  EVK_REQUIRE(q_hi && k_hi && ids_row && ids_col && counts && pos_dot && row_pos, "evk_mpce_pos_from_lists: null pointer");
+  EVK_REQUIRE((ids2_row == nullptr) == (ids2_col == nullptr), "evk_mpce_pos_from_lists: ids2_row/ids2_col must both be set or both null");
+  EVK_REQUIRE(n_rows > 0 && n_cols > 0 && d > 0 && d <= 4096 && pos_slots >= 1 && pos_slots <= 32,
+              "evk_mpce_pos_from_lists: bad shape (d <= 4096, 1..32 slots)");
+  EVK_REQUIRE(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_q >= d && ld_k >= d && evk_aligned16(q_hi) && evk_aligned16(k_hi),
+              "evk_mpce_pos_from_lists: operands need 16-byte aligned rows (ld %% 8 == 0)");
+  const int64_t blocks = (n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int d_vec = (int)((d + 7) / 8);
+  auto* qp = static_cast<const __nv_bfloat16*>(q_hi);
+  auto* kp = static_cast<const __nv_bfloat16*>(k_hi);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d_vec <= 128)
+    pos_from_lists_kernel<4><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, s>>>(qp, ld_q, kp, ld_k, n_rows, n_cols, d_vec, ids_row,
+                                                                            ids2_row, ids_col, ids2_col, diag_offset, clear_diag,
+                                                                            counts, pos_dot, pos_slots, inv_tau, row_pos);
+  else
+    pos_from_lists_kernel<16><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, s>>>(qp, ld_q, kp, ld_k, n_rows, n_cols, d_vec, ids_row,
+                                                                             ids2_row, ids_col, ids2_col, diag_offset, clear_diag,
+                                                                             counts, pos_dot, pos_slots, inv_tau, row_pos);
+  EVK_CHECK_LAUNCH("mpce_pos_from_lists");
+  return EVK_OK;
+}
 
 extern "C" int evk_mpce_pos_logits(const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k, int64_t n_rows,
                                    int64_t d, const int32_t* pos_idx, const int32_t* counts, int pos_slots,

@@ -200,6 +200,7 @@ stats_fused_kernel(const float* __restrict__ rs_part, int64_t row_parts, int64_t
       } else {
         loss_out[0] = l;
       }
+      *ticket = 0u;                                  // a persistent workspace is ready for the next call
     }
   }
 }
@@ -212,7 +213,8 @@ int stats_fused_impl(const float* rs_part, int64_t row_parts, int64_t ld_row, co
                      const float* cs_part, int64_t col_parts,
                      int64_t ld_col, int64_t n_cols, int64_t col_lo, int64_t col_hi, float shift,
                      float pos_weight, double inv_count, float* a_row, float* b_col, float* loss_out,
-                     void* workspace, int64_t workspace_bytes, const StatPush& push, evk_stream_t stream) {
+                     void* workspace, int64_t workspace_bytes, const StatPush& push, evk_stream_t stream,
+                     bool workspace_persistent = false) {
   EVK_REQUIRE(rs_part && rp_part && a_row && (loss_out || push.n > 0) && workspace && n_rows > 0 && row_parts >= 1 &&
                   ld_row >= n_rows && pos_parts >= 1 && ld_pos >= n_rows, "evk_mpce_stats_fused: bad row arguments");
   EVK_REQUIRE(!cs_part || ((b_col || push.n > 0) && col_parts >= 1 && ld_col >= n_cols && n_cols > 0),
@@ -224,7 +226,7 @@ int stats_fused_impl(const float* rs_part, int64_t row_parts, int64_t ld_row, co
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   unsigned int* ticket = static_cast<unsigned int*>(workspace);
   double* partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + 16);
-  EVK_CUDA(cudaMemsetAsync(ticket, 0, 16, s));
+  if (!workspace_persistent) EVK_CUDA(cudaMemsetAsync(ticket, 0, 16, s));
   stats_fused_kernel<<<dim3((unsigned)blocks, 3), kStatThreads, 0, s>>>(rs_part, row_parts, ld_row, rp_part, pos_parts, ld_pos,
                                                               counts, n_rows,
                                                               cs_part, col_parts, ld_col, cs_part ? n_cols : 0, col_lo,
@@ -253,7 +255,7 @@ extern "C" int evk_mpce_shard_stats_push(const float* rs_part, int64_t row_parts
                                          const float* cs_part, int64_t col_parts, int64_t ld_col, int64_t n_cols,
                                          float shift, float pos_weight, double inv_count, float* a_row,
                                          const uint64_t* slot_ptrs, int n_dst, int64_t slot_offset, void* workspace,
-                                         int64_t workspace_bytes, evk_stream_t stream) {
+                                         int64_t workspace_bytes, int workspace_persistent, evk_stream_t stream) {
   EVK_REQUIRE(slot_ptrs && n_dst >= 1 && n_dst <= 16 && slot_offset >= 0 && cs_part, "evk_mpce_shard_stats_push: bad destinations");
   StatPush push;
   memset(&push, 0, sizeof(push));
@@ -265,7 +267,7 @@ extern "C" int evk_mpce_shard_stats_push(const float* rs_part, int64_t row_parts
   }
   return stats_fused_impl(rs_part, row_parts, ld_row, rp_part, pos_parts, ld_pos, counts, n_rows, cs_part, col_parts, ld_col,
                           n_cols, 0, 0, shift, pos_weight, inv_count, a_row, nullptr, nullptr, workspace, workspace_bytes,
-                          push, stream);
+                          push, stream, workspace_persistent != 0);
 }
 
 extern "C" int evk_reduce_partials(const float* part, int64_t parts, int64_t ld, int64_t n, const int32_t* divisor,

@@ -196,18 +196,77 @@ w_pos_kernel(__nv_bfloat16* __restrict__ strip, int64_t ld_e, int64_t n_rows, in
   }
 }
 
+// Pass 2 without the dense mask (bits == NULL): rows with more positives than list slots find them by scanning
+// the column ids.  A warp takes 32 consecutive rows and keeps those with counts > skip_upto (normally none).
+template <int kQVec>
+__global__ void __launch_bounds__(kPatchWarps * 32)
+w_pos_ids_kernel(__nv_bfloat16* __restrict__ strip, int64_t ld_e, int64_t n_rows, int64_t n_cols,
+                 const int32_t* __restrict__ ids_row, const int32_t* __restrict__ ids2_row,
+                 const int32_t* __restrict__ ids_col, const int32_t* __restrict__ ids2_col, int64_t diag_offset,
+                 int clear_diag, const int32_t* __restrict__ counts, const float* __restrict__ a_row,
+                 const float* __restrict__ b_col, const __nv_bfloat16* __restrict__ q_hi, int64_t ld_q,
+                 const __nv_bfloat16* __restrict__ k_hi, int64_t ld_k, int d_vec, float inv_tau, int skip_upto) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kPatchWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kPatchWarps;
+  const float c1 = inv_tau * 1.4426950408889634f;
+  for (int64_t rb = warp0 * 32; rb < n_rows; rb += nwarps * 32) {
+    const int cnt_l = (rb + lane < n_rows) ? __ldg(counts + rb + lane) : 0;
+    uint32_t need = __ballot_sync(0xffffffffu, cnt_l > skip_upto);
+    while (need) {
+      const int rl = __ffs(need) - 1;
+      need &= need - 1;
+      const int64_t i = rb + rl;
+      const int cnt = __shfl_sync(0xffffffffu, cnt_l, rl);
+      const int32_t key = __ldg(ids_row + i);
+      const int32_t key2 = ids2_row ? __ldg(ids2_row + i) : 0;
+      const int64_t diag = clear_diag ? i + diag_offset : -1;
+      const float ai = __ldg(a_row + i);
+      const float pc = -2.f / (float)max(cnt, 1);
+      __nv_bfloat16* srow = strip + i * ld_e;
+      const uint4* qa = reinterpret_cast<const uint4*>(q_hi + i * ld_q);
+      uint4 qv[kQVec];
+#pragma unroll
+      for (int t = 0; t < kQVec; ++t) qv[t] = (lane + 32 * t < d_vec) ? __ldg(qa + lane + 32 * t) : make_uint4(0u, 0u, 0u, 0u);
+      for (int64_t j0 = 0; j0 < n_cols; j0 += 32) {
+        const int64_t jl = j0 + lane;
+        bool hit = jl < n_cols && __ldg(ids_col + jl) == key && jl != diag;
+        if (hit && ids2_col) hit = __ldg(ids2_col + jl) == key2;
+        uint32_t any = __ballot_sync(0xffffffffu, hit);
+        while (any) {
+          const int b = __ffs(any) - 1;
+          any &= any - 1;
+          const int64_t j = j0 + b;
+          const uint4* kb = reinterpret_cast<const uint4*>(k_hi + j * ld_k);
+          float sdot = 0.f;
+#pragma unroll
+          for (int t = 0; t < kQVec; ++t)
+            if (lane + 32 * t < d_vec) sdot = dot8_bf16(qv[t], __ldg(kb + lane + 32 * t), sdot);
+          sdot = warp_sum(sdot);
+          if (lane == 0) srow[j] = __float2bfloat16_rn(fmaf(exp2f(fmaf(sdot, c1, -c1)), ai + __ldg(b_col + j), pc));
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int evk_mpce_w_from_e(void* strip, int64_t ld_e, int64_t n_rows, int64_t n_cols, const uint32_t* bits,
                                  int64_t ld_words, const int32_t* counts, const float* a_row, const float* b_col,
                                  const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k, int64_t d, float inv_tau,
-                                 const int32_t* pos_idx, const float* pos_dot, int pos_slots, evk_stream_t stream) {
-  EVK_REQUIRE(strip && bits && counts && a_row && b_col, "evk_mpce_w_from_e: null pointer");
+                                 const int32_t* pos_idx, const float* pos_dot, int pos_slots, const int32_t* ids_row,
+                                 const int32_t* ids2_row, const int32_t* ids_col, const int32_t* ids2_col,
+                                 int64_t diag_offset, int clear_diag, evk_stream_t stream) {
+  EVK_REQUIRE(strip && counts && a_row && b_col, "evk_mpce_w_from_e: null pointer");
+  EVK_REQUIRE(bits || (ids_row && ids_col && pos_idx && pos_dot && q_hi && k_hi),
+              "evk_mpce_w_from_e: without the dense mask (bits == NULL) the positive lists, the operands and the ids are required");
+  EVK_REQUIRE((ids2_row == nullptr) == (ids2_col == nullptr), "evk_mpce_w_from_e: ids2_row/ids2_col must both be set or both null");
   EVK_REQUIRE(n_rows > 0 && n_cols > 0, "evk_mpce_w_from_e: empty problem");
   EVK_REQUIRE(evk_aligned16(strip) && ld_e % 8 == 0 && ld_e >= ((n_cols + 7) / 8) * 8,
               "evk_mpce_w_from_e: strip needs a 16-byte aligned base and ld_e %% 8 == 0, ld_e >= n_cols rounded up to 8");
   EVK_REQUIRE(evk_aligned16(b_col), "evk_mpce_w_from_e: b_col must be 16-byte aligned");
-  EVK_REQUIRE(ld_words >= (n_cols + 31) / 32, "evk_mpce_w_from_e: ld_words too small");
+  EVK_REQUIRE(!bits || ld_words >= (n_cols + 31) / 32, "evk_mpce_w_from_e: ld_words too small");
   if (q_hi) {
     EVK_REQUIRE(d <= 4096, "evk_mpce_w_from_e: d=%lld > 4096 is not supported by the exact-positives pass", (long long)d);
     EVK_REQUIRE(k_hi && d > 0 && ld_q % 8 == 0 && ld_k % 8 == 0 && ld_q >= d && ld_k >= d && evk_aligned16(q_hi) &&
@@ -238,10 +297,22 @@ extern "C" int evk_mpce_w_from_e(void* strip, int64_t ld_e, int64_t n_rows, int6
   const int64_t blocks = skip_upto > 0 ? (n_rows + 32 * kPatchWarps - 1) / (32 * kPatchWarps)
                                        : (n_rows + kPatchWarps - 1) / kPatchWarps;
   const int d_vec = (int)((d + 7) / 8);
-  const int mask_vec_ok = (ld_words % 4 == 0 && evk_aligned16(bits)) ? 1 : 0;
+  const int mask_vec_ok = (bits && ld_words % 4 == 0 && evk_aligned16(bits)) ? 1 : 0;
   auto* sp = static_cast<__nv_bfloat16*>(strip);
   auto* qp = static_cast<const __nv_bfloat16*>(q_hi);
   auto* kp = static_cast<const __nv_bfloat16*>(k_hi);
+  if (!bits) {                                        // overflow rows find their positives by scanning the ids
+    if (d_vec <= 128)
+      w_pos_ids_kernel<4><<<(unsigned)blocks, kPatchWarps * 32, 0, s>>>(sp, ld_e, n_rows, n_cols, ids_row, ids2_row, ids_col,
+                                                                     ids2_col, diag_offset, clear_diag, counts, a_row, b_col,
+                                                                     qp, ld_q, kp, ld_k, d_vec, inv_tau, skip_upto);
+    else
+      w_pos_ids_kernel<16><<<(unsigned)blocks, kPatchWarps * 32, 0, s>>>(sp, ld_e, n_rows, n_cols, ids_row, ids2_row, ids_col,
+                                                                      ids2_col, diag_offset, clear_diag, counts, a_row, b_col,
+                                                                      qp, ld_q, kp, ld_k, d_vec, inv_tau, skip_upto);
+    EVK_CHECK_LAUNCH("w_pos_ids");
+    return EVK_OK;
+  }
   if (d_vec <= 128)
     w_pos_kernel<4><<<(unsigned)blocks, kPatchWarps * 32, 0, s>>>(sp, ld_e, n_rows, n_cols, bits, ld_words, counts, a_row,
                                                                b_col, qp, ld_q, kp, ld_k, d_vec, inv_tau, mask_vec_ok, skip_upto);

@@ -168,16 +168,20 @@ def peer_forward(ops, pc, inv_tau: float, row_ids: DeviceIds, image: torch.Tenso
     q_hi = torch.empty((n, pc.ld), dtype=torch.bfloat16, device=dev)
     wq = _round_up(d, 4)
     dq = torch.empty((n, wq), dtype=torch.float32, device=dev) if need_grad else None
+    counts = torch.empty(n, dtype=torch.int32, device=dev)          # zeroed by the prologue kernel
     overlap_gather = OVERLAP_GATHER and world > 1
+    folded = pc.sync(1) is not None and not overlap_gather           # syncs folded into the consumer kernels
     # inputs as the caller holds them (strided [:,0,:] head views, bf16/fp16): the prologue's loader honours them
     _lib.call("evk_shard_prologue", text.data_ptr(), ops._dtype_code(text), text.stride(0), text.stride(1),
               image.data_ptr(), ops._dtype_code(image), image.stride(0), image.stride(1), n, d,
               1 if overlap_gather else world, pc.table("khat_local") if overlap_gather else pc.table("khat"), pc.ld, lo_,
               k_norm.data_ptr(), q_hi.data_ptr(), q_norm.data_ptr(),
               row_ids.key.data_ptr(), row_ids.key2.data_ptr() if two else None, world, pc.table("ids"),
-              pc.table("ids2") if two else None, None if dq is None else dq.data_ptr(), wq, pc.step.data_ptr(),
-              pc.error.data_ptr(), stream)
-    pc.barrier()
+              pc.table("ids2") if two else None, None if dq is None else dq.data_ptr(), wq, counts.data_ptr(), n,
+              pc.step.data_ptr(), pc.error.data_ptr(), stream)
+    if not folded:
+        pc.barrier()
+    sync1 = pc.sync(1) if folded else None
     qn = ops.Normalized(n=n, d=d, norm=q_norm, hi=q_hi, lo=None, ld=pc.ld)
     kn_all = ops.Normalized(n=n_total, d=d, norm=None, hi=pc.khat, lo=None, ld=pc.ld)
     kn_local = ops.Normalized(n=n, d=d, norm=k_norm, hi=pc.khat[lo_:lo_ + n], lo=None, ld=pc.ld)
@@ -207,38 +211,53 @@ def peer_forward(ops, pc, inv_tau: float, row_ids: DeviceIds, image: torch.Tenso
         return rs, rp, cs, e, (ld_e if store else 0)
 
     pos = None
+    mask_free = need_grad and ops.MASK_FREE and not overlap_gather
     if need_grad:
-        bits, counts, pos_idx = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_, want_list=True)
+        bits, counts, pos_idx = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_, want_list=True,
+                                                  want_bits=not mask_free, counts=counts, sync=sync1)
+
+        def positives():
+            pd = ops.pos_logits(qn, kn_all, pos_idx, counts)
+            rp = ops.pos_from_lists(qn, kn_all, row_ids, ids_all, counts, pd, inv_tau, clear_diag=False,
+                                    diag_offset=lo_) if mask_free else None
+            return pd, rp
+
         if overlap or overlap_gather:      # exact positive logits (O(n D)) next to K3, once every shard has landed
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 if overlap_gather:
                     _lib.call("evk_peer_wait_landed", pc.landed.data_ptr(), world, pc.step.data_ptr(),
                               pc.error.data_ptr(), pc.timeout_ms, side.cuda_stream)
-                pos_dot = ops.pos_logits(qn, kn_all, pos_idx, counts)
+                pos_dot, row_pos_l = positives()
             ops._shared_with(side, q_hi, pos_idx, counts)
         else:
-            pos_dot = ops.pos_logits(qn, kn_all, pos_idx, counts)
+            pos_dot, row_pos_l = positives()
         pos = (pos_idx, pos_dot)
-        rs_part, rp_part, cs_part, e, ld_e = sweep(bits, True)
+        if mask_free:
+            rs_part, _, cs_part, e, ld_e = ops.tc_fwd_store(qn, kn_all, None, inv_tau, ops.FLAG_NO_POS, lo_)
+            if overlap:
+                main.wait_stream(side)      # the statistics need the positive sums computed next to K3
+                ops._shared_with(main, pos_dot, row_pos_l)
+            rp_part = row_pos_l.unsqueeze(0)
+        else:
+            rs_part, rp_part, cs_part, e, ld_e = sweep(bits, True)
     else:
-        bits, counts = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_)
+        bits, counts = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_, counts=counts, sync=sync1)
         rs_part, rp_part, cs_part, e, ld_e = sweep(bits, False)
     # exchange 2 (one launch): partials -> a_row, and this rank's slot (partial column sums of its rows +
     # its row-side loss term) into every rank's slot buffer
     a_row = torch.empty(n, dtype=torch.float32, device=dev)
-    ws = torch.empty(_lib.size("evk_stats_workspace_bytes", n, n_total), dtype=torch.uint8, device=dev)
     _lib.call("evk_mpce_shard_stats_push", rs_part.data_ptr(), int(rs_part.shape[0]), n, rp_part.data_ptr(),
               int(rp_part.shape[0]), n, counts.data_ptr(), n, cs_part.data_ptr(), int(cs_part.shape[0]), n_total,
               n_total, float(inv_tau), 2.0, 0.5 / n_total, a_row.data_ptr(), pc.table("slots"), world,
-              rank * pc.ld_slot, ws.data_ptr(), ws.numel(), stream)
-    pc.barrier()
+              rank * pc.ld_slot, pc.ws_stats.data_ptr(), pc.ws_stats.numel(), 1, stream)
+    if not folded:
+        pc.barrier()
     b_col = torch.empty(n_total, dtype=torch.float32, device=dev)
     loss = torch.empty(1, dtype=torch.float32, device=dev)
-    ws2 = torch.empty(_lib.size("evk_shard_finish_workspace_bytes", n_total), dtype=torch.uint8, device=dev)
     _lib.call("evk_mpce_shard_finish", pc.slots.data_ptr(), world, pc.ld_slot, n_total, float(inv_tau), 0.5 / n_total,
-              b_col.data_ptr(), loss.data_ptr(), ws2.data_ptr(), ws2.numel(), pc.error.data_ptr(),
-              pc.error_host.data_ptr(), stream)
+              b_col.data_ptr(), loss.data_ptr(), pc.ws_finish.data_ptr(), pc.ws_finish.numel(), 1, pc.error.data_ptr(),
+              pc.error_host.data_ptr(), pc.sync(2) if folded else None, stream)
     if overlap_gather or (need_grad and overlap):
         main.wait_stream(side)              # the push (and the positives) are part of this step
         if need_grad:
@@ -247,6 +266,8 @@ def peer_forward(ops, pc, inv_tau: float, row_ids: DeviceIds, image: torch.Tenso
     st.ops, st.pc, st.inv_tau = ops, pc, inv_tau
     st.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, e, ld_e, dq)
     st.pos = pos
+    st.folded = folded
+    st.ids = (row_ids, ids_all)
     st.image, st.text = image, text
     return loss, st
 
@@ -264,7 +285,8 @@ def peer_backward(st, g: torch.Tensor):
     scale = 0.5 * inv_tau / n_total
     overlap = ops.OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
     main = torch.cuda.current_stream()
-    ops.tc_w_from_e(e, ld_e, n_total, bits, counts, a_row, b_col, qn, kn_all, inv_tau, pos=st.pos)
+    ops.tc_w_from_e(e, ld_e, n_total, bits, counts, a_row, b_col, qn, kn_all, inv_tau, pos=st.pos, ids=st.ids,
+                    clear_diag=False, diag_offset=pc.rank * n)
     # exchange 3, fused: the tiles of this rank's partial dKhat are stored straight into their owners'
     # per-source buffers (posted NVLink stores from the GEMM epilogue; no split-K, no zero fill)
     _lib.call("evk_mpce_bwd_gemm_scatter", e.data_ptr(), None, ld_e, n, n_total, qn.hi.data_ptr(), None, qn.ld, qn.d,
@@ -290,9 +312,10 @@ def peer_backward(st, g: torch.Tensor):
         # contraction does), so that they may overwrite them in the next step: join before signalling
         main.wait_stream(side)
         ops._shared_with(main, d_image)
-    pc.barrier()                           # every rank's partial for these rows has landed
+    if not st.folded:
+        pc.barrier()                       # every rank's partial for these rows has landed
     d_text = ops.l2norm_bwd(text, kn_local, pc.dk_parts[0], scale_dev=g, scale_host=scale,
-                            parts=(pc.world, n * pc.width), error=pc.error)
+                            parts=(pc.world, n * pc.width), error=pc.error, sync=pc.sync(3) if st.folded else None)
     if not torch.cuda.is_current_stream_capturing():
         st.sv = (qn, kn_local, kn_all, bits, counts, a_row, b_col, None, 0, None)
     return d_image, d_text

@@ -34,6 +34,10 @@ OVERLAP_STREAMS = os.environ.get("EVOKE_B200_OVERLAP", "0") == "1"   # side-stre
 # bf16 mode: K3 stores E = exp(S - 1/tau) as a bf16 row strip and the backward turns it into W in place
 # (HBM-bound K4t) instead of recomputing the similarity tiles (K4a): 6 N^2 D executed FLOP instead of 8.
 E_STRIP = os.environ.get("EVOKE_B200_ESTRIP", "1") == "1"
+# ... and then nothing of size N^2 is derived from the ids either: K2 builds only the per-row positive lists, the
+# positive-logit sums and the exact W entries come from those (rows with more positives than list slots: id scan).
+# EVOKE_B200_MASK_FREE=0 keeps the dense bit mask in the K3 epilogue (round-1 behaviour, for A/B measurements).
+MASK_FREE = os.environ.get("EVOKE_B200_MASK_FREE", "1") == "1"
 
 
 def _row_parts() -> int:
@@ -130,10 +134,11 @@ def l2norm_fwd(x: torch.Tensor, *, want_f32: bool, want_hi: bool, want_lo: bool,
 
 def l2norm_bwd(x: torch.Tensor, nrm: Normalized, g_hat: torch.Tensor, *, scale_dev: Optional[torch.Tensor],
                scale_host: float, gather: Optional[torch.Tensor] = None, parts=None,
-               error: Optional[torch.Tensor] = None) -> torch.Tensor:
+               error: Optional[torch.Tensor] = None, sync=None) -> torch.Tensor:
     """Backward of K1 fused with the loss scale; returns dx with x's shape and dtype.
     parts = (n_parts, stride_in_elements): g_hat is the first of n_parts partial buffers to be summed.
-    error: the sharded transport's failure flag (device int32): non-zero -> the gradients are NaN."""
+    error: the sharded transport's failure flag (device int32): non-zero -> the gradients are NaN.
+    sync: ctypes pointer to an evk_peer_sync_t - the kernel first waits for the peers (sharded path)."""
     if gather is not None:
         dx = torch.zeros(x.shape, dtype=x.dtype, device=x.device)       # filtered rows get zero gradient
     else:
@@ -141,26 +146,42 @@ def l2norm_bwd(x: torch.Tensor, nrm: Normalized, g_hat: torch.Tensor, *, scale_d
     n_parts, part_stride = parts if parts is not None else (1, 0)
     _lib.call("evk_l2norm_bwd_parts", _ptr(x), _dtype_code(x), nrm.n, nrm.d, x.stride(0), x.stride(1), _ptr(gather),
               _ptr(nrm.norm), _ptr(g_hat), _dtype_code(g_hat), g_hat.stride(0), int(n_parts), int(part_stride), _ptr(scale_dev),
-              float(scale_host), _ptr(dx), _dtype_code(dx), dx.stride(0), 0, _ptr(error), _stream())
+              float(scale_host), _ptr(dx), _dtype_code(dx), dx.stride(0), 0, _ptr(error), sync, _stream())
     return dx
 
 
 POS_SLOTS = 8          # listed positives per row (rows with more fall back to scanning the mask)
 
 
-def posmask_build(rows: DeviceIds, cols: DeviceIds, *, clear_diag: bool, diag_offset: int = 0, want_list: bool = False):
+def posmask_build(rows: DeviceIds, cols: DeviceIds, *, clear_diag: bool, diag_offset: int = 0, want_list: bool = False,
+                  want_bits: bool = True, counts: Optional[torch.Tensor] = None, sync=None):
     """K2: bit-packed positive mask [n_rows, ld_words] (uint32 stored as int32) + counts[n_rows]
-    (+ pos_idx [n_rows, POS_SLOTS], the first positives of every row, with want_list)."""
+    (+ pos_idx [n_rows, POS_SLOTS], the first positives of every row, with want_list).
+    want_bits=False (needs want_list): counts and lists only, bits is None.
+    counts: a buffer the caller has already zeroed (sharded path: the prologue kernel does); sync: evk_peer_sync_t."""
     n_rows, n_cols = len(rows), len(cols)
     dev = rows.key.device
     ld_words = _lib.size("evk_posmask_ld_words", n_cols)                 # whole 256-column tiles
-    bits = torch.empty((n_rows, ld_words), dtype=torch.int32, device=dev)
-    counts = torch.empty(n_rows, dtype=torch.int32, device=dev)
+    bits = torch.empty((n_rows, ld_words), dtype=torch.int32, device=dev) if want_bits else None
+    zeroed = counts is not None
+    if counts is None:
+        counts = torch.empty(n_rows, dtype=torch.int32, device=dev)
     pos_idx = torch.empty((n_rows, POS_SLOTS), dtype=torch.int32, device=dev) if want_list else None
     _lib.call("evk_posmask_build", _ptr(rows.key), _ptr(rows.key2), n_rows, _ptr(cols.key), _ptr(cols.key2),
               n_cols, diag_offset, int(clear_diag), _ptr(bits), ld_words, _ptr(counts), _ptr(pos_idx), POS_SLOTS,
-              _stream())
+              int(zeroed), sync, _stream())
     return (bits, counts, pos_idx) if want_list else (bits, counts)
+
+
+def pos_from_lists(q: Normalized, k: Normalized, rows: DeviceIds, cols: DeviceIds, counts: torch.Tensor,
+                   pos_dot: torch.Tensor, inv_tau: float, *, clear_diag: bool, diag_offset: int = 0) -> torch.Tensor:
+    """row_pos[i] = sum_j M_ij S_ij from the K2 lists (id scan for rows with more positives than slots): the
+    mask-free replacement of K3's positive sums."""
+    row_pos = torch.empty(q.n, dtype=torch.float32, device=q.hi.device)
+    _lib.call("evk_mpce_pos_from_lists", _ptr(q.hi), q.ld, _ptr(k.hi), k.ld, q.n, k.n, q.d, _ptr(rows.key), _ptr(rows.key2),
+              _ptr(cols.key), _ptr(cols.key2), int(diag_offset), int(clear_diag), _ptr(counts), _ptr(pos_dot), POS_SLOTS,
+              float(inv_tau), _ptr(row_pos), _stream())
+    return row_pos
 
 
 def pos_logits(q: Normalized, k: Normalized, pos_idx: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
@@ -259,25 +280,31 @@ def tc_fwd_store(q: Normalized, k: Normalized, bits, inv_tau: float, flags: int,
     ld_e = _lib.size("evk_mpce_strip_ld", k.n)
     e = torch.empty((q.n, ld_e), dtype=torch.bfloat16, device=dev)
     _lib.call("evk_mpce_fwd_store", _ptr(q.hi), q.ld, _ptr(k.hi), k.ld, q.n, k.n, q.d,
-              _ptr(bits) if want_pos else None, bits.stride(0) if want_pos else 0, float(inv_tau), flags, diag_offset,
+              _ptr(bits) if want_pos else None, bits.stride(0) if want_pos else 0, float(inv_tau), flags, int(diag_offset),
               _ptr(rs_part), _ptr(rp_part), q.n, _ptr(cs_part), k.n, _ptr(e), ld_e, _stream())
     return rs_part, rp_part, cs_part, e, ld_e
 
 
 def tc_w_from_e(e: torch.Tensor, ld_e: int, n_cols: int, bits, counts, a_row, b_col, q: Optional[Normalized],
                 k: Optional[Normalized], inv_tau: float, row0: int = 0, rows: Optional[int] = None,
-                pos=None) -> None:
+                pos=None, ids=None, clear_diag: bool = False, diag_offset: int = 0) -> None:
     """K4t: rows [row0, row0+rows) of the E strip become W, in place.  q / k: the forward's operands, from
     which the positive entries are recomputed in fp32 (None: every entry from the strip).
-    pos = (pos_idx, pos_dot): the forward's positive lists - then no mask scan / dot products are needed."""
+    pos = (pos_idx, pos_dot): the forward's positive lists - then no mask scan / dot products are needed.
+    bits = None (mask-free mode): ids = (row DeviceIds, column DeviceIds) serve the rows with more positives than slots."""
     rows = int(e.shape[0]) - row0 if rows is None else rows
     exact = q is not None and k is not None
-    _lib.call("evk_mpce_w_from_e", _ptr(e[row0:]), ld_e, rows, n_cols, _ptr(bits[row0:]), bits.stride(0),
+    rid, cid = ids if ids is not None else (None, None)
+    _lib.call("evk_mpce_w_from_e", _ptr(e[row0:]), ld_e, rows, n_cols, None if bits is None else _ptr(bits[row0:]),
+              0 if bits is None else bits.stride(0),
               _ptr(counts[row0:]), _ptr(a_row[row0:]), _ptr(b_col),
               _ptr(q.hi[row0:]) if exact else None, q.ld if exact else 0, _ptr(k.hi) if exact else None,
               k.ld if exact else 0, q.d if exact else 0, float(inv_tau),
               _ptr(pos[0][row0:]) if pos is not None else None, _ptr(pos[1][row0:]) if pos is not None else None,
-              POS_SLOTS, _stream())
+              POS_SLOTS, None if rid is None else _ptr(rid.key[row0:]),
+              None if rid is None or rid.key2 is None else _ptr(rid.key2[row0:]),
+              None if cid is None else _ptr(cid.key), None if cid is None or cid.key2 is None else _ptr(cid.key2),
+              int(diag_offset) + row0, int(clear_diag), _stream())
 
 
 def rows_of(x: Normalized, r0: int, r1: int) -> Normalized:
@@ -426,9 +453,11 @@ def mpce_forward(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tens
         use_strip = E_STRIP and not split and any(need_grad)
         pos_idx = pos_dot = None
 
+        mask_free = use_strip and MASK_FREE
+
         def build_mask():
             if use_strip:
-                return posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc, want_list=True)
+                return posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc, want_list=True, want_bits=not mask_free)
             return posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc) + (None,)
 
         if overlap:
@@ -449,14 +478,26 @@ def mpce_forward(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tens
         if use_strip:
             # exact logits of the listed positives (O(N*D)), next to K3 on the side stream; the backward's
             # K4t needs them for the entries where softmax and target cancel
+            def positives():
+                pd = pos_logits(qn, kn, pos_idx, counts)
+                rp = pos_from_lists(qn, kn, cfg.row_ids, cfg.row_ids, counts, pd, cfg.inv_tau,
+                                    clear_diag=mpc) if mask_free else None
+                return pd, rp
+
             if overlap:
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    pos_dot = pos_logits(qn, kn, pos_idx, counts)
+                    pos_dot, row_pos_l = positives()
                 _shared_with(side, qn.hi, kn.hi, pos_idx, counts)
             else:
-                pos_dot = pos_logits(qn, kn, pos_idx, counts)
-            rs_part, rp_part, cs_part, e_strip, ld_e = tc_fwd_store(qn, kn, bits, cfg.inv_tau, flags)
+                pos_dot, row_pos_l = positives()
+            rs_part, rp_part, cs_part, e_strip, ld_e = tc_fwd_store(qn, kn, bits, cfg.inv_tau,
+                                                                    flags | (FLAG_NO_POS if mask_free else 0))
+            if mask_free:
+                if overlap:                     # the statistics need the positive sums computed next to K3
+                    main.wait_stream(side)
+                    _shared_with(main, pos_dot, row_pos_l)
+                rp_part = row_pos_l
             st.e_strip = (e_strip, ld_e)
             st.pos = (pos_idx, pos_dot)
         else:
@@ -508,7 +549,8 @@ def mpce_backward(st: _State, g: torch.Tensor):
             if strip is None:
                 return tc_bwd_w(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
             e, ld_e = strip
-            tc_w_from_e(e, ld_e, kn.n, bits, counts, a_row, b_col, qn, kn, cfg.inv_tau, pos=st.pos)
+            tc_w_from_e(e, ld_e, kn.n, bits, counts, a_row, b_col, qn, kn, cfg.inv_tau, pos=st.pos,
+                        ids=(cfg.row_ids, cfg.row_ids), clear_diag=mpc)
             return e, None, ld_e
 
         if not overlap:

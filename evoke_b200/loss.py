@@ -79,7 +79,7 @@ def global_alignment(image: torch.Tensor, text: torch.Tensor, patient_ids, temp:
             def fwd(im, tx, ids, need):
                 return Fn.mpce_forward(Fn.LossConfig(kind="G", inv_tau=inv_tau, precision=precision, path=path,
                                                      row_ids=ids), im, tx, need)
-            key = ("G", inv_tau, precision, path, Fn.E_STRIP, Fn.OVERLAP_STREAMS)
+            key = ("G", inv_tau, precision, path, Fn.E_STRIP, Fn.OVERLAP_STREAMS, Fn.MASK_FREE)
             return graphs.graphed_call(key, fwd, Fn.mpce_backward, image, text, dev_ids)
         cfg = Fn.LossConfig(kind="G", inv_tau=inv_tau, precision=precision, path=path, row_ids=dev_ids)
         return Fn.multi_positive_ce(cfg, image, text)

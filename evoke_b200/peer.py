@@ -29,6 +29,8 @@ import torch.distributed as dist
 from . import _lib
 
 _ALIGN = 1024
+# EVOKE_B200_FOLDED_SYNC=0: separate evk_peer_barrier launches between producer and consumer kernels (round 1)
+FOLDED_SYNC = os.environ.get("EVOKE_B200_FOLDED_SYNC", "1") == "1"
 
 
 def _round_up(x: int, m: int) -> int:
@@ -65,7 +67,7 @@ class PeerContext:
         off = 0
         self.off = {}
         for name, nbytes in (("khat", big_n * self.ld * 2), ("ids", big_n * 4), ("ids2", big_n * 4 if two_keys else 0),
-                             ("slots", r * self.ld_slot * 4), ("dk_parts", r * n * self.width * esize), ("flags", 64), ("landed", 64), ("err", 64)):
+                             ("slots", r * self.ld_slot * 4), ("dk_parts", r * n * self.width * esize), ("flags", 64), ("landed", 64), ("err", 64), ("sync", 64)):
             self.off[name] = off
             off += _round_up(nbytes, _ALIGN)
         self.nbytes = off
@@ -117,6 +119,10 @@ class PeerContext:
         # can raise without synchronising the device
         self.error = self._view("err", 64).view(torch.int32)[:1]       # in symmetric memory: any rank's barrier may raise it
         self.error_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        # persistent, zero-initialised workspaces of the statistics kernels (their tickets reset themselves)
+        self.ws_stats = torch.zeros(_lib.size("evk_stats_workspace_bytes", n, big_n), dtype=torch.uint8, device=self.device)
+        self.ws_finish = torch.zeros(_lib.size("evk_shard_finish_workspace_bytes", big_n), dtype=torch.uint8, device=self.device)
+        self._syncs = {}
         self.ptrs = {name: (ctypes.c_uint64 * self.world)(*[b + o for b in self.bases]) for name, o in self.off.items()}
         # where THIS rank's partial for owner t goes: part `rank` of t's dk_parts
         mine = self.rank * n * self.width * esize
@@ -131,6 +137,28 @@ class PeerContext:
     def table(self, name: str):
         """HOST array of the per-rank device addresses of one buffer (argument of the C entry points)."""
         return self.ptrs[name]
+
+    SYNCS_PER_STEP = 3
+
+    def sync(self, index: int):
+        """ctypes pointer to the evk_peer_sync_t of the step's index-th sync point (1: ids / key rows landed, 2:
+        statistics slots landed, 3: gradient partials landed and the gathered rows are free again), folded into the
+        head of its first consumer kernel instead of a barrier launch."""
+        if not FOLDED_SYNC:
+            return None
+        hit = self._syncs.get(index)
+        if hit is None:
+            ps = _lib.PeerSync()
+            for t in range(self.world):
+                ps.flag_ptrs[t] = self.bases[t] + self.off["sync"]
+                ps.err_ptrs[t] = self.bases[t] + self.off["err"]
+            ps.err_host = self.error_host.data_ptr()
+            ps.step = self.step.data_ptr()
+            ps.n_ranks, ps.rank, ps.index, ps.per_step = self.world, self.rank, index, self.SYNCS_PER_STEP
+            ps.timeout_ms = self.timeout_ms
+            hit = (ps, ctypes.byref(ps))
+            self._syncs[index] = hit
+        return hit[1]
 
     def barrier(self) -> None:
         """Enqueue the cross-GPU barrier on the current stream."""

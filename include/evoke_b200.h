@@ -61,6 +61,22 @@ extern "C" {
 
 typedef void* evk_stream_t;
 
+/* Cross-GPU synchronisation folded into the head of a consumer kernel of the sharded path (HOST struct, read
+ * during the call).  The kernel publishes what this GPU stored into peer memory in EARLIER kernels of the stream
+ * (system fence + release store of the epoch into every rank's flag area) and waits until every peer has done the
+ * same, i.e. it is evk_peer_barrier without the extra launch.  epoch = per_step * (*step) + index: `step` is the
+ * transport's device step counter (advanced by evk_shard_prologue), `index` in 1..per_step numbers the sync points
+ * of one step.  flag_ptrs[t] / err_ptrs[t]: rank t's flag area (>= 16 uint32, zeroed at start, used by these
+ * folded syncs only) and failure flag, peer-mapped.  Timeout semantics as evk_peer_barrier. */
+typedef struct evk_peer_sync {
+  uint64_t flag_ptrs[16];
+  uint64_t err_ptrs[16];
+  int* err_host;
+  const int* step;
+  int n_ranks, rank, index, per_step;
+  int64_t timeout_ms;
+} evk_peer_sync_t;
+
 #if defined(__GNUC__)
 #define EVK_API __attribute__((visibility("default")))
 #else
@@ -117,13 +133,14 @@ EVK_API int evk_l2norm_bwd(const void* x, int x_dtype, int64_t n_out, int64_t d,
  * order): g_total[r, c] = sum_p g[p * part_stride + r * ld_g + c] (g_dtype: EVK_DTYPE_F32 or _BF16).  Closes the fused reduce-scatter of
  * evk_mpce_bwd_gemm_scatter(store = 1): part p is what rank p's contraction stored for this rank's rows.
  * error (may be NULL): device int; when it is non-zero (a cross-GPU barrier of this step timed out,
- * evk_peer_barrier) every gradient written is NaN instead of a silently wrong value. */
+ * evk_peer_barrier) every gradient written is NaN instead of a silently wrong value.
+ * sync (may be NULL): see evk_peer_sync_t - the partial buffers were stored by the peers' contractions. */
 EVK_API int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, int64_t d,
                          int64_t stride_row, int64_t stride_col, const int32_t* gather,
                          const float* norm, const void* g, int g_dtype, int64_t ld_g, int n_parts, int64_t part_stride,
                          const float* scale_dev, float scale_host,
                          void* dx, int dx_dtype, int64_t ld_dx, int accumulate, const int* error,
-                         evk_stream_t stream);
+                         const evk_peer_sync_t* sync, evk_stream_t stream);
 
 /* ---- K2: positive-mask builder -------------------------------------------------------------
  * Replaces (ids.reshape(-1,1) == ids.reshape(1,-1)) + .float().to(device) + rowsum at
@@ -133,14 +150,19 @@ EVK_API int evk_l2norm_bwd_parts(const void* x, int x_dtype, int64_t n_out, int6
  * (patient AND study, the reference's "p<subject>_s<study>" string, dataloaders_v0401.py:83).
  * With clear_diag the bit at column (r + diag_offset) is cleared (:424).  All ld_words words
  * of every row are written (bits at columns >= n_cols are zero); ld_words >= ceil(n_cols/32).
+ * bits == NULL (then pos_idx is required): counts and lists only - nothing of size N^2 is written; the bf16
+ * mode of the large path runs on those (evk_mpce_pos_from_lists, evk_mpce_w_from_e).
  * pos_idx (may be NULL): [n_rows, pos_slots] int32, pos_idx[r, s] = column of the s-th positive of row r for
  * s < min(counts[r], pos_slots), unspecified order, other entries untouched: the sparse form of the same mask
- * for the O(N) consumers (evk_mpce_pos_logits, evk_mpce_w_from_e). */
+ * for the O(N) consumers (evk_mpce_pos_logits, evk_mpce_w_from_e).
+ * counts_zeroed != 0: the caller guarantees counts is all zero on entry (evk_shard_prologue zeroes it), so no
+ * memset node is enqueued.  sync (may be NULL): see evk_peer_sync_t - the column ids were stored by the peers. */
 EVK_API int evk_posmask_build(const int32_t* ids_row, const int32_t* ids2_row, int64_t n_rows,
                       const int32_t* ids_col, const int32_t* ids2_col, int64_t n_cols,
                       int64_t diag_offset, int clear_diag,
                       uint32_t* bits, int64_t ld_words, int32_t* counts,
-                      int32_t* pos_idx, int pos_slots, evk_stream_t stream);
+                      int32_t* pos_idx, int pos_slots, int counts_zeroed, const evk_peer_sync_t* sync,
+                      evk_stream_t stream);
 
 /* ---- small path: fp32 SIMT fused kernels (reference-sized batches, N <~ 1k) ---------------
  * One launch handles the rows of `q` against all columns `k` (both already normalised, fp32):
@@ -287,6 +309,18 @@ EVK_API int evk_mpce_pos_logits(const void* q_hi, int64_t ld_q, const void* k_hi
                         int64_t n_rows, int64_t d, const int32_t* pos_idx, const int32_t* counts, int pos_slots,
                         float* pos_dot, evk_stream_t stream);
 
+/* Positive-logit sums WITHOUT the dense mask, for use with EVK_FLAG_NO_POS in bf16 mode:
+ *   row_pos[i] = inv_tau * sum_{j in P_i} q_i . k_j   (the sum_j Y_ij S_ij term of :501-502 / :443 before the 1/c_i)
+ * from the K2 lists (pos_dot of evk_mpce_pos_logits) when counts[i] <= pos_slots, else by scanning the column
+ * ids for the row's key (clear_diag / diag_offset as in K2) and computing the dot products.  O(N) + O(D) per
+ * positive; nothing of size N^2 is read. */
+EVK_API int evk_mpce_pos_from_lists(const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k,
+                            int64_t n_rows, int64_t n_cols, int64_t d,
+                            const int32_t* ids_row, const int32_t* ids2_row,
+                            const int32_t* ids_col, const int32_t* ids2_col, int64_t diag_offset, int clear_diag,
+                            const int32_t* counts, const float* pos_dot, int pos_slots, float inv_tau,
+                            float* row_pos, evk_stream_t stream);
+
 /* Sharded K3 that starts before the all-gather of the key rows has finished.  k_hi is this rank's buffer of ALL
  * key rows, filled by every rank's evk_peer_push_shard while the sweep runs: column c belongs to source
  * c / cols_per_source, and landed[s] (this rank's landed-flag area) reaches *step once source s's rows are
@@ -312,12 +346,17 @@ EVK_API int evk_mpce_fwd_store_gathered(const void* q_hi, int64_t ld_q, const vo
  * where softmax and target cancel, and it keeps cold temperatures inside the bf16-mode tolerance.
  * q_hi == NULL skips this (all entries from the strip).  With pos_idx / pos_dot (K2's lists and
  * evk_mpce_pos_logits' values, [n_rows, pos_slots]) rows with at most pos_slots positives take their exact
- * entries from the lists - no mask scan, no dot products in the backward; the other rows scan the mask. */
+ * entries from the lists - no mask scan, no dot products in the backward; the other rows scan the mask.
+ * bits == NULL (no dense mask was built: evk_posmask_build with bits == NULL): the lists, the operands and the
+ * ids are required, and rows with more than pos_slots positives find them by scanning the column ids
+ * (ids_row [n_rows] / ids_col [n_cols], optional second key component, clear_diag / diag_offset as in K2). */
 EVK_API int evk_mpce_w_from_e(void* strip, int64_t ld_e, int64_t n_rows, int64_t n_cols,
                       const uint32_t* bits, int64_t ld_words, const int32_t* counts,
                       const float* a_row, const float* b_col,
                       const void* q_hi, int64_t ld_q, const void* k_hi, int64_t ld_k, int64_t d, float inv_tau,
-                      const int32_t* pos_idx, const float* pos_dot, int pos_slots, evk_stream_t stream);
+                      const int32_t* pos_idx, const float* pos_dot, int pos_slots,
+                      const int32_t* ids_row, const int32_t* ids2_row, const int32_t* ids_col, const int32_t* ids2_col,
+                      int64_t diag_offset, int clear_diag, evk_stream_t stream);
 
 /* Positive-logit sums from the bit mask, for use with EVK_FLAG_NO_POS:
  *   row_pos[i] = sum_j M_ij S_ij = inv_tau * sum_{j: bit (i,j) set} q_i . k_j
@@ -378,7 +417,7 @@ EVK_API int evk_peer_bcast(const void* src, int64_t bytes, int n_dst, const uint
  * sides plus what a sharded run must exchange before the similarity sweep.  n_dst = 1 with only this rank's
  * own buffer keeps the key rows local (evk_peer_push_shard then moves them next to the sweep); the ids always go
  * to all n_ids_dst ranks.  step_counter (may be NULL): device int advanced by one per launch - the epoch of the
- * landed flags.  error (may be NULL): the transport's sticky failure flag (evk_peer_barrier); once set the
+ * landed flags.  zero_i32 (may be NULL): n_zero_i32 int32 to zero (K2's counts).  error (may be NULL): the transport's sticky failure flag (evk_peer_barrier); once set the
  * kernel writes nothing, in particular nothing into peer memory. */
 EVK_API int evk_shard_prologue(const void* text, int text_dtype, int64_t text_stride, int64_t text_col_stride,
                        const void* image, int image_dtype, int64_t image_stride, int64_t image_col_stride,
@@ -386,8 +425,8 @@ EVK_API int evk_shard_prologue(const void* text, int text_dtype, int64_t text_st
                        int64_t row_offset, float* k_norm, void* q_hi, float* q_norm,
                        const int32_t* ids, const int32_t* ids2, int n_ids_dst,
                        const uint64_t* ids_ptrs, const uint64_t* ids2_ptrs,
-                       float* zero_buf, int64_t ld_zero, int* step_counter, const int* error,
-                       evk_stream_t stream);
+                       float* zero_buf, int64_t ld_zero, int32_t* zero_i32, int64_t n_zero_i32,
+                       int* step_counter, const int* error, evk_stream_t stream);
 
 /* The all-gather of the key rows, overlapped with the similarity sweep.  Copies this rank's shard (`bytes` at
  * `src`, normally its own rows inside its own buffer) to byte offset dst_offset_bytes of every OTHER rank's
@@ -408,14 +447,15 @@ EVK_API int evk_peer_wait_landed(const void* landed, int n_ranks, const int* ste
  * stores this rank's statistics slot - the raw partial column sums (n_cols floats) followed by its row-side
  * loss term inv_count * sum_i (shift + ln R_i - pos_weight pos_i / c_i) - at element offset slot_offset of
  * EVERY rank's slot buffer (slot_ptrs: host table of n_dst peer-mapped addresses).  evk_mpce_shard_finish
- * closes the forward after a barrier.  workspace as for evk_mpce_stats_fused. */
+ * closes the forward after a barrier.  workspace as for evk_mpce_stats_fused; workspace_persistent as for
+ * evk_mpce_shard_finish. */
 EVK_API int evk_mpce_shard_stats_push(const float* rs_part, int64_t row_parts, int64_t ld_row,
                               const float* rp_part, int64_t pos_parts, int64_t ld_pos,
                               const int32_t* counts, int64_t n_rows,
                               const float* cs_part, int64_t col_parts, int64_t ld_col, int64_t n_cols,
                               float shift, float pos_weight, double inv_count, float* a_row,
                               const uint64_t* slot_ptrs, int n_dst, int64_t slot_offset,
-                              void* workspace, int64_t workspace_bytes, evk_stream_t stream);
+                              void* workspace, int64_t workspace_bytes, int workspace_persistent, evk_stream_t stream);
 
 /* Symmetric buffers for that transport.  evk_peer_alloc is the ONE place the library allocates device
  * memory (cudaMalloc + cudaMemset, i.e. it also synchronises; called once per transport context, never per step): CUDA-IPC handles name whole allocations, so the exchanged buffers
@@ -450,11 +490,14 @@ EVK_API int evk_peer_barrier(const uint64_t* flag_ptrs, const uint64_t* error_pt
  * (:501-503 on the concatenated batch).  Fixed summation order: every rank computes identical bits.
  * workspace: evk_shard_finish_workspace_bytes(n_cols) bytes, 16-byte aligned, contents irrelevant.
  * error (may be NULL): when *error != 0 (a barrier timed out, here or on a peer) loss and b_col are NaN and
- * error_host (may be NULL, pinned host int) is set. */
+ * error_host (may be NULL, pinned host int) is set.
+ * workspace_persistent != 0: the caller keeps this workspace for these calls only and zeroed it once; the kernel
+ * leaves its ticket zero again, so no memset node is enqueued.  sync (may be NULL): see evk_peer_sync_t - the
+ * slots were stored by the peers. */
 EVK_API int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_slot, int64_t n_cols, float shift,
                           double inv_count, float* b_col, float* loss_out,
-                          void* workspace, int64_t workspace_bytes, const int* error, int* error_host,
-                          evk_stream_t stream);
+                          void* workspace, int64_t workspace_bytes, int workspace_persistent,
+                          const int* error, int* error_host, const evk_peer_sync_t* sync, evk_stream_t stream);
 
 /* K4b with the reduce-scatter fused into its epilogue: the partial dKhat of this rank's row block,
  *   out_owner(j)[j % rows_per_owner, :] += alpha * sum_i W[i, j] x[i, :],   owner(j) = j / rows_per_owner,

@@ -15,6 +15,7 @@ HEADER = os.path.join(ROOT, "include", "evoke_b200.h")
 def _declared():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"typedef struct.*?\}\s*\w+;", "", text, flags=re.S)
     out = {}
     for m in re.finditer(r"EVK_API\s+[\w\s\*]+?\b(evk_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
         args = m.group(2).strip()
@@ -47,4 +48,4 @@ def test_argument_validation_needs_no_gpu():
     rc = lib.evk_l2norm_fwd(None, 0, 4, 8, 8, 1, None, None, 8, None, None, 8, None, None)
     assert rc == _lib.EVK_ERR_INVALID and "non-null" in _lib.last_error()
     with pytest.raises(ValueError):
-        _lib.call("evk_posmask_build", None, None, 4, None, None, 4, 0, 0, None, 1, None, None, 0, None)
+        _lib.call("evk_posmask_build", None, None, 4, None, None, 4, 0, 0, None, 1, None, None, 0, 0, None, None)

@@ -87,9 +87,10 @@ def test_k4t_matches_k4a(n_rows, n_cols, d, use_lists):
     assert ((got - want).abs()[m] <= 2.0 ** -8 * want.abs()[m] + 1e-6 * scale).all()
 
 
-def _grads(n, d, tau, monkeypatch, *, strip, overlap=False):
+def _grads(n, d, tau, monkeypatch, *, strip, overlap=False, mask_free=True):
     monkeypatch.setattr(Fn, "E_STRIP", strip)
     monkeypatch.setattr(Fn, "OVERLAP_STREAMS", overlap)
+    monkeypatch.setattr(Fn, "MASK_FREE", mask_free)
     ids = synth.make_study_ids(n, seed=n)
     xi = synth.make_embeddings(ids, d, seed=1)
     xt = synth.make_embeddings(ids, d, seed=2)
@@ -104,7 +105,8 @@ def _grads(n, d, tau, monkeypatch, *, strip, overlap=False):
     return (xi, xt, ids), out.item(), image.grad.cpu().numpy(), text.grad.cpu().numpy(), outm.item(), x.grad.cpu().numpy()
 
 
-@pytest.mark.parametrize("variant", [dict(strip=False), dict(strip=True), dict(strip=True, overlap=True)],
+@pytest.mark.parametrize("variant", [dict(strip=False), dict(strip=True), dict(strip=True, overlap=True),
+                                     dict(strip=True, mask_free=False), dict(strip=True, overlap=True, mask_free=False)],
                          ids=lambda v: "-".join(f"{k}{int(x)}" for k, x in v.items()))
 @pytest.mark.parametrize("n,d,tau", [(4096, 768, 0.5), (2500, 512, 0.07)])
 def test_backward_variants_against_oracle(n, d, tau, variant, monkeypatch):
@@ -119,9 +121,12 @@ def test_backward_variants_against_oracle(n, d, tau, variant, monkeypatch):
     assert rel_max(d_x, w_x) <= tol["grad"]
 
 
-def test_rows_with_more_positives_than_list_slots_fall_back_to_the_mask(monkeypatch):
-    """Groups of 12 views (> POS_SLOTS) next to ordinary ones: list path and mask-scan path in one launch."""
+@pytest.mark.parametrize("mask_free", [True, False])
+def test_rows_with_more_positives_than_list_slots_fall_back_to_the_mask(monkeypatch, mask_free):
+    """Groups of 12 views (> POS_SLOTS) next to ordinary ones: list path and the overflow path (id scan in mask-free
+    mode, mask scan otherwise) in one launch - forward positive sums and exact W entries."""
     monkeypatch.setattr(Fn, "E_STRIP", True)
+    monkeypatch.setattr(Fn, "MASK_FREE", mask_free)
     n, d, tau = 1536, 128, 0.2
     rng = np.random.default_rng(3)
     ids = np.concatenate([np.arange(600) // 12, 1000 + np.arange(n - 600) // 2]).astype(np.int32)
@@ -137,6 +142,12 @@ def test_rows_with_more_positives_than_list_slots_fall_back_to_the_mask(monkeypa
     assert abs(out.item() - want) <= TOL["bf16"]["loss"] * abs(want)
     assert rel_max(image.grad.cpu().numpy(), w_i) <= TOL["bf16"]["grad"]
     assert rel_max(text.grad.cpu().numpy(), w_t) <= TOL["bf16"]["grad"]
+    x = torch.tensor(xi, device=DEV, requires_grad=True)              # MPC: diagonal excluded in the id scan too
+    outm = evoke_b200.multi_pos_contra_images(x, ids, tau, precision="bf16", path="tc")
+    outm.backward()
+    wantm, w_x = orc.mpc_closed_form(xi, ids, tau)
+    assert abs(outm.item() - wantm) <= TOL["bf16"]["loss"] * abs(wantm)
+    assert rel_max(x.grad.cpu().numpy(), w_x) <= TOL["bf16"]["grad"]
 
 
 def test_strip_and_recompute_backwards_agree_closely(monkeypatch):
