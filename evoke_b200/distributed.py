@@ -444,3 +444,132 @@ def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local,
                                "and CUDA-IPC peer mapping between the ranks' GPUs")
     sym = mode == "sym" or (mode in ("auto", "peer") and world >= 8)
     return _ShardedG.apply(ops, group, inv_tau, precision, sym, row_ids, image, text)
+
+
+# ------------------------------------------------------------------------------------- sharded MPC (a7)
+class _ShardedMPC(torch.autograd.Function):
+    """multi_pos_contra_images_v0401 (reference :421-446) of the GLOBAL set of views from this rank's shard.
+
+    The objective is symmetric (one matrix on both sides), so one exchange suffices: the raw view
+    rows are all-gathered once, every rank normalises the kept rows (views whose study has another view somewhere in
+    the global batch, :424-429) and sweeps its own row block against all of them - E strip / statistics exactly as
+    on one device, rectangular [n' x N'] with the diagonal at column offset k0.  The row exp-sums of all ranks are
+    exchanged in one packed all-reduce (W needs a_j = 1/R_j of every column: W_ij = E_ij (a_i + a_j) - 2 M_ij / c_i
+    carries both the query-side and the key-side term of dS + dS^T), after which dX_r = W_r Xhat / (M' tau) is a
+    LOCAL contraction: no reduce-scatter, 4 n' N' D FLOP per rank."""
+
+    @staticmethod
+    def forward(ctx, ops, group, inv_tau: float, precision: str, codes_all, x: torch.Tensor):
+        import numpy as np
+        from . import ids as idmod
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        m = int(x.shape[0])
+        lo = rank * m
+        dev = x.device
+        keep_all = idmod.multi_view_rows(codes_all)                      # sorted global indices of the kept rows
+        n_keep = int(len(keep_all))
+        k0, k1 = int(np.searchsorted(keep_all, lo)), int(np.searchsorted(keep_all, lo + m))
+        split = precision == "fp32"
+        flags = ops.FLAG_EXCLUDE_DIAG | ops.FLAG_NO_COLSUM | (ops.FLAG_SPLIT_BF16 if split else 0)
+        xg = x.detach() if x.dtype == torch.float64 else x.detach().to(torch.float32)       # (fp64: CPU choreography tests)
+        x_all, work = _all_gather_rows(xg, group, async_op=True)                             # [N, D] raw rows
+        keep_dev = torch.from_numpy(np.ascontiguousarray(keep_all)).to(dev)
+        ids_keep = DeviceIds(torch.from_numpy(np.ascontiguousarray(codes_all[keep_all])).to(dev))
+        work.wait()
+        kn = ops.l2norm_fwd(x_all, want_f32=False, want_hi=True, want_lo=split, gather=keep_dev)       # [N', ld]
+        packed = torch.zeros(2 * n_keep, dtype=torch.float64 if x.dtype == torch.float64 else torch.float32, device=dev)
+        st = None
+        if k1 > k0:
+            qn = ops.rows_of(kn, k0, k1)
+            row_ids = DeviceIds(ids_keep.key[k0:k1])
+            use_strip = hasattr(ops, "tc_fwd_store") and ops.E_STRIP and not split and ctx.needs_input_grad[5]
+            mask_free = use_strip and ops.MASK_FREE
+            if use_strip:
+                bits, counts, pos_idx = ops.posmask_build(row_ids, ids_keep, clear_diag=True, diag_offset=k0, want_list=True,
+                                                          want_bits=not mask_free)
+                pos_dot = ops.pos_logits(qn, kn, pos_idx, counts)
+                if mask_free:
+                    rs_part, _, _, e, ld_e = ops.tc_fwd_store(qn, kn, None, inv_tau, flags | ops.FLAG_NO_POS, k0)
+                    rp_part = ops.pos_from_lists(qn, kn, row_ids, ids_keep, counts, pos_dot, inv_tau, clear_diag=True,
+                                                 diag_offset=k0).unsqueeze(0)
+                else:
+                    rs_part, rp_part, _, e, ld_e = ops.tc_fwd_store(qn, kn, bits, inv_tau, flags, k0)
+                strip, pos = (e, ld_e), (pos_idx, pos_dot)
+            else:
+                bits, counts = ops.posmask_build(row_ids, ids_keep, clear_diag=True, diag_offset=k0)
+                rs_part, rp_part, _ = ops.tc_fwd_partials(qn, kn, bits, inv_tau, flags, k0)
+                strip = pos = None
+            ops.reduce_partials(rs_part, int(rs_part.shape[0]), k1 - k0, out=packed[k0:k1])
+            ops.reduce_partials(rp_part, int(rp_part.shape[0]), k1 - k0, out=packed[n_keep + k0: n_keep + k1], divisor=counts)
+            st = (qn, row_ids, bits, counts, strip, pos)
+        # the one exchange after the sweep: [row exp-sums | pos_i / c_i] of every kept row (own slice, zeros elsewhere)
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        a_all, _, loss = ops.stats_fused(packed[:n_keep], packed[n_keep:], None, None, shift=inv_tau, pos_weight=1.0,
+                                         inv_count=1.0 / n_keep)
+        ctx.ops, ctx.inv_tau, ctx.flags = ops, inv_tau, flags
+        ctx.sv = (st, kn, ids_keep, a_all, k0, k1, n_keep, keep_dev, lo)
+        ctx.save_for_backward(x)
+        out = loss.reshape(())
+        return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        ops, inv_tau, flags = ctx.ops, ctx.inv_tau, ctx.flags
+        st, kn, ids_keep, a_all, k0, k1, n_keep, keep_dev, lo = ctx.sv
+        (x,) = ctx.saved_tensors
+        if st is None:                                   # no kept row in this shard
+            return None, None, None, None, None, torch.zeros_like(x)
+        qn, row_ids, bits, counts, strip, pos = st
+        g = grad_out.reshape(1).to(torch.float32).contiguous()
+        a_row = a_all[k0:k1].contiguous()
+        if strip is not None:
+            e, ld_e = strip
+            ops.tc_w_from_e(e, ld_e, n_keep, bits, counts, a_row, a_all, qn, kn, inv_tau, pos=pos, ids=(row_ids, ids_keep),
+                            clear_diag=True, diag_offset=k0)
+            w_hi, w_lo, ld_w = e, None, ld_e
+        else:
+            w_hi, w_lo, ld_w = ops.tc_bwd_w(qn, kn, bits, counts, a_row, a_all, inv_tau, flags, k0)
+        dq = ops.tc_bwd_gemm(w_hi, w_lo, ld_w, k1 - k0, n_keep, False, kn, flags)
+        local_rows = (keep_dev[k0:k1] - lo).to(torch.int32).contiguous()
+        d_x = ops.l2norm_bwd(x, qn, dq, scale_dev=g, scale_host=inv_tau / n_keep, gather=local_rows)
+        return None, None, None, None, None, d_x
+
+
+def multi_pos_contra_images_sharded(image: torch.Tensor, ids_local, temp: float, *, group=None, precision: str = "bf16",
+                                    ops=None) -> torch.Tensor:
+    """Image<->image multi-positive loss (reference :421-446) of the GLOBAL set of views from this rank's shard
+    (same number of views on every rank).  ids_local: this rank's integer study ids (numpy / tensor; string keys
+    must be factorised with a vocabulary shared by all ranks).  Returns the global loss (identical on every rank;
+    tensor([0.0]) leaf of shape [1] when no study of the global batch has a second view, :427-428);
+    .backward() yields d(global loss)/d(local shard).  One host round trip for the ids, as in the reference (:427)."""
+    import numpy as np
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    if ops is None:
+        from . import functional as ops
+        ops._require_cuda(image, "image")
+    if precision not in ("fp32", "bf16"):
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+    from .loss import _inv_tau
+    inv_tau = _inv_tau(temp)
+    m = int(image.shape[0])
+    if isinstance(ids_local, DeviceIds):
+        if ids_local.key2 is not None:
+            raise TypeError("sharded MPC takes one integer key per view (combine (patient, study) on the host)")
+        ids_local = ids_local.key
+    if isinstance(ids_local, np.ndarray):
+        if ids_local.dtype.kind not in "iu":
+            raise TypeError("sharded ids must be integers (factorise string keys with a vocabulary shared by all ranks)")
+        ids_local = torch.from_numpy(np.ascontiguousarray(ids_local.astype(np.int64)))
+    ids_t = torch.as_tensor(ids_local).reshape(-1).to(device=image.device, dtype=torch.int64)
+    if int(ids_t.shape[0]) != m:
+        raise ValueError(f"ids_local has {int(ids_t.shape[0])} entries for {m} views")
+    world = dist.get_world_size(group)
+    ids_all = torch.empty(world * m, dtype=torch.int64, device=image.device)
+    dist.all_gather_into_tensor(ids_all, ids_t.contiguous(), group=group)
+    from . import ids as idmod
+    codes_all = idmod.factorize(ids_all.cpu().numpy())                 # the size-determining host sync (:427)
+    if len(idmod.multi_view_rows(codes_all)) == 0:
+        return torch.tensor([0.0], requires_grad=True, device=image.device)
+    return _ShardedMPC.apply(ops, group, inv_tau, precision, codes_all, image)

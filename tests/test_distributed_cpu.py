@@ -24,7 +24,8 @@ def _oracle_ops():
     from oracle import evoke_oracle as orc
 
     ops = types.SimpleNamespace()
-    ops.FLAG_SPLIT_BF16 = 4
+    ops.FLAG_SPLIT_BF16, ops.FLAG_EXCLUDE_DIAG, ops.FLAG_NO_COLSUM, ops.FLAG_NO_POS = 4, 1, 2, 8
+    ops.E_STRIP = ops.MASK_FREE = False
 
     @dataclass
     class Normalized:
@@ -39,25 +40,36 @@ def _oracle_ops():
     ops.Normalized = Normalized
 
     def l2norm_fwd(x, *, want_f32, want_hi, want_lo, gather=None):
-        xh, nrm = orc.l2_normalize(x.detach().double().numpy())
+        xs = x.detach().double().numpy()
+        if gather is not None:
+            xs = xs[gather.numpy()]
+        xh, nrm = orc.l2_normalize(xs)
         hi = torch.from_numpy(xh)                                  # "hi" carries the exact unit rows here
         lo = torch.zeros_like(hi) if want_lo else None
-        return Normalized(n=x.shape[0], d=x.shape[1], norm=torch.from_numpy(nrm.reshape(-1)), hi=hi, lo=lo, ld=x.shape[1])
+        return Normalized(n=xs.shape[0], d=xs.shape[1], norm=torch.from_numpy(nrm.reshape(-1)), hi=hi, lo=lo, ld=xs.shape[1])
+
+    def rows_of(x, r0, r1):
+        return Normalized(n=r1 - r0, d=x.d, norm=None if x.norm is None else x.norm[r0:r1], hi=x.hi[r0:r1],
+                          lo=None if x.lo is None else x.lo[r0:r1], ld=x.ld)
 
     def posmask_build(rows, cols, *, clear_diag, diag_offset=0):
         m = orc.posmask_dense(rows.key.numpy(), cols.key.numpy(), clear_diag, diag_offset)
         return torch.from_numpy(m), torch.from_numpy(m.sum(1).astype(np.int32))
 
-    def _e(q, k, inv_tau):
+    def _e(q, k, inv_tau, flags=0, diag_offset=0):
         s = (q.hi + (q.lo if q.lo is not None else 0)) @ (k.hi + (k.lo if k.lo is not None else 0)).T * inv_tau
-        return s, torch.exp(s - inv_tau)
+        e = torch.exp(s - inv_tau)
+        if flags & ops.FLAG_EXCLUDE_DIAG:                          # column (row + diag_offset) leaves the softmax (:438)
+            r = torch.arange(e.shape[0])
+            e[r, r + diag_offset] = 0.0
+        return s, e
 
     def tc_fwd(q, k, bits, inv_tau, flags, diag_offset=0):
-        s, e = _e(q, k, inv_tau)
+        s, e = _e(q, k, inv_tau, flags, diag_offset)
         return e.sum(1), (s * bits).sum(1), e.sum(0)
 
     def tc_fwd_partials(q, k, bits, inv_tau, flags, diag_offset=0):
-        s, e = _e(q, k, inv_tau)
+        s, e = _e(q, k, inv_tau, flags, diag_offset)
         # two row partials and three column partials, as the tiled kernel would produce
         half = e.shape[1] // 2
         rs = torch.stack([e[:, :half].sum(1), e[:, half:].sum(1)])
@@ -78,16 +90,18 @@ def _oracle_ops():
     def stats_fused(rs_part, rp_part, cs_part, counts, *, shift, pos_weight, inv_count, col_lo=0, col_hi=None):
         row_sum = rs_part if rs_part.dim() == 1 else rs_part.sum(0)
         row_pos = rp_part if rp_part.dim() == 1 else rp_part.sum(0)
-        col_sum = cs_part if cs_part.dim() == 1 else cs_part.sum(0)
-        col_hi = col_sum.shape[0] if col_hi is None else col_hi
         if counts is not None:
             row_pos = row_pos / counts
         acc = (shift + row_sum.log() - pos_weight * row_pos).sum()
+        if cs_part is None:                                        # MPC: no column statistics
+            return 1.0 / row_sum, None, (acc * inv_count).reshape(1)
+        col_sum = cs_part if cs_part.dim() == 1 else cs_part.sum(0)
+        col_hi = col_sum.shape[0] if col_hi is None else col_hi
         acc = acc + (shift + col_sum[col_lo:col_hi].log()).sum()
         return 1.0 / row_sum, 1.0 / col_sum, (acc * inv_count).reshape(1)
 
     def tc_bwd_w(q, k, bits, counts, a_row, b_col, inv_tau, flags, diag_offset=0):
-        _, e = _e(q, k, inv_tau)
+        _, e = _e(q, k, inv_tau, flags, diag_offset)
         w = e * (a_row[:, None] + b_col[None, :]) - 2.0 * bits / counts[:, None]
         return w, None, w.shape[1]
 
@@ -96,11 +110,17 @@ def _oracle_ops():
         return (w_hi.T @ xm) if transpose_w else (w_hi @ xm)
 
     def l2norm_bwd(x, nrm, g_hat, *, scale_dev, scale_host, gather=None):
-        g = orc.l2_normalize_bwd(x.detach().double().numpy(), g_hat.numpy())
+        xs = x.detach().double().numpy()
+        if gather is None:
+            g = orc.l2_normalize_bwd(xs, g_hat.numpy())
+        else:                                                      # filtered rows get zero gradient (:429)
+            idx = gather.numpy()
+            g = np.zeros_like(xs)
+            g[idx] = orc.l2_normalize_bwd(xs[idx], g_hat.numpy())
         return (torch.from_numpy(g) * (scale_host * scale_dev.double().item())).to(x.dtype)
 
     for f in (l2norm_fwd, posmask_build, tc_fwd, tc_fwd_partials, reduce_partials, stats_fused, tc_bwd_w, tc_bwd_gemm,
-              l2norm_bwd):
+              l2norm_bwd, rows_of):
         setattr(ops, f.__name__, f)
     return ops
 
@@ -156,3 +176,61 @@ def test_sharded_rejects_string_ids_and_uninitialised_group():
     x = torch.randn(4, 8)
     with pytest.raises(RuntimeError, match="not initialised"):
         global_alignment_sharded(x, x, np.arange(4), 0.5, ops=_oracle_ops())
+
+
+def _mpc_worker(rank, world, port, n_total, d, tau, ids_kind, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from evoke_b200.distributed import multi_pos_contra_images_sharded
+        ids = _mpc_ids(n_total, ids_kind)
+        from evoke_b200 import synth
+        x = synth.make_embeddings(ids, d, seed=42).astype(np.float64)
+        m = n_total // world
+        sl = slice(rank * m, (rank + 1) * m)
+        xs = torch.tensor(x[sl], requires_grad=True)
+        loss = multi_pos_contra_images_sharded(xs, ids[sl].copy(), tau, precision="fp32", ops=_oracle_ops())
+        if loss.grad_fn is not None:
+            (1.5 * loss).backward()
+            grad = xs.grad.numpy()
+        else:
+            grad = np.zeros_like(x[sl])
+        np.savez(os.path.join(out_dir, f"mpc{rank}.npz"), loss=loss.detach().numpy().reshape(-1), grad=grad, leaf=loss.grad_fn is None)
+    finally:
+        dist.destroy_process_group()
+
+
+def _mpc_ids(n_total, kind):
+    from evoke_b200 import synth
+    if kind == "mixed":
+        return synth.make_study_ids(n_total, seed=41)
+    if kind == "single":                       # no study has a second view: the shape-[1] zero leaf (:427-428)
+        return np.arange(n_total, dtype=np.int32)
+    # "lopsided": every multi-view study lives on rank 0's rows only, rank 1 keeps nothing
+    ids = np.arange(n_total, dtype=np.int32)
+    ids[: n_total // 4] = ids[: n_total // 4] // 2
+    return ids
+
+
+@pytest.mark.parametrize("ids_kind", ["mixed", "lopsided", "single"])
+def test_sharded_mpc_equals_global_batch(tmp_path, ids_kind):
+    """multi_pos_contra_images_v0401 (:421-446) sharded over 2 ranks == the single-device reference on all views:
+    cross-rank positives, rows dropped as queries AND keys, a rank without kept rows, the empty case."""
+    from evoke_b200 import synth
+    from oracle import evoke_oracle as orc
+    world, n_total, d, tau = 2, 56, 24, 0.5
+    port = 29500 + (os.getpid() % 150) + ["mixed", "lopsided", "single"].index(ids_kind) * 3
+    mp.spawn(_mpc_worker, args=(world, port, n_total, d, tau, ids_kind, str(tmp_path)), nprocs=world, join=True)
+    ids = _mpc_ids(n_total, ids_kind)
+    x = synth.make_embeddings(ids, d, seed=42).astype(np.float64)
+    want, dx = orc.mpc_closed_form(x, ids, tau)
+    m = n_total // world
+    for r in range(world):
+        got = np.load(tmp_path / f"mpc{r}.npz")
+        if want is None:
+            assert bool(got["leaf"]) and got["loss"].shape == (1,) and float(got["loss"][0]) == 0.0
+            continue
+        assert abs(float(got["loss"][0]) - want) < 1e-9 * abs(want)
+        assert np.abs(got["grad"] - 1.5 * dx[r * m:(r + 1) * m]).max() < 1e-7 * np.abs(dx).max() * 1.5

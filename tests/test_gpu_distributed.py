@@ -233,3 +233,59 @@ def test_a_rank_that_misses_a_barrier_poisons_the_step(tmp_path):
         got = np.load(tmp_path / f"late{r}.npz")
         assert np.isfinite(got["healthy"])
         assert np.isnan(got["loss"]) and bool(got["grad_nan"]) and bool(got["raised"]), (r, dict(got))
+
+
+def _mpc_worker(rank, world, port, n_total, d, tau, precision, kind, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from evoke_b200 import synth
+        from evoke_b200.distributed import multi_pos_contra_images_sharded
+        ids = _mpc_ids(n_total, kind)
+        x = synth.make_embeddings(ids, d, seed=62)
+        m = n_total // world
+        sl = slice(rank * m, (rank + 1) * m)
+        xs = torch.tensor(x[sl], device="cuda", requires_grad=True)
+        loss = multi_pos_contra_images_sharded(xs, ids[sl].copy(), tau, precision=precision)
+        if loss.grad_fn is not None:
+            loss.backward()
+        torch.cuda.synchronize()
+        grad = xs.grad.cpu().numpy() if xs.grad is not None else np.zeros_like(x[sl])
+        np.savez(os.path.join(out_dir, f"mpc{rank}.npz"), loss=loss.detach().float().cpu().numpy().reshape(-1), grad=grad)
+    finally:
+        dist.destroy_process_group()
+
+
+def _mpc_ids(n_total, kind):
+    from evoke_b200 import synth
+    if kind == "mixed":
+        return synth.make_study_ids(n_total, seed=61)
+    ids = np.arange(n_total, dtype=np.int32)            # "lopsided": only rank 0's first rows have second views
+    ids[: n_total // 8] = ids[: n_total // 8] // 2
+    return ids
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("kind", ["mixed", "lopsided"])
+@pytest.mark.parametrize("precision,ltol,gtol", [("fp32", 1e-5, 1e-4), ("bf16", 2e-5, 2e-2)])
+def test_sharded_mpc_equals_oracle(tmp_path, precision, ltol, gtol, kind, world):
+    """multi_pos_contra_images_v0401 (:421-446) over the views of all ranks: cross-rank positives, rows dropped from
+    queries and keys, a rank without kept rows; E strip + mask-free lists in bf16 mode on a rectangular row block."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from evoke_b200 import synth
+    from oracle import evoke_oracle as orc
+    n_total, d, tau = 640 * world, 256, 0.5
+    port = _port(200 + world * 8 + (1 if precision == "fp32" else 0) + (2 if kind == "mixed" else 0))
+    mp.spawn(_mpc_worker, args=(world, port, n_total, d, tau, precision, kind, str(tmp_path)), nprocs=world, join=True)
+    ids = _mpc_ids(n_total, kind)
+    x = synth.make_embeddings(ids, d, seed=62)
+    want, dx = orc.mpc_closed_form(x, ids, tau)
+    m = n_total // world
+    for r in range(world):
+        got = np.load(tmp_path / f"mpc{r}.npz")
+        assert abs(float(got["loss"][0]) - want) <= ltol * abs(want)
+        assert np.abs(got["grad"] - dx[r * m:(r + 1) * m]).max() <= gtol * np.abs(dx).max()

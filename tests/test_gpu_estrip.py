@@ -153,7 +153,9 @@ def test_rows_with_more_positives_than_list_slots_fall_back_to_the_mask(monkeypa
 def test_strip_and_recompute_backwards_agree_closely(monkeypatch):
     a = _grads(3000, 768, 0.5, monkeypatch, strip=False)
     b = _grads(3000, 768, 0.5, monkeypatch, strip=True, overlap=True)
-    assert a[1] == b[1] and a[4] == b[4]                     # same forward statistics -> identical loss
+    # same exp-sums; the positive sums come from the tensor-core accumulators (recompute mode: K3 epilogue) resp. from
+    # fp32 dot products of the same bf16 operands (mask-free strip mode): equal to fp32 rounding
+    assert abs(a[1] - b[1]) <= 1e-6 * abs(a[1]) and abs(a[4] - b[4]) <= 1e-6 * abs(a[4])
     for ga, gb in ((a[2], b[2]), (a[3], b[3]), (a[5], b[5])):
         assert rel_max(gb, ga) <= 4e-3                       # both carry bf16 W; they differ by one more rounding
 
