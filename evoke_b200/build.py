@@ -17,8 +17,8 @@ ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "libevoke_b200.so")
 STAMP_PATH = os.path.join(PKG_DIR, "csrc", ".build_stamp")
 
-SOURCES = ["evk_api.cu", "k1_l2norm.cu", "k2_posmask.cu", "k_small.cu", "k_stats.cu", "k_pos.cu", "k_peer.cu", "k_wstrip.cu", "k_local.cu", "tc_engine.cu"]
-HEADERS = ["evk_common.cuh", "tc_ptx.cuh", os.path.join(ROOT, "include", "evoke_b200.h")]
+SOURCES = ["evk_api.cu", "k1_l2norm.cu", "k2_posmask.cu", "k_small.cu", "k_stats.cu", "k_pos.cu", "k_peer.cu", "k_wstrip.cu", "k_local.cu", "k_topk.cu", "tc_engine.cu"]
+HEADERS = ["evk_common.cuh", "tc_ptx.cuh", "peer_sync.cuh", os.path.join(ROOT, "include", "evoke_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

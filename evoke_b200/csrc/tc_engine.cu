@@ -1196,6 +1196,22 @@ extern "C" int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int
                      0, 0, use_cta_pairs(), static_cast<cudaStream_t>(stream));
 }
 
+// f4 (retrieval, reference modules/multiview/trainer.py:543-653): scores = A B^T for the exact inner-product top-k.
+// Plain stores (every element written once, c needs no zero fill); a_lo / b_lo select the 3-segment split mode.
+extern "C" int evk_tc_gemm_nt(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo,
+                              int64_t ldb, int64_t m, int64_t n, int64_t k, float* c, int64_t ldc, evk_stream_t stream) {
+  int rc = check_device();
+  if (rc != EVK_OK) return rc;
+  EVK_REQUIRE(a_hi && b_hi && c && ((a_lo == nullptr) == (b_lo == nullptr)), "evk_tc_gemm_nt: null operand (a_lo / b_lo both or neither)");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.flags = kIntStore;
+  const void* a_ptrs[3] = {a_hi, a_hi, a_lo};
+  const void* b_ptrs[3] = {b_hi, b_lo, b_hi};
+  return gemm_common(p, a_ptrs, lda, false, b_ptrs, ldb, false, a_lo ? 3 : 1, m, n, k, 1.f, c, ldc, 0, 0, use_cta_pairs(),
+                     static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int evk_tc_gemm_probe(const void* a, int64_t lda, int a_major, const void* b, int64_t ldb, int b_major,
                                  int64_t m, int64_t n, int64_t k, float* c, int64_t ldc, int variant, int splits,
                                  evk_stream_t stream) {

@@ -520,6 +520,25 @@ EVK_API int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int64_
                               const uint64_t* out_ptrs, int n_owners, int64_t rows_per_owner, int64_t ld_out,
                               int store, int first_owner, evk_stream_t stream);
 
+/* ---- f4: exact inner-product top-k retrieval ------------------------------------------------------------------
+ * Replaces the faiss index of PretrainTester.predict (modules/multiview/trainer.py:543-653: IndexIVFFlat with
+ * METRIC_INNER_PRODUCT, `train_index.search(ret, k)`; faiss is a third-party dependency that is not vendored in
+ * the reference) by an EXACT search: scores = Q C^T on the tcgen05 main loop, folded chunk by chunk into the
+ * running top-k of every query.
+ * evk_tc_gemm_nt: c[m, n] = a[m, k] b[n, k]^T, bf16 operands (row-major, K contiguous, ld % 8 == 0, 16-byte aligned),
+ * fp32 output written with plain stores (no zero fill needed).  a_lo / b_lo (both or neither): the low halves of a
+ * (hi, lo) bf16 split of fp32 features -> 3-segment product (hi.hi + hi.lo + lo.hi, ~2^-17 relative). */
+EVK_API int evk_tc_gemm_nt(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
+                   int64_t m, int64_t n, int64_t k, float* c, int64_t ldc, evk_stream_t stream);
+/* Fold a chunk of scores [n_q, n_c] (row pitch ld; column c is corpus entry col_offset + c) into the running top-k
+ * lists best_val / best_idx [n_q, k] (k <= 64; sorted by score descending, ties by corpus index ascending;
+ * init != 0: start from empty lists, else continue from their contents; unused slots hold -inf / -1).
+ * q_group [n_q] / c_group [corpus] (both or neither): entries of the query's own group are not candidates (the
+ * reference drops the retrieved reports of the query's own study, trainer.py:590-607).  NaN scores are skipped. */
+EVK_API int evk_topk_update(const float* scores, int64_t ld, int64_t n_q, int64_t n_c, int64_t col_offset,
+                    const int32_t* q_group, const int32_t* c_group, int k, float* best_val, int32_t* best_idx,
+                    int init, evk_stream_t stream);
+
 /* Debug/bring-up: plain C[m,n] = A[m,k] B[n,k]^T (or MN-major operands) through the same
  * tcgen05 main loop, fp32 out.  a_major/b_major: 0 = K contiguous, 1 = M/N contiguous
  * (then A is stored [k, m] / B is stored [k, n]).  c must be zeroed by the caller (the epilogue

@@ -220,3 +220,17 @@ def test_committed_fingerprints_belong_to_the_bench_workloads():
     assert max(abs(a - b) for a, b in zip(got["d_image_row_norms"], want["d_image_row_norms"])) <= 1e-12
     for cfg in ("cfg3", "cfg4"):
         assert os.path.isfile(os.path.join(root, "tests", "golden", f"fingerprint_{cfg}.json"))
+
+
+def test_retrieval_oracle_known_answers():
+    """f4: exact inner-product search, best first, stable ties, own-group exclusion, padded short lists."""
+    import numpy as np
+    from oracle import retrieval_oracle as ro
+    q = np.array([[1.0, 0.0], [0.0, 1.0]])
+    c = np.array([[1.0, 0.0], [0.5, 0.5], [0.0, 2.0], [1.0, 0.0]])
+    val, idx = ro.topk_inner_product(q, c, 3)
+    assert idx.tolist() == [[0, 3, 1], [2, 1, 0]] and val.tolist() == [[1.0, 1.0, 0.5], [2.0, 0.5, 0.0]]
+    val, idx = ro.topk_inner_product(q, c, 3, [0, 1], [0, 0, 1, 1])
+    assert idx.tolist() == [[3, 2, -1], [1, 0, -1]] and np.isneginf(val[:, 2]).all()
+    val, idx = ro.topk_inner_product(q, c[:2], 4)
+    assert idx.shape == (2, 4) and (idx[:, 2:] == -1).all()
