@@ -428,7 +428,11 @@ def run_cuda(args):
     # ---- sustained: the same replay for >= 1 s
     sustained = None
     if graphed is not None and not args.no_sustained:
-        reps = max(args.steps, int(1.05e3 / max(ms_total / args.steps, 1e-3)) + 1)
+        # every rank must replay the SAME number of steps (the sharded step contains cross-GPU syncs): agree on it
+        t_loc = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_loc, op=dist.ReduceOp.MAX)
+        reps = max(args.steps, int(1.05e3 / max(float(t_loc.item()) / args.steps, 1e-3)) + 1)
         s_beg, s_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         s_beg.record()

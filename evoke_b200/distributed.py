@@ -433,6 +433,7 @@ def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local,
             from . import graphs
             use_graph = graphs.DROPIN_GRAPHS if graph is None else bool(graph)
             if use_graph and not torch.cuda.is_current_stream_capturing():
+                pc.raise_if_failed()          # (a replayed graph never re-enters peer_forward's own check)
                 # collective: every rank captures at the same call (same shapes on every rank); the warm-up and the
                 # captured sequences contain the flag barriers
                 def fwd(im, tx, ids, need):
