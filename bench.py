@@ -710,13 +710,56 @@ def run_cuda(args):
         raise SystemExit(3)
 
 
+def run_cfg5(args):
+    """BASELINE.json config 5: the full pre-training step (tools/pretrain_step.py), timed with this library's losses and -
+    same model, same data - with the reference's loss op sequences in CUDA eager.  One JSON line (rank 0)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import pretrain_step
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
+    steps, warmup = min(args.steps, 20), max(min(args.warmup, 5), 3)
+    if args.impl == "reference":
+        out = pretrain_step.run(steps, warmup, 32, "reference", True)
+        ref = None
+    else:
+        out = pretrain_step.run(steps, warmup, 32, "evoke_b200", True)
+        torch.cuda.empty_cache()
+        ref = pretrain_step.run(max(3, steps // 2), warmup, 32, "reference", True)
+    if rank == 0:
+        workload = ("cfg5: full EVOKE pre-training step on synthetic 224x224 multi-view CXRs: " + out["model"] +
+                    "; all_loss = instance + sen_text + mul_pos, clip_grad_value_(0.1), Adam; bf16 autocast encoders")
+        line = {"metric": "pretrain step pairs/sec (32 studies per GPU)", "value": out["value"], "unit": "pairs/s",
+                "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": out["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": workload, "global_batch": 32 * world, "dim": 768,
+                           "l2": "every step runs ResNet-101 and BERT over fresh synthetic images: nothing stays cached"},
+                "gpu_launches": out["gpu_launches"], "loss": out["loss"], "ms_loss_forward": out["ms_loss_forward"],
+                "losses": out["losses"], "roofline": None, "cpu_baseline": None,
+                "e2e": {"value": out["value"], "unit": "pairs/s", "h2d_bytes_per_step": int(69 * 3 * 224 * 224 * 4 + 32 * 100 * 16) * world,
+                        "d2h_bytes_per_step": 4 * world,
+                        "note": "the step's images and token ids are generated on the host and copied H2D inside the timed step"},
+                "same_model_reference_losses": None if ref is None else {
+                    "value": ref["value"], "ms_per_step": ref["ms_per_step"], "ms_loss_forward": ref["ms_loss_forward"],
+                    "what": "identical model, data and optimiser; the three losses as the reference's PyTorch op sequence in "
+                            "CUDA eager on each rank's own batch (oracle ports)"}}
+        if args.impl == "reference":
+            line["impl"] = "reference"
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        sys.stdout.flush()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="evoke_b200", choices=["evoke_b200", "reference"])
-    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS),
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS) + ["cfg5"],
                     help="workload (BASELINE.json configs): cfg3 = the metric's configuration (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-eager", action="store_true", help="skip the CUDA-eager reference-port baseline")
@@ -730,7 +773,9 @@ def main():
                     help="N>1: peer = exchanges by this library's kernels over peer-mapped memory (default when possible); "
                          "rs / sym = NCCL transports (reduce-scatter of partial dK / recomputed key-side block)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.config == "cfg5":
+        run_cfg5(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_cuda(args)

@@ -353,3 +353,20 @@ def multi_pos_contra_images_port(x, ids, tau: float):
     logits.fill_diagonal_(-1e9)
     logits = logits - logits.max(dim=-1, keepdim=True).values.detach()
     return F.cross_entropy(logits, target)
+
+
+def local_text_token_alignment_port(local_image, local_text, tau: float):
+    """The op sequence of Pretrain.local_text_token_alignment_loss (:506-526) on whatever device the inputs live on
+    (timed baseline of the full-step harness, tools/pretrain_step.py)."""
+    import torch
+    import torch.nn.functional as F
+    sim = local_text @ local_image.permute(0, 2, 1)
+    sco = F.softmax(sim / math.sqrt(local_image.shape[2]), dim=-1)
+    out = F.normalize(torch.bmm(sco, local_image), dim=-1, p=2)
+    text = F.normalize(local_text, dim=-1, p=2)
+    word = torch.bmm(text, out.permute(0, 2, 1)) / tau
+    b, n1, n2 = word.shape
+    targets = torch.arange(n1, device=word.device).long().repeat(b)
+    l1 = F.cross_entropy(word.reshape(b * n1, n2), targets)
+    l2 = F.cross_entropy(word.permute(0, 2, 1).reshape(b * n2, n1), targets)
+    return (l1 + l2) / 2.0
