@@ -49,7 +49,7 @@ SIGNATURES = {
     "evk_mpce_pos": [P, P, L, P, P, L, L, L, L, P, L, F, P, P],
     "evk_mpce_fwd": [P, P, L, P, P, L, L, L, L, P, L, F, I, L, P, P, L, P, L, P],
     "evk_mpce_bwd_w": [P, P, L, P, P, L, L, L, L, P, L, P, P, P, F, I, L, P, P, L, P],
-    "evk_mpce_bwd_gemm": [P, P, L, L, L, I, P, P, L, L, F, I, P, L, P],
+    "evk_mpce_bwd_gemm": [P, P, L, L, L, I, P, P, L, L, F, I, P, L, I, P],
     "evk_mpce_fwd_store": [P, L, P, L, L, L, L, P, L, F, I, L, P, P, L, P, L, P, L, P],
     "evk_mpce_w_from_e": [P, L, L, L, P, L, P, P, P, P, L, P, L, L, F, P, P, I, P, P, P, P, L, I, P],
     "evk_mpce_pos_logits": [P, L, P, L, L, L, P, P, I, P, P],
@@ -68,7 +68,7 @@ SIGNATURES = {
     "evk_peer_close": [P],
     "evk_peer_barrier": [P, P, I, I, P, P, L, P],
     "evk_mpce_shard_finish": [P, I, L, L, F, D, P, P, P, L, I, P, P, P, P],
-    "evk_mpce_bwd_gemm_scatter": [P, P, L, L, L, P, P, L, L, F, I, P, I, L, L, I, I, P],
+    "evk_mpce_bwd_gemm_scatter": [P, P, L, L, L, P, P, L, L, F, I, P, I, L, L, I, I, I, P],
     "evk_l2norm_bwd_parts": [P, I, L, L, L, L, P, P, P, I, L, I, L, P, F, P, I, L, I, P, P, P],
     "evk_tc_gemm_nt": [P, P, L, P, P, L, L, L, L, P, L, P],
     "evk_topk_update": [P, L, L, L, L, P, P, I, P, P, I, P],

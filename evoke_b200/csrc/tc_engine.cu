@@ -44,6 +44,7 @@ constexpr int kEpiWarpsFwd = 16;
 // default number of epilogue warps of an epilogue kind (K3 variants are chosen at launch, see mpce_fwd_impl)
 __host__ __device__ constexpr int epi_warps(int epi) { return kEpiWarps; }
 constexpr int kTmemCols = 512;
+constexpr int kK3DefaultVariant = 0;          // see k3_variant()
 constexpr int kMaxSegs = 3;
 
 enum { EPI_FWD = 0, EPI_BWD_W = 1, EPI_GEMM = 2, EPI_FWD_E = 3, EPI_GEMM_TMA = 4 };
@@ -83,6 +84,7 @@ struct alignas(64) TcParams {
   // landed[source] >= *step before its first load from a source's columns.
   const uint32_t* landed; const int* step; int* error; int64_t cols_per_source; int rot_tiles;
   int rot_m_tiles;               // EPI_GEMM_TMA scatter: first row block (pair tile) to visit, see Sched
+  int cta_limit;                 // > 0: launch at most this many CTAs (two contractions sharing the GPU side by side)
   // EPI_GEMM
   float* out; int64_t ld_out; float alpha;
   // EPI_GEMM, reduce-scatter fused into the epilogue: output row i belongs to rank i / rows_per_owner and
@@ -103,11 +105,18 @@ constexpr int epi_smem_bytes() {
          : (EPI == EPI_BWD_W ? kEpiWarps * 8192
             : (EPI == EPI_FWD_E ? 2 * 4 * BN * 4 : (EPI == EPI_GEMM_TMA ? kEpiWarps * 8192 : 0)));
 }
+// Split-role epilogue of K3 with the strip store (EPI_FWD_E, sixteen epilogue warps, two staging boxes): warps 0-7
+// turn the accumulator into the statistics (exp, row / column sums, positives), warps 8-15 into the bf16 E strip
+// (exp, pack, swizzled staging, TMA stores).  Both read the same TMEM tile (TMEM reads are free, the exp is done
+// twice); the tile's epilogue time becomes max(statistics, store) instead of their sum.
+template <int EPI, int EW, int SB> constexpr bool split_epi() { return EPI == EPI_FWD_E && EW == 16 && SB == 2; }
+// warps that stage E boxes
+template <int EPI, int EW, int SB> constexpr int store_warps() { return EPI != EPI_FWD_E ? 0 : (split_epi<EPI, EW, SB>() ? 8 : EW); }
 // EW epilogue warps, SB staging boxes (4 KiB each) per warp for the E-strip store of EPI_FWD_E
 template <int EPI, int STAGES, bool CTA2, int EW = kEpiWarps, int SB = 2>
 constexpr int smem_bytes_total() {
   return 1024 /*align slack*/ + STAGES * stage_bytes<CTA2>() + epi_smem_bytes<EPI>() +
-         (EPI == EPI_FWD_E ? EW * SB * 4096 : 0) + (2 * STAGES + 4) * 8 + 16;
+         store_warps<EPI, EW, SB>() * SB * 4096 + (2 * STAGES + 4) * 8 + 16;
 }
 
 // Work decomposition, identical in the three warp roles.
@@ -199,7 +208,8 @@ tc_kernel(const __grid_constant__ TcParams p) {
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t epi_base = smem_base + STAGES * kStage;
   uint8_t* epi_gen = smem_gen + STAGES * kStage;
-  constexpr int kEpiBytes = epi_smem_bytes<EPI>() + (EPI == EPI_FWD_E ? EW * SB * 4096 : 0);
+  constexpr int kEpiBytes = epi_smem_bytes<EPI>() + store_warps<EPI, EW, SB>() * SB * 4096;
+  constexpr bool kSplitEpi = split_epi<EPI, EW, SB>();
   const uint32_t bar_base = epi_base + kEpiBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -358,8 +368,12 @@ tc_kernel(const __grid_constant__ TcParams p) {
   } else {
     // ===================================================================== epilogue warps
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int hh = warp >> 2;                     // which part (half / quarter) of the tile's columns this warp owns
-    constexpr int kChunks = BN / 32 / (kEW / 4);  // 32-column chunks per warp: 4 (eight warps) or 2 (sixteen)
+    // split roles: warps 0-7 statistics, 8-15 strip store; each group covers the tile like the eight-warp layout
+    const int role = kSplitEpi ? (warp >> 3) : 0;
+    const int gw = kSplitEpi ? (warp & 7) : warp; // warp index within its role group
+    constexpr int kGroupWarps = kSplitEpi ? 8 : kEW;
+    const int hh = gw >> 2;                       // which part (half / quarter) of the tile's columns this warp owns
+    constexpr int kChunks = BN / 32 / (kGroupWarps / 4);  // 32-column chunks per warp: 4 (eight warps) or 2 (sixteen)
     const int row = q * 32 + lane;                // tile row owned by this thread
     const int et = warp * 32 + lane;              // 0 .. 32*kEW-1
     const int c_lo = hh * kChunks;                // first 32-column chunk of this warp
@@ -391,10 +405,12 @@ tc_kernel(const __grid_constant__ TcParams p) {
         // EPI_FWD_E: this warp's private staging for its 32 rows x (32 kChunks) columns of E (bf16),
         // 128B-swizzled [32 x 64] boxes, stored with its own TMA stores (as in EPI_BWD_W)
         // SB staging buffers per warp: with fewer buffers than boxes a buffer is reused after its store has been read
-        const uint32_t wstg = epi_base + 2 * 4 * BN * 4 + warp * (SB * 4096);
+        const uint32_t wstg = epi_base + 2 * 4 * BN * 4 + gw * (SB * 4096);
         const int m_warp = m0 + q * 32;
-        const bool want_col = (p.flags & EVK_FLAG_NO_COLSUM) == 0;
-        const bool want_pos = (p.flags & EVK_FLAG_NO_POS) == 0;   // else evk_mpce_pos supplies the positive sums
+        const bool do_stats = !kSplitEpi || role == 0;            // this warp produces the statistics
+        const bool do_store = kStoreE && (!kSplitEpi || role == 1);   // ... the E strip
+        const bool want_col = do_stats && (p.flags & EVK_FLAG_NO_COLSUM) == 0;
+        const bool want_pos = do_stats && (p.flags & EVK_FLAG_NO_POS) == 0;   // else evk_mpce_pos supplies the positive sums
         const uint32_t* mrow = want_pos ? p.bits + (row_ok ? i : 0) * p.ld_words + (n0 >> 5) : nullptr;
         const int64_t dcol = i + p.diag_offset - n0;              // diagonal column inside this tile?
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f, rp = 0.f;
@@ -413,12 +429,56 @@ tc_kernel(const __grid_constant__ TcParams p) {
             for (int k = 0; k < kChunks; ++k) mw4[k] = __ldg(mrow + c_lo + k);
           }
         }
-        if (kStoreE) {
+        if (do_store) {
           if (lane == 0) tma_store_wait_read<0>();                // this warp's previous stores have left smem
           __syncwarp();
         }
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
+        if (kSplitEpi && role == 1) {
+          // ---- store warps: accumulator -> exp -> bf16 -> swizzled staging -> TMA store; nothing else
+#pragma unroll 1
+          for (int cc = 0; cc < kChunks; ++cc) {
+            const int c = c_lo + cc;
+            float v[32];
+            tmem_ld_32x32(taddr + c * 32, v);
+            tmem_ld_wait(v);
+            if (cc == kChunks - 1) release_tmem(as);              // last read of this warp: the stage may be refilled
+            const int cbase = n0 + c * 32;
+            uint32_t live = (cbase + 32 <= p.n_cols) ? 0xffffffffu
+                            : (cbase >= p.n_cols ? 0u : ((1u << (int)(p.n_cols - cbase)) - 1u));
+            if (!row_ok) live = 0u;
+            if (excl && dcol >= 0 && (dcol >> 5) == c) live &= ~(1u << (int)(dcol & 31));
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = ex2_approx(fmaf(v[k], c1, -c1));
+            if (live != 0xffffffffu) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) v[k] = ((live >> k) & 1u) ? v[k] : 0.f;
+            }
+            const int box = cc >> 1;
+            const uint32_t row_st = wstg + (box % SB) * 4096 + lane * 128;
+            const int u0 = (cc & 1) * 4;
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+              const uint32_t h0 = pack_bf16x2(v[8 * uu + 0], v[8 * uu + 1]);
+              const uint32_t h1 = pack_bf16x2(v[8 * uu + 2], v[8 * uu + 3]);
+              const uint32_t h2 = pack_bf16x2(v[8 * uu + 4], v[8 * uu + 5]);
+              const uint32_t h3 = pack_bf16x2(v[8 * uu + 6], v[8 * uu + 7]);
+              const uint32_t off = static_cast<uint32_t>(((u0 + uu) ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_st + off), "r"(h0), "r"(h1), "r"(h2),
+                           "r"(h3) : "memory");
+            }
+            if (cc & 1) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&p.out_map[0], wstg + (box % SB) * 4096, n0 + (c - 1) * 32, m_warp, p.policy_out);
+                tma_store_commit();
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll 1
         for (int cc = 0; cc < kChunks; ++cc) {
           const int c = c_lo + cc;
@@ -447,7 +507,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
           for (int k = 0; k < 32; k += 4) {
             rs0 += v[k]; rs1 += v[k + 1]; rs2 += v[k + 2]; rs3 += v[k + 3];
           }
-          if (kStoreE) {                                          // E -> bf16 -> swizzled staging (dead entries are 0)
+          if (kStoreE && !kSplitEpi) {                            // E -> bf16 -> swizzled staging (dead entries are 0)
             const int box = cc >> 1;
             if ((cc & 1) == 0 && box >= SB) {                     // buffer reuse within the tile
               if (lane == 0) tma_store_wait_read<0>();
@@ -481,12 +541,12 @@ tc_kernel(const __grid_constant__ TcParams p) {
         }
         release_tmem(as);                                         // TMEM stage drained
         if (row_ok) {
-          const int64_t po = ((int64_t)nb * (kEW / 4) + hh) * p.ld_rowpart + i;
+          const int64_t po = ((int64_t)nb * (kGroupWarps / 4) + hh) * p.ld_rowpart + i;
           p.row_sum_part[po] = (rs0 + rs1) + (rs2 + rs3);
           if (want_pos) p.row_pos_part[po] = rp;
         }
         if (want_col) {
-          named_bar_sync(1, kEW * 32);
+          named_bar_sync(1, kGroupWarps * 32);                    // the statistics warps only
           if (et < BN) {
             const float s = (colpart[et] + colpart[BN + et]) + (colpart[2 * BN + et] + colpart[3 * BN + et]);
             // each CTA (128-row block) writes its own partial row: index = global 128-row block
@@ -799,12 +859,13 @@ bool use_cta_pairs() {
 }
 
 int k3_variant() {
-  // EVK_K3_VARIANT: 0 = 8 epilogue warps, 4 stages (default); 1 = 16 epilogue warps; 2 = 8 warps, 5 stages with
-  // single-buffered E staging.  evk_mpce_row_parts() tells the caller how many row-partial rows K3 writes.
+  // EVK_K3_VARIANT: 0 = 8 epilogue warps, 4 stages; 1 = 16 epilogue warps (32 x 64 columns each); 2 = 8 warps, 5 stages
+  // with single-buffered E staging; 3 = 16 warps in two roles (8 statistics + 8 strip store), 4 stages.
+  // evk_mpce_row_parts() tells the caller how many row-partial rows K3 writes.
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("EVK_K3_VARIANT");
-    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+    v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : kK3DefaultVariant;
   }
   return v;
 }
@@ -845,7 +906,9 @@ int launch(const TcParams& p, cudaStream_t s) {
     EVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (dev >= 0 && dev < 64) attr_set |= 1ull << dev;
   }
-  const int sms = evk_sm_count();
+  int sms = evk_sm_count();
+  if (p.cta_limit > 0 && p.cta_limit < sms) sms = p.cta_limit & ~1;
+  if (sms < 2) sms = 2;
   // stream-K (splits == 0): every group gets a range; a range should hold at least a few k-blocks
   const int64_t items = (int64_t)p.m_tiles * p.n_tiles * p.num_segs * p.kb_per_seg;
   const int units = p.splits > 0 ? p.m_tiles * p.n_tiles * p.splits : (int)(items / 4 < sms ? (items / 4 > 0 ? items / 4 : 1) : sms);
@@ -989,6 +1052,7 @@ int mpce_fwd_impl(const void* q_hi, const void* q_lo, int64_t ld_q, const void* 
     switch (k3_variant()) {
       case 1: return launch<EPI_FWD_E, false, false, 4, true, 16, 1>(p, s);   // 16 epilogue warps, 4 stages
       case 2: return launch<EPI_FWD_E, false, false, 5, true, 8, 1>(p, s);    // 8 warps, one staging box each, 5 stages
+      case 3: return launch<EPI_FWD_E, false, false, 4, true, 16, 2>(p, s);   // 8 statistics + 8 store warps
       default: return launch<EPI_FWD_E, false, false, 4, true, 8, 2>(p, s);   // 8 warps, two boxes each, 4 stages
     }
   }
@@ -1092,7 +1156,9 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
   p.n_rows = m;
   p.n_cols = n;
   const int total_kb = p.num_segs * p.kb_per_seg;
-  const int groups = cta2 ? evk_sm_count() / 2 : evk_sm_count();
+  int sm_avail = evk_sm_count();
+  if (p.cta_limit > 0 && p.cta_limit < sm_avail) sm_avail = p.cta_limit & ~1;
+  const int groups = cta2 ? sm_avail / 2 : sm_avail;
   p.splits = force_splits > 0 ? force_splits : (use_stream_k() ? 0 : choose_splits(p.m_tiles * p.n_tiles, total_kb, groups));
   if (p.flags & kIntStore) p.splits = 1;      // store epilogue: every output element is written by exactly one unit
   if (p.splits > total_kb) p.splits = total_kb;
@@ -1140,14 +1206,17 @@ int gemm_common(TcParams& p, const void* const* a_ptrs, int64_t lda, bool a_mn, 
 
 extern "C" int evk_mpce_bwd_gemm(const void* w_hi, const void* w_lo, int64_t ld_w, int64_t n_rows, int64_t n_cols,
                                  int transpose_w, const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d,
-                                 float alpha, int flags, float* out, int64_t ld_out, evk_stream_t stream) {
+                                 float alpha, int flags, float* out, int64_t ld_out, int cta_limit,
+                                 evk_stream_t stream) {
   flags &= EVK_FLAG_PUBLIC_MASK;
   int rc = check_device();
   if (rc != EVK_OK) return rc;
   const bool split = (flags & EVK_FLAG_SPLIT_BF16) != 0;
   EVK_REQUIRE(w_hi && x_hi && (!split || (w_lo && x_lo)), "evk_mpce_bwd_gemm: null operand");
+  EVK_REQUIRE(cta_limit >= 0, "evk_mpce_bwd_gemm: negative cta_limit");
   TcParams p;
   memset(&p, 0, sizeof(p));
+  p.cta_limit = cta_limit;
   const void* a_ptrs[3] = {w_hi, w_hi, w_lo};
   const void* b_ptrs[3] = {x_hi, x_lo, x_hi};
   // W is stored [n_rows, n_cols].  Not transposed: A = W is K-major (K = columns).  Transposed:
@@ -1161,7 +1230,8 @@ extern "C" int evk_mpce_bwd_gemm(const void* w_hi, const void* w_lo, int64_t ld_
 extern "C" int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int64_t ld_w, int64_t n_rows, int64_t n_cols,
                                          const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d, float alpha,
                                          int flags, const uint64_t* out_ptrs, int n_owners, int64_t rows_per_owner,
-                                         int64_t ld_out, int store, int first_owner, evk_stream_t stream) {
+                                         int64_t ld_out, int store, int first_owner, int cta_limit,
+                                         evk_stream_t stream) {
   flags &= EVK_FLAG_PUBLIC_MASK;
   int rc = check_device();
   if (rc != EVK_OK) return rc;
@@ -1178,7 +1248,8 @@ extern "C" int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int
     EVK_REQUIRE(p.out_peer[r] && evk_aligned16(p.out_peer[r]), "evk_mpce_bwd_gemm_scatter: owner buffers must be 16-byte aligned");
   }
   p.rows_per_owner = rows_per_owner;
-  EVK_REQUIRE(first_owner >= 0 && first_owner < n_owners, "evk_mpce_bwd_gemm_scatter: first_owner out of range");
+  p.cta_limit = cta_limit;
+  EVK_REQUIRE(first_owner >= 0 && first_owner < n_owners && cta_limit >= 0, "evk_mpce_bwd_gemm_scatter: first_owner / cta_limit out of range");
   {
     // the row blocks (keys) of owner `first_owner` are computed - and sent - first
     const int64_t tile_m = use_cta_pairs() ? 2 * BM : BM;

@@ -289,18 +289,21 @@ def peer_backward(st, g: torch.Tensor):
                     clear_diag=False, diag_offset=pc.rank * n)
     # exchange 3, fused: the tiles of this rank's partial dKhat are stored straight into their owners'
     # per-source buffers (posted NVLink stores from the GEMM epilogue; no split-K, no zero fill)
+    # with two streams the two contractions run side by side, half of the SMs each: the scattering one is bound by
+    # NVLink (its tiles leave as remote stores), so it gives up SMs it cannot use while the local one fills them
+    half = SIDE_BY_SIDE_CTAS if (overlap and pc.world > 1) else 0
+    w_ready = main.record_event() if overlap else None       # W is complete: both contractions may start
     _lib.call("evk_mpce_bwd_gemm_scatter", e.data_ptr(), None, ld_e, n, n_total, qn.hi.data_ptr(), None, qn.ld, qn.d,
               1.0, 0, pc.table("dk_mine"), pc.world, n, pc.width, 2 if pc.exchange == "bf16" else 1,
-              SCATTER_FIRST_OWNER(pc), main.cuda_stream)
+              SCATTER_FIRST_OWNER(pc), half, main.cuda_stream)
 
     def image_side():
-        ops.tc_bwd_gemm(e, None, ld_e, n, n_total, False, kn_all, 0, out=dq)      # dq was zeroed by the prologue
+        ops.tc_bwd_gemm(e, None, ld_e, n, n_total, False, kn_all, 0, out=dq, cta_limit=half)   # dq was zeroed by the prologue
         return ops.l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, error=pc.error)
 
     if overlap:
         # the local contraction fills the SMs as the scattering one drains (it may be NVLink-bound)
         side = ops._side_stream(image.device)
-        w_ready = main.record_event()
         with torch.cuda.stream(side):
             side.wait_event(w_ready)
             d_image = image_side()
@@ -367,6 +370,9 @@ def SCATTER_FIRST_OWNER(pc) -> int:
     return (pc.rank + 1) % pc.world if os.environ.get("EVOKE_B200_SCATTER_ROTATE", "1") == "1" else 0
 
 
+# CTAs each of the two backward contractions of the sharded step may use when they run side by side (0: all SMs, one
+# after the other as in round 1)
+SIDE_BY_SIDE_CTAS = int(os.environ.get("EVOKE_B200_SIDE_BY_SIDE_CTAS", "74"))
 PEER_EXCHANGE = os.environ.get("EVOKE_B200_PEER_EXCHANGE", "bf16")     # dtype of the dKhat partials on NVLink: bf16 | fp32
 # EVOKE_B200_OVERLAP_GATHER=1: the key rows travel on a side stream WHILE K3 runs (per-source landed flags, staggered
 # pushes).  Measured slower on B200 x 8 (0.383 vs 0.321 ms/step: the copy kernel and K2 contend with the sweep), so off.

@@ -377,13 +377,15 @@ def tc_bwd_w(q: Normalized, k: Normalized, bits, counts, a_row, b_col, inv_tau: 
 
 
 def tc_bwd_gemm(w_hi, w_lo, ld_w: int, n_rows: int, n_cols: int, transpose_w: bool, x: Normalized, flags: int,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """K4b: out (+)= W x  (or W^T x).  ``out`` fp32 [rows_out, d]; zero-initialised here if None."""
+                out: Optional[torch.Tensor] = None, cta_limit: int = 0) -> torch.Tensor:
+    """K4b: out (+)= W x  (or W^T x).  ``out`` fp32 [rows_out, d]; zero-initialised here if None.
+    cta_limit > 0: use at most that many SMs (a second contraction runs beside this one on another stream)."""
     rows_out = n_cols if transpose_w else n_rows
     if out is None:
         out = torch.zeros((rows_out, _round_up(x.d, 4)), dtype=torch.float32, device=w_hi.device)
     _lib.call("evk_mpce_bwd_gemm", _ptr(w_hi), _ptr(w_lo), ld_w, n_rows, n_cols, int(transpose_w),
-              _ptr(x.hi), _ptr(x.lo), x.ld, x.d, 1.0, flags & FLAG_SPLIT_BF16, _ptr(out), out.stride(0), _stream())
+              _ptr(x.hi), _ptr(x.lo), x.ld, x.d, 1.0, flags & FLAG_SPLIT_BF16, _ptr(out), out.stride(0), int(cta_limit),
+              _stream())
     return out
 
 

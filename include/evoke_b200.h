@@ -387,7 +387,7 @@ EVK_API int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q,
 EVK_API int evk_mpce_bwd_gemm(const void* w_hi, const void* w_lo, int64_t ld_w,
                       int64_t n_rows, int64_t n_cols, int transpose_w,
                       const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d,
-                      float alpha, int flags, float* out, int64_t ld_out, evk_stream_t stream);
+                      float alpha, int flags, float* out, int64_t ld_out, int cta_limit, evk_stream_t stream);
 
 /* ---- peer-memory transport for the sharded path (NVLink / NVSwitch) --------------------------
  * dst_* are HOST arrays of n_dst device base addresses: the per-rank buffers of one symmetric
@@ -512,13 +512,16 @@ EVK_API int evk_mpce_shard_finish(const float* slots, int n_slots, int64_t ld_sl
  * first_owner: the tiles of this owner's rows are computed and sent first, then first_owner + 1, ... (wrapping).
  * Every rank should pass a different value ((rank + 1) % n_owners): with the same order on every rank all GPUs
  * would store into the same owner at the same time and its NVLink ingress (not the sum over GPUs) would bound
- * the exchange. */
+ * the exchange.
+ * cta_limit (also on evk_mpce_bwd_gemm; 0 = every SM): launch at most this many CTAs, so that two contractions
+ * enqueued on different streams run SIDE BY SIDE on disjoint SMs (persistent CTAs use a whole SM each): in the
+ * sharded backward the NVLink-bound scattering contraction and the local one overlap instead of queueing. */
 EVK_API int evk_mpce_bwd_gemm_scatter(const void* w_hi, const void* w_lo, int64_t ld_w,
                               int64_t n_rows, int64_t n_cols,
                               const void* x_hi, const void* x_lo, int64_t ld_x, int64_t d,
                               float alpha, int flags,
                               const uint64_t* out_ptrs, int n_owners, int64_t rows_per_owner, int64_t ld_out,
-                              int store, int first_owner, evk_stream_t stream);
+                              int store, int first_owner, int cta_limit, evk_stream_t stream);
 
 /* ---- f4: exact inner-product top-k retrieval ------------------------------------------------------------------
  * Replaces the faiss index of PretrainTester.predict (modules/multiview/trainer.py:543-653: IndexIVFFlat with
