@@ -42,7 +42,9 @@ def topk_inner_product(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, q
     """(scores [Q, k] fp32, indices [Q, k] int64): the k corpus rows with the largest inner product per query, sorted
     by score descending (ties: lower index first).  query_groups / corpus_groups (int tensors): corpus rows of the
     query's own group are skipped (the reference removes hits of the query's own study, trainer.py:590-607).
-    precision "fp32": 3-segment split-bf16 operands (scores to ~1e-5 of fp32); "bf16": single-pass bf16 operands.
+    precision "fp32": 3-segment split-bf16 operands (products exact to ~2^-17; the tensor cores' fp32 accumulation
+    truncates, which biases a d = 38400 score low by ~3e-4 relative - proportionally for every candidate, so the
+    ranking is that of the exact search); "bf16": single-pass bf16 operands.
     Slots beyond the number of candidates hold -inf / -1."""
     if not (queries.is_cuda and corpus.is_cuda):
         raise RuntimeError("evoke_b200.retrieval runs on a CUDA (sm_100a) device only; there is no CPU path")
