@@ -57,9 +57,9 @@ SIGNATURES = {
     "evk_l2norm_fwd_bcast": [P, I, L, L, L, L, I, P, P, L, L, P, P],
     "evk_peer_bcast": [P, L, I, P, L, P],
     "evk_shard_prologue": [P, I, L, L, P, I, L, L, L, L, I, P, L, L, P, P, P, P, P, I, P, P, P, L, P, L, P, P, P],
-    "evk_peer_push_shard": [P, L, I, I, P, L, P, P, P, P],
-    "evk_peer_wait_landed": [P, I, P, P, L, P],
-    "evk_mpce_fwd_store_gathered": [P, L, P, L, L, L, L, P, L, F, I, L, P, P, L, P, L, P, L, P, P, P, L, L, P],
+    "evk_peer_push_shard": [P, L, I, I, P, L, P, I, P],
+    "evk_peer_wait_landed": [P, I, P, I, P, L, P],
+    "evk_mpce_fwd_store_gathered": [P, L, P, L, L, L, L, P, L, F, I, L, P, P, L, P, L, P, L, P, P, P, L, L, I, P],
     "evk_mpce_shard_stats_push": [P, L, L, P, L, L, P, L, P, L, L, L, F, F, D, P, P, I, L, P, L, I, P],
     "evk_peer_alloc": [L, P],
     "evk_peer_free": [P],

@@ -12,6 +12,7 @@
 // the caller's job: a symmetric-memory barrier between producer and consumer kernels.
 #include "evk_common.cuh"
 #include "peer_sync.cuh"
+#include "tc_ptx.cuh"
 
 #include <string.h>
 
@@ -291,51 +292,66 @@ shard_finish_kernel(const float* __restrict__ slots, int n_slots, int64_t ld_slo
   }
 }
 
-// All-gather that runs NEXT TO the similarity sweep: this rank's shard (already in its own buffer) is copied
-// to the peers one destination at a time, in the order rank+1, rank+2, ... - at any moment every GPU receives
-// from exactly one source at full NVLink rate, so the shards land in a known order - and after each destination
-// the last CTA to finish raises that destination's `landed` flag for this source (epoch = the step counter).
-// K3 consumes the column blocks in the same order and waits per source (tc_engine.cu).
+// All-gather that runs NEXT TO the similarity sweep: this rank's shard (already in its own buffer) is copied to the
+// peers one destination at a time, in the order rank+1, rank+2, ... - at any moment every GPU receives from exactly
+// one source, so the shards land in a known order and K3 (tc_engine.cu) consumes the column blocks in that order,
+// waiting per source.  The copy must not compete with K3 for issue slots or registers: ONE thread per CTA drives TMA
+// bulk copies (global -> 8 KiB of shared memory -> peer memory over NVLink, two stages), nothing else runs.  A CTA
+// that has finished its chunks for a destination waits for its bulk stores to complete, fences at system scope and
+// adds 1 to landed[source] on that destination; a source has landed when the counter reaches CTAs * step.
+constexpr int kPushChunk = 8192;
+constexpr int kPushStages = 2;
+
 struct PushArgs {
-  uint4* dst[kMaxPeers];
-  uint32_t* landed[kMaxPeers];          // landed[t] = base of rank t's landed-flag area (entry s: source s)
+  uint8_t* dst[kMaxPeers];
+  uint32_t* landed[kMaxPeers];          // landed[t] = base of rank t's landed-counter area (entry s: source s)
   int n, rank;
 };
 
-__global__ void __launch_bounds__(256)
-peer_push_kernel(const uint4* __restrict__ src, int64_t n_vec, PushArgs a, int64_t dst_offset_vec,
-                 const int* __restrict__ step, unsigned int* __restrict__ counters) {
-  __shared__ bool s_last;
-  const uint32_t epoch = (uint32_t)*step;
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.landed[a.rank] + a.rank), "r"(epoch) : "memory");
+__global__ void __launch_bounds__(32)
+peer_push_bulk_kernel(const uint8_t* __restrict__ src, int64_t bytes, PushArgs a, int64_t dst_offset) {
+  extern __shared__ __align__(128) uint8_t push_stage[];
+  __shared__ __align__(8) uint64_t bars[kPushStages];
+  if (threadIdx.x != 0) return;
+  const uint32_t sbase = (tc::smem_u32(push_stage) + 127u) & ~127u;
+  for (int st = 0; st < kPushStages; ++st) tc::mbar_init(tc::smem_u32(&bars[st]), 1);
+  tc::fence_mbar_init();
+  // this rank's own rows were written by the prologue, earlier in stream order
+  if (blockIdx.x == 0) atomicAdd_system(a.landed[a.rank] + a.rank, gridDim.x);
+  const int64_t n_chunks = (bytes + kPushChunk - 1) / kPushChunk;
+  uint32_t phase = 0;                   // bit st = parity of stage st's barrier
+  int it = 0;
   for (int k = 1; k < a.n; ++k) {
     const int t = (a.rank + k) % a.n;
-    uint4* out = a.dst[t] + dst_offset_vec;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x)
-      out[i] = __ldg(src + i);
+    uint8_t* out = a.dst[t] + dst_offset;
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+      const int st = it % kPushStages;
+      const uint32_t sm = sbase + st * kPushChunk, bar = tc::smem_u32(&bars[st]);
+      const int64_t off = c * kPushChunk;
+      const uint32_t len = (uint32_t)((bytes - off) < kPushChunk ? (bytes - off) : kPushChunk);
+      // the bulk store that used this stage two chunks ago has finished READING it
+      asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPushStages - 1) : "memory");
+      tc::mbar_expect_tx(bar, len);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(sm), "l"(src + off), "r"(len), "r"(bar) : "memory");
+      tc::mbar_wait(bar, (phase >> st) & 1u);
+      phase ^= 1u << st;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + off), "r"(sm), "r"(len) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this CTA's stores to destination t are complete
     __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned int done = atomicAdd(counters + k, 1u);
-      s_last = done == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-      counters[k] = 0;                                           // ready for the next step (graph replay)
-      __threadfence_system();
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.landed[t] + a.rank), "r"(epoch) : "memory");
-    }
+    atomicAdd_system(a.landed[t] + a.rank, 1u);
   }
 }
 
 // waits until every source's shard of this step has landed here (side-stream consumers of the gathered rows)
 __global__ void __launch_bounds__(32)
-peer_wait_landed_kernel(const uint32_t* __restrict__ landed, int n, const int* __restrict__ step, int* __restrict__ error,
-                        uint64_t timeout_ns) {
+peer_wait_landed_kernel(const uint32_t* __restrict__ landed, int n, const int* __restrict__ step, int per_step,
+                        int* __restrict__ error, uint64_t timeout_ns) {
   const int t = threadIdx.x;
   if (t < n) {
-    const uint32_t epoch = (uint32_t)*step;
+    const uint32_t epoch = (uint32_t)*step * (uint32_t)per_step;     // landed[s] counts the push CTAs of source s
     const uint64_t t0 = global_timer_ns();
     for (;;) {
       uint32_t v;
@@ -540,37 +556,34 @@ extern "C" int evk_shard_prologue(const void* text, int text_dtype, int64_t text
 }
 
 extern "C" int evk_peer_push_shard(const void* src, int64_t bytes, int n_ranks, int rank, const uint64_t* dst_ptrs,
-                                   int64_t dst_offset_bytes, const uint64_t* landed_ptrs, const int* step,
-                                   void* counters, evk_stream_t stream) {
-  EVK_REQUIRE(src && dst_ptrs && landed_ptrs && step && counters && bytes > 0 && bytes % 16 == 0 &&
-                  dst_offset_bytes >= 0 && dst_offset_bytes % 16 == 0 && evk_aligned16(src),
+                                   int64_t dst_offset_bytes, const uint64_t* landed_ptrs, int n_ctas,
+                                   evk_stream_t stream) {
+  EVK_REQUIRE(src && dst_ptrs && landed_ptrs && bytes > 0 && bytes % 16 == 0 && dst_offset_bytes >= 0 &&
+                  dst_offset_bytes % 16 == 0 && evk_aligned16(src),
               "evk_peer_push_shard: bad arguments (16-byte aligned multiples)");
-  EVK_REQUIRE(n_ranks >= 1 && n_ranks <= kMaxPeers && rank >= 0 && rank < n_ranks, "evk_peer_push_shard: bad rank / world");
+  EVK_REQUIRE(n_ranks >= 1 && n_ranks <= kMaxPeers && rank >= 0 && rank < n_ranks && n_ctas >= 1 && n_ctas <= 1024,
+              "evk_peer_push_shard: bad rank / world / CTA count");
   PushArgs a;
   memset(&a, 0, sizeof(a));
   a.n = n_ranks;
   a.rank = rank;
   for (int t = 0; t < n_ranks; ++t) {
-    a.dst[t] = reinterpret_cast<uint4*>(dst_ptrs[t]);
+    a.dst[t] = reinterpret_cast<uint8_t*>(dst_ptrs[t]);
     a.landed[t] = reinterpret_cast<uint32_t*>(landed_ptrs[t]);
     EVK_REQUIRE(a.dst[t] && a.landed[t] && evk_aligned16(a.dst[t]), "evk_peer_push_shard: null / misaligned destination");
   }
-  const int64_t n_vec = bytes / 16;
-  int64_t blocks = (n_vec + 255) / 256;
-  const int64_t cap = evk_sm_count();                // one small CTA per SM: it shares the SMs with the K3 CTAs
-  if (blocks > cap) blocks = cap;
-  peer_push_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(src), n_vec, a, dst_offset_bytes / 16, step, static_cast<unsigned int*>(counters));
+  peer_push_bulk_kernel<<<(unsigned)n_ctas, 32, kPushStages * kPushChunk + 128, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(src), bytes, a, dst_offset_bytes);
   EVK_CHECK_LAUNCH("peer_push_shard");
   return EVK_OK;
 }
 
-extern "C" int evk_peer_wait_landed(const void* landed, int n_ranks, const int* step, int* error, int64_t timeout_ms,
-                                    evk_stream_t stream) {
-  EVK_REQUIRE(landed && step && error && n_ranks >= 1 && n_ranks <= kMaxPeers, "evk_peer_wait_landed: bad arguments");
+extern "C" int evk_peer_wait_landed(const void* landed, int n_ranks, const int* step, int per_step, int* error,
+                                    int64_t timeout_ms, evk_stream_t stream) {
+  EVK_REQUIRE(landed && step && error && n_ranks >= 1 && n_ranks <= kMaxPeers && per_step >= 1, "evk_peer_wait_landed: bad arguments");
   const uint64_t timeout_ns = (uint64_t)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
   peer_wait_landed_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint32_t*>(landed), n_ranks,
-                                                                        step, error, timeout_ns);
+                                                                        step, per_step, error, timeout_ns);
   EVK_CHECK_LAUNCH("peer_wait_landed");
   return EVK_OK;
 }

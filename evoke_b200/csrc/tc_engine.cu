@@ -83,6 +83,7 @@ struct alignas(64) TcParams {
   // are then visited column-block-major starting at this rank's own columns (rot_tiles), and the producer waits for
   // landed[source] >= *step before its first load from a source's columns.
   const uint32_t* landed; const int* step; int* error; int64_t cols_per_source; int rot_tiles;
+  int landed_per_step;           // landed[s] counts the push CTAs of source s: it has landed at landed_per_step * step
   int rot_m_tiles;               // EPI_GEMM_TMA scatter: first row block (pair tile) to visit, see Sched
   int cta_limit;                 // > 0: launch at most this many CTAs (two contractions sharing the GPU side by side)
   // EPI_GEMM
@@ -274,7 +275,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
           const int own = (int)(((int64_t)p.rot_tiles * BN) / p.cols_per_source);   // written by this GPU's prologue
           for (int src = src_lo; src <= src_hi; ++src) {
             if (src == have_src || src == own) continue;
-            const uint32_t epoch = (uint32_t)*p.step;
+            const uint32_t epoch = (uint32_t)*p.step * (uint32_t)p.landed_per_step;
             uint64_t t0 = 0;
             for (uint32_t spins = 0;; ++spins) {
               uint32_t v;
@@ -1006,7 +1007,8 @@ int mpce_fwd_impl(const void* q_hi, const void* q_lo, int64_t ld_q, const void* 
                   int64_t ld_words, float inv_tau, int flags, int64_t diag_offset, float* row_sum_part,
                   float* row_pos_part, int64_t ld_rowpart, float* col_sum_part, int64_t ld_colpart,
                   void* e_out, int64_t ld_e, evk_stream_t stream, const uint32_t* landed = nullptr,
-                  const int* step = nullptr, int* error = nullptr, int64_t cols_per_source = 0, int64_t first_col = 0) {
+                  const int* step = nullptr, int* error = nullptr, int64_t cols_per_source = 0, int64_t first_col = 0,
+                  int landed_per_step = 1) {
   flags &= EVK_FLAG_PUBLIC_MASK;
   int rc = check_device();
   if (rc != EVK_OK) return rc;
@@ -1041,6 +1043,7 @@ int mpce_fwd_impl(const void* q_hi, const void* q_lo, int64_t ld_q, const void* 
     p.error = error;
     p.cols_per_source = cols_per_source;
     p.rot_tiles = (int)(first_col / BN);
+    p.landed_per_step = landed_per_step > 0 ? landed_per_step : 1;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (e_out) {
@@ -1088,12 +1091,12 @@ extern "C" int evk_mpce_fwd_store_gathered(const void* q_hi, int64_t ld_q, const
                                            float* row_pos_part, int64_t ld_rowpart, float* col_sum_part,
                                            int64_t ld_colpart, void* e_out, int64_t ld_e, const uint32_t* landed,
                                            const int* step, int* error, int64_t cols_per_source, int64_t first_col,
-                                           evk_stream_t stream) {
+                                           int landed_per_step, evk_stream_t stream) {
   EVK_REQUIRE(landed && step && error, "evk_mpce_fwd_store_gathered: null flag pointers");
   EVK_REQUIRE(!e_out || evk_aligned16(e_out), "evk_mpce_fwd_store_gathered: e_out must be 16-byte aligned");
   return mpce_fwd_impl(q_hi, nullptr, ld_q, k_hi, nullptr, ld_k, n_rows, n_cols, d, bits, ld_words, inv_tau, flags,
                        diag_offset, row_sum_part, row_pos_part, ld_rowpart, col_sum_part, ld_colpart, e_out, ld_e, stream,
-                       landed, step, error, cols_per_source, first_col);
+                       landed, step, error, cols_per_source, first_col, landed_per_step);
 }
 
 extern "C" int evk_mpce_bwd_w(const void* q_hi, const void* q_lo, int64_t ld_q, const void* k_hi, const void* k_lo,

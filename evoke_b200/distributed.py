@@ -170,7 +170,7 @@ def peer_forward(ops, pc, inv_tau: float, row_ids: DeviceIds, image: torch.Tenso
     dq = torch.empty((n, wq), dtype=torch.float32, device=dev) if need_grad else None
     counts = torch.empty(n, dtype=torch.int32, device=dev)          # zeroed by the prologue kernel
     overlap_gather = OVERLAP_GATHER and world > 1
-    folded = pc.sync(1) is not None and not overlap_gather           # syncs folded into the consumer kernels
+    folded = pc.sync(1) is not None                                  # syncs folded into the consumer kernels
     # inputs as the caller holds them (strided [:,0,:] head views, bf16/fp16): the prologue's loader honours them
     _lib.call("evk_shard_prologue", text.data_ptr(), ops._dtype_code(text), text.stride(0), text.stride(1),
               image.data_ptr(), ops._dtype_code(image), image.stride(0), image.stride(1), n, d,
@@ -190,28 +190,25 @@ def peer_forward(ops, pc, inv_tau: float, row_ids: DeviceIds, image: torch.Tenso
         side.wait_stream(main)
         with torch.cuda.stream(side):
             _lib.call("evk_peer_push_shard", pc.khat[lo_:].data_ptr(), n * pc.ld * 2, world, rank, pc.table("khat"),
-                      lo_ * pc.ld * 2, pc.table("landed"), pc.step.data_ptr(), pc.counters.data_ptr(), side.cuda_stream)
+                      lo_ * pc.ld * 2, pc.table("landed"), PUSH_CTAS, side.cuda_stream)
 
     def sweep(bits, store):
         """K3 over this rank's row block (with the per-source waits when the gather is still in flight)."""
-        n_ct = (n_total + ops.TILE_N - 1) // ops.TILE_N
-        n_rt = (n + ops.TILE_M - 1) // ops.TILE_M
         if not overlap_gather:
             return ops.tc_fwd_store(qn, kn_all, bits, inv_tau, 0, lo_) if store else \
                 ops.tc_fwd_partials(qn, kn_all, bits, inv_tau, 0, lo_) + (None, 0)
-        rs = torch.empty((n_ct * ops._row_parts(), n), dtype=torch.float32, device=dev)
-        rp = torch.empty((n_ct * ops._row_parts(), n), dtype=torch.float32, device=dev)
-        cs = torch.empty((n_rt, n_total), dtype=torch.float32, device=dev)
-        ld_e = _round_up(n_total, 64)
+        rs, rp, cs = ops.alloc_partials(n, n_total, dev, bits is not None, True)
+        ld_e = _lib.size("evk_mpce_strip_ld", n_total)
         e = torch.empty((n, ld_e), dtype=torch.bfloat16, device=dev) if store else None
         _lib.call("evk_mpce_fwd_store_gathered", q_hi.data_ptr(), pc.ld, pc.khat.data_ptr(), pc.ld, n, n_total, d,
-                  bits.data_ptr(), bits.stride(0), float(inv_tau), 0, lo_, rs.data_ptr(), rp.data_ptr(), n,
+                  None if bits is None else bits.data_ptr(), 0 if bits is None else bits.stride(0), float(inv_tau),
+                  ops.FLAG_NO_POS if bits is None else 0, lo_, rs.data_ptr(), None if rp is None else rp.data_ptr(), n,
                   cs.data_ptr(), n_total, None if e is None else e.data_ptr(), ld_e, pc.landed.data_ptr(),
-                  pc.step.data_ptr(), pc.error.data_ptr(), n, lo_, stream)
+                  pc.step.data_ptr(), pc.error.data_ptr(), n, lo_, PUSH_CTAS, stream)
         return rs, rp, cs, e, (ld_e if store else 0)
 
     pos = None
-    mask_free = need_grad and ops.MASK_FREE and not overlap_gather
+    mask_free = need_grad and ops.MASK_FREE
     if need_grad:
         bits, counts, pos_idx = ops.posmask_build(row_ids, ids_all, clear_diag=False, diag_offset=lo_, want_list=True,
                                                   want_bits=not mask_free, counts=counts, sync=sync1)
@@ -226,14 +223,19 @@ def peer_forward(ops, pc, inv_tau: float, row_ids: DeviceIds, image: torch.Tenso
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 if overlap_gather:
-                    _lib.call("evk_peer_wait_landed", pc.landed.data_ptr(), world, pc.step.data_ptr(),
+                    _lib.call("evk_peer_wait_landed", pc.landed.data_ptr(), world, pc.step.data_ptr(), PUSH_CTAS,
                               pc.error.data_ptr(), pc.timeout_ms, side.cuda_stream)
                 pos_dot, row_pos_l = positives()
             ops._shared_with(side, q_hi, pos_idx, counts)
         else:
             pos_dot, row_pos_l = positives()
         pos = (pos_idx, pos_dot)
-        if mask_free:
+        if mask_free and overlap_gather:
+            rs_part, _, cs_part, e, ld_e = sweep(None, True)
+            main.wait_stream(side)          # the statistics need the positive sums; the push is part of this step
+            ops._shared_with(main, pos_dot, row_pos_l)
+            rp_part = row_pos_l.unsqueeze(0)
+        elif mask_free:
             rs_part, _, cs_part, e, ld_e = ops.tc_fwd_store(qn, kn_all, None, inv_tau, ops.FLAG_NO_POS, lo_)
             if overlap:
                 main.wait_stream(side)      # the statistics need the positive sums computed next to K3
@@ -374,9 +376,11 @@ def SCATTER_FIRST_OWNER(pc) -> int:
 # after the other as in round 1)
 SIDE_BY_SIDE_CTAS = int(os.environ.get("EVOKE_B200_SIDE_BY_SIDE_CTAS", "74"))
 PEER_EXCHANGE = os.environ.get("EVOKE_B200_PEER_EXCHANGE", "bf16")     # dtype of the dKhat partials on NVLink: bf16 | fp32
-# EVOKE_B200_OVERLAP_GATHER=1: the key rows travel on a side stream WHILE K3 runs (per-source landed flags, staggered
-# pushes).  Measured slower on B200 x 8 (0.383 vs 0.321 ms/step: the copy kernel and K2 contend with the sweep), so off.
+# EVOKE_B200_OVERLAP_GATHER=1: the key rows travel on a side stream WHILE K3 runs (TMA bulk copies driven by one
+# thread per CTA, one destination at a time; per-source landed counters; K3 sweeps its own columns first and waits per
+# source).  Round 1's version (an SM-resident copy kernel) lost 0.383 vs 0.321 ms at 8 GPUs; see profiles/r2_experiments.md.
 OVERLAP_GATHER = os.environ.get("EVOKE_B200_OVERLAP_GATHER", "0") == "1"
+PUSH_CTAS = int(os.environ.get("EVOKE_B200_PUSH_CTAS", "148"))          # one driving thread each
 
 
 def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local, temp: float, *,

@@ -323,8 +323,8 @@ EVK_API int evk_mpce_pos_from_lists(const void* q_hi, int64_t ld_q, const void* 
 
 /* Sharded K3 that starts before the all-gather of the key rows has finished.  k_hi is this rank's buffer of ALL
  * key rows, filled by every rank's evk_peer_push_shard while the sweep runs: column c belongs to source
- * c / cols_per_source, and landed[s] (this rank's landed-flag area) reaches *step once source s's rows are
- * complete.  The column blocks are visited starting at first_col (this rank's own rows, already in place) and the
+ * c / cols_per_source, and landed[s] (this rank's landed-counter area) reaches landed_per_step * *step once
+ * source s's rows are complete (landed_per_step = the n_ctas of evk_peer_push_shard).  The column blocks are visited starting at first_col (this rank's own rows, already in place) and the
  * TMA producer waits for a source's flag before its first load from that source's columns; if a flag does not
  * arrive within 2 s *error is set and the sweep continues (a dead peer must not hang the GPU).
  * e_out may be NULL (statistics only).  Otherwise as evk_mpce_fwd_store. */
@@ -336,7 +336,7 @@ EVK_API int evk_mpce_fwd_store_gathered(const void* q_hi, int64_t ld_q, const vo
                                 float* col_sum_part, int64_t ld_colpart,
                                 void* e_out, int64_t ld_e,
                                 const uint32_t* landed, const int* step, int* error,
-                                int64_t cols_per_source, int64_t first_col, evk_stream_t stream);
+                                int64_t cols_per_source, int64_t first_col, int landed_per_step, evk_stream_t stream);
 
 /* K4t, in place over the strip written by evk_mpce_fwd_store (or any row range of it: offset the
  * strip / bits / counts / a_row pointers):  strip[i, j] <- bf16( E_ij (a_row[i] + b_col[j]) - 2 M_ij / c_i ),
@@ -431,17 +431,20 @@ EVK_API int evk_shard_prologue(const void* text, int text_dtype, int64_t text_st
 /* The all-gather of the key rows, overlapped with the similarity sweep.  Copies this rank's shard (`bytes` at
  * `src`, normally its own rows inside its own buffer) to byte offset dst_offset_bytes of every OTHER rank's
  * buffer, one destination at a time in the order rank+1, rank+2, ... (every GPU then receives from one source at
- * a time, at full NVLink rate, and the shards land in a known order), and after each destination raises that
- * destination's landed flag for this source: landed_ptrs[t][rank] = *step (release, system scope).  Its own flag
- * is raised at once.  counters: >= 64 bytes of zeroed device memory owned by the caller (reset by the kernel). */
+ * a time, at full NVLink rate, and the shards land in a known order).  n_ctas CTAs of ONE driving thread each move
+ * 8 KiB chunks with TMA bulk copies (global -> shared -> peer): the copy takes no issue slots or registers from the
+ * sweep that runs beside it.  A CTA that is done with a destination adds 1 (system scope, after its stores have
+ * completed) to that destination's landed counter of this source, landed_ptrs[t][rank]; the counters are monotonic
+ * over the steps (zeroed once at allocation): source s has landed in step k when landed[s] >= n_ctas * k.  Its own
+ * counter is advanced by n_ctas at once. */
 EVK_API int evk_peer_push_shard(const void* src, int64_t bytes, int n_ranks, int rank,
                         const uint64_t* dst_ptrs, int64_t dst_offset_bytes,
-                        const uint64_t* landed_ptrs, const int* step, void* counters, evk_stream_t stream);
+                        const uint64_t* landed_ptrs, int n_ctas, evk_stream_t stream);
 
-/* Waits (one tiny kernel) until landed[s] >= *step for every source s < n_ranks: for consumers of the gathered
- * rows other than K3.  Sets *error after timeout_ms (<= 0: 2000) instead of hanging. */
-EVK_API int evk_peer_wait_landed(const void* landed, int n_ranks, const int* step, int* error, int64_t timeout_ms,
-                         evk_stream_t stream);
+/* Waits (one tiny kernel) until landed[s] >= per_step * *step for every source s < n_ranks: for consumers of the
+ * gathered rows other than K3.  Sets *error after timeout_ms (<= 0: 2000) instead of hanging. */
+EVK_API int evk_peer_wait_landed(const void* landed, int n_ranks, const int* step, int per_step, int* error,
+                         int64_t timeout_ms, evk_stream_t stream);
 
 /* Sharded form of evk_mpce_stats_fused: reduces K3's partials of this rank's row block, writes a_row, and
  * stores this rank's statistics slot - the raw partial column sums (n_cols floats) followed by its row-side

@@ -28,7 +28,10 @@ def _head_view(x: np.ndarray, tokens: int, dtype=torch.float32) -> torch.Tensor:
 
 def _worker(rank, world, port, n_total, d, tau, precision, mode, out_dir, views=False, in_dtype="float32"):
     sys.path.insert(0, ROOT)
-    if mode.startswith("peer-"):                     # "peer-fp32": fp32 partials on NVLink instead of bf16
+    if mode == "peer-gather":                        # the all-gather pushed from a side stream WHILE K3 sweeps
+        os.environ["EVOKE_B200_OVERLAP_GATHER"] = "1"
+        mode = "peer"
+    elif mode.startswith("peer-"):                   # "peer-fp32": fp32 partials on NVLink instead of bf16
         os.environ["EVOKE_B200_PEER_EXCHANGE"] = mode.split("-")[1]
         mode = "peer"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -129,7 +132,7 @@ def _port(salt: int) -> int:
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("mode", ["rs", "sym", "peer", "peer-fp32"])
+@pytest.mark.parametrize("mode", ["rs", "sym", "peer", "peer-fp32", "peer-gather"])
 @pytest.mark.parametrize("precision,ltol,gtol", [("fp32", 1e-5, 1e-4), ("bf16", 2e-5, 2e-2)])
 def test_sharded_equals_oracle(tmp_path, precision, ltol, gtol, mode, world):
     if torch.cuda.device_count() < world:
@@ -141,7 +144,7 @@ def test_sharded_equals_oracle(tmp_path, precision, ltol, gtol, mode, world):
     from evoke_b200 import synth
     from oracle import evoke_oracle as orc
     n_total, d, tau = 768 * world, 256, 0.5
-    port = _port(world * 16 + (1 if precision == "fp32" else 0) + 2 * ["rs", "sym", "peer", "peer-fp32"].index(mode))
+    port = _port(world * 16 + (1 if precision == "fp32" else 0) + 2 * ["rs", "sym", "peer", "peer-fp32", "peer-gather"].index(mode))
     mp.spawn(_worker, args=(world, port, n_total, d, tau, precision, mode, str(tmp_path)), nprocs=world, join=True)
     ids = synth.make_study_ids(n_total, seed=31)
     xi = synth.make_embeddings(ids, d, seed=32)
