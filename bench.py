@@ -754,13 +754,119 @@ def run_cfg5(args):
         os._exit(0)
 
 
+def run_f1(args):
+    """f1: Pretrain.local_text_token_alignment_loss (:506-526) at the reference's shape - B = 32 samples,
+    L - 1 = 99 text tokens, P = 49 patch tokens, D = 768 - forward + backward.  One JSON line."""
+    import numpy as np
+    import torch
+    import evoke_b200
+    from evoke_b200 import _lib
+    from oracle import evoke_oracle as orc
+    b, l, pt, d = 32, 99, 49, 768
+    rng = np.random.default_rng(1234)
+    v_np = rng.standard_normal((b, pt, d)).astype(np.float32)
+    t_np = rng.standard_normal((b, l, d)).astype(np.float32)
+
+    def port_ms(device, reps, warm):
+        v = torch.tensor(v_np, device=device, requires_grad=True)
+        t = torch.tensor(t_np, device=device, requires_grad=True)
+        ts = []
+        for it in range(warm + reps):
+            v.grad = t.grad = None
+            if device != "cpu":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            loss = orc.local_text_token_alignment_port(v, t, TAU)
+            loss.backward()
+            if device != "cpu":
+                torch.cuda.synchronize()
+            if it >= warm:
+                ts.append(time.perf_counter() - t0)
+        return float(np.mean(ts)) * 1e3, float(loss.item())
+
+    workload = ("f1: local_text_token_alignment_loss fwd+bwd at the reference's shape: 32 samples x 99 text tokens x 49 patch "
+                "tokens, D=768, fp32, tau=0.5")
+    config = {"workload": workload, "global_batch": b, "dim": d,
+              "l2": "inputs (7.4 MB) stay L2-resident by nature of the workload: the step is launch / latency bound"}
+    if args.impl == "reference":
+        torch.set_num_threads(os.cpu_count() or 1)
+        ms, loss = port_ms("cpu", args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "local token alignment fwd+bwd samples/sec at B=32,L=99,P=49,D=768", "value": b / (ms * 1e-3),
+                "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": b / (ms * 1e-3), "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                 "sample": "the full workload, PyTorch-CPU port of the reference op sequence"},
+                "e2e": {"value": b / (ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "loss": loss}
+        print(json.dumps(line), flush=True)
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    g = evoke_b200.GraphedLocalTokenAlign(b, pt, l, d, TAU, device=dev)
+    g.load(torch.tensor(v_np, device=dev), torch.tensor(t_np, device=dev))
+    before = _lib.launch_count
+    g.capture()
+    per_replay = (_lib.launch_count - before) // 4
+    for _ in range(max(args.warmup, 3)):
+        g.step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(physical_gpu_index(0))
+    sampler.start()
+    a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        loss = g.step()
+    z.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(z) / args.steps
+    clocks = sampler.stop()
+    # drop-in (eager launches of the method) and e2e (pinned host inputs every step)
+    v = torch.tensor(v_np, device=dev, requires_grad=True)
+    t = torch.tensor(t_np, device=dev, requires_grad=True)
+    for _ in range(3):
+        evoke_b200.local_text_token_alignment(v, t, TAU).backward()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(args.steps):
+        v.grad = t.grad = None
+        evoke_b200.local_text_token_alignment(v, t, TAU).backward()
+    z.record()
+    torch.cuda.synchronize()
+    ms_eager = a.elapsed_time(z) / args.steps
+    hv, ht = torch.from_numpy(v_np).pin_memory(), torch.from_numpy(t_np).pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g.load(hv, ht)
+        last = g.step().item()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    want = orc.local_token_alignment_closed_form(v_np, t_np, TAU)[0]
+    ms_cuda, _ = port_ms(str(dev), 20, 5)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ms_cpu, _ = port_ms("cpu", 10, 2)
+    flop = 2.0 * b * (2 * l * pt * d + 2 * l * l * d) * 3           # forward products x (1 fwd + 2 bwd)
+    line = {"metric": "local token alignment fwd+bwd samples/sec at B=32,L=99,P=49,D=768", "value": b / (ms * 1e-3), "unit": "samples/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "gpu_launches": per_replay * args.steps, "loss": float(loss.item()), "loss_rel_err_vs_fp64_oracle": abs(last - want) / abs(want),
+            "ms_per_step_eager": ms_eager,
+            "e2e": {"value": b / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(hv.numel() + ht.numel()) * 4, "d2h_bytes_per_step": 4},
+            "roofline": {"bound": "latency", "achieved": flop / (ms * 1e-3) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
+                         "traffic": None, "note": "~1.1 GFLOP in ~20 dependent fp32 SIMT launches: neither HBM nor the tensor pipe is the bound"},
+            "cpu_baseline": {"value": b / (ms_cpu * 1e-3), "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+                             "sample": "the full workload, 10 reps after 2 warm-up"},
+            "cuda_eager_baseline": {"value": b / (ms_cuda * 1e-3), "unit": "samples/s", "ms_per_step": ms_cuda,
+                                    "what": "the reference's op sequence (:506-526) in PyTorch CUDA eager fp32 on this GPU"}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="evoke_b200", choices=["evoke_b200", "reference"])
-    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS) + ["cfg5"],
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS) + ["cfg5", "f1"],
                     help="workload (BASELINE.json configs): cfg3 = the metric's configuration (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-eager", action="store_true", help="skip the CUDA-eager reference-port baseline")
@@ -776,6 +882,8 @@ def main():
     args = ap.parse_args()
     if args.config == "cfg5":
         run_cfg5(args)
+    elif args.config == "f1":
+        run_f1(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -54,8 +54,6 @@ SIGNATURES = {
     "evk_mpce_w_from_e": [P, L, L, L, P, L, P, P, P, P, L, P, L, L, F, P, P, I, P, P, P, P, L, I, P],
     "evk_mpce_pos_logits": [P, L, P, L, L, L, P, P, I, P, P],
     "evk_mpce_pos_from_lists": [P, L, P, L, L, L, L, P, P, P, P, L, I, P, P, I, F, P, P],
-    "evk_l2norm_fwd_bcast": [P, I, L, L, L, L, I, P, P, L, L, P, P],
-    "evk_peer_bcast": [P, L, I, P, L, P],
     "evk_shard_prologue": [P, I, L, L, P, I, L, L, L, L, I, P, L, L, P, P, P, P, P, I, P, P, P, L, P, L, P, P, P],
     "evk_peer_push_shard": [P, L, I, I, P, L, P, I, P],
     "evk_peer_wait_landed": [P, I, P, I, P, L, P],
@@ -130,8 +128,8 @@ def check(rc: int, what: str) -> None:
 KERNELS_PER_CALL = {
     "evk_l2norm_fwd": 1, "evk_l2norm_bwd": 1, "evk_posmask_build": 1, "evk_mpce_small_fwd": 1,
     "evk_mpce_small_bwd": 1, "evk_reduce_partials": 1, "evk_mpce_finalize": 1, "evk_mpce_stats_fused": 1, "evk_mpce_pos": 1, "evk_mpce_fwd": 1,
-    "evk_mpce_bwd_w": 1, "evk_mpce_bwd_gemm": 1, "evk_tc_gemm_probe": 1, "evk_l2norm_fwd_bcast": 1,
-    "evk_peer_bcast": 1, "evk_mpce_fwd_store": 1, "evk_mpce_w_from_e": 3, "evk_mpce_pos_logits": 1, "evk_mpce_pos_from_lists": 1, "evk_tc_gemm_nt": 1, "evk_topk_update": 1,
+    "evk_mpce_bwd_w": 1, "evk_mpce_bwd_gemm": 1, "evk_tc_gemm_probe": 1,
+    "evk_mpce_fwd_store": 1, "evk_mpce_w_from_e": 3, "evk_mpce_pos_logits": 1, "evk_mpce_pos_from_lists": 1, "evk_tc_gemm_nt": 1, "evk_topk_update": 1,
     "evk_peer_barrier": 1, "evk_mpce_small_fwd_batched": 1, "evk_mpce_small_bwd_batched": 1,
     "evk_local_attend_fwd": 1, "evk_local_attend_bwd": 2, "evk_token_sim_fwd": 1, "evk_token_sim_bwd": 1, "evk_peer_push_shard": 1, "evk_peer_wait_landed": 1, "evk_mpce_fwd_store_gathered": 1, "evk_mpce_finalize_avgpos": 1, "evk_shard_prologue": 1, "evk_mpce_shard_stats_push": 1, "evk_l2norm_bwd_parts": 1, "evk_mpce_shard_finish": 1, "evk_mpce_bwd_gemm_scatter": 1,
 }

@@ -2,10 +2,10 @@
 // straight into the symmetric buffers of EVERY rank, so the all-gather is part of the producing
 // kernel instead of a separate NCCL launch.
 //
-//   evk_l2norm_fwd_bcast : K1 fused with the all-gather of the normalised bf16 rows
+//   evk_shard_prologue   : K1 of both sides fused with the all-gather of the normalised bf16 key rows and the ids
 //                          (F.normalize of v0520.py:495-496, then what a sharded run must exchange)
-//   evk_peer_bcast       : push a small local block (ids, the per-rank statistics slot) into the same
-//                          offset of every rank's buffer
+//   evk_peer_push_shard  : the same all-gather as TMA bulk copies next to the similarity sweep (opt-in)
+//   evk_peer_barrier / evk_mpce_shard_finish / evk_peer_* : ordering, statistics exchange, symmetric buffers
 //
 // Destination pointers are the per-rank base addresses of a symmetric allocation (peer-mapped device
 // pointers; the local one included).  Cross-rank ordering (all shards landed / buffers free again) is
@@ -30,60 +30,6 @@ struct PeerDst {
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
-}
-
-// fp32 input, unit column stride, 16-byte aligned rows, d % 8 == 0, d <= kIters*256
-template <int kIters>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-l2norm_fwd_bcast_kernel(const float* __restrict__ x, int64_t n_rows, int d, int64_t stride_row, PeerDst dst,
-                        int64_t ld_bf16, int64_t row_offset, float* __restrict__ norm) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-  for (int64_t r = warp0; r < n_rows; r += nwarps) {
-    const float* xr = x + r * stride_row;
-    float v[kIters][8];
-    float ss = 0.f;
-#pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int c = (it * 32 + lane) * 8;
-      if (c < d) {
-        const float4 p0 = __ldg(reinterpret_cast<const float4*>(xr + c));
-        const float4 p1 = __ldg(reinterpret_cast<const float4*>(xr + c + 4));
-        v[it][0] = p0.x; v[it][1] = p0.y; v[it][2] = p0.z; v[it][3] = p0.w;
-        v[it][4] = p1.x; v[it][5] = p1.y; v[it][6] = p1.z; v[it][7] = p1.w;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) ss = fmaf(v[it][e], v[it][e], ss);
-      }
-    }
-    ss = warp_sum(ss);
-    const float nrm = sqrtf(ss);
-    const float den = fmaxf(nrm, EVK_NORM_EPS);
-    if (lane == 0) norm[r] = nrm;
-    const int64_t out_off = (row_offset + r) * ld_bf16;
-#pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int c = (it * 32 + lane) * 8;
-      if (c < d) {
-        float h[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) h[e] = v[it][e] / den;
-        uint4 hi, lo;
-        hi.x = pack2(h[0], h[1]); hi.y = pack2(h[2], h[3]); hi.z = pack2(h[4], h[5]); hi.w = pack2(h[6], h[7]);
-        const bool want_lo = dst.lo[0] != nullptr;
-        if (want_lo) {
-          float l[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) l[e] = h[e] - __bfloat162float(__float2bfloat16_rn(h[e]));
-          lo.x = pack2(l[0], l[1]); lo.y = pack2(l[2], l[3]); lo.z = pack2(l[4], l[5]); lo.w = pack2(l[6], l[7]);
-        }
-        for (int p = 0; p < dst.n; ++p) {          // one 128-bit store per destination rank (NVLink for peers)
-          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(dst.hi[p]) + out_off + c) = hi;
-          if (want_lo) *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(dst.lo[p]) + out_off + c) = lo;
-        }
-      }
-    }
-  }
 }
 
 // Prologue of a sharded step in ONE launch: K1 of the key rows (text) stored into every rank's buffer
@@ -181,14 +127,6 @@ shard_prologue_kernel(const Prologue p) {
       float4* z = reinterpret_cast<float4*>(p.zero + r * p.ld_zero);
       for (int c = lane; c * 4 < p.zero_width; c += 32) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-peer_bcast_kernel(const uint4* __restrict__ src, int64_t n_vec, PeerDst dst, int64_t dst_offset_vec) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint4 v = __ldg(src + i);
-    for (int p = 0; p < dst.n; ++p) static_cast<uint4*>(dst.hi[p])[dst_offset_vec + i] = v;
   }
 }
 
@@ -380,49 +318,6 @@ int fill_dst(PeerDst& dst, int n_dst, const uint64_t* hi, const uint64_t* lo) {
 }
 
 }  // namespace
-
-extern "C" int evk_l2norm_fwd_bcast(const void* x, int x_dtype, int64_t n_rows, int64_t d, int64_t stride_row,
-                                    int64_t stride_col, int n_dst, const uint64_t* dst_hi, const uint64_t* dst_lo,
-                                    int64_t ld_bf16, int64_t row_offset, float* norm, evk_stream_t stream) {
-  EVK_REQUIRE(x && norm && n_rows > 0 && d > 0, "evk_l2norm_fwd_bcast: bad arguments");
-  EVK_REQUIRE(x_dtype == EVK_DTYPE_F32 && stride_col == 1 && d % 8 == 0 && d <= 2048 && stride_row % 4 == 0 &&
-                  evk_aligned16(x),
-              "evk_l2norm_fwd_bcast: needs contiguous fp32 rows, d %% 8 == 0, d <= 2048 (use the NCCL transport otherwise)");
-  EVK_REQUIRE(ld_bf16 >= d && ld_bf16 % 8 == 0 && row_offset >= 0, "evk_l2norm_fwd_bcast: bad output pitch/offset");
-  PeerDst dst;
-  int rc = fill_dst(dst, n_dst, dst_hi, dst_lo);
-  if (rc != EVK_OK) return rc;
-  int64_t blocks = (n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int64_t cap = (int64_t)evk_sm_count() * 8;
-  if (blocks > cap) blocks = cap;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const float* xf = static_cast<const float*>(x);
-  if (d <= 1024)
-    l2norm_fwd_bcast_kernel<4><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, s>>>(xf, n_rows, (int)d, stride_row, dst,
-                                                                                ld_bf16, row_offset, norm);
-  else
-    l2norm_fwd_bcast_kernel<8><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, s>>>(xf, n_rows, (int)d, stride_row, dst,
-                                                                                ld_bf16, row_offset, norm);
-  EVK_CHECK_LAUNCH("l2norm_fwd_bcast");
-  return EVK_OK;
-}
-
-extern "C" int evk_peer_bcast(const void* src, int64_t bytes, int n_dst, const uint64_t* dst, int64_t dst_offset_bytes,
-                              evk_stream_t stream) {
-  EVK_REQUIRE(src && bytes > 0 && bytes % 16 == 0 && dst_offset_bytes >= 0 && dst_offset_bytes % 16 == 0 &&
-                  evk_aligned16(src), "evk_peer_bcast: src / sizes must be 16-byte aligned multiples");
-  PeerDst d;
-  int rc = fill_dst(d, n_dst, dst, nullptr);
-  if (rc != EVK_OK) return rc;
-  const int64_t n_vec = bytes / 16;
-  int64_t blocks = (n_vec + 255) / 256;
-  const int64_t cap = (int64_t)evk_sm_count() * 4;
-  if (blocks > cap) blocks = cap;
-  peer_bcast_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(src), n_vec, d, dst_offset_bytes / 16);
-  EVK_CHECK_LAUNCH("peer_bcast");
-  return EVK_OK;
-}
 
 // ---- symmetric buffers: allocation and CUDA-IPC exchange ------------------------------------------
 extern "C" int evk_peer_alloc(int64_t bytes, void** ptr_out) {

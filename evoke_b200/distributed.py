@@ -331,10 +331,12 @@ class _ShardedGPeer(torch.autograd.Function):
     NVLink - the prologue kernel stores the normalised key rows and the ids into every rank's buffers
     (all-gather), the statistics slots are pushed the same way, and the key-side gradient contraction stores
     its tiles straight into the owning rank's per-source buffer, which K1b sums (reduce-scatter fused into the
-    GEMM epilogue).  Three flag barriers per step order them; NCCL is not on the data path.  The forward keeps
-    E as a bf16 strip (K3 store variant), so the backward needs no second similarity sweep: 6 nND FLOP per rank.
-    15 launches per step: prologue, barrier, K2, positives, K3, statistics+push, barrier, finish | K4t x3,
-    contraction+scatter, contraction, K1b, barrier, K1b."""
+    GEMM epilogue).  Three cross-GPU syncs per step order them, folded into the first consumer kernel of each
+    exchange (K2, finish, the final K1b); NCCL is not on the data path.  The forward keeps E as a bf16 strip (K3 store
+    variant), so the backward needs no second similarity sweep: 6 nND FLOP per rank.  Launches per step: prologue, K2
+    (lists), positives x2, K3, statistics+push, finish | K4t x3, contraction+scatter beside the local contraction
+    (half of the SMs each), K1b, K1b over the partials.  peer_forward / peer_backward are plain functions so that
+    the same sequence is also captured into CUDA graphs (evoke_b200/graphs.py)."""
 
     @staticmethod
     def forward(ctx, ops, pc, inv_tau: float, row_ids: DeviceIds, image: torch.Tensor, text: torch.Tensor):

@@ -13,7 +13,8 @@ flag barrier kernel (``evk_peer_barrier``) - no NCCL call sits on the data path:
                           stores its tiles for these rows into part s (posted NVLink stores), K1b adds them up
   flags  [16]     uint32  barrier flags (entry r written by rank r only)
   err    [1]      int32   failure flag: a barrier that times out on ANY rank raises it on EVERY rank
-  landed [16]     uint32  landed[s] = step in which source s's key rows last arrived here completely
+  landed [16]     uint32  landed[s] = push CTAs of source s that have delivered their rows (monotonic; opt-in overlapped gather)
+  sync   [16]     uint32  flags of the syncs folded into the consumer kernels (entry r written by rank r only)
 
 Only torch.distributed's object all-gather is used, once per context, for the handles.
 """
@@ -112,7 +113,6 @@ class PeerContext:
             torch.bfloat16 if exchange == "bf16" else torch.float32).view(r, n, self.width)
         self.landed = self._view("landed", 64).view(torch.int32)
         self.step = torch.zeros(1, dtype=torch.int32, device=self.device)          # advanced by the prologue kernel
-        self.counters = torch.zeros(16, dtype=torch.int32, device=self.device)     # push kernel's per-destination tickets
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
         # failure flag of the transport (a peer missed a barrier): sticky device int read by the step's closing kernels
         # (NaN loss / gradients), mirrored by the barrier kernel into pinned HOST memory so that the next step's entry

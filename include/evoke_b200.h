@@ -390,22 +390,9 @@ EVK_API int evk_mpce_bwd_gemm(const void* w_hi, const void* w_lo, int64_t ld_w,
                       float alpha, int flags, float* out, int64_t ld_out, int cta_limit, evk_stream_t stream);
 
 /* ---- peer-memory transport for the sharded path (NVLink / NVSwitch) --------------------------
- * dst_* are HOST arrays of n_dst device base addresses: the per-rank buffers of one symmetric
- * allocation (peer-mapped pointers, the local rank included).  Ordering across ranks is the caller's
- * (symmetric-memory barrier between producer and consumer kernels).
- *
- * K1 fused with the all-gather: row r of this rank is normalised and written as bf16 at row
- * (row_offset + r) of EVERY destination (hi, and lo when dst_lo != NULL).  Contiguous fp32 input,
- * d % 8 == 0, d <= 2048. */
-EVK_API int evk_l2norm_fwd_bcast(const void* x, int x_dtype, int64_t n_rows, int64_t d,
-                         int64_t stride_row, int64_t stride_col,
-                         int n_dst, const uint64_t* dst_hi, const uint64_t* dst_lo,
-                         int64_t ld_bf16, int64_t row_offset, float* norm, evk_stream_t stream);
-
-/* Copy `bytes` (multiple of 16) from src to byte offset dst_offset_bytes of every destination:
- * ids shard, per-rank statistics slot. */
-EVK_API int evk_peer_bcast(const void* src, int64_t bytes, int n_dst, const uint64_t* dst,
-                   int64_t dst_offset_bytes, evk_stream_t stream);
+ * *_ptrs are HOST arrays of device base addresses: the per-rank buffers of one symmetric
+ * allocation (peer-mapped pointers, the local rank included).  Ordering across ranks: evk_peer_sync_t folded into
+ * the consumer kernels, or evk_peer_barrier between producer and consumer kernels. */
 
 /* Prologue of a sharded step in one launch: K1 of this rank's key rows (text) stored as bf16 at rows
  * row_offset.. of EVERY rank's key buffer (khat_ptrs: host table, n_dst entries), K1 of its query rows (image)
