@@ -351,6 +351,38 @@ class _ShardedGPeer(torch.autograd.Function):
         return None, None, None, None, d_image, d_text
 
 
+class _GatheredLoss(torch.autograd.Function):
+    """Small global batches (reference-sized per-GPU batches: 32 studies per rank): sharding the N x N work would
+    only add exchange latency, so every rank all-gathers the embeddings and ids ONCE, evaluates the whole loss with the
+    single-device kernels, and keeps the gradient rows of its own shard - no collective in the backward at all.
+    kind "G": (image, text) -> global_alignment_loss; kind "MPC": image only, rows filtered as on one device."""
+
+    @staticmethod
+    def forward(ctx, ops, group, cfg_of, image: torch.Tensor, text: Optional[torch.Tensor]):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n = int(image.shape[0])
+        img_all, w1 = _all_gather_rows(image.detach(), group, async_op=True)
+        txt_all, w2 = (None, None) if text is None else _all_gather_rows(text.detach(), group, async_op=True)
+        w1.wait()
+        if w2 is not None:
+            w2.wait()
+        loss, ctx.st = ops.mpce_forward(cfg_of(), img_all, txt_all, (True, text is not None))
+        ctx.ops, ctx.rows = ops, (rank * n, (rank + 1) * n)
+        out = loss.reshape(())
+        return out if image.dtype == torch.float32 else out.to(image.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        d_i, d_t = ctx.ops.mpce_backward(ctx.st, grad_out.reshape(1).to(torch.float32).contiguous())
+        lo, hi = ctx.rows
+        return None, None, None, d_i[lo:hi], None if d_t is None else d_t[lo:hi]
+
+
+# global batches up to this many rows are gathered and evaluated on every rank instead of being sharded
+GATHER_ALL_MAX = int(os.environ.get("EVOKE_B200_GATHER_ALL_MAX", "2048"))
+
+
 def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -435,6 +467,17 @@ def global_alignment_sharded(image: torch.Tensor, text: torch.Tensor, ids_local,
     if mode not in ("auto", "rs", "sym", "peer"):
         raise ValueError(f"mode must be 'auto', 'rs', 'sym' or 'peer', got {mode!r}")
     world = dist.get_world_size(group)
+    n_total = int(image.shape[0]) * world
+    if mode == "auto" and n_total <= GATHER_ALL_MAX and hasattr(ops, "mpce_forward"):
+        key_all, _ = _all_gather_rows(row_ids.key, group)
+        key2_all = None if row_ids.key2 is None else _all_gather_rows(row_ids.key2, group)[0]
+        d = int(image.shape[1])
+        path = ops.choose_path("auto", n_total, n_total, d)
+
+        def cfg_of():
+            return ops.LossConfig(kind="G", inv_tau=inv_tau, precision=precision, path=path,
+                                  row_ids=DeviceIds(key_all, key2_all))
+        return _GatheredLoss.apply(ops, group, cfg_of, image, text)
     if mode in ("auto", "peer") and hasattr(ops, "tc_fwd_store"):
         pc = None
         if peer_eligible(image, text, precision, world):
@@ -583,6 +626,17 @@ def multi_pos_contra_images_sharded(image: torch.Tensor, ids_local, temp: float,
     dist.all_gather_into_tensor(ids_all, ids_t.contiguous(), group=group)
     from . import ids as idmod
     codes_all = idmod.factorize(ids_all.cpu().numpy())                 # the size-determining host sync (:427)
-    if len(idmod.multi_view_rows(codes_all)) == 0:
+    keep_all = idmod.multi_view_rows(codes_all)
+    if len(keep_all) == 0:
         return torch.tensor([0.0], requires_grad=True, device=image.device)
+    if world * m <= GATHER_ALL_MAX and hasattr(ops, "mpce_forward"):
+        n_keep = len(keep_all)
+        gather = None if n_keep == world * m else torch.from_numpy(np.ascontiguousarray(keep_all)).to(image.device)
+        codes_dev = torch.from_numpy(np.ascontiguousarray(codes_all if gather is None else codes_all[keep_all])).to(image.device)
+        path = ops.choose_path("auto", n_keep, n_keep, int(image.shape[1]))
+
+        def cfg_of():
+            return ops.LossConfig(kind="MPC", inv_tau=inv_tau, precision=precision, path=path,
+                                  row_ids=DeviceIds(codes_dev), gather=gather)
+        return _GatheredLoss.apply(ops, group, cfg_of, image, None)
     return _ShardedMPC.apply(ops, group, inv_tau, precision, codes_all, image)

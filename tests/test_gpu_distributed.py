@@ -238,8 +238,10 @@ def test_a_rank_that_misses_a_barrier_poisons_the_step(tmp_path):
         assert np.isnan(got["loss"]) and bool(got["grad_nan"]) and bool(got["raised"]), (r, dict(got))
 
 
-def _mpc_worker(rank, world, port, n_total, d, tau, precision, kind, out_dir):
+def _mpc_worker(rank, world, port, n_total, d, tau, precision, kind, out_dir, gather_all=True):
     sys.path.insert(0, ROOT)
+    if not gather_all:                                # force the row-sharded form even for a small global batch
+        os.environ["EVOKE_B200_GATHER_ALL_MAX"] = "0"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -272,18 +274,21 @@ def _mpc_ids(n_total, kind):
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("gather_all", [False, True], ids=["sharded", "gathered"])
 @pytest.mark.parametrize("kind", ["mixed", "lopsided"])
 @pytest.mark.parametrize("precision,ltol,gtol", [("fp32", 1e-5, 1e-4), ("bf16", 2e-5, 2e-2)])
-def test_sharded_mpc_equals_oracle(tmp_path, precision, ltol, gtol, kind, world):
+def test_sharded_mpc_equals_oracle(tmp_path, precision, ltol, gtol, kind, gather_all, world):
     """multi_pos_contra_images_v0401 (:421-446) over the views of all ranks: cross-rank positives, rows dropped from
     queries and keys, a rank without kept rows; E strip + mask-free lists in bf16 mode on a rectangular row block."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    if gather_all and world > 2:
+        pytest.skip("the gathered form (small global batches) is covered at world 2")
     from evoke_b200 import synth
     from oracle import evoke_oracle as orc
     n_total, d, tau = 640 * world, 256, 0.5
-    port = _port(200 + world * 8 + (1 if precision == "fp32" else 0) + (2 if kind == "mixed" else 0))
-    mp.spawn(_mpc_worker, args=(world, port, n_total, d, tau, precision, kind, str(tmp_path)), nprocs=world, join=True)
+    port = _port(200 + world * 8 + (1 if precision == "fp32" else 0) + (2 if kind == "mixed" else 0) + (4 if gather_all else 0))
+    mp.spawn(_mpc_worker, args=(world, port, n_total, d, tau, precision, kind, str(tmp_path), gather_all), nprocs=world, join=True)
     ids = _mpc_ids(n_total, kind)
     x = synth.make_embeddings(ids, d, seed=62)
     want, dx = orc.mpc_closed_form(x, ids, tau)
@@ -292,3 +297,46 @@ def test_sharded_mpc_equals_oracle(tmp_path, precision, ltol, gtol, kind, world)
         got = np.load(tmp_path / f"mpc{r}.npz")
         assert abs(float(got["loss"][0]) - want) <= ltol * abs(want)
         assert np.abs(got["grad"] - dx[r * m:(r + 1) * m]).max() <= gtol * np.abs(dx).max()
+
+
+def _small_g_worker(rank, world, port, n_total, d, tau, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from evoke_b200 import synth
+        from evoke_b200.distributed import global_alignment_sharded
+        ids = synth.make_study_ids(n_total, seed=71)
+        n = n_total // world
+        sl = slice(rank * n, (rank + 1) * n)
+        image = torch.tensor(synth.make_embeddings(ids, d, seed=72)[sl], device="cuda", requires_grad=True)
+        text = torch.tensor(synth.make_embeddings(ids, d, seed=73)[sl], device="cuda", requires_grad=True)
+        loss = global_alignment_sharded(image, text, ids[sl].copy(), tau, precision="fp32")        # mode="auto"
+        (2.0 * loss).backward()
+        torch.cuda.synchronize()
+        np.savez(os.path.join(out_dir, f"small{rank}.npz"), loss=loss.item(), d_image=image.grad.cpu().numpy(),
+                 d_text=text.grad.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_small_global_batches_are_gathered_not_sharded(tmp_path):
+    """32 pairs per rank (the reference's per-GPU batch): mode='auto' all-gathers once, evaluates the whole loss on
+    every rank with the single-device (small-path) kernels and keeps its own gradient rows."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from evoke_b200 import synth
+    from oracle import evoke_oracle as orc
+    world, n_total, d, tau = 2, 64, 768, 0.5
+    mp.spawn(_small_g_worker, args=(world, _port(321), n_total, d, tau, str(tmp_path)), nprocs=world, join=True)
+    ids = synth.make_study_ids(n_total, seed=71)
+    want, d_i, d_t, _ = orc.g_loss_closed_form(synth.make_embeddings(ids, d, seed=72), synth.make_embeddings(ids, d, seed=73), ids, tau)
+    n = n_total // world
+    for r in range(world):
+        got = np.load(tmp_path / f"small{r}.npz")
+        sl = slice(r * n, (r + 1) * n)
+        assert abs(float(got["loss"]) - want) <= 1e-5 * abs(want)
+        assert np.abs(got["d_image"] - 2.0 * d_i[sl]).max() <= 1e-4 * np.abs(d_i).max() * 2.0
+        assert np.abs(got["d_text"] - 2.0 * d_t[sl]).max() <= 1e-4 * np.abs(d_t).max() * 2.0
