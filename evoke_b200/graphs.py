@@ -150,6 +150,8 @@ from collections import OrderedDict as _OrderedDict
 DROPIN_GRAPHS = _os.environ.get("EVOKE_B200_GRAPHS", "1") == "1"     # default of the reference-signature calls
 _MAX_CACHED = int(_os.environ.get("EVOKE_B200_GRAPH_CACHE", "6"))
 _CACHE: "_OrderedDict[tuple, GraphedStep]" = _OrderedDict()
+import threading as _threading
+_CACHE_LOCK = _threading.Lock()          # nn.DataParallel calls the loss from one host thread per GPU
 
 
 class GraphedStep:
@@ -245,14 +247,17 @@ def graphed_call(key: tuple, fwd, bwd, image: torch.Tensor, text: Optional[torch
     need = (image.requires_grad and torch.is_grad_enabled(),
             text is not None and text.requires_grad and torch.is_grad_enabled())
     key = key + (tuple(image.shape), image.dtype, image.device.index, ids.key2 is not None, need)
-    gs = _CACHE.get(key)
+    with _CACHE_LOCK:
+        gs = _CACHE.get(key)
+        if gs is not None:
+            _CACHE.move_to_end(key)
     if gs is None:
+        # (captured outside the lock: a capture takes tens of milliseconds and, on the sharded path, is collective)
         gs = GraphedStep(fwd, bwd, image.detach(), None if text is None else text.detach(), ids, need)
-        _CACHE[key] = gs
-        while len(_CACHE) > _MAX_CACHED:
-            _CACHE.popitem(last=False)                # least recently used: frees its graphs and their memory pool
-    else:
-        _CACHE.move_to_end(key)
+        with _CACHE_LOCK:
+            _CACHE[key] = gs
+            while len(_CACHE) > _MAX_CACHED:
+                _CACHE.popitem(last=False)            # least recently used: frees its graphs and their memory pool
     return _GraphedLoss.apply(gs, ids, image, text)
 
 
