@@ -113,20 +113,25 @@ class Normalized:
 
 
 def l2norm_fwd(x: torch.Tensor, *, want_f32: bool, want_hi: bool, want_lo: bool,
-               gather: Optional[torch.Tensor] = None) -> Normalized:
+               gather: Optional[torch.Tensor] = None, out: Optional[Normalized] = None) -> Normalized:
     """K1: xhat = x / max(||x||, 1e-12) (F.normalize, v0520.py:495-496, :436), honouring the
-    strides of ``x`` and an optional row gather."""
+    strides of ``x`` and an optional row gather.  ``out``: write into the buffers of an earlier result of the same
+    shape (the static operands of a captured graph) instead of allocating."""
     n = int(gather.shape[0]) if gather is not None else int(x.shape[0])
     d = int(x.shape[1])
     dev = x.device
-    out = Normalized(n=n, d=d, norm=torch.empty(n, dtype=torch.float32, device=dev))
-    if want_f32:
-        out.f32 = torch.empty((n, d), dtype=torch.float32, device=dev)
-    if want_hi:
-        out.ld = _round_up(d, 8)
-        out.hi = torch.empty((n, out.ld), dtype=torch.bfloat16, device=dev)
-        if want_lo:
-            out.lo = torch.empty((n, out.ld), dtype=torch.bfloat16, device=dev)
+    if out is not None:
+        if out.n != n or out.d != d:
+            raise ValueError(f"l2norm_fwd: out holds {out.n} x {out.d}, input is {n} x {d}")
+    else:
+        out = Normalized(n=n, d=d, norm=torch.empty(n, dtype=torch.float32, device=dev))
+        if want_f32:
+            out.f32 = torch.empty((n, d), dtype=torch.float32, device=dev)
+        if want_hi:
+            out.ld = _round_up(d, 8)
+            out.hi = torch.empty((n, out.ld), dtype=torch.bfloat16, device=dev)
+            if want_lo:
+                out.lo = torch.empty((n, out.ld), dtype=torch.bfloat16, device=dev)
     _lib.call("evk_l2norm_fwd", _ptr(x), _dtype_code(x), n, d, x.stride(0), x.stride(1), _ptr(gather),
               _ptr(out.f32), d, _ptr(out.hi), _ptr(out.lo), out.ld, _ptr(out.norm), _stream())
     return out
@@ -424,8 +429,20 @@ class _State:
     pass
 
 
-def mpce_forward(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor], need_grad=(True, True)):
-    """Forward kernel sequence of the G / MPC loss.  Returns (loss [1] fp32, state).  need_grad = (image, text)."""
+def normalize_pair(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tensor], out=None):
+    """K1 of both sides for a loss configuration -> (qn, kn); ``out`` = an earlier result to overwrite."""
+    small = cfg.path == "small"
+    split = (not small) and cfg.precision == "fp32"
+    kw = dict(want_f32=small, want_hi=not small, want_lo=split)
+    qn = l2norm_fwd(image, gather=cfg.gather, out=None if out is None else out[0], **kw)
+    kn = qn if cfg.kind == "MPC" else l2norm_fwd(text, out=None if out is None else out[1], **kw)
+    return qn, kn
+
+
+def mpce_forward(cfg: LossConfig, image: Optional[torch.Tensor], text: Optional[torch.Tensor], need_grad=(True, True),
+                 pre=None):
+    """Forward kernel sequence of the G / MPC loss.  Returns (loss [1] fp32, state).  need_grad = (image, text).
+    pre = (qn, kn): the operands are already normalised (K1 ran outside: the captured-graph form)."""
     st = _State()
     st.e_strip = None
     st.pos = None
@@ -437,8 +454,7 @@ def mpce_forward(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tens
     if mpc:
         flags |= FLAG_EXCLUDE_DIAG | FLAG_NO_COLSUM
     if small:
-        qn = l2norm_fwd(image, gather=cfg.gather, **kw)
-        kn = qn if mpc else l2norm_fwd(text, **kw)
+        qn, kn = pre if pre is not None else normalize_pair(cfg, image, text)
         n = qn.n
         pos_weight, inv_count = (1.0, 1.0 / n) if mpc else (2.0, 0.5 / n)
         bits, counts = posmask_build(cfg.row_ids, cfg.row_ids, clear_diag=mpc)
@@ -464,14 +480,13 @@ def mpce_forward(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tens
 
         if overlap:
             main = torch.cuda.current_stream()
-            side = _side_stream(image.device)
+            side = _side_stream(image.device if image is not None else pre[0].norm.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 bits, counts, pos_idx = build_mask()
         else:
             bits, counts, pos_idx = build_mask()
-        qn = l2norm_fwd(image, gather=cfg.gather, **kw)
-        kn = qn if mpc else l2norm_fwd(text, **kw)
+        qn, kn = pre if pre is not None else normalize_pair(cfg, image, text)
         n = qn.n
         pos_weight, inv_count = (1.0, 1.0 / n) if mpc else (2.0, 0.5 / n)
         if overlap:
@@ -514,12 +529,27 @@ def mpce_forward(cfg: LossConfig, image: torch.Tensor, text: Optional[torch.Tens
     st.cfg, st.flags, st.qn, st.kn = cfg, flags, qn, kn
     st.aux = (bits, counts, a_row, b_col)
     st.image, st.text = image, text
-    st.need_grad = (bool(need_grad[0]), bool(need_grad[1]) if text is not None else False)
+    st.need_grad = (bool(need_grad[0]), bool(need_grad[1]) if (text is not None or (pre is not None and not mpc)) else False)
     return loss, st
 
 
-def mpce_backward(st: _State, g: torch.Tensor):
-    """Backward kernel sequence; g = upstream gradient, fp32 [1] on the device.  Returns (d_image, d_text)."""
+def mpce_scale(st: _State) -> float:
+    """Host part of the gradient scale: 1/(M' tau) for MPC, 1/(2 N tau) for G (the device part is the upstream gradient)."""
+    return st.cfg.inv_tau / st.qn.n if st.cfg.kind == "MPC" else 0.5 * st.cfg.inv_tau / st.qn.n
+
+
+def mpce_finish(st: _State, image: torch.Tensor, text: Optional[torch.Tensor], dq, dk, g: torch.Tensor):
+    """K1b of both sides: (dQhat, dKhat) of mpce_backward(finish=False) -> gradients of the caller's tensors."""
+    scale = mpce_scale(st)
+    d_image = None if dq is None else l2norm_bwd(image, st.qn, dq, scale_dev=g, scale_host=scale, gather=st.cfg.gather)
+    d_text = None if dk is None else l2norm_bwd(text, st.kn, dk, scale_dev=g, scale_host=scale)
+    return d_image, d_text
+
+
+def mpce_backward(st: _State, g: torch.Tensor, finish: bool = True):
+    """Backward kernel sequence; g = upstream gradient, fp32 [1] on the device.  Returns (d_image, d_text), or with
+    finish=False the gradients (dQhat, dKhat) of the NORMALISED operands (fp32 [n, ld]): K1b then runs outside, on
+    the caller's tensors (the captured-graph form, mpce_finish)."""
     cfg, flags, qn, kn = st.cfg, st.flags, st.qn, st.kn
     bits, counts, a_row, b_col = st.aux
     image, text = st.image, st.text
@@ -528,16 +558,18 @@ def mpce_backward(st: _State, g: torch.Tensor):
     scale = cfg.inv_tau / n if mpc else 0.5 * cfg.inv_tau / n
     need_q = st.need_grad[0]
     need_k = (not mpc) and st.need_grad[1]
-    d_image = d_text = None
+    d_image = d_text = dq = dk = None
     if cfg.path == "small":
         if need_q:
             dq = small_bwd(qn, kn, bits, counts, a_row, b_col, cfg.inv_tau, flags)
-            d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
+            if finish:
+                d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
         if need_k:
             dk = small_bwd(kn, qn, bits, counts, b_col, a_row, cfg.inv_tau, flags)   # M is symmetric
-            d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
+            if finish:
+                d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
     elif need_q or need_k:
-        dev = image.device
+        dev = qn.norm.device
         width = _round_up(qn.d, 4)
         overlap = OVERLAP_STREAMS or torch.cuda.is_current_stream_capturing()
         strip = st.e_strip
@@ -559,10 +591,12 @@ def mpce_backward(st: _State, g: torch.Tensor):
             w_hi, w_lo, ld_w = weights()
             if need_q:
                 dq = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, False, kn, flags)
-                d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
+                if finish:
+                    d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
             if need_k:
                 dk = tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, True, qn, flags)
-                d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
+                if finish:
+                    d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
         else:
             main = torch.cuda.current_stream()
             side = _side_stream(dev)
@@ -584,16 +618,17 @@ def mpce_backward(st: _State, g: torch.Tensor):
                 with torch.cuda.stream(side):
                     side.wait_event(w_ready)
                     tc_bwd_gemm(w_hi, w_lo, ld_w, qn.n, kn.n, True, qn, flags, out=dk)
-                    d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
+                    if finish:
+                        d_text = l2norm_bwd(text, kn, dk, scale_dev=g, scale_host=scale)
                 _shared_with(side, w_hi, w_lo, qn.hi, qn.lo, g, text, kn.norm)
-            if need_q:
+            if need_q and finish:
                 d_image = l2norm_bwd(image, qn, dq, scale_dev=g, scale_host=scale, gather=cfg.gather)
             if need_k:
                 main.wait_stream(side)
-                _shared_with(main, d_text)
+                _shared_with(main, d_text, dk)
         if strip is not None and not torch.cuda.is_current_stream_capturing():
             st.e_strip = (None, 0)                  # drop the N^2 buffer as soon as it has been consumed
-    return d_image, d_text
+    return (d_image, d_text) if finish else (dq, dk)
 
 
 class _MultiPositiveCE(torch.autograd.Function):

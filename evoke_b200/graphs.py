@@ -155,20 +155,34 @@ _CACHE_LOCK = _threading.Lock()          # nn.DataParallel calls the loss from o
 
 
 class GraphedStep:
-    """Forward and backward of one loss call, captured as TWO CUDA graphs over static buffers, so that the
-    reference-signature call (``model.global_alignment_loss(image, text, ids)`` ... ``all_loss.backward()``) costs two
-    graph launches instead of ~20 kernel launches: the forward graph is replayed inside the autograd Function's
-    forward, the backward graph - which reads the upstream gradient from a static device scalar - inside its
-    backward.  Semantics are those of ``torch.cuda.make_graphed_callables``: the returned gradients are static
-    buffers, valid until the next call with the same signature; a backward must follow its own forward
-    (a stale or repeated backward raises).
+    """Forward and backward of one loss call, captured as TWO CUDA graphs, so that the reference-signature call
+    (``model.global_alignment_loss(image, text, ids)`` ... ``all_loss.backward()``) costs two graph launches instead
+    of ~20 kernel launches: the forward graph is replayed inside the autograd Function's forward, the backward
+    graph - which reads the upstream gradient from a static device scalar - inside its backward.  A backward must
+    follow its own forward (a stale or repeated backward raises).  An entry keeps its buffers - in bf16 mode the
+    N x N bf16 strip, 0.5 GB at N = 16384 - until it leaves the cache (EVOKE_B200_GRAPH_CACHE entries, least
+    recently used first; ``clear_graph_cache()`` frees everything).
 
-    fwd(image, text, ids, need) -> (loss [1] fp32, state);  bwd(state, g) -> (d_image, d_text | None)."""
+    Two forms:
+      * ``norm`` / ``finish`` given (the single-device loss): the kernels that touch the CALLER's tensors stay outside
+        the graphs - K1 (``norm``) reads the embeddings as they are (any strides) and writes the static normalised
+        operands, the graphs hold everything in between, K1b (``finish``) turns the graph's dQhat / dKhat into fresh
+        gradient tensors.  No copy of the inputs, no static outputs.
+            norm(image, text, out | None) -> operands;  fwd(operands, ids, need) -> (loss, state);
+            bwd(state, g) -> (dq, dk);  finish(state, image, text, dq, dk, g) -> (d_image, d_text)
+      * otherwise (the sharded peer path): the inputs are copied into static buffers and the returned gradients are
+        static buffers, valid until the next call with the same signature (torch.cuda.make_graphed_callables semantics).
+            fwd(image, text, ids, need) -> (loss, state);  bwd(state, g) -> (d_image, d_text)"""
 
-    def __init__(self, fwd, bwd, image: torch.Tensor, text: Optional[torch.Tensor], ids: DeviceIds, need, warmup: int = 3):
+    def __init__(self, fwd, bwd, image: torch.Tensor, text: Optional[torch.Tensor], ids: DeviceIds, need, warmup: int = 3,
+                 norm=None, finish=None):
         dev = image.device
-        self.image = torch.empty(image.shape, dtype=image.dtype, device=dev)
-        self.text = None if text is None else torch.empty(text.shape, dtype=text.dtype, device=dev)
+        self.norm, self.finish = norm, finish
+        self.zero_copy = norm is not None
+        self.image = self.text = self.pre = None
+        if not self.zero_copy:
+            self.image = torch.empty(image.shape, dtype=image.dtype, device=dev)
+            self.text = None if text is None else torch.empty(text.shape, dtype=text.dtype, device=dev)
         self.key = torch.empty_like(ids.key)
         self.key2 = None if ids.key2 is None else torch.empty_like(ids.key2)
         self.ids = DeviceIds(self.key, self.key2)
@@ -176,34 +190,48 @@ class GraphedStep:
         self.need = (bool(need[0]), bool(need[1]))
         self.gen = 0               # forward generation; a backward must present the generation it belongs to
         self.bwd_gen = -1
-        self._load(image, text, ids)
+        with torch.no_grad():
+            if self.zero_copy:
+                self.pre = norm(image, text, None)             # allocates the static operands
+            self._load(image, text, ids)
         torch.cuda.synchronize(dev)
+
+        def run_fwd():
+            return fwd(self.pre, self.ids, self.need) if self.zero_copy else fwd(self.image, self.text, self.ids, self.need)
+
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(warmup):                    # first-call work (kernel attributes, context binding) before capture
-                loss, st = fwd(self.image, self.text, self.ids, self.need)
+                if self.zero_copy:
+                    norm(image, text, self.pre)
+                loss, st = run_fwd()
                 if any(self.need):
-                    bwd(st, self.g)
+                    out = bwd(st, self.g)
+                    if self.zero_copy:
+                        finish(st, image, text, out[0], out[1], self.g)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph_f = torch.cuda.CUDAGraph()
         # thread_local: other host threads (a DataLoader's pin-memory thread ...) may keep calling CUDA during capture
         with torch.no_grad(), torch.cuda.graph(self.graph_f, capture_error_mode="thread_local"):
-            self.loss, self.state = fwd(self.image, self.text, self.ids, self.need)
+            self.loss, self.state = run_fwd()
         self.graph_b = None
-        self.d_image = self.d_text = None
+        self.out_a = self.out_b = None                 # (d_image, d_text) static, or (dq, dk) in the zero-copy form
         if any(self.need):
             self.graph_b = torch.cuda.CUDAGraph()
             with torch.no_grad(), torch.cuda.graph(self.graph_b, pool=self.graph_f.pool(), capture_error_mode="thread_local"):
-                self.d_image, self.d_text = bwd(self.state, self.g)
+                self.out_a, self.out_b = bwd(self.state, self.g)
             # the capture itself ran neither graph: the E strip of `state` is produced by the first replay
 
     def _load(self, image, text, ids: DeviceIds):
         with torch.no_grad():
-            self.image.copy_(image, non_blocking=True)             # also gathers strided [:,0,:] views
-            if self.text is not None:
-                self.text.copy_(text, non_blocking=True)
+            if self.zero_copy:
+                self.norm(image, text, self.pre)                       # K1 straight from the caller's tensors
+            else:
+                self.image.copy_(image, non_blocking=True)             # also gathers strided [:,0,:] views
+                if self.text is not None:
+                    self.text.copy_(text, non_blocking=True)
             self.key.copy_(ids.key, non_blocking=True)
             if self.key2 is not None:
                 self.key2.copy_(ids.key2, non_blocking=True)
@@ -214,7 +242,7 @@ class GraphedStep:
         self.gen += 1
         return self.gen
 
-    def run_backward(self, gen: int, grad_out: torch.Tensor):
+    def run_backward(self, gen: int, grad_out: torch.Tensor, image=None, text=None):
         if gen != self.gen:
             raise RuntimeError("evoke_b200: backward of a stale graphed loss call: another forward with the same signature "
                                "ran in between (set EVOKE_B200_GRAPHS=0 or graph=False to keep several calls alive)")
@@ -223,8 +251,10 @@ class GraphedStep:
         self.bwd_gen = gen
         with torch.no_grad():
             self.g.copy_(grad_out.reshape(1), non_blocking=True)
-        self.graph_b.replay()
-        return self.d_image, self.d_text
+            self.graph_b.replay()
+            if self.zero_copy:
+                return self.finish(self.state, image, text, self.out_a, self.out_b, self.g)
+        return self.out_a, self.out_b
 
 
 class _GraphedLoss(torch.autograd.Function):
@@ -232,17 +262,25 @@ class _GraphedLoss(torch.autograd.Function):
     def forward(ctx, gs: GraphedStep, ids: DeviceIds, image: torch.Tensor, text: Optional[torch.Tensor]):
         ctx.gs = gs
         ctx.gen = gs.run_forward(image, text, ids)
+        if gs.zero_copy:                                # K1b reads the caller's embeddings again
+            ctx.save_for_backward(*([image] if text is None else [image, text]))
+        ctx.has_text = text is not None
         out = gs.loss.clone().reshape(())
         return out if image.dtype == torch.float32 else out.to(image.dtype)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        d_image, d_text = ctx.gs.run_backward(ctx.gen, grad_out.to(torch.float32))
+        image = text = None
+        if ctx.gs.zero_copy:
+            saved = ctx.saved_tensors
+            image, text = saved[0], (saved[1] if ctx.has_text else None)
+        d_image, d_text = ctx.gs.run_backward(ctx.gen, grad_out.to(torch.float32), image, text)
         return None, None, d_image if ctx.needs_input_grad[2] else None, d_text if ctx.needs_input_grad[3] else None
 
 
-def graphed_call(key: tuple, fwd, bwd, image: torch.Tensor, text: Optional[torch.Tensor], ids: DeviceIds) -> torch.Tensor:
+def graphed_call(key: tuple, fwd, bwd, image: torch.Tensor, text: Optional[torch.Tensor], ids: DeviceIds,
+                 norm=None, finish=None) -> torch.Tensor:
     """Run one loss call through the graph cache (capturing on first use of this signature)."""
     need = (image.requires_grad and torch.is_grad_enabled(),
             text is not None and text.requires_grad and torch.is_grad_enabled())
@@ -253,7 +291,7 @@ def graphed_call(key: tuple, fwd, bwd, image: torch.Tensor, text: Optional[torch
             _CACHE.move_to_end(key)
     if gs is None:
         # (captured outside the lock: a capture takes tens of milliseconds and, on the sharded path, is collective)
-        gs = GraphedStep(fwd, bwd, image.detach(), None if text is None else text.detach(), ids, need)
+        gs = GraphedStep(fwd, bwd, image.detach(), None if text is None else text.detach(), ids, need, norm=norm, finish=finish)
         with _CACHE_LOCK:
             _CACHE[key] = gs
             while len(_CACHE) > _MAX_CACHED:

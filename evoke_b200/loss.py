@@ -52,9 +52,9 @@ def global_alignment(image: torch.Tensor, text: torch.Tensor, patient_ids, temp:
     patient_ids: what the reference passes (numpy array of str/int, length >= B; only the first B
     are used, :488), a (patient, study) pair, or an integer tensor already on the device.
     graph: replay the call from the CUDA-graph cache (evoke_b200.graphs.GraphedStep: one graph for the forward,
-    one for the backward, captured on first use of a (shape, dtype, precision, temperature) signature; the returned
-    gradients are static buffers, as with torch.cuda.make_graphed_callables).  None: EVOKE_B200_GRAPHS (default on),
-    never inside an outer capture.
+    one for the backward, captured on first use of a (shape, dtype, precision, temperature) signature; K1 and K1b
+    stay outside the graphs and work on the caller's tensors, so nothing is copied and the gradients are fresh
+    tensors).  None: EVOKE_B200_GRAPHS (default on), never inside an outer capture.
     """
     Fn._require_cuda(image, "global_image_embed")
     Fn._require_cuda(text, "global_text_embed")
@@ -76,11 +76,20 @@ def global_alignment(image: torch.Tensor, text: torch.Tensor, patient_ids, temp:
         from . import graphs
         use_graph = graphs.DROPIN_GRAPHS if graph is None else bool(graph)
         if use_graph and not torch.cuda.is_current_stream_capturing():
-            def fwd(im, tx, ids, need):
-                return Fn.mpce_forward(Fn.LossConfig(kind="G", inv_tau=inv_tau, precision=precision, path=path,
-                                                     row_ids=ids), im, tx, need)
+            def cfg_of(ids):
+                return Fn.LossConfig(kind="G", inv_tau=inv_tau, precision=precision, path=path, row_ids=ids)
+
+            def norm(im, tx, out):                     # K1: outside the graphs, straight from the caller's tensors
+                return Fn.normalize_pair(cfg_of(dev_ids), im, tx, out)
+
+            def fwd(pre, ids, need):
+                return Fn.mpce_forward(cfg_of(ids), None, None, need, pre=pre)
+
+            def bwd(st, g):
+                return Fn.mpce_backward(st, g, finish=False)
+
             key = ("G", inv_tau, precision, path, Fn.E_STRIP, Fn.OVERLAP_STREAMS, Fn.MASK_FREE)
-            return graphs.graphed_call(key, fwd, Fn.mpce_backward, image, text, dev_ids)
+            return graphs.graphed_call(key, fwd, bwd, image, text, dev_ids, norm=norm, finish=Fn.mpce_finish)
         cfg = Fn.LossConfig(kind="G", inv_tau=inv_tau, precision=precision, path=path, row_ids=dev_ids)
         return Fn.multi_positive_ce(cfg, image, text)
 
