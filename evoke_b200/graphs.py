@@ -149,6 +149,11 @@ from collections import OrderedDict as _OrderedDict
 
 DROPIN_GRAPHS = _os.environ.get("EVOKE_B200_GRAPHS", "1") == "1"     # default of the reference-signature calls
 _MAX_CACHED = int(_os.environ.get("EVOKE_B200_GRAPH_CACHE", "6"))
+# the single-device loss with K1 / K1b OUTSIDE the graphs (no input copy, fresh gradient tensors).  Measured slower than
+# copying the inputs into static buffers (1.39 vs 1.31 ms at N = 16384; 0.25 vs 0.20 ms at N = 4096): outside the
+# graphs those four kernels no longer run beside K2 / the second contraction, and every eager-kernel <-> graph-launch
+# transition costs launch latency.  Off by default.
+ZERO_COPY = _os.environ.get("EVOKE_B200_GRAPH_ZERO_COPY", "0") == "1"
 _CACHE: "_OrderedDict[tuple, GraphedStep]" = _OrderedDict()
 import threading as _threading
 _CACHE_LOCK = _threading.Lock()          # nn.DataParallel calls the loss from one host thread per GPU

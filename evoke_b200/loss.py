@@ -52,9 +52,11 @@ def global_alignment(image: torch.Tensor, text: torch.Tensor, patient_ids, temp:
     patient_ids: what the reference passes (numpy array of str/int, length >= B; only the first B
     are used, :488), a (patient, study) pair, or an integer tensor already on the device.
     graph: replay the call from the CUDA-graph cache (evoke_b200.graphs.GraphedStep: one graph for the forward,
-    one for the backward, captured on first use of a (shape, dtype, precision, temperature) signature; K1 and K1b
-    stay outside the graphs and work on the caller's tensors, so nothing is copied and the gradients are fresh
-    tensors).  None: EVOKE_B200_GRAPHS (default on), never inside an outer capture.
+    one for the backward, captured on first use of a (shape, dtype, precision, temperature) signature; the inputs
+    are copied into static buffers and the returned gradients are static buffers, as with
+    torch.cuda.make_graphed_callables.  EVOKE_B200_GRAPH_ZERO_COPY=1 keeps K1 / K1b outside the graphs instead - no
+    copy, fresh gradient tensors, but 6 % slower at N = 16384 because those kernels no longer overlap their
+    neighbours).  None: EVOKE_B200_GRAPHS (default on), never inside an outer capture.
     """
     Fn._require_cuda(image, "global_image_embed")
     Fn._require_cuda(text, "global_text_embed")
@@ -88,8 +90,13 @@ def global_alignment(image: torch.Tensor, text: torch.Tensor, patient_ids, temp:
             def bwd(st, g):
                 return Fn.mpce_backward(st, g, finish=False)
 
-            key = ("G", inv_tau, precision, path, Fn.E_STRIP, Fn.OVERLAP_STREAMS, Fn.MASK_FREE)
-            return graphs.graphed_call(key, fwd, bwd, image, text, dev_ids, norm=norm, finish=Fn.mpce_finish)
+            key = ("G", inv_tau, precision, path, Fn.E_STRIP, Fn.OVERLAP_STREAMS, Fn.MASK_FREE, graphs.ZERO_COPY)
+            if graphs.ZERO_COPY:
+                return graphs.graphed_call(key, fwd, bwd, image, text, dev_ids, norm=norm, finish=Fn.mpce_finish)
+
+            def fwd_all(im, tx, ids, need):            # everything inside the graphs, inputs copied into static buffers
+                return Fn.mpce_forward(cfg_of(ids), im, tx, need)
+            return graphs.graphed_call(key, fwd_all, Fn.mpce_backward, image, text, dev_ids)
         cfg = Fn.LossConfig(kind="G", inv_tau=inv_tau, precision=precision, path=path, row_ids=dev_ids)
         return Fn.multi_positive_ce(cfg, image, text)
 

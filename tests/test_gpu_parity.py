@@ -174,14 +174,16 @@ def test_cuda_graph_step_matches_eager_and_tracks_new_inputs():
 
 
 # ------------------------------------------------------------------------------------- drop-in graph cache
+@pytest.mark.parametrize("zero_copy", [False, True], ids=["static-inputs", "zero-copy"])
 @pytest.mark.parametrize("precision,path,n,d", [("bf16", "tc", 1536, 256), ("fp32", "tc", 700, 128), ("fp32", "small", 64, 768)])
-def test_graph_cached_call_equals_the_eager_launch_sequence(precision, path, n, d):
+def test_graph_cached_call_equals_the_eager_launch_sequence(precision, path, n, d, zero_copy, monkeypatch):
     """global_alignment(graph=True) replays two captured graphs over static buffers; the kernels are those of the eager
     call, so loss and gradients agree to fp32 rounding (not bitwise: the split-K reduce-adds land in L2 in any order, and
     a strided input is gathered into the static buffer before K1 instead of being read through K1's strided loader) -
     on fresh data of the same signature too, with strided inputs, and under no_grad."""
     from evoke_b200 import graphs
     graphs.clear_graph_cache()
+    monkeypatch.setattr(graphs, "ZERO_COPY", zero_copy)      # both forms of the cache (see evoke_b200/graphs.py)
     for seed in (1, 2, 3):
         ids = synth.make_study_ids(n, seed=seed)
         xi = synth.make_embeddings(ids, d, seed=seed + 10)
