@@ -547,7 +547,7 @@ def run_cuda(args):
                 kern[name]["tflops"] = flop_launch / (float(np.mean(ms)) * 1e-3) / 1e12
     tck = [k for k in kern if k in TC]
     dom = max(tck, key=lambda k: kern[k]["avg_ms"]) if tck else None
-    traffic = None
+    traffic = None          # (N > 1: ncu cannot wrap a multi-rank command, so there is no per-launch DRAM capture)
     if world == 1 and cfg == "cfg3":
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:

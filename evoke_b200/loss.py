@@ -232,11 +232,14 @@ def local_text_token_alignment_loss(self, local_image_embed, local_text_embed):
     return local_text_token_alignment(local_image_embed, local_text_embed, self.args["region_temp"])
 
 
-def patch_pretrain(target, precision: str = DEFAULT_PRECISION, local_tokens: bool = False, graphs: Optional[bool] = None):
+def patch_pretrain(target, precision: str = DEFAULT_PRECISION, local_tokens: bool = False, graphs: Optional[bool] = None,
+                   fusion: bool = False):
     """Rebind the two loss methods (and, with ``local_tokens=True``, ``local_text_token_alignment_loss`` :506) on a
     reference ``Pretrain`` class (affects every instance) or on a single instance.  Works for all six model files because only the method names and
     ``self.args`` are relied upon.  ``graphs``: run ``global_alignment_loss`` from the CUDA-graph cache (None: the
-    EVOKE_B200_GRAPHS default, on).  Returns ``target``."""
+    EVOKE_B200_GRAPHS default, on).  ``fusion=True`` also rebinds ``multiview_fusion`` (:456-484) to the loop-free form
+    of evoke_b200.fusion (same sub-modules and parameters: ``layer_norm_1/2``, ``multiview_cross_attention``,
+    ``visual_head``).  Returns ``target``."""
     if precision not in ("fp32", "bf16"):
         raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
     if isinstance(target, type):
@@ -246,6 +249,9 @@ def patch_pretrain(target, precision: str = DEFAULT_PRECISION, local_tokens: boo
             target.local_text_token_alignment_loss = local_text_token_alignment_loss
         target._evoke_b200_precision = precision
         target._evoke_b200_graphs = graphs
+        if fusion:
+            from .fusion import MultiviewFusion
+            target.multiview_fusion = MultiviewFusion.forward
     else:
         import types
         target.global_alignment_loss = types.MethodType(global_alignment_loss, target)
@@ -254,6 +260,9 @@ def patch_pretrain(target, precision: str = DEFAULT_PRECISION, local_tokens: boo
             target.local_text_token_alignment_loss = types.MethodType(local_text_token_alignment_loss, target)
         target._evoke_b200_precision = precision
         target._evoke_b200_graphs = graphs
+        if fusion:
+            from .fusion import patch_multiview_fusion
+            patch_multiview_fusion(target)
     return target
 
 

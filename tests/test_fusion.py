@@ -104,3 +104,19 @@ def test_multiview_fusion_against_the_golden_fixture_gpu():
 def test_partner_lists_follow_the_reference_order():
     assert fusion.partner_lists(IDS, 5) == [[5, 6], [], [7], [], []]
     assert fusion.partner_lists(torch.tensor([3, 3, 1, 3]), 2) == [[1, 3], [0, 3]]
+
+
+@pytest.mark.reference
+def test_patch_pretrain_fusion_rebinds_the_method_on_a_reference_style_module():
+    """patch_pretrain(..., fusion=True): the reference's own sub-modules, the loop-free forward."""
+    import evoke_b200
+    from oracle import ref_shim
+    d, d_out, p, b = 32, 16, 5, 5
+    holder = ref_shim.make_fusion_self(d, d_out, seed=5)
+    holder.args = {"instance_temp": 0.5, "region_temp": 0.5}
+    holder.eval()
+    gi, li = _inputs(len(IDS), p, d, seed=4)
+    want = ref_shim.multiview_fusion(holder, gi, li, IDS, b)
+    evoke_b200.patch_pretrain(holder, fusion=True)
+    got = holder.multiview_fusion(gi, li, IDS, b)
+    assert torch.allclose(got[0], want[0], atol=2e-5, rtol=1e-4) and torch.allclose(got[1], want[1], atol=2e-5, rtol=1e-4)
