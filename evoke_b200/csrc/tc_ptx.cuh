@@ -71,13 +71,17 @@ __device__ __forceinline__ void cluster_sync_all() {          // every thread of
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of this cluster
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of this cluster.
+// Relaxed on purpose: the only caller hands a TMEM stage back after tcgen05.wait::ld + tcgen05.fence::before_thread_sync,
+// so no generic-proxy write has to be published.  The .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR, which
+// makes the odd CTA of a pair wait for its outstanding E-strip stores before the stage is freed (9 % of K3's warp
+// samples in profiles/r2_ncu_k3_stalls.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(bar), "r"(cta) : "memory");
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even CTA of a pair
