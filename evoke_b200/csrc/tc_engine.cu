@@ -295,10 +295,17 @@ tc_kernel(const __grid_constant__ TcParams p) {
           asm volatile("fence.proxy.async;" ::: "memory");       // the landed rows are read by TMA (async proxy)
         }
         __syncwarp();
+        // segment / offset of the k-block are carried along (no division per k-block) and everything that does not
+        // depend on the slot is computed BEFORE the wait: the time from "slot free" to "TMA issued" is on the critical
+        // path of a four-stage ring (profiles/r2_ncu_k3_stalls.txt)
+        int seg = kb0 / p.kb_per_seg, kin = kb0 - seg * p.kb_per_seg;
         for (int kb = kb0; kb < kb1; ++kb) {
-          const int seg = kb / p.kb_per_seg, kk = (kb - seg * p.kb_per_seg) * BK;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const int kk = kin * BK;
+          const CUtensorMap* const a_map = &p.a_map[seg];
+          const CUtensorMap* const b_map = &p.b_map[seg];
           const uint32_t a_dst = smem_base + stage * kStage, b_dst = a_dst + kABytes;
+          if (++kin == p.kb_per_seg) { kin = 0; ++seg; }
+          mbar_wait(empty_bar(stage), phase ^ 1u);
           if (elect_one()) {
           // the (leader's) full barrier expects the bytes of every CTA that feeds this stage
           if (leader) mbar_expect_tx(full_bar(stage), kStage * (CTA2 ? 2 : 1));
@@ -307,16 +314,16 @@ tc_kernel(const __grid_constant__ TcParams p) {
             else tma_load_2d(dst, m, full_bar(stage), c0, c1, pol);
           };
           if (!A_MN) {
-            load(a_dst, &p.a_map[seg], kk, m0, p.policy_a);
+            load(a_dst, a_map, kk, m0, p.policy_a);
           } else {
 #pragma unroll
-            for (int b = 0; b < BM / 64; ++b) load(a_dst + b * 8192, &p.a_map[seg], m0 + 64 * b, kk, p.policy_a);
+            for (int b = 0; b < BM / 64; ++b) load(a_dst + b * 8192, a_map, m0 + 64 * b, kk, p.policy_a);
           }
           if (!B_MN) {
-            load(b_dst, &p.b_map[seg], kk, n0, p.policy_b);
+            load(b_dst, b_map, kk, n0, p.policy_b);
           } else {
 #pragma unroll
-            for (int b = 0; b < kBRows / 64; ++b) load(b_dst + b * 8192, &p.b_map[seg], n0 + 64 * b, kk, p.policy_b);
+            for (int b = 0; b < kBRows / 64; ++b) load(b_dst + b * 8192, b_map, n0 + 64 * b, kk, p.policy_b);
           }
           }
           __syncwarp();
