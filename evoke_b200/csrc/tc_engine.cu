@@ -51,6 +51,7 @@ enum { EPI_FWD = 0, EPI_BWD_W = 1, EPI_GEMM = 2, EPI_FWD_E = 3, EPI_GEMM_TMA = 4
 // Bits of TcParams::flags above the public EVK_FLAG_* set.  They are set by this file only: every extern "C" entry
 // point masks the caller's flags with EVK_FLAG_PUBLIC_MASK first.
 enum {
+  kIntNoEpiPipe = 0x8000,  // K3 epilogue without the software-pipelined TMEM loads (A/B, EVK_K3_PIPE=0)
   kIntDropOut = 0x100,   // evk_tc_gemm_probe(variant & 8): run the main loop, drop the output (main-loop rate probe)
   kIntStore = 0x200,     // gradient contraction: whole-K units, plain stores instead of reduce-add
   kIntBf16Out = 0x2000,  // gradient contraction, store mode: bf16 [32 x 64] output boxes
@@ -487,13 +488,10 @@ tc_kernel(const __grid_constant__ TcParams p) {
           }
           continue;
         }
-#pragma unroll 1
-        for (int cc = 0; cc < kChunks; ++cc) {
+        // one 32-column chunk of this warp's rows: v = the accumulator values (destroyed)
+        auto chunk = [&](float (&v)[32], const int cc) {
           const int c = c_lo + cc;
           const uint32_t mword = cc == 0 ? mw4[0] : (cc == 1 ? mw4[1] : (cc == 2 ? mw4[2] : mw4[3]));
-          float v[32];
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait(v);
           const int cbase = n0 + c * 32;
           uint32_t live = (cbase + 32 <= p.n_cols) ? 0xffffffffu
                           : (cbase >= p.n_cols ? 0u : ((1u << (int)(p.n_cols - cbase)) - 1u));
@@ -546,8 +544,33 @@ tc_kernel(const __grid_constant__ TcParams p) {
             const float cs = warp_transpose_sum(v, lane);
             colpart[q * BN + c * 32 + lane] = cs;
           }
+        };
+        // The chunks are software-pipelined over two register buffers: the tcgen05.ld of chunk cc+1 is in flight
+        // while chunk cc is processed, and the TMEM stage goes back to the MMA warp as soon as the LAST load has
+        // completed - one chunk's worth of exp / pack / transpose earlier than after the loop (kChunks is 2 or 4).
+        if (p.flags & kIntNoEpiPipe) {                            // A/B switch (EVK_K3_PIPE=0): load, wait, process
+          float v[32];
+#pragma unroll 1
+          for (int cc = 0; cc < kChunks; ++cc) {
+            tmem_ld_32x32(taddr + (c_lo + cc) * 32, v);
+            tmem_ld_wait(v);
+            if (cc == kChunks - 1) release_tmem(as);
+            chunk(v, cc);
+          }
+        } else {
+          float va[32], vb[32];
+          tmem_ld_32x32(taddr + c_lo * 32, va);
+#pragma unroll 1
+          for (int cc = 0; cc < kChunks; cc += 2) {
+            tmem_ld_wait(va);
+            tmem_ld_32x32(taddr + (c_lo + cc + 1) * 32, vb);
+            chunk(va, cc);
+            tmem_ld_wait(vb);
+            if (cc + 2 < kChunks) tmem_ld_32x32(taddr + (c_lo + cc + 2) * 32, va);
+            else release_tmem(as);                                // TMEM stage drained
+            chunk(vb, cc + 1);
+          }
         }
-        release_tmem(as);                                         // TMEM stage drained
         if (row_ok) {
           const int64_t po = ((int64_t)nb * (kGroupWarps / 4) + hh) * p.ld_rowpart + i;
           p.row_sum_part[po] = (rs0 + rs1) + (rs2 + rs3);
@@ -1034,6 +1057,10 @@ int mpce_fwd_impl(const void* q_hi, const void* q_lo, int64_t ld_q, const void* 
   p.inv_tau = inv_tau;
   p.flags = flags;
   if (bits && evk_aligned16(bits) && ld_words % 4 == 0) p.flags |= kIntVecMask;     // 128-bit mask loads
+  {
+    static const bool no_pipe = [] { const char* e = getenv("EVK_K3_PIPE"); return e && e[0] == '0'; }();
+    if (no_pipe) p.flags |= kIntNoEpiPipe;
+  }
   p.diag_offset = diag_offset;
   p.bits = bits;
   p.ld_words = ld_words;
