@@ -5,6 +5,8 @@
 #   gpurun --gpus N   -- 'bash tools/r2_profile.sh dist N'  multi-GPU parity tests of world N (and 2)
 #   gpurun --gpus N   -- 'bash tools/r2_profile.sh ab N'    sharded bench with the A/B switches of profiles/r2_experiments.md §5
 #   gpurun --gpus N   -- 'bash tools/r2_profile.sh bench N [extra bench.py flags]'
+#   gpurun            -- 'bash tools/r2_profile.sh ncu TAG'  ncu --set full of K3 / K4t / K4b -> gpurun_out/TAG_prof_hot.ncu-rep
+#   gpurun            -- 'bash tools/r2_profile.sh final'    n1 + the f1 line + smoke + ncu
 set -u
 mode=${1:-n1}
 O=gpurun_out
@@ -40,5 +42,16 @@ ab)
 bench)
   N=${2:-8}; shift 2
   tr 29631 --steps 20 --warmup 5 --no-cpu-baseline --no-cuda-eager "$@" > $O/r2_bench_n$N.json 2> $O/r2_bench_n$N.err; echo "bench rc=$?"
+  ;;
+ncu)
+  T=${2:-r2}
+  C="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-cuda-eager --no-graph --no-clocks --no-dropin --no-sustained --no-kernel-events"
+  $C > $O/${T}_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"tc_kernel|w_scale" -s 12 -c 4 -o $O/${T}_prof_hot $C > $O/${T}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+  ;;
+final)
+  bash "$0" n1
+  python bench.py --config f1 --steps 50 --warmup 5 > $O/r2_bench_f1_n1.json 2>> $O/r2_bench_n1.err; echo "f1 rc=$?"
+  python -c "import __graft_entry__ as g; g.smoke()" > $O/r2_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $O/r2_smoke.log
+  bash "$0" ncu r2d
   ;;
 esac
