@@ -548,7 +548,8 @@ tc_kernel(const __grid_constant__ TcParams p) {
         // The chunks are software-pipelined over two register buffers: the tcgen05.ld of chunk cc+1 is in flight
         // while chunk cc is processed, and the TMEM stage goes back to the MMA warp as soon as the LAST load has
         // completed - one chunk's worth of exp / pack / transpose earlier than after the loop (kChunks is 2 or 4).
-        if (p.flags & kIntNoEpiPipe) {                            // A/B switch (EVK_K3_PIPE=0): load, wait, process
+        constexpr bool kPipe = kEW <= 8;                          // the sixteen-warp variants are capped at 96 registers
+        if (!kPipe || (p.flags & kIntNoEpiPipe)) {                // (EVK_K3_PIPE=0: A/B switch) load, wait, process
           float v[32];
 #pragma unroll 1
           for (int cc = 0; cc < kChunks; ++cc) {
