@@ -9,6 +9,8 @@
 // Layouts: text [B, L, D], image [B, P, D], att / ds [B, L, P], out [B, L, D], all contiguous fp32.
 #include "evk_common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -507,6 +509,122 @@ token_sim_fwd_kernel(const float* __restrict__ th, const float* __restrict__ oh,
   }
 }
 
+// The same for a CLUSTER of kTSC CTAs per sample (d % 4 == 0): one CTA per sample leaves 116 of 148 SMs idle at the
+// reference's batch (B = 32).  CTA r multiplies the r-th quarter of the feature chunks into a partial L x L tile, the
+// partial tiles are summed through distributed shared memory in rank order (deterministic), and CTA r finishes rows
+// [32 r, 32 r + 32) - exp, row sums, diagonal, column partials; rank 0 adds the column partials of the four CTAs.
+constexpr int kTSC = 4;
+namespace cg = cooperative_groups;
+
+__global__ void __cluster_dims__(kTSC, 1, 1) __launch_bounds__(kThreads)
+token_sim_fwd_cluster_kernel(const float* __restrict__ th, const float* __restrict__ oh, int l, int d, float inv_tau,
+                             float* __restrict__ e_out, float* __restrict__ row_sum, float* __restrict__ row_pos,
+                             float* __restrict__ col_sum) {
+  __shared__ float as[kKC][kTS + 4];
+  __shared__ float bs[kKC][kTS + 4];
+  __shared__ float colp[4][kTS];
+  __shared__ float colq[kTS];
+  extern __shared__ __align__(16) float sm[];                    // part[kTS][kTS]: this CTA's partial tile
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / kTSC;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const float* a_base = th + (int64_t)b * l * d;
+  const float* b_base = oh + (int64_t)b * l * d;
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+  const int nchunk = (d + kKC - 1) / kKC;
+  const int k_lo = (nchunk * rank / kTSC) * kKC, k_hi = (nchunk * (rank + 1) / kTSC) * kKC;
+  float4 pa[2], pb[2];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = t + kThreads * i;
+      const int row = idx >> 2, q4 = idx & 3;
+      const bool ok = row < l && k0 + 4 * q4 < d;
+      pa[i] = ok ? __ldg(reinterpret_cast<const float4*>(a_base + (int64_t)row * d + k0) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      pb[i] = ok ? __ldg(reinterpret_cast<const float4*>(b_base + (int64_t)row * d + k0) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if (k_lo < k_hi) fetch(k_lo);
+  for (int k0 = k_lo; k0 < k_hi; k0 += kKC) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = t + kThreads * i;
+      const int row = idx >> 2, kk = (idx & 3) * 4;
+      as[kk][row] = pa[i].x; as[kk + 1][row] = pa[i].y; as[kk + 2][row] = pa[i].z; as[kk + 3][row] = pa[i].w;
+      bs[kk][row] = pb[i].x; bs[kk + 1][row] = pb[i].y; bs[kk + 2][row] = pb[i].z; bs[kk + 3][row] = pb[i].w;
+    }
+    __syncthreads();
+    if (k0 + kKC < k_hi) fetch(k0 + kKC);
+#pragma unroll
+    for (int kk = 0; kk < kKC; ++kk) {
+      float av[8], bv[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) av[r] = as[kk][ty * 8 + r];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) bv[c] = bs[kk][tx + 16 * c];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+  float* part = sm;
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) part[(ty * 8 + r) * kTS + tx + 16 * c] = acc[r][c];
+  cluster.sync();                                                  // every CTA's partial tile is complete
+  // rows [32 rank, 32 rank + 32) = ty in [4 rank, 4 rank + 4) = warps 2 rank and 2 rank + 1 (whole warps)
+  if ((ty >> 2) == rank) {
+    const float* ps[kTSC];
+#pragma unroll
+    for (int sr = 0; sr < kTSC; ++sr) ps[sr] = cluster.map_shared_rank(part, sr);
+    const float shift = inv_tau;
+    float cs[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) cs[c] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = ty * 8 + r;
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int j = tx + 16 * c;
+        const int o = i * kTS + j;
+        const float sacc = ((ps[0][o] + ps[1][o]) + ps[2][o]) + ps[3][o];   // fixed order: deterministic
+        const bool ok = i < l && j < l;
+        const float sv = sacc * inv_tau;
+        const float e = ok ? expf(sv - shift) : 0.f;
+        if (ok) e_out[((int64_t)b * l + i) * l + j] = e;
+        if (ok && i == j) row_pos[(int64_t)b * l + i] = sv;
+        rs += e;
+        cs[c] += e;
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+      if (tx == 0 && i < l) row_sum[(int64_t)b * l + i] = rs;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) colp[ty & 3][tx + 16 * c] = cs[c];
+  }
+  __syncthreads();
+  if (t < kTS) colq[t] = ((colp[0][t] + colp[1][t]) + colp[2][t]) + colp[3][t];
+  cluster.sync();                                                  // column partials of the four row quarters
+  if (rank == 0 && t < l) {
+    float sum = 0.f;
+#pragma unroll
+    for (int sr = 0; sr < kTSC; ++sr) sum += cluster.map_shared_rank(colq, sr)[t];
+    col_sum[(int64_t)b * l + t] = sum;
+  }
+  cluster.sync();                                                  // a CTA's shared memory must outlive the peers' reads
+}
+
 // d_th[b, i, c] = sum_j W_ij Ohat[j, c],  d_oh[b, j, c] = sum_i W_ij That[i, c],  W = E (a_i + b_j) - 2 [i == j]
 // (identity targets: c_i = 1).  CTA = (64 feature columns, sample); W, the Ohat and That column slabs in shared memory.
 constexpr int kDC = 64;
@@ -635,6 +753,15 @@ extern "C" int evk_token_sim_fwd(const float* th, const float* oh, int64_t batch
   EVK_REQUIRE(batch >= 1 && l >= 1 && l <= kTS && d >= 1, "evk_token_sim_fwd: needs 1 <= l <= %d tokens per sample", kTS);
   EVK_REQUIRE(inv_tau > 0.f && inv_tau <= EVK_MAX_INV_TAU, "evk_token_sim_fwd: 1/tau=%g outside (0, %g] (fixed-shift softmax)", inv_tau, EVK_MAX_INV_TAU);
   const bool vec = d % 4 == 0 && evk_aligned16(th) && evk_aligned16(oh);
+  static const bool use_cluster = [] { const char* e = getenv("EVK_F1_CLUSTER"); return !(e && e[0] == '0'); }();
+  if (vec && use_cluster) {                                       // kTSC CTAs per sample, partial tiles summed through DSMEM
+    const size_t smem = sizeof(float) * (size_t)kTS * kTS;
+    EVK_CUDA(cudaFuncSetAttribute(token_sim_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    token_sim_fwd_cluster_kernel<<<(unsigned)(batch * kTSC), kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        th, oh, (int)l, (int)d, inv_tau, e_out, row_sum, row_pos, col_sum);
+    EVK_CHECK_LAUNCH("token_sim_fwd_cluster");
+    return EVK_OK;
+  }
   auto kern = vec ? token_sim_fwd_kernel<true> : token_sim_fwd_kernel<false>;
   kern<<<(unsigned)batch, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(th, oh, (int)l, (int)d, inv_tau, e_out, row_sum, row_pos,
                                                                          col_sum);
