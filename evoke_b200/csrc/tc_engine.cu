@@ -35,14 +35,8 @@ using namespace tc;
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int kABytes = BM * BK * 2;          // 16 KiB: this CTA's 128 rows of A
 constexpr int kEpiWarps = 8;                  // two per SMSP; warp w reads TMEM lanes 32*(w%4)..+31
-constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 64 + kEpiThreads;    // + TMA producer warp + MMA issuer warp
-// K3 (EPI_FWD / EPI_FWD_E) runs SIXTEEN epilogue warps (four per SMSP, 32 rows x 64 columns each): its epilogue
-// - exp, row/column sums, bf16 pack - sets the pace of the kernel (ncu: the MMA waits for TMEM stages, 45% of the
-// epilogue's warp samples are fixed-latency / scoreboard stalls that two warps per scheduler cannot hide).
-constexpr int kEpiWarpsFwd = 16;
-// default number of epilogue warps of an epilogue kind (K3 variants are chosen at launch, see mpce_fwd_impl)
-__host__ __device__ constexpr int epi_warps(int epi) { return kEpiWarps; }
+// (+ one TMA producer warp + one MMA issuer warp per CTA; the sixteen-warp K3 variants are chosen at launch, see
+// mpce_fwd_impl / k3_variant())
 constexpr int kTmemCols = 512;
 constexpr int kK3DefaultVariant = 0;          // see k3_variant()
 constexpr int kMaxSegs = 3;
@@ -944,8 +938,7 @@ int launch(const TcParams& p, cudaStream_t s) {
   // stream-K (splits == 0): every group gets a range; a range should hold at least a few k-blocks
   const int64_t items = (int64_t)p.m_tiles * p.n_tiles * p.num_segs * p.kb_per_seg;
   const int units = p.splits > 0 ? p.m_tiles * p.n_tiles * p.splits : (int)(items / 4 < sms ? (items / 4 > 0 ? items / 4 : 1) : sms);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   if (CTA2) {
     const int groups = units < sms / 2 ? units : sms / 2;
