@@ -60,10 +60,11 @@ def test_local_token_alignment_reference_shapes_strided_inputs_and_patched_metho
 
 
 def test_local_token_alignment_batched_small_path_and_long_sequences(monkeypatch):
-    """The fallback (batched small-path kernels) on the same inputs, and l > 128 which always takes it."""
+    """The fallback (batched small-path kernels) on the same inputs, l > 128 which always takes it, and D % 4 != 0,
+    which takes the scalar-load variants of the attention / token-similarity kernels (no 128-bit loads, no cluster)."""
     from evoke_b200 import functional as Fn
     rng = np.random.default_rng(5)
-    for (b, l, p, d, force) in ((3, 40, 20, 96, True), (2, 150, 49, 64, False)):
+    for (b, l, p, d, force) in ((3, 40, 20, 96, True), (2, 150, 49, 64, False), (2, 20, 9, 30, False), (3, 33, 7, 50, False)):
         monkeypatch.setattr(Fn, "F1_TOKEN_SIM", not force)
         v = rng.standard_normal((b, p, d)).astype(np.float32)
         t = rng.standard_normal((b, l, d)).astype(np.float32)
